@@ -1,0 +1,224 @@
+/*
+ * nrslam_b200.h — C ABI of the B200-native deformable-SLAM optimisation core.
+ *
+ * This is the drop-in boundary for the ONE hot path of endomapper/NR-SLAM:
+ *   - CameraPoseOptimization                 modules/optimization/g2o_optimization.h:27   (.cc:50-146)
+ *   - CameraPoseAndDeformationOptimization   modules/optimization/g2o_optimization.h:29-32 (.cc:148-557)
+ *   - LocalDeformableBundleAdjustment        modules/optimization/g2o_optimization.h:39-40 (.cc:880-1161)
+ *   - LucasKanadeTracker::{SetReferenceImage,Track,Get/InsertPhotometricInformation,clear}
+ *                                            modules/matching/lucas_kanade_tracker.h:55-70 (.cc:47-631)
+ *   - RegularizationGraph::{GetEdges,UpdateVertex}   modules/map/regularization_graph.h:73,78 (.cc:71-146)
+ * The reference has no FFI of its own; INTEGRATION.md shows the C++ shim that forwards the four
+ * reference signatures to these entry points (nr-slam_b200/host/g2o_optimization_b200.cc).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, all pointers are HOST pointers unless a name ends in _dev.
+ *   - geometry is fp32 at the boundary (the reference stores Eigen::Vector3f / Sophus::SE3f), indices int32.
+ *   - a pose is 7 floats [qx qy qz qw tx ty tz] = Sophus::SE3f camera_transform_world (unit quaternion + t).
+ *   - statuses use the reference enum values (utilities/landmark_status.h:23-30).
+ *   - return value: 0 ok; < 0 CUDA / allocation / argument error; > 0 numerical condition
+ *     (1 = fewer points than the reference needs, nothing done). Never throws, never aborts.
+ *     nrslam_b200_last_error(ctx) returns a description of the last non-zero return.
+ *   - a ctx is single-caller (not re-entrant); calls block until results are in the host buffers.
+ *   - there is NO CPU fallback: every entry point that computes fails with NRSLAM_B200_ERR_NO_DEVICE
+ *     when no sm_100 device is present.
+ */
+#ifndef NRSLAM_B200_H
+#define NRSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRSLAM_B200_ABI_VERSION 1
+
+#define NRSLAM_B200_OK 0
+#define NRSLAM_B200_ERR_NO_DEVICE (-1)
+#define NRSLAM_B200_ERR_CUDA (-2)
+#define NRSLAM_B200_ERR_ARG (-3)
+#define NRSLAM_B200_ERR_ALLOC (-4)
+#define NRSLAM_B200_ERR_NCCL (-5)
+#define NRSLAM_B200_NUM_TOO_FEW (1)
+#define NRSLAM_B200_NUM_NONFINITE (2)
+
+/* LandmarkStatus — utilities/landmark_status.h:23-30 */
+enum {
+  NRSLAM_TRACKED_WITH_3D = 0,
+  NRSLAM_TRACKED = 1,
+  NRSLAM_JUST_TRIANGULATED = 2,
+  NRSLAM_BAD = 3,
+  NRSLAM_OUT_IMAGE_BOUNDARIES = 4,
+  NRSLAM_BAD_FEATURE = 5
+};
+/* RegularizationGraph::Status — map/regularization_graph.h:41-46 */
+enum { NRSLAM_EDGE_VERIFIED = 0, NRSLAM_EDGE_NEIGHBOR = 1, NRSLAM_EDGE_NEUTRAL = 2, NRSLAM_EDGE_BAD = 3 };
+
+/* CameraModel — calibration/pin_hole.cc (model 0: fx fy cx cy), calibration/kannala_brandt_8.cc
+ * (model 1: fx fy cx cy k0 k1 k2 k3). Evaluated in fp32 like the reference (camera_model.h:89-95). */
+typedef struct nrslam_b200_camera {
+  int32_t model;
+  float params[8];
+} nrslam_b200_camera;
+
+/* Every literal of g2o_optimization.cc with the reference value as default. */
+typedef struct nrslam_b200_options {
+  float th_huber_2dof_sq;        /* 5.99   g2o_optimization.cc:63,197,960 */
+  float th_huber_3dof_sq;        /* 0.584  :200,963 */
+  float sigma_reprojection;      /* 0.5 px :203,966 */
+  float sigma_position;          /* 0.1    :206,969 */
+  float sigma_spatial_factor;    /* 0.1 (x scale) :209,972 */
+  float spring_k;                /* 1.1    :328,1069 */
+  int32_t regularizers_per_point;/* 10 (loop admits 11) :195,958 */
+  int32_t pose_only_iterations[3];   /* {10,10,10} :103 */
+  int32_t pose_deform_iterations[2]; /* {10,10}    :338 */
+  int32_t lost_iterations;       /* 10 :538 */
+  int32_t ba_iterations;         /* 5  :1143 */
+  int32_t lm_max_trials;         /* 10  optimization_algorithm_levenberg.cpp:52 */
+  double lm_tau;                 /* 1e-5 :43 */
+  /* Linear solver. The reference factorises exactly (sparse LL^T); the GPU core runs a matrix-free
+   * block-preconditioned CG to this relative residual ||r||_M^-1 / ||b||_M^-1. */
+  double pcg_rel_tol;            /* default 1e-8 */
+  int32_t pcg_max_iterations;    /* default 2000 */
+  int32_t device;                /* CUDA device ordinal, default: LOCAL_RANK env or 0 */
+  int32_t grid_ctas;             /* persistent-kernel CTAs, 0 = auto from problem size */
+} nrslam_b200_options;
+
+/* Regularisation graph (map/regularization_graph.h:48-58,89) as CSR over map points.
+ * Vertices are map points in ASCENDING MapPoint id (the btree_map order); row entries ascending too.
+ * One attribute record per undirected edge (the reference shares one Edge object between both
+ * endpoints, regularization_graph.cc:53-54); eid[] maps each CSR entry to its record. */
+typedef struct nrslam_b200_graph {
+  int32_t n_vertices;
+  int32_t n_edges;            /* undirected */
+  const int32_t* rowptr;      /* [n_vertices + 1] */
+  const int32_t* col;         /* [2 * n_edges] neighbour vertex */
+  const int32_t* eid;         /* [2 * n_edges] undirected edge id */
+  float* weight;              /* [n_edges] in/out  Edge::weight */
+  const float* first_distance;/* [n_edges]         Edge::first_distance */
+  float* min_distance;        /* [n_edges] in/out */
+  float* max_distance;        /* [n_edges] in/out */
+  uint8_t* status;            /* [n_edges] in/out  NRSLAM_EDGE_* */
+  float weight_sigma;         /* Options::weight_sigma */
+  float stretching_th;        /* Options::streching_th (1.1, map.cc:28-29) */
+} nrslam_b200_graph;
+
+#define NRSLAM_B200_TRACE 64
+typedef struct nrslam_b200_stats {
+  int32_t lm_iterations;      /* LM iterations (g2o solve() calls) */
+  int32_t lm_trials;          /* damped linear solves */
+  int32_t pcg_iterations;     /* total CG iterations */
+  int32_t n_sweeps;           /* normal-equation sweeps (linearise + assemble) */
+  int32_t n_chi2_passes;      /* residual-only passes */
+  int32_t n_reproj_edges, n_pair_edges, n_spring_edges, n_damper_edges, n_fixed_edges;
+  int32_t n_points, n_poses;
+  int32_t kernel_launches;    /* kernels launched by this call */
+  int32_t n_trace;
+  double chi2_trace[NRSLAM_B200_TRACE]; /* accepted robust chi2 after each LM iteration */
+  double lambda_final;
+  float gpu_ms;               /* device time of the solve stage (CUDA events on the ctx stream) */
+  float host_ms;              /* wall time of the whole call */
+  float stage_ms;             /* host edge selection + H2D */
+} nrslam_b200_stats;
+
+typedef struct nrslam_b200_ctx nrslam_b200_ctx;
+
+void nrslam_b200_default_options(nrslam_b200_options* opt);
+int nrslam_b200_abi_version(void);
+/* opt == NULL -> defaults */
+int nrslam_b200_create(const nrslam_b200_options* opt, nrslam_b200_ctx** out);
+void nrslam_b200_destroy(nrslam_b200_ctx* ctx);
+const char* nrslam_b200_last_error(const nrslam_b200_ctx* ctx);
+/* Device the ctx is bound to and its SM count (diagnostics). */
+int nrslam_b200_device_info(const nrslam_b200_ctx* ctx, int32_t* device, int32_t* sm_count);
+
+/* ---- CameraPoseOptimization (g2o_optimization.cc:50-146) -------------------------------------
+ * n TRACKED_WITH_3D observations: uv[2n] keypoints, X[3n] world positions. pose_io: seed in, result out.
+ * inlier_out[n] (optional): the reference's `inliers` vector after the third round. */
+int nrslam_b200_pose_only(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                          const float* X, float* pose_io, uint8_t* inlier_out, nrslam_b200_stats* stats);
+
+/* ---- CameraPoseAndDeformationOptimization (g2o_optimization.cc:148-557) -----------------------
+ * n optimised points in frame order (Frame::Get*WithStatus({TRACKED_WITH_3D}), frame.cc:83-118):
+ *   uv[2n], X_rest[3n] (landmark positions), point_vertex[n] = graph vertex of each point.
+ * vertex_frame_status[g->n_vertices]: -1 if the map point is not in Frame::MapPointIdToIndex(), else its
+ *   LandmarkStatus in the frame (drives the "lost" classification, :264-273).
+ * last_world_position_io[3 * n_vertices]: MapPoint::GetLastWorldPosition of every graph vertex; updated
+ *   for inliers (:446) and for lost points (:550).
+ * Outputs (all optional except pose_io):
+ *   deformation_out[3n]      optimised deformation per point
+ *   X_out[3n]                Frame::LandmarkPositions after the call (rest + d where accepted, :444)
+ *   chi2_out[n]              final reprojection chi2 (:424)
+ *   status_out[n]            LandmarkStatus after the call (TRACKED_WITH_3D / TRACKED / BAD, :428,435,472)
+ *   median_deformation_out   Frame::SetDeformationMaginitud (:455)
+ *   lost_vertex_out[n_vertices], n_lost_out : returned set of lost map points (graph vertices, ascending)
+ * The graph attribute arrays are updated in place (RegularizationGraph::UpdateVertex, :458-474). */
+int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                            const float* X_rest, const int32_t* point_vertex,
+                            const int8_t* vertex_frame_status, nrslam_b200_graph* g, float scale,
+                            float* pose_io, float* last_world_position_io, float* deformation_out,
+                            float* X_out, float* chi2_out, uint8_t* status_out,
+                            float* median_deformation_out, int32_t* lost_vertex_out, int32_t* n_lost_out,
+                            nrslam_b200_stats* stats);
+
+/* ---- LocalDeformableBundleAdjustment (g2o_optimization.cc:880-1161) ---------------------------
+ * n_kf keyframes of the window, OLDEST FIRST (the reference walks keyframes_in_optimization.rbegin(),
+ * :930,982). n_obs observations grouped by keyframe in that order, inside a keyframe in
+ * KeyFrame::Get*WithStatus({TRACKED_WITH_3D}) order: obs_kf[n_obs] (non-decreasing slot in
+ * [0,n_kf)), obs_vertex[n_obs] graph vertex (map point), uv[2 n_obs], X_io[3 n_obs] per-keyframe
+ * landmark positions (in: KeyFrame::LandmarkPositions, out: optimised). kf_pose_io[7 n_kf].
+ * The reference hard-codes a 5-keyframe window (:894) and returns when < 3 (:922): window selection is
+ * the caller's; n_kf < 3 returns NRSLAM_B200_NUM_TOO_FEW untouched. iterations <= 0 -> options. */
+int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n_kf,
+                         float* kf_pose_io, int32_t n_obs, const int32_t* obs_kf,
+                         const int32_t* obs_vertex, const float* uv, float* X_io,
+                         const nrslam_b200_graph* g, float scale, int32_t iterations,
+                         nrslam_b200_stats* stats);
+
+/* Re-run the device solve of the most recently staged problem on its HBM-resident inputs (no host<->device
+ * copies, no host bookkeeping). which: 0 pose_only, 1 pose_deform (both robust rounds), 2 local_ba.
+ * Benchmark / profiler hook: results are identical to the staged call's. */
+int nrslam_b200_resolve(nrslam_b200_ctx* ctx, int32_t which, nrslam_b200_stats* stats);
+
+/* ---- RegularizationGraph (map/regularization_graph.cc:71-146) ---------------------------------
+ * get_edges: neighbours of `vertex` sorted by (status asc, weight desc, neighbour asc — E13 tie-break)
+ * truncated at the first weight < min_weight; writes CSR entry indices (into col/eid) to out, returns count.
+ * update_vertex: UpdateVertex; returns the number of good connections. positions = last world positions. */
+int32_t nrslam_b200_graph_get_edges(const nrslam_b200_graph* g, int32_t vertex, int32_t* out_entries,
+                                    int32_t capacity);
+int32_t nrslam_b200_graph_update_vertex(nrslam_b200_graph* g, int32_t vertex, const float* positions);
+
+/* ---- LucasKanadeTracker (matching/lucas_kanade_tracker.h:55-92) -------------------------------
+ * One tracker object per reference image. Images are 8-bit single channel, `pitch` bytes per row.
+ * Point i of every call is point i of SetReferenceImage (+ inserted ones): KLT index == frame index. */
+typedef struct nrslam_b200_klt nrslam_b200_klt;
+int nrslam_b200_klt_create(nrslam_b200_ctx* ctx, int32_t win_size, int32_t max_level, int32_t max_iters,
+                           float epsilon, float min_eig_threshold, nrslam_b200_klt** out);
+void nrslam_b200_klt_destroy(nrslam_b200_klt* klt);
+/* SetReferenceImage (.cc:47-168). mask may be NULL (cv::Mat()). */
+int nrslam_b200_klt_set_reference(nrslam_b200_klt* klt, const uint8_t* image, int32_t width, int32_t height,
+                                  int32_t pitch, int32_t n_points, const float* pts_xy, const uint8_t* mask,
+                                  int32_t mask_pitch);
+/* Track (.cc:170-596). pts_io[2n]: initial flow in (if use_initial_flow) / tracked positions out.
+ * status_io[n]: LandmarkStatus in/out. n_tracked_out: the reference's return value. */
+int nrslam_b200_klt_track(nrslam_b200_klt* klt, const uint8_t* image, int32_t width, int32_t height,
+                          int32_t pitch, int32_t n_points, float* pts_io, uint8_t* status_io,
+                          int32_t use_initial_flow, float min_ssim, const uint8_t* mask, int32_t mask_pitch,
+                          int32_t* n_tracked_out);
+/* Get/InsertPhotometricInformation (.cc:598-620): per level (max_level+1) a win*win int16 patch, a
+ * win*win*2 int16 gradient patch, mean and mean^2. valid_out[level] = 0 when the reference holds an empty Mat. */
+int nrslam_b200_klt_get_patch(nrslam_b200_klt* klt, int32_t idx, int16_t* gray_out, int16_t* grad_out,
+                              float* mean_out, float* mean2_out, uint8_t* valid_out);
+int nrslam_b200_klt_insert_patch(nrslam_b200_klt* klt, float x, float y, const int16_t* gray,
+                                 const int16_t* grad, const float* mean, const float* mean2,
+                                 const uint8_t* valid);
+int nrslam_b200_klt_clear(nrslam_b200_klt* klt);
+int32_t nrslam_b200_klt_num_points(const nrslam_b200_klt* klt);
+/* Re-run the last Track on the device-resident image/points (benchmark hook); device ms out. */
+int nrslam_b200_klt_retrack(nrslam_b200_klt* klt, float* gpu_ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRSLAM_B200_H */

@@ -1,0 +1,847 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.h / orc_lm.h headers for scope and citations).
+#include "orc_lm.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <limits>
+#include <set>
+#include <unordered_map>
+#include <unordered_set>
+
+namespace orc {
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// =============================================================================================
+// Sparse LL^T, up-looking (CSparse cs_etree / cs_ereach / cs_chol as published in T. Davis, "Direct
+// Methods for Sparse Linear Systems", 2006 — the algorithm Eigen::SimplicialLLT implements, which is
+// what g2o::LinearSolverEigen calls: solvers/eigen/linear_solver_eigen.h:56-57,116-136).
+// =============================================================================================
+class SparseChol {
+ public:
+  int n = 0;
+  std::vector<int> perm, pinv;  // perm[new] = old
+  std::vector<int> parent, Lp, Li;
+  std::vector<double> Lx;
+  bool analyzed = false;
+
+  // Minimum-degree ordering on the block graph (stand-in for Eigen's AMDOrdering,
+  // linear_solver_eigen.h:159-161 — any fill-reducing permutation gives the same x up to rounding).
+  static std::vector<int> min_degree(int nb, const std::vector<std::pair<int, int>>& pairs,
+                                     const std::vector<char>& force_last) {
+    std::vector<std::unordered_set<int>> adj(nb);
+    for (auto& pr : pairs)
+      if (!force_last[pr.first] && !force_last[pr.second]) {
+        adj[pr.first].insert(pr.second);
+        adj[pr.second].insert(pr.first);
+      }
+    std::set<std::pair<int, int>> pq;
+    for (int i = 0; i < nb; i++)
+      if (!force_last[i]) pq.insert({(int)adj[i].size(), i});
+    std::vector<int> order;
+    order.reserve(nb);
+    std::vector<int> nbv;
+    while (!pq.empty()) {
+      int v = pq.begin()->second;
+      pq.erase(pq.begin());
+      order.push_back(v);
+      nbv.assign(adj[v].begin(), adj[v].end());
+      for (int a : nbv) {
+        pq.erase({(int)adj[a].size(), a});
+        adj[a].erase(v);
+      }
+      for (size_t s = 0; s < nbv.size(); s++)
+        for (size_t t = s + 1; t < nbv.size(); t++)
+          if (adj[nbv[s]].insert(nbv[t]).second) adj[nbv[t]].insert(nbv[s]);
+      for (int a : nbv) pq.insert({(int)adj[a].size(), a});
+      std::unordered_set<int>().swap(adj[v]);
+    }
+    for (int i = 0; i < nb; i++)
+      if (force_last[i]) order.push_back(i);
+    return order;
+  }
+
+  // C: upper-triangular CSC of the permuted matrix (row indices unsorted is fine).
+  void analyze(int n_, const std::vector<int>& Cp, const std::vector<int>& Ci) {
+    n = n_;
+    parent.assign(n, -1);
+    std::vector<int> ancestor(n, -1);
+    for (int k = 0; k < n; k++) {
+      for (int p = Cp[k]; p < Cp[k + 1]; p++) {
+        int i = Ci[p];
+        while (i != -1 && i < k) {
+          int inext = ancestor[i];
+          ancestor[i] = k;
+          if (inext == -1) parent[i] = k;
+          i = inext;
+        }
+      }
+    }
+    // column counts by walking every row pattern (O(nnz(L)))
+    std::vector<int> cnt(n, 1), s(n), w(n, 0);
+    for (int k = 0; k < n; k++) {
+      int top = ereach(Cp, Ci, k, s.data(), w.data());
+      for (int t = top; t < n; t++) cnt[s[t]]++;
+    }
+    Lp.assign(n + 1, 0);
+    for (int k = 0; k < n; k++) Lp[k + 1] = Lp[k] + cnt[k];
+    Li.assign(Lp[n], 0);
+    Lx.assign(Lp[n], 0.0);
+    analyzed = true;
+  }
+
+  int ereach(const std::vector<int>& Cp, const std::vector<int>& Ci, int k, int* s, int* w) const {
+    int top = n;
+    w[k] = 1;
+    for (int p = Cp[k]; p < Cp[k + 1]; p++) {
+      int i = Ci[p];
+      if (i > k) continue;
+      int len = 0;
+      for (; !w[i]; i = parent[i]) {
+        s[len++] = i;
+        w[i] = 1;
+      }
+      while (len > 0) s[--top] = s[--len];
+    }
+    for (int p = top; p < n; p++) w[s[p]] = 0;
+    w[k] = 0;
+    return top;
+  }
+
+  bool factorize(const std::vector<int>& Cp, const std::vector<int>& Ci, const std::vector<double>& Cx) {
+    std::vector<int> c(Lp.begin(), Lp.end() - 1), s(n), w(n, 0);
+    std::vector<double> x(n, 0.0);
+    for (int k = 0; k < n; k++) {
+      int top = ereach(Cp, Ci, k, s.data(), w.data());
+      x[k] = 0;
+      for (int p = Cp[k]; p < Cp[k + 1]; p++)
+        if (Ci[p] <= k) x[Ci[p]] = Cx[p];
+      double d = x[k];
+      x[k] = 0;
+      for (; top < n; top++) {
+        int i = s[top];
+        double lki = x[i] / Lx[Lp[i]];
+        x[i] = 0;
+        for (int p = Lp[i] + 1; p < c[i]; p++) x[Li[p]] -= Lx[p] * lki;
+        d -= lki * lki;
+        int p = c[i]++;
+        Li[p] = k;
+        Lx[p] = lki;
+      }
+      if (!(d > 0)) return false;  // not positive definite (Eigen: info() != Success)
+      int p = c[k]++;
+      Li[p] = k;
+      Lx[p] = std::sqrt(d);
+    }
+    return true;
+  }
+
+  void solve(const double* b, double* xout) const {
+    std::vector<double> y(n);
+    for (int k = 0; k < n; k++) y[k] = b[perm[k]];
+    for (int j = 0; j < n; j++) {
+      y[j] /= Lx[Lp[j]];
+      for (int p = Lp[j] + 1; p < Lp[j + 1]; p++) y[Li[p]] -= Lx[p] * y[j];
+    }
+    for (int j = n - 1; j >= 0; j--) {
+      for (int p = Lp[j] + 1; p < Lp[j + 1]; p++) y[j] -= Lx[p] * y[Li[p]];
+      y[j] /= Lx[Lp[j]];
+    }
+    for (int k = 0; k < n; k++) xout[perm[k]] = y[k];
+  }
+};
+
+Optimizer::~Optimizer() { delete chol_; }
+
+// =============================================================================================
+// Edges
+// =============================================================================================
+static inline int pair_slot(int n, int m, int nv) {
+  // (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) for nv = 4 ; (0,1) for nv = 2
+  int k = 0;
+  for (int a = 0; a < nv; a++)
+    for (int b = a + 1; b < nv; b++) {
+      if (a == n && b == m) return k;
+      k++;
+    }
+  return -1;
+}
+
+bool Optimizer::all_vertices_fixed(const Edge& e) const {
+  for (int i = 0; i < e.nv; i++)
+    if (!vertices[e.v[i]].fixed) return false;
+  return true;
+}
+
+void Optimizer::compute_error(Edge& e) const {
+  switch (e.type) {
+    case E_REPROJ_ONLY_POSE: {
+      double pc[3], uv[2];
+      se3_map(vertices[e.v[0]].pose, e.Xw, pc);
+      project_d(cam_, pc, uv);
+      e.err[0] = e.meas[0] - uv[0];
+      e.err[1] = e.meas[1] - uv[1];
+    } break;
+    case E_REPROJ_DEFORM: {
+      const double* d = vertices[e.v[1]].x;
+      double Xd[3] = {d[0] + e.Xw[0], d[1] + e.Xw[1], d[2] + e.Xw[2]}, pc[3], uv[2];
+      se3_map(vertices[e.v[0]].pose, Xd, pc);
+      project_d(cam_, pc, uv);
+      e.err[0] = e.meas[0] - uv[0];
+      e.err[1] = e.meas[1] - uv[1];
+    } break;
+    case E_REPROJ_BA: {
+      double pc[3], uv[2];
+      se3_map(vertices[e.v[0]].pose, vertices[e.v[1]].x, pc);
+      project_d(cam_, pc, uv);
+      e.err[0] = e.meas[0] - uv[0];
+      e.err[1] = e.meas[1] - uv[1];
+    } break;
+    case E_SPATIAL_DEFORM: {
+      const double *a = vertices[e.v[0]].x, *b = vertices[e.v[1]].x;
+      for (int i = 0; i < 3; i++) e.err[i] = e.weight * (a[i] - b[i]);
+    } break;
+    case E_SPATIAL_FIXED: {
+      const double *a = vertices[e.v[0]].x, *b = vertices[e.ref_vertex].x;
+      for (int i = 0; i < 3; i++) e.err[i] = e.weight * (a[i] - b[i]);
+    } break;
+    case E_POSITION_DEFORM: {
+      const double *a = vertices[e.v[0]].x, *b = vertices[e.v[1]].x;
+      double df[3];
+      for (int i = 0; i < 3; i++) df[i] = (e.rest1[i] + a[i]) - (e.rest2[i] + b[i]);
+      double dist = std::sqrt(df[0] * df[0] + df[1] * df[1] + df[2] * df[2]);
+      e.err[0] = e.k * (dist - e.meas[0]) / e.meas[0];
+    } break;
+    case E_POSITION_BA: {
+      const double *a = vertices[e.v[0]].x, *b = vertices[e.v[1]].x;
+      double df[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+      double dist = std::sqrt(df[0] * df[0] + df[1] * df[1] + df[2] * df[2]);
+      e.err[0] = e.k * (dist - e.meas[0]) / e.meas[0];
+    } break;
+    case E_DAMPER_BA: {
+      const double *p1c = vertices[e.v[0]].x, *p2c = vertices[e.v[1]].x;
+      const double *p1n = vertices[e.v[2]].x, *p2n = vertices[e.v[3]].x;
+      for (int i = 0; i < 3; i++) e.err[i] = e.weight * ((p1n[i] - p1c[i]) - (p2n[i] - p2c[i]));
+    } break;
+  }
+}
+
+static void reproj_jacobians(const Camera& cam, const SE3& T, const double Xw[3], double Jpose[18], double* Jpt) {
+  double pc[3], Jp[6];
+  se3_map(T, Xw, pc);
+  projection_jacobian_d(cam, pc, Jp);
+  for (int i = 0; i < 6; i++) Jp[i] = -Jp[i];
+  const double x = pc[0], y = pc[1], z = pc[2];
+  const double M[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+  for (int r = 0; r < 2; r++)
+    for (int c = 0; c < 6; c++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += Jp[r * 3 + k] * M[k * 6 + c];
+      Jpose[r * 6 + c] = s;
+    }
+  if (Jpt) {
+    double R[9];
+    quat_to_R(T.q, R);
+    for (int r = 0; r < 2; r++)
+      for (int c = 0; c < 3; c++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += Jp[r * 3 + k] * R[k * 3 + c];
+        Jpt[r * 3 + c] = s;
+      }
+  }
+}
+
+void Optimizer::linearize(const Edge& e, double J[4][18]) const {
+  switch (e.type) {
+    case E_REPROJ_ONLY_POSE:
+      reproj_jacobians(cam_, vertices[e.v[0]].pose, e.Xw, J[0], nullptr);
+      break;
+    case E_REPROJ_DEFORM: {
+      const double* d = vertices[e.v[1]].x;
+      double Xd[3] = {d[0] + e.Xw[0], d[1] + e.Xw[1], d[2] + e.Xw[2]};
+      reproj_jacobians(cam_, vertices[e.v[0]].pose, Xd, J[0], J[1]);
+    } break;
+    case E_REPROJ_BA:
+      reproj_jacobians(cam_, vertices[e.v[0]].pose, vertices[e.v[1]].x, J[0], J[1]);
+      break;
+    case E_SPATIAL_DEFORM:
+      for (int i = 0; i < 9; i++) {
+        J[0][i] = (i % 4 == 0) ? e.weight : 0.0;
+        J[1][i] = (i % 4 == 0) ? -e.weight : 0.0;
+      }
+      break;
+    case E_SPATIAL_FIXED:
+      for (int i = 0; i < 9; i++) J[0][i] = (i % 4 == 0) ? e.weight : 0.0;
+      break;
+    case E_POSITION_DEFORM: {
+      // position_regularizer_with_deformation.cc:45-56: a = k / (2 d0 dist), v = 2 c1 - 2 c2
+      const double *a = vertices[e.v[0]].x, *b = vertices[e.v[1]].x;
+      double c1[3], c2[3];
+      for (int i = 0; i < 3; i++) {
+        c1[i] = e.rest1[i] + a[i];
+        c2[i] = e.rest2[i] + b[i];
+      }
+      double df[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+      double dist = std::sqrt(df[0] * df[0] + df[1] * df[1] + df[2] * df[2]);
+      double aa = e.k / (2 * e.meas[0] * dist);
+      for (int i = 0; i < 3; i++) {
+        double v = 2 * c1[i] - 2 * c2[i];
+        J[0][i] = aa * v;
+        J[1][i] = -aa * v;
+      }
+    } break;
+    case E_POSITION_BA: {
+      // position_regularizer.cc:45-60 (quirk E1): (k/d0) * (1/sqrt(dist)) * (+-2 diff)
+      const double *a = vertices[e.v[0]].x, *b = vertices[e.v[1]].x;
+      double df[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+      double dist = std::sqrt(df[0] * df[0] + df[1] * df[1] + df[2] * df[2]);
+      double k_div_d0 = e.k / e.meas[0];
+      double dcs = 1.f / std::sqrt(dist);
+      for (int i = 0; i < 3; i++) {
+        J[0][i] = k_div_d0 * dcs * (2.f * df[i]);
+        J[1][i] = k_div_d0 * dcs * (-2.f * df[i]);
+      }
+    } break;
+    case E_DAMPER_BA:
+      for (int i = 0; i < 9; i++) {
+        double d = (i % 4 == 0) ? e.weight : 0.0;
+        J[0][i] = -d;
+        J[1][i] = d;
+        J[2][i] = d;
+        J[3][i] = -d;
+      }
+      break;
+  }
+}
+
+// =============================================================================================
+// SparseOptimizer
+// =============================================================================================
+// sparse_optimizer.cpp:213-285 (+ buildIndexMapping :171-196, sortVectorContainers :517-521)
+bool Optimizer::initialize_optimization(int level) {
+  if (edges.empty()) return false;
+  for (int i : index_mapping_) vertices[i].hidx = -1;
+  std::vector<char> vact(vertices.size(), 0);
+  active_edges_.clear();
+  for (size_t k = 0; k < edges.size(); k++) {
+    const Edge& e = edges[k];
+    if (level >= 0 && e.level != level) continue;
+    if (all_vertices_fixed(e)) continue;
+    active_edges_.push_back((int)k);  // insertion order == internalId order
+    for (int i = 0; i < e.nv; i++) vact[e.v[i]] = 1;
+  }
+  active_vertices_.clear();
+  for (size_t i = 0; i < vertices.size(); i++)
+    if (vact[i]) active_vertices_.push_back((int)i);  // ascending id
+  index_mapping_.clear();
+  for (int i : active_vertices_) {
+    if (!vertices[i].fixed) {
+      vertices[i].hidx = (int)index_mapping_.size();
+      index_mapping_.push_back(i);
+    } else {
+      vertices[i].hidx = -1;
+    }
+  }
+  structure_dirty_ = true;
+  return !index_mapping_.empty();
+}
+
+void Optimizer::compute_active_errors() {
+  for (int k : active_edges_) compute_error(edges[k]);
+}
+
+// sparse_optimizer.cpp:100-114
+double Optimizer::active_robust_chi2() const {
+  double chi = 0;
+  for (int k : active_edges_) {
+    const Edge& e = edges[k];
+    if (e.delta > 0) {
+      double rho[3];
+      huber(chi2(e), e.delta, rho);
+      chi += rho[0];
+    } else {
+      chi += chi2(e);
+    }
+  }
+  return chi;
+}
+
+// block_solver.hpp:108-159 (non-Schur part)
+void Optimizer::build_structure() {
+  n_scalar_ = 0;
+  for (int i : index_mapping_) {
+    vertices[i].col = n_scalar_;
+    n_scalar_ += vertices[i].dim;
+  }
+  blocks_.clear();
+  std::unordered_map<uint64_t, int> slot;
+  for (int k : active_edges_) {
+    Edge& e = edges[k];
+    for (int n = 0; n < e.nv; n++)
+      for (int m = n + 1; m < e.nv; m++) {
+        int ps = pair_slot(n, m, e.nv);
+        e.hb[ps] = -1;
+        const Vertex &vn = vertices[e.v[n]], &vm = vertices[e.v[m]];
+        if (vn.fixed || vm.fixed) continue;
+        int hi = vn.hidx, hj = vm.hidx;
+        bool tr = hi > hj;
+        if (tr) std::swap(hi, hj);
+        uint64_t key = ((uint64_t)hi << 32) | (uint32_t)hj;
+        auto it = slot.find(key);
+        int idx;
+        if (it == slot.end()) {
+          idx = (int)blocks_.size();
+          slot[key] = idx;
+          OffBlock b;
+          b.i = hi;
+          b.j = hj;
+          b.rows = vertices[index_mapping_[hi]].dim;
+          b.cols = vertices[index_mapping_[hj]].dim;
+          std::memset(b.m, 0, sizeof(b.m));
+          blocks_.push_back(b);
+        } else {
+          idx = it->second;
+        }
+        e.hb[ps] = idx;
+        e.hbT[ps] = tr;
+      }
+  }
+  b_.assign(n_scalar_, 0.0);
+  x_.assign(n_scalar_, 0.0);
+  delete chol_;
+  chol_ = nullptr;
+  structure_dirty_ = false;
+}
+
+// block_solver.hpp:495-562 + base_fixed_sized_edge.hpp:49-133
+void Optimizer::build_system() {
+  for (int i : index_mapping_) {
+    std::memset(vertices[i].A, 0, sizeof(vertices[i].A));
+    std::memset(vertices[i].b, 0, sizeof(vertices[i].b));
+  }
+  for (auto& b : blocks_) std::memset(b.m, 0, sizeof(b.m));
+  double J[4][18];
+  for (int k : active_edges_) {
+    Edge& e = edges[k];
+    linearize(e, J);
+    double omega = e.info, we[3];
+    if (e.delta > 0) {
+      double rho[3];
+      huber(chi2(e), e.delta, rho);
+      for (int i = 0; i < e.dim; i++) we[i] = -e.info * e.err[i] * rho[1];
+      omega = rho[1] * e.info;  // base_edge.h:158-164 (second-order term commented out)
+    } else {
+      for (int i = 0; i < e.dim; i++) we[i] = -e.info * e.err[i];
+    }
+    for (int n = 0; n < e.nv; n++) {
+      Vertex& vn = vertices[e.v[n]];
+      if (vn.fixed) continue;
+      const int dn = vn.dim;
+      // b += A^T * weightedError ; A += A^T omega A
+      for (int c = 0; c < dn; c++) {
+        double s = 0;
+        for (int r = 0; r < e.dim; r++) s += J[n][r * dn + c] * we[r];
+        vn.b[c] += s;
+      }
+      for (int a = 0; a < dn; a++)
+        for (int c = 0; c < dn; c++) {
+          double s = 0;
+          for (int r = 0; r < e.dim; r++) s += J[n][r * dn + a] * omega * J[n][r * dn + c];
+          vn.A[a * dn + c] += s;
+        }
+      for (int m = n + 1; m < e.nv; m++) {
+        const Vertex& vm = vertices[e.v[m]];
+        if (vm.fixed) continue;
+        const int dm = vm.dim;
+        int ps = pair_slot(n, m, e.nv);
+        OffBlock& B = blocks_[e.hb[ps]];
+        for (int a = 0; a < dn; a++)
+          for (int c = 0; c < dm; c++) {
+            double s = 0;
+            for (int r = 0; r < e.dim; r++) s += J[n][r * dn + a] * omega * J[m][r * dm + c];
+            if (!e.hbT[ps])
+              B.m[a * B.cols + c] += s;
+            else
+              B.m[c * B.cols + a] += s;
+          }
+      }
+    }
+  }
+  for (int i : index_mapping_)
+    for (int c = 0; c < vertices[i].dim; c++) b_[vertices[i].col + c] = vertices[i].b[c];
+}
+
+bool Optimizer::solve_pcg(double lambda) {
+  // Experiment only: block-Jacobi PCG on the assembled blocks (mirrors what the CUDA engine does).
+  const int nb = (int)index_mapping_.size();
+  const int n = n_scalar_;
+  std::vector<double> Minv(nb * 36, 0.0);
+  for (int h = 0; h < nb; h++) {
+    const Vertex& v = vertices[index_mapping_[h]];
+    const int d = v.dim;
+    double A[36], L[36] = {0};
+    for (int i = 0; i < d * d; i++) A[i] = v.A[i];
+    for (int i = 0; i < d; i++) A[i * d + i] += lambda;
+    // invert SPD by Cholesky
+    bool ok = true;
+    for (int j = 0; j < d && ok; j++) {
+      double s = A[j * d + j];
+      for (int k = 0; k < j; k++) s -= L[j * d + k] * L[j * d + k];
+      if (!(s > 0)) { ok = false; break; }
+      L[j * d + j] = std::sqrt(s);
+      for (int i = j + 1; i < d; i++) {
+        double t = A[i * d + j];
+        for (int k = 0; k < j; k++) t -= L[i * d + k] * L[j * d + k];
+        L[i * d + j] = t / L[j * d + j];
+      }
+    }
+    if (!ok) return false;
+    for (int c = 0; c < d; c++) {
+      double y[6];
+      for (int i = 0; i < d; i++) {
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < i; k++) s -= L[i * d + k] * y[k];
+        y[i] = s / L[i * d + i];
+      }
+      for (int i = d - 1; i >= 0; i--) {
+        double s = y[i];
+        for (int k = i + 1; k < d; k++) s -= L[k * d + i] * y[k];
+        y[i] = s / L[i * d + i];
+      }
+      for (int i = 0; i < d; i++) Minv[h * 36 + i * d + c] = y[i];
+    }
+  }
+  auto matvec = [&](const std::vector<double>& p, std::vector<double>& q) {
+    for (int h = 0; h < nb; h++) {
+      const Vertex& v = vertices[index_mapping_[h]];
+      const int d = v.dim;
+      for (int a = 0; a < d; a++) {
+        double s = lambda * p[v.col + a];
+        for (int c = 0; c < d; c++) s += v.A[a * d + c] * p[v.col + c];
+        q[v.col + a] = s;
+      }
+    }
+    for (const auto& B : blocks_) {
+      const int ci = vertices[index_mapping_[B.i]].col, cj = vertices[index_mapping_[B.j]].col;
+      for (int a = 0; a < B.rows; a++)
+        for (int c = 0; c < B.cols; c++) {
+          q[ci + a] += B.m[a * B.cols + c] * p[cj + c];
+          q[cj + c] += B.m[a * B.cols + c] * p[ci + a];
+        }
+    }
+  };
+  auto precond = [&](const std::vector<double>& r, std::vector<double>& z) {
+    for (int h = 0; h < nb; h++) {
+      const Vertex& v = vertices[index_mapping_[h]];
+      const int d = v.dim;
+      for (int a = 0; a < d; a++) {
+        double s = 0;
+        for (int c = 0; c < d; c++) s += Minv[h * 36 + a * d + c] * r[v.col + c];
+        z[v.col + a] = s;
+      }
+    }
+  };
+  std::vector<double> x(n, 0.0), r(b_), z(n), p(n), q(n);
+  precond(r, z);
+  p = z;
+  double rz = 0, rz0;
+  for (int i = 0; i < n; i++) rz += r[i] * z[i];
+  rz0 = rz;
+  int it = 0;
+  for (; it < pcg_max_iter && rz > pcg_tol * pcg_tol * rz0 && rz > 0; it++) {
+    matvec(p, q);
+    double pq = 0;
+    for (int i = 0; i < n; i++) pq += p[i] * q[i];
+    double alpha = rz / pq;
+    for (int i = 0; i < n; i++) {
+      x[i] += alpha * p[i];
+      r[i] -= alpha * q[i];
+    }
+    precond(r, z);
+    double rzn = 0;
+    for (int i = 0; i < n; i++) rzn += r[i] * z[i];
+    double beta = rzn / rz;
+    rz = rzn;
+    for (int i = 0; i < n; i++) p[i] = z[i] + beta * p[i];
+  }
+  pcg_iters_total += it;
+  x_ = x;
+  return true;
+}
+
+bool Optimizer::solve_linear(double lambda) {
+  const int n = n_scalar_;
+  if (use_pcg) return solve_pcg(lambda);
+  if (dense_) {
+    // linear_solver_dense.h:56-104 — dense copy + LDLT; "isPositive" <=> all pivots > 0.
+    std::vector<double> H(n * n, 0.0);
+    for (int i : index_mapping_) {
+      const Vertex& v = vertices[i];
+      for (int a = 0; a < v.dim; a++)
+        for (int c = 0; c < v.dim; c++) H[(v.col + a) * n + v.col + c] = v.A[a * v.dim + c];
+    }
+    for (const auto& B : blocks_) {
+      int ci = vertices[index_mapping_[B.i]].col, cj = vertices[index_mapping_[B.j]].col;
+      for (int a = 0; a < B.rows; a++)
+        for (int c = 0; c < B.cols; c++) {
+          H[(ci + a) * n + cj + c] = B.m[a * B.cols + c];
+          H[(cj + c) * n + ci + a] = B.m[a * B.cols + c];
+        }
+    }
+    for (int i = 0; i < n; i++) H[i * n + i] += lambda;
+    // LDL^T without pivoting
+    std::vector<double> L(n * n, 0.0), D(n, 0.0);
+    for (int j = 0; j < n; j++) {
+      double d = H[j * n + j];
+      for (int k = 0; k < j; k++) d -= L[j * n + k] * L[j * n + k] * D[k];
+      D[j] = d;
+      if (!(d > 0)) return false;
+      L[j * n + j] = 1;
+      for (int i = j + 1; i < n; i++) {
+        double s = H[i * n + j];
+        for (int k = 0; k < j; k++) s -= L[i * n + k] * L[j * n + k] * D[k];
+        L[i * n + j] = s / d;
+      }
+    }
+    std::vector<double> y(n);
+    for (int i = 0; i < n; i++) {
+      double s = b_[i];
+      for (int k = 0; k < i; k++) s -= L[i * n + k] * y[k];
+      y[i] = s;
+    }
+    for (int i = 0; i < n; i++) y[i] /= D[i];
+    for (int i = n - 1; i >= 0; i--) {
+      double s = y[i];
+      for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x_[k];
+      x_[i] = s;
+    }
+    return true;
+  }
+  // ---- sparse path ----
+  const int nb = (int)index_mapping_.size();
+  if (!chol_) {
+    double t0 = now_s();
+    chol_ = new SparseChol();
+    std::vector<std::pair<int, int>> pairs;
+    pairs.reserve(blocks_.size());
+    for (const auto& B : blocks_) pairs.push_back({B.i, B.j});
+    std::vector<char> force_last(nb, 0);
+    for (int h = 0; h < nb; h++)
+      if (vertices[index_mapping_[h]].type == V_POSE) force_last[h] = 1;
+    std::vector<int> border = SparseChol::min_degree(nb, pairs, force_last);
+    chol_->perm.resize(n);
+    chol_->pinv.resize(n);
+    int k = 0;
+    for (int h : border) {
+      const Vertex& v = vertices[index_mapping_[h]];
+      for (int a = 0; a < v.dim; a++) chol_->perm[k++] = v.col + a;
+    }
+    for (int i = 0; i < n; i++) chol_->pinv[chol_->perm[i]] = i;
+    stats.t_order += now_s() - t0;
+  }
+  double t0 = now_s();
+  // upper-triangular CSC of P A P^T
+  const std::vector<int>& pinv = chol_->pinv;
+  std::vector<int> Cp(n + 1, 0);
+  auto count = [&](int r, int c) {
+    int pr = pinv[r], pc = pinv[c];
+    Cp[std::max(pr, pc) + 1]++;
+  };
+  for (int i : index_mapping_) {
+    const Vertex& v = vertices[i];
+    for (int a = 0; a < v.dim; a++)
+      for (int c = a; c < v.dim; c++) count(v.col + a, v.col + c);
+  }
+  for (const auto& B : blocks_) {
+    int ci = vertices[index_mapping_[B.i]].col, cj = vertices[index_mapping_[B.j]].col;
+    for (int a = 0; a < B.rows; a++)
+      for (int c = 0; c < B.cols; c++) count(ci + a, cj + c);
+  }
+  for (int i = 0; i < n; i++) Cp[i + 1] += Cp[i];
+  std::vector<int> Ci(Cp[n]), w(Cp.begin(), Cp.end() - 1);
+  std::vector<double> Cx(Cp[n]);
+  auto put = [&](int r, int c, double val) {
+    int pr = pinv[r], pc = pinv[c];
+    int col = std::max(pr, pc), row = std::min(pr, pc);
+    int p = w[col]++;
+    Ci[p] = row;
+    Cx[p] = val;
+  };
+  for (int i : index_mapping_) {
+    const Vertex& v = vertices[i];
+    for (int a = 0; a < v.dim; a++)
+      for (int c = a; c < v.dim; c++) put(v.col + a, v.col + c, v.A[a * v.dim + c] + (a == c ? lambda : 0.0));
+  }
+  for (const auto& B : blocks_) {
+    int ci = vertices[index_mapping_[B.i]].col, cj = vertices[index_mapping_[B.j]].col;
+    for (int a = 0; a < B.rows; a++)
+      for (int c = 0; c < B.cols; c++) put(ci + a, cj + c, B.m[a * B.cols + c]);
+  }
+  if (!chol_->analyzed) chol_->analyze(n, Cp, Ci);
+  bool ok = chol_->factorize(Cp, Ci, Cx);
+  if (ok) chol_->solve(b_.data(), x_.data());
+  stats.t_factor += now_s() - t0;
+  if (!ok) stats.chol_fail++;
+  return ok;
+}
+
+// sparse_optimizer.cpp:457-470 ; vertex_se3_expmap.cpp:48-51 ; landmark_vertex.cc:40-43
+void Optimizer::update(const std::vector<double>& dx) {
+  for (int i : index_mapping_) {
+    Vertex& v = vertices[i];
+    const double* u = dx.data() + v.col;
+    if (v.type == V_POSE) {
+      v.pose = se3_mul(se3_exp(u), v.pose);
+    } else {
+      v.x[0] += u[0];
+      v.x[1] += u[1];
+      v.x[2] += u[2];
+    }
+  }
+}
+
+void Optimizer::push() {
+  for (int i : active_vertices_) {
+    Vertex& v = vertices[i];
+    std::array<double, 7> s;
+    if (v.type == V_POSE) {
+      for (int k = 0; k < 4; k++) s[k] = v.pose.q[k];
+      for (int k = 0; k < 3; k++) s[4 + k] = v.pose.t[k];
+    } else {
+      for (int k = 0; k < 3; k++) s[k] = v.x[k];
+    }
+    v.stack.push_back(s);
+  }
+}
+void Optimizer::pop() {
+  for (int i : active_vertices_) {
+    Vertex& v = vertices[i];
+    const auto& s = v.stack.back();
+    if (v.type == V_POSE) {
+      for (int k = 0; k < 4; k++) v.pose.q[k] = s[k];
+      for (int k = 0; k < 3; k++) v.pose.t[k] = s[4 + k];
+    } else {
+      for (int k = 0; k < 3; k++) v.x[k] = s[k];
+    }
+    v.stack.pop_back();
+  }
+}
+void Optimizer::discard_top() {
+  for (int i : active_vertices_) vertices[i].stack.pop_back();
+}
+
+// optimization_algorithm_levenberg.cpp:57-151.  returns 0 = OK, 1 = Terminate
+int Optimizer::lm_solve(int iteration) {
+  if (iteration == 0) build_structure();
+  compute_active_errors();
+  double currentChi = active_robust_chi2();
+  double tb = now_s();
+  build_system();
+  stats.t_build += now_s() - tb;
+  if (iteration == 0) {
+    stats.chi2_init = currentChi;
+    // computeLambdaInit :153-165
+    double maxDiagonal = 0;
+    for (int i : index_mapping_) {
+      const Vertex& v = vertices[i];
+      for (int j = 0; j < v.dim; j++) maxDiagonal = std::max(std::fabs(v.A[j * v.dim + j]), maxDiagonal);
+    }
+    lambda_ = 1e-5 * maxDiagonal;
+    ni_ = 2;
+  }
+  double rho = 0;
+  int qmax = 0;
+  do {
+    push();
+    bool ok2 = solve_linear(lambda_);
+    stats.trials++;
+    update(x_);
+    compute_active_errors();
+    double tempChi = active_robust_chi2();
+    if (!ok2) tempChi = std::numeric_limits<double>::max();
+    rho = currentChi - tempChi;
+    double scale = 0;
+    for (int j = 0; j < n_scalar_; j++) scale += x_[j] * (lambda_ * x_[j] + b_[j]);
+    scale += 1e-3;
+    rho /= scale;
+    if (rho > 0 && std::isfinite(tempChi)) {
+      double alpha = 1. - std::pow((2 * rho - 1), 3);
+      alpha = std::min(alpha, 2. / 3.);
+      double scaleFactor = std::max(1. / 3., alpha);
+      lambda_ *= scaleFactor;
+      ni_ = 2;
+      currentChi = tempChi;
+      discard_top();
+    } else {
+      lambda_ *= ni_;
+      ni_ *= 2;
+      pop();
+      if (!std::isfinite(lambda_)) break;
+    }
+    qmax++;
+  } while (rho < 0 && qmax < 10);
+  stats.lambda = lambda_;
+  stats.chi2_final = currentChi;
+  stats.chi2_trace.push_back(currentChi);
+  if (qmax == 10 || rho == 0 || !std::isfinite(lambda_)) return 1;
+  return 0;
+}
+
+// sparse_optimizer.cpp:392-455
+int Optimizer::optimize(int iterations) {
+  if (index_mapping_.empty()) return -1;
+  structure_dirty_ = true;  // algorithm->init(): solver re-initialised on every optimize() call
+  int cj = 0;
+  bool ok = true;
+  for (int i = 0; i < iterations && ok; i++) {
+    int result = lm_solve(i);
+    ok = (result == 0);
+    stats.iterations++;
+    ++cj;
+  }
+  return cj;
+}
+
+int sparse_solve_triplets(int n, int block, int nnz, const int* rows, const int* cols, const double* vals,
+                          const double* b, double* x) {
+  const int nb = n / block;
+  std::set<std::pair<int, int>> pairs;
+  for (int k = 0; k < nnz; k++) {
+    int bi = rows[k] / block, bj = cols[k] / block;
+    if (bi != bj) pairs.insert({std::min(bi, bj), std::max(bi, bj)});
+  }
+  std::vector<std::pair<int, int>> pl(pairs.begin(), pairs.end());
+  std::vector<char> fl(nb, 0);
+  std::vector<int> border = SparseChol::min_degree(nb, pl, fl);
+  SparseChol ch;
+  ch.perm.resize(n);
+  ch.pinv.resize(n);
+  int k = 0;
+  for (int h : border)
+    for (int a = 0; a < block; a++) ch.perm[k++] = h * block + a;
+  for (int i = 0; i < n; i++) ch.pinv[ch.perm[i]] = i;
+  std::vector<int> Cp(n + 1, 0);
+  for (int t = 0; t < nnz; t++) {
+    if (rows[t] > cols[t]) continue;
+    Cp[std::max(ch.pinv[rows[t]], ch.pinv[cols[t]]) + 1]++;
+  }
+  for (int i = 0; i < n; i++) Cp[i + 1] += Cp[i];
+  std::vector<int> Ci(Cp[n]), w(Cp.begin(), Cp.end() - 1);
+  std::vector<double> Cx(Cp[n]);
+  for (int t = 0; t < nnz; t++) {
+    if (rows[t] > cols[t]) continue;
+    int pr = ch.pinv[rows[t]], pc = ch.pinv[cols[t]];
+    int p = w[std::max(pr, pc)]++;
+    Ci[p] = std::min(pr, pc);
+    Cx[p] = vals[t];
+  }
+  ch.analyze(n, Cp, Ci);
+  if (!ch.factorize(Cp, Ci, Cx)) return 1;
+  ch.solve(b, x);
+  return 0;
+}
+
+}  // namespace orc
