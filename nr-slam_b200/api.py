@@ -1,0 +1,156 @@
+"""ctypes binding of libnrslam_b200.so (include/nrslam_b200.h) — the host-side mirror of the reference seam:
+
+    Core.pose_only    <->  CameraPoseOptimization                 modules/optimization/g2o_optimization.h:27
+    Core.pose_deform  <->  CameraPoseAndDeformationOptimization   modules/optimization/g2o_optimization.h:29-32
+    Core.local_ba     <->  LocalDeformableBundleAdjustment        modules/optimization/g2o_optimization.h:39-40
+    Core.graph_*      <->  RegularizationGraph::GetEdges/UpdateVertex   modules/map/regularization_graph.h:73,78
+
+There is no CPU fallback: `load()` raises if the library has not been built, and `Core()` raises when no
+sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .abi import Camera, Graph, Options, Stats, ptr  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnrslam_b200.so")
+_LIB = None
+
+ERRORS = {-1: "no sm_100 device", -2: "CUDA error", -3: "bad argument", -4: "allocation failed", -5: "NCCL error",
+          -6: "not implemented", 1: "too few points / keyframes", 2: "non-finite result"}
+
+
+class NrslamError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("nrslam_b200 error %d (%s): %s" % (code, ERRORS.get(code, "?"), msg))
+        self.code = code
+
+
+def load():
+    """Load the C-ABI library. Raises (no fallback) when it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libnrslam_b200.so not built — run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(LIB_PATH)
+        lib.nrslam_b200_last_error.restype = C.c_char_p
+        lib.nrslam_b200_graph_get_edges.restype = C.c_int32
+        lib.nrslam_b200_graph_update_vertex.restype = C.c_int32
+        lib.nrslam_b200_klt_num_points.restype = C.c_int32
+        _LIB = lib
+    return _LIB
+
+
+def default_options():
+    o = Options()
+    load().nrslam_b200_default_options(C.byref(o))
+    return o
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+class Core:
+    """One context = one GPU. Method names / argument meaning follow the reference functions."""
+
+    def __init__(self, opt=None):
+        self.L = load()
+        self.opt = opt or default_options()
+        self._ctx = C.c_void_p()
+        rc = self.L.nrslam_b200_create(C.byref(self.opt), C.byref(self._ctx))
+        if rc != 0:
+            raise NrslamError(rc, "nrslam_b200_create failed")
+
+    def close(self):
+        if self._ctx:
+            self.L.nrslam_b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(self._ctx) or b"").decode())
+        return rc
+
+    def device_info(self):
+        d, s = C.c_int32(), C.c_int32()
+        self._check(self.L.nrslam_b200_device_info(self._ctx, C.byref(d), C.byref(s)))
+        return d.value, s.value
+
+    def pose_only(self, cam, uv, X, pose):
+        n = len(uv)
+        uv, X = _f32(uv), _f32(X)
+        pose = np.array(pose, np.float32)
+        inl = np.zeros(n, np.uint8)
+        st = Stats()
+        rc = self._check(self.L.nrslam_b200_pose_only(self._ctx, C.byref(cam), n, ptr(uv, C.c_float),
+                                                      ptr(X, C.c_float), ptr(pose, C.c_float), ptr(inl, C.c_uint8),
+                                                      C.byref(st)))
+        return dict(rc=rc, pose=pose, inliers=inl, stats=st.as_dict())
+
+    def pose_deform(self, cam, uv, X_rest, point_vertex, vfs, graph, scale, pose, last_pos):
+        """`graph` (abi.GraphArrays) and nothing else is updated in place; everything else is returned."""
+        n = len(uv)
+        M = graph.n_vertices
+        uv, X_rest = _f32(uv), _f32(X_rest)
+        pv = np.ascontiguousarray(point_vertex, np.int32)
+        vfs = np.ascontiguousarray(vfs, np.int8)
+        pose = np.array(pose, np.float32)
+        last_pos = np.array(last_pos, np.float32)
+        d = np.zeros((n, 3), np.float32)
+        Xo = np.zeros((n, 3), np.float32)
+        chi2 = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        med = C.c_float(0)
+        lost = np.zeros(max(M, 1), np.int32)
+        nl = C.c_int32(0)
+        st = Stats()
+        g = graph.struct()
+        rc = self._check(self.L.nrslam_b200_pose_deform(
+            self._ctx, C.byref(cam), n, ptr(uv, C.c_float), ptr(X_rest, C.c_float), ptr(pv, C.c_int32),
+            ptr(vfs, C.c_int8), C.byref(g), C.c_float(scale), ptr(pose, C.c_float), ptr(last_pos, C.c_float),
+            ptr(d, C.c_float), ptr(Xo, C.c_float), ptr(chi2, C.c_float), ptr(status, C.c_uint8), C.byref(med),
+            ptr(lost, C.c_int32), C.byref(nl), C.byref(st)))
+        return dict(rc=rc, pose=pose, deformation=d, X=Xo, chi2=chi2, status=status, median=med.value,
+                    lost=lost[: nl.value].copy(), last_pos=last_pos, stats=st.as_dict())
+
+    def local_ba(self, cam, kf_pose, obs_kf, obs_vertex, uv, X, graph, scale, iterations=0):
+        F = len(kf_pose)
+        O = len(obs_kf)
+        kf_pose = np.array(kf_pose, np.float32)
+        X = np.array(X, np.float32)
+        ok = np.ascontiguousarray(obs_kf, np.int32)
+        ov = np.ascontiguousarray(obs_vertex, np.int32)
+        uv = _f32(uv)
+        st = Stats()
+        g = graph.struct()
+        rc = self._check(self.L.nrslam_b200_local_ba(
+            self._ctx, C.byref(cam), F, ptr(kf_pose, C.c_float), O, ptr(ok, C.c_int32), ptr(ov, C.c_int32),
+            ptr(uv, C.c_float), ptr(X, C.c_float), C.byref(g), C.c_float(scale), int(iterations), C.byref(st)))
+        return dict(rc=rc, kf_pose=kf_pose, X=X, stats=st.as_dict())
+
+    def resolve(self, which):
+        """Re-run the device program of the last staged problem (0 pose_only, 1 pose_deform, 2 local_ba)."""
+        st = Stats()
+        self._check(self.L.nrslam_b200_resolve(self._ctx, int(which), C.byref(st)))
+        return st.as_dict()
+
+    def graph_get_edges(self, graph, vertex):
+        g = graph.struct()
+        out = np.zeros(graph.rowptr[vertex + 1] - graph.rowptr[vertex] + 1, np.int32)
+        n = self.L.nrslam_b200_graph_get_edges(C.byref(g), int(vertex), ptr(out, C.c_int32), len(out))
+        return out[:n].copy()
+
+    def graph_update_vertex(self, graph, vertex, positions):
+        g = graph.struct()
+        positions = _f32(positions)
+        return self.L.nrslam_b200_graph_update_vertex(C.byref(g), int(vertex), ptr(positions, C.c_float))

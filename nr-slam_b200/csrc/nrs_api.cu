@@ -1,0 +1,909 @@
+// nrs_api.cu — C ABI of libnrslam_b200 (include/nrslam_b200.h): context management and the host side of the
+// three optimisation drivers. The host does what the reference does on the host as bookkeeping — neighbour
+// selection from the regularisation graph, de-duplication, status / IQR gating, graph refresh — in the
+// reference's order so that index bookkeeping is bit-exact; all arithmetic of the optimisation itself runs in
+// the persistent sm_100a kernel of nrs_engine.cu. There is no CPU fallback.
+//
+// Reference (paths relative to /root/reference):
+//   modules/optimization/g2o_optimization.cc:50-146    CameraPoseOptimization
+//   modules/optimization/g2o_optimization.cc:148-557   CameraPoseAndDeformationOptimization
+//   modules/optimization/g2o_optimization.cc:880-1161  LocalDeformableBundleAdjustment
+//   modules/map/regularization_graph.cc:28-31,61-146   min weight, GetEdges, UpdateConnection, UpdateVertex
+//   modules/utilities/geometry_toolbox.cc:26-28        InterpolationWeight
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <cstdio>
+#include <numeric>
+#include <set>
+#include <vector>
+
+#include "nrs_host.h"
+
+using namespace nrs;
+
+namespace {
+
+double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int fail(nrslam_b200_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define NRS_CUDA(ctx, call)                                                                          \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(ctx, NRSLAM_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// RegularizationGraph helpers
+// ---------------------------------------------------------------------------------------------------
+inline float interpolation_weight(float distance, float sigma) {  // geometry_toolbox.cc:26-28
+  return std::exp(-(distance * distance) / (2 * sigma * sigma));
+}
+inline float graph_min_weight(const nrslam_b200_graph* g) {  // regularization_graph.cc:28-31
+  return interpolation_weight((float)(g->weight_sigma * 1.5), g->weight_sigma);
+}
+
+// GetEdges (regularization_graph.cc:61-87): CSR entries of `vertex` ordered by (status asc, weight desc,
+// neighbour asc — the documented tie-break for the reference's unstable std::sort), cut at the first
+// weight < min_weight. Appends to `out`, returns the count.
+int graph_sorted_entries(const nrslam_b200_graph* g, int vertex, float min_w, std::vector<int>& out) {
+  const size_t base = out.size();
+  for (int p = g->rowptr[vertex]; p < g->rowptr[vertex + 1]; p++) out.push_back(p);
+  std::sort(out.begin() + base, out.end(), [g](int a, int b) {
+    const int ea = g->eid[a], eb = g->eid[b];
+    if (g->status[ea] != g->status[eb]) return g->status[ea] < g->status[eb];
+    if (g->weight[ea] != g->weight[eb]) return g->weight[ea] > g->weight[eb];
+    return g->col[a] < g->col[b];
+  });
+  size_t keep = base;
+  while (keep < out.size() && !(g->weight[g->eid[out[keep]]] < min_w)) keep++;
+  out.resize(keep);
+  return (int)(keep - base);
+}
+
+int graph_update_vertex(nrslam_b200_graph* g, int vertex, const float* pos) {  // regularization_graph.cc:89-146
+  int n_good = 0;
+  const float* p1 = pos + 3 * (size_t)vertex;
+  for (int p = g->rowptr[vertex]; p < g->rowptr[vertex + 1]; p++) {
+    const float* p2 = pos + 3 * (size_t)g->col[p];
+    const int e = g->eid[p];
+    const float dx = p1[0] - p2[0], dy = p1[1] - p2[1], dz = p1[2] - p2[2];
+    const float distance = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (distance > g->max_distance[e]) g->max_distance[e] = distance;
+    if (distance < g->min_distance[e]) g->min_distance[e] = distance;
+    g->weight[e] = interpolation_weight(g->max_distance[e], g->weight_sigma);
+    if (std::fabs((g->max_distance[e] - g->min_distance[e]) / g->min_distance[e]) > g->stretching_th)
+      g->status[e] = NRSLAM_EDGE_BAD;
+    else
+      n_good++;
+  }
+  return n_good;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host description of one engine problem, then staging into HBM.
+// ---------------------------------------------------------------------------------------------------
+struct HostProblem {
+  int F = 0, V = 0;
+  bool poses_fixed = false, points_fixed = false;
+  int spring_kind = SPRING_NONE;
+  Cam cam;
+  double info_reproj = 1, delta_reproj = -1, info_spatial = 1, delta_spatial = -1, info_spring = 1, delta_spring = -1,
+         spring_k = 1.1f;
+  float th2f = 5.99f, th3f = 0.584f;
+  std::vector<double> pose_seed;        // 7F
+  std::vector<double> x_seed, rest;     // 4V
+  std::vector<double> uv;               // 2V
+  std::vector<int> pt_kf;               // V
+  std::vector<int> pair_i, pair_j;
+  std::vector<double> pair_w, pair_d0;
+  std::vector<int> dmp_v;               // 4D
+  std::vector<double> dmp_w;
+  std::vector<int> un_ptr;              // V+1 or empty
+  std::vector<double> un_w;             // U
+  std::vector<int> un_ref;              // U
+  bool want_fixed_flags = false;        // reserve a per-vertex fixed-flag array (filled later)
+  std::vector<int> kf_begin;            // F+1: rows of pose slot k are [kf_begin[k], kf_begin[k+1]) (rows w/o pose: slot 0)
+  std::vector<int> ops, op_args;
+};
+
+template <typename T>
+size_t put(Arena& a, const std::vector<T>& v, size_t min_elems = 1) {
+  const size_t n = std::max(v.size(), min_elems);
+  const size_t off = a.take<T>(n);
+  if (!v.empty()) memcpy(a.h<T>(off), v.data(), v.size() * sizeof(T));
+  return off;
+}
+
+int pick_block(const nrslam_b200_ctx* ctx, int V) {
+  const char* env = getenv("NRSLAM_B200_BLOCK");
+  if (env) {
+    int b = atoi(env);
+    if (b >= 64 && b <= 256 && b % 32 == 0) return b;
+  }
+  (void)ctx;
+  if (V <= 8192) return 128;
+  return 256;
+}
+
+int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
+  const int F = hp.F, V = hp.V, P = (int)hp.pair_i.size(), D = (int)hp.dmp_w.size();
+  const int U = (int)hp.un_w.size();
+  st.valid = false;
+  const int block = pick_block(ctx, V);
+  // chunks: contiguous rows of one pose slot, at most `block` rows each
+  std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr(F + 1, 0);
+  for (int k = 0; k < F; k++) {
+    kf_chunk_ptr[k] = (int)chunk_kf.size();
+    for (int b = hp.kf_begin[k]; b < hp.kf_begin[k + 1]; b += block) {
+      chunk_kf.push_back(k);
+      chunk_begin.push_back(b);
+      chunk_end.push_back(std::min(b + block, hp.kf_begin[k + 1]));
+    }
+  }
+  kf_chunk_ptr[F] = (int)chunk_kf.size();
+  const int n_chunks = (int)chunk_kf.size();
+  // incidence lists
+  std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P);
+  for (int e = 0; e < P; e++) {
+    inc_ptr[hp.pair_i[e] + 1]++;
+    inc_ptr[hp.pair_j[e] + 1]++;
+  }
+  for (int i = 0; i < V; i++) inc_ptr[i + 1] += inc_ptr[i];
+  {
+    std::vector<int> w(inc_ptr.begin(), inc_ptr.end() - 1);
+    for (int e = 0; e < P; e++) {
+      int a = w[hp.pair_i[e]]++;
+      inc_other[a] = hp.pair_j[e];
+      inc_ent[a] = 2 * e;
+      a = w[hp.pair_j[e]]++;
+      inc_other[a] = hp.pair_i[e];
+      inc_ent[a] = 2 * e + 1;
+    }
+  }
+  std::vector<int> dinc_ptr(V + 1, 0), dinc_ent(4 * (size_t)D);
+  for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ptr[hp.dmp_v[t] + 1]++;
+  for (int i = 0; i < V; i++) dinc_ptr[i + 1] += dinc_ptr[i];
+  {
+    std::vector<int> w(dinc_ptr.begin(), dinc_ptr.end() - 1);
+    for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ent[w[hp.dmp_v[t]]++] = (int)t;  // id*4 + role
+  }
+
+  // ---- input arena
+  size_t need = 0;
+  auto sz = [&](size_t bytes) { need += ((bytes + 255) & ~size_t(255)) + 256; };
+  sz(7 * F * 8); sz(4 * (size_t)V * 8); sz(4 * (size_t)V * 8); sz(2 * (size_t)V * 8); sz((size_t)V * 4);
+  sz((size_t)P * 4); sz((size_t)P * 4); sz((size_t)P * 8); sz((size_t)P * 8);
+  sz(((size_t)V + 1) * 4); sz(2 * (size_t)P * 4); sz(2 * (size_t)P * 4);
+  sz(4 * (size_t)D * 4); sz((size_t)D * 8); sz(((size_t)V + 1) * 4); sz(4 * (size_t)D * 4);
+  sz(((size_t)V + 1) * 4); sz((size_t)U * 8); sz((size_t)U * 4); sz((size_t)V);
+  sz((size_t)n_chunks * 4 * 3); sz(((size_t)F + 1) * 4);
+  need += 8192;
+  if (!st.in.reserve(need, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "input arena allocation failed");
+  Arena& in = st.in;
+  Params& p = st.p;
+  memset(&p, 0, sizeof(p));
+  p.F = F; p.V = V; p.P = P; p.D = D; p.n_chunks = n_chunks;
+  p.poses_fixed = hp.poses_fixed; p.points_fixed = hp.points_fixed; p.spring_kind = hp.spring_kind;
+  p.cam = hp.cam;
+  p.info_reproj = hp.info_reproj; p.delta_reproj = hp.delta_reproj;
+  p.info_spatial = hp.info_spatial; p.delta_spatial = hp.delta_spatial;
+  p.info_spring = hp.info_spring; p.delta_spring = hp.delta_spring; p.spring_k = hp.spring_k;
+  p.th2f = hp.th2f; p.th3f = hp.th3f;
+  p.lm_tau = ctx->opt.lm_tau; p.lm_max_trials = ctx->opt.lm_max_trials;
+  p.pcg_tol = ctx->opt.pcg_rel_tol; p.pcg_max_iter = ctx->opt.pcg_max_iterations;
+  p.n_ops = (int)hp.ops.size();
+  if (p.n_ops > kMaxOps) return fail(ctx, NRSLAM_B200_ERR_ARG, "program too long");
+  for (int i = 0; i < p.n_ops; i++) {
+    p.op[i] = hp.ops[i];
+    p.op_arg[i] = hp.op_args[i];
+  }
+  p.pose_seed = in.d<double>(put(in, hp.pose_seed));
+  p.x_seed = in.d<double>(put(in, hp.x_seed));
+  p.rest = in.d<double>(put(in, hp.rest));
+  p.uv = in.d<double>(put(in, hp.uv));
+  p.pt_kf = in.d<int>(put(in, hp.pt_kf));
+  p.pair_i = in.d<int>(put(in, hp.pair_i));
+  p.pair_j = in.d<int>(put(in, hp.pair_j));
+  p.pair_w = in.d<double>(put(in, hp.pair_w));
+  p.pair_d0 = in.d<double>(put(in, hp.pair_d0));
+  p.inc_ptr = in.d<int>(put(in, inc_ptr));
+  p.inc_other = in.d<int>(put(in, inc_other));
+  p.inc_ent = in.d<int>(put(in, inc_ent));
+  p.dmp_v = in.d<int>(put(in, hp.dmp_v, 4));
+  p.dmp_w = in.d<double>(put(in, hp.dmp_w));
+  p.dinc_ptr = in.d<int>(put(in, dinc_ptr));
+  p.dinc_ent = in.d<int>(put(in, dinc_ent));
+  if (!hp.un_ptr.empty()) {
+    p.un_ptr = in.d<int>(put(in, hp.un_ptr));
+    p.un_w = in.d<double>(put(in, hp.un_w));
+    p.un_ref = in.d<int>(put(in, hp.un_ref));
+  }
+  if (hp.want_fixed_flags) {
+    st.o_fixed = in.take<unsigned char>(V);
+    memset(in.h<unsigned char>(st.o_fixed), 0, V);
+  }
+  p.chunk_kf = in.d<int>(put(in, chunk_kf));
+  p.chunk_begin = in.d<int>(put(in, chunk_begin));
+  p.chunk_end = in.d<int>(put(in, chunk_end));
+  p.kf_chunk_ptr = in.d<int>(put(in, kf_chunk_ptr));
+  st.h2d_bytes = in.used();
+
+  // ---- launch geometry
+  st.block = block;
+  st.smem = engine_smem_bytes(F, block);
+  if (st.smem > 200 * 1024) return fail(ctx, NRSLAM_B200_ERR_ARG, "too many poses for the shared-memory pose blocks");
+  int max_grid = engine_max_grid(block, st.smem);
+  if (max_grid <= 0) return fail(ctx, NRSLAM_B200_ERR_CUDA, "kernel cannot be made resident");
+  int grid = std::max(1, std::min(n_chunks, max_grid));
+  if (ctx->opt.grid_ctas > 0) grid = std::min(grid, ctx->opt.grid_ctas);
+  const char* genv = getenv("NRSLAM_B200_GRID");
+  if (genv && atoi(genv) > 0) grid = std::min(max_grid, atoi(genv));
+  st.grid = grid;
+
+  // ---- results + work arrays
+  Arena& out = st.out;
+  size_t oneed = 7 * F * 8 + 4 * (size_t)V * 8 + (size_t)V * 8 + V + P + sizeof(EngineStats) + 8 * 256 + 4096;
+  if (!out.reserve(oneed, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "output arena allocation failed");
+  st.o_pose = out.take<double>(7 * F);
+  st.o_x = out.take<double>(4 * (size_t)V);
+  st.o_chi2 = out.take<double>(V);
+  st.o_rp_level = out.take<unsigned char>(V);
+  st.o_sp_level = out.take<unsigned char>(std::max(P, 1));
+  st.o_stats = out.take<EngineStats>(1);
+  st.d2h_bytes = out.used();
+  p.pose = out.d<double>(st.o_pose);
+  p.x = out.d<double>(st.o_x);
+  p.rp_chi2 = out.d<double>(st.o_chi2);
+  p.rp_level = out.d<unsigned char>(st.o_rp_level);
+  p.sp_level = out.d<unsigned char>(st.o_sp_level);
+  p.stats = out.d<EngineStats>(st.o_stats);
+
+  Arena& wk = st.work;
+  size_t wneed = (size_t)V * 8 * (4 + 20 + 8 + 4 + 8 + 4 + 4 + 4 + 16) + (size_t)P * 64 + (size_t)D * 32 +
+                 2 * (size_t)n_chunks * kChunkVals * 8 + 2 * (size_t)grid * kSlotVals * 8 + 32 * 256 + 4096;
+  if (!wk.reserve(wneed, false)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "work arena allocation failed");
+  p.x_bak = wk.d<double>(wk.take<double>(4 * (size_t)V));
+  p.jac = wk.d<double>(wk.take<double>(20 * (size_t)V));
+  p.dg = wk.d<double>(wk.take<double>(8 * (size_t)V));
+  p.bvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
+  p.minv = wk.d<double>(wk.take<double>(8 * (size_t)V));
+  p.xcg = wk.d<double>(wk.take<double>(4 * (size_t)V));
+  p.rvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
+  p.qvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
+  p.rec = wk.d<double>(wk.take<double>(16 * (size_t)V));
+  p.pc = wk.d<double>(wk.take<double>(8 * (size_t)std::max(P, 1)));
+  p.dc = wk.d<double>(wk.take<double>(4 * (size_t)std::max(D, 1)));
+  p.chunk_part = wk.d<double>(wk.take<double>(2 * (size_t)n_chunks * kChunkVals));
+  p.slots = wk.d<double>(wk.take<double>(2 * (size_t)grid * kSlotVals));
+  p.bar = ctx->bar;
+
+  NRS_CUDA(ctx, cudaMemcpyAsync(in.dev(), in.host(), in.used(), cudaMemcpyHostToDevice, ctx->stream));
+  // dg[.][6] (unary diagonal weight) is read by the matvec even when no unary edges exist
+  NRS_CUDA(ctx, cudaMemsetAsync(wk.dev(), 0, wk.used(), ctx->stream));
+  NRS_CUDA(ctx, cudaMemsetAsync(out.dev(), 0, out.used(), ctx->stream));
+  st.valid = true;
+  return 0;
+}
+
+// Launch the staged program, bring the results back, fill stats. Blocks until done.
+int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool copy_back = true,
+               const Params* override_params = nullptr) {
+  if (!st.valid) return fail(ctx, NRSLAM_B200_ERR_ARG, "no staged problem");
+  NRS_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  const int rc = launch_engine(override_params ? *override_params : st.p, st.grid, st.block, st.smem, ctx->stream);
+  if (rc != 0)
+    return fail(ctx, NRSLAM_B200_ERR_CUDA, std::string("engine launch: ") + cudaGetErrorString((cudaError_t)rc));
+  NRS_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  if (copy_back)
+    NRS_CUDA(ctx, cudaMemcpyAsync(st.out.host(), st.out.dev(), st.out.used(), cudaMemcpyDeviceToHost, ctx->stream));
+  else
+    NRS_CUDA(ctx, cudaMemcpyAsync(st.out.h<char>(st.o_stats), st.out.d<char>(st.o_stats), sizeof(EngineStats),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  NRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    const EngineStats* es = st.out.h<EngineStats>(st.o_stats);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    stats->gpu_ms += ms;
+    stats->lm_iterations += es->lm_iterations;
+    stats->lm_trials += es->lm_trials;
+    stats->pcg_iterations += es->pcg_iterations;
+    stats->n_sweeps += es->n_sweeps;
+    stats->n_chi2_passes += es->n_chi2_passes;
+    stats->kernel_launches += 1;
+    for (int i = 0; i < es->n_trace && stats->n_trace < NRSLAM_B200_TRACE; i++)
+      stats->chi2_trace[stats->n_trace++] = es->chi2_trace[i];
+    stats->lambda_final = es->lambda_final;
+    if (getenv("NRSLAM_B200_PROF")) {
+      fprintf(stderr, "[nrs prof] grid %d block %d barriers %d cycles:", st.grid, st.block, es->barriers);
+      for (int i = 0; i < 16; i++) fprintf(stderr, " %lld", es->prof[i]);
+      fprintf(stderr, "\n");
+    }
+  }
+  return 0;
+}
+
+Cam to_cam(const nrslam_b200_camera* c) {
+  Cam cam;
+  cam.model = c->model;
+  for (int i = 0; i < 8; i++) cam.p[i] = c->params[i];
+  return cam;
+}
+
+}  // namespace
+
+extern "C" {
+
+void nrslam_b200_default_options(nrslam_b200_options* o) {
+  if (!o) return;
+  o->th_huber_2dof_sq = 5.99f;
+  o->th_huber_3dof_sq = 0.584f;
+  o->sigma_reprojection = 0.5f;
+  o->sigma_position = 0.1f;
+  o->sigma_spatial_factor = 0.1f;
+  o->spring_k = 1.1f;
+  o->regularizers_per_point = 10;
+  o->pose_only_iterations[0] = o->pose_only_iterations[1] = o->pose_only_iterations[2] = 10;
+  o->pose_deform_iterations[0] = o->pose_deform_iterations[1] = 10;
+  o->lost_iterations = 10;
+  o->ba_iterations = 5;
+  o->lm_max_trials = 10;
+  o->lm_tau = 1e-5;
+  o->pcg_rel_tol = 1e-8;
+  o->pcg_max_iterations = 2000;
+  const char* lr = getenv("LOCAL_RANK");
+  o->device = lr ? atoi(lr) : 0;
+  o->grid_ctas = 0;
+}
+
+int nrslam_b200_abi_version(void) { return NRSLAM_B200_ABI_VERSION; }
+
+int nrslam_b200_create(const nrslam_b200_options* opt, nrslam_b200_ctx** out) {
+  if (!out) return NRSLAM_B200_ERR_ARG;
+  *out = nullptr;
+  nrslam_b200_options o;
+  if (opt)
+    o = *opt;
+  else
+    nrslam_b200_default_options(&o);
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return NRSLAM_B200_ERR_NO_DEVICE;
+  if (o.device < 0 || o.device >= n_dev) return NRSLAM_B200_ERR_ARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess) return NRSLAM_B200_ERR_CUDA;
+  if (prop.major != 10) return NRSLAM_B200_ERR_NO_DEVICE;  // sm_100a cubin only
+  if (cudaSetDevice(o.device) != cudaSuccess) return NRSLAM_B200_ERR_CUDA;
+  nrslam_b200_ctx* ctx = new nrslam_b200_ctx();
+  ctx->opt = o;
+  ctx->device = o.device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaMalloc(&ctx->bar, 256) != cudaSuccess) {
+    delete ctx;
+    return NRSLAM_B200_ERR_CUDA;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void nrslam_b200_destroy(nrslam_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& s : ctx->staged) {
+    s.in.release();
+    s.work.release();
+    s.out.release();
+  }
+  if (ctx->bar) cudaFree(ctx->bar);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* nrslam_b200_last_error(const nrslam_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nrslam_b200_device_info(const nrslam_b200_ctx* ctx, int32_t* device, int32_t* sm_count) {
+  if (!ctx) return NRSLAM_B200_ERR_ARG;
+  if (device) *device = ctx->device;
+  if (sm_count) *sm_count = ctx->sm_count;
+  return 0;
+}
+
+int32_t nrslam_b200_graph_get_edges(const nrslam_b200_graph* g, int32_t vertex, int32_t* out_entries,
+                                    int32_t capacity) {
+  if (!g || vertex < 0 || vertex >= g->n_vertices) return -1;
+  std::vector<int> ent;
+  const int n = graph_sorted_entries(g, vertex, graph_min_weight(g), ent);
+  for (int i = 0; i < n && i < capacity; i++) out_entries[i] = ent[i];
+  return n;
+}
+
+int32_t nrslam_b200_graph_update_vertex(nrslam_b200_graph* g, int32_t vertex, const float* positions) {
+  if (!g || vertex < 0 || vertex >= g->n_vertices || !positions) return -1;
+  return graph_update_vertex(g, vertex, positions);
+}
+
+// =====================================================================================================
+// CameraPoseOptimization — g2o_optimization.cc:50-146
+// =====================================================================================================
+int nrslam_b200_pose_only(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                          const float* X, float* pose_io, uint8_t* inlier_out, nrslam_b200_stats* stats) {
+  if (!ctx || !cam || !uv || !X || !pose_io || n < 0) return fail(ctx, NRSLAM_B200_ERR_ARG, "pose_only: bad argument");
+  const double t0 = wall_ms();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "pose_only: no observations");
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const nrslam_b200_options& opt = ctx->opt;
+  HostProblem hp;
+  hp.F = 1;
+  hp.V = n;
+  hp.points_fixed = true;
+  hp.cam = to_cam(cam);
+  hp.info_reproj = 1.0;                                    // :90 Matrix2d::Identity()
+  hp.delta_reproj = (double)std::sqrt(opt.th_huber_2dof_sq);  // :64 float sqrt
+  hp.th2f = opt.th_huber_2dof_sq;
+  hp.pose_seed.resize(7);
+  pose_from_f7(pose_io, hp.pose_seed.data());
+  hp.x_seed.assign(4 * (size_t)n, 0.0);
+  hp.rest.resize(4 * (size_t)n);
+  hp.uv.resize(2 * (size_t)n);
+  hp.pt_kf.assign(n, 0);
+  for (int i = 0; i < n; i++) {
+    for (int k = 0; k < 3; k++) hp.rest[4 * (size_t)i + k] = X[3 * (size_t)i + k];
+    hp.rest[4 * (size_t)i + 3] = 0;
+    hp.uv[2 * (size_t)i] = uv[2 * (size_t)i];
+    hp.uv[2 * (size_t)i + 1] = uv[2 * (size_t)i + 1];
+  }
+  hp.kf_begin = {0, n};
+  hp.ops.push_back(OP_CLEAR_LEVELS);
+  hp.op_args.push_back(0);
+  for (int it = 0; it < 3; it++) {
+    hp.ops.push_back(OP_RESET);
+    hp.op_args.push_back(0);
+    hp.ops.push_back(OP_OPTIMIZE);
+    hp.op_args.push_back(opt.pose_only_iterations[it]);
+    hp.ops.push_back(OP_RELEVEL_POSE);
+    hp.op_args.push_back(0);
+  }
+  Staged& st = ctx->staged[0];
+  int rc = stage_problem(ctx, st, hp);
+  if (rc) return rc;
+  const double t1 = wall_ms();
+  rc = run_staged(ctx, st, stats);
+  if (rc) return rc;
+  const double* pose = st.out.h<double>(st.o_pose);
+  for (int i = 0; i < 7; i++)
+    if (!std::isfinite(pose[i])) return fail(ctx, NRSLAM_B200_NUM_NONFINITE, "pose_only: non-finite pose");
+  pose_to_f7(pose, pose_io);
+  if (inlier_out) {
+    const unsigned char* lvl = st.out.h<unsigned char>(st.o_rp_level);
+    for (int i = 0; i < n; i++) inlier_out[i] = lvl[i] == 0;
+  }
+  if (stats) {
+    stats->n_reproj_edges = n;
+    stats->n_poses = 1;
+    stats->stage_ms = (float)(t1 - t0);
+    stats->host_ms = (float)(wall_ms() - t0);
+  }
+  return 0;
+}
+
+// =====================================================================================================
+// CameraPoseAndDeformationOptimization — g2o_optimization.cc:148-557
+// =====================================================================================================
+int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                            const float* X_rest, const int32_t* point_vertex,
+                            const int8_t* vfs, nrslam_b200_graph* g, float scale, float* pose_io,
+                            float* last_pos, float* deformation_out, float* X_out, float* chi2_out,
+                            uint8_t* status_out, float* median_deformation_out, int32_t* lost_vertex_out,
+                            int32_t* n_lost_out, nrslam_b200_stats* stats) {
+  if (!ctx || !cam || !uv || !X_rest || !point_vertex || !vfs || !g || !pose_io || !last_pos || n < 0)
+    return fail(ctx, NRSLAM_B200_ERR_ARG, "pose_deform: bad argument");
+  const double t0 = wall_ms();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_lost_out) *n_lost_out = 0;
+  if (n == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "pose_deform: no observations");
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const nrslam_b200_options& opt = ctx->opt;
+  const int M = g->n_vertices;
+  for (int i = 0; i < n; i++)
+    if (point_vertex[i] < 0 || point_vertex[i] >= M) return fail(ctx, NRSLAM_B200_ERR_ARG, "pose_deform: bad vertex");
+
+  const int regularizers_per_point = opt.regularizers_per_point;
+  const float th2 = opt.th_huber_2dof_sq, th3 = opt.th_huber_3dof_sq;
+  const float info_reprojection = 1.0f / (opt.sigma_reprojection * opt.sigma_reprojection);  // :203-204
+  const float info_position = 1.0f / (opt.sigma_position * opt.sigma_position);              // :206-207
+  const float sigma_spatial = (float)((double)opt.sigma_spatial_factor * scale);             // :209
+  const float info_spatial = 1.0f / (sigma_spatial * sigma_spatial);
+  const float min_w = graph_min_weight(g);
+
+  HostProblem hp;
+  hp.F = 1;
+  hp.V = n;
+  hp.cam = to_cam(cam);
+  hp.spring_kind = SPRING_DEFORM;
+  hp.info_reproj = info_reprojection;
+  hp.delta_reproj = (double)std::sqrt(th2);
+  hp.info_spatial = info_spatial;
+  hp.delta_spatial = (double)std::sqrt(th3);
+  hp.info_spring = info_position;
+  hp.delta_spring = (double)std::sqrt(th3);
+  hp.spring_k = (double)opt.spring_k;  // :328 float literal 1.1f widened
+  hp.th2f = th2;
+  hp.th3f = th3;
+  hp.pose_seed.resize(7);
+  pose_from_f7(pose_io, hp.pose_seed.data());
+  hp.x_seed.assign(4 * (size_t)n, 0.0);  // deformation vertices start at the origin (:188,345-348)
+  hp.rest.resize(4 * (size_t)n);
+  hp.uv.resize(2 * (size_t)n);
+  hp.pt_kf.assign(n, 0);
+  std::vector<int> opt_index(M, -1);  // mappoint_id_to_index (:177,191)
+  for (int i = 0; i < n; i++) {
+    for (int k = 0; k < 3; k++) hp.rest[4 * (size_t)i + k] = X_rest[3 * (size_t)i + k];
+    hp.rest[4 * (size_t)i + 3] = 0;
+    hp.uv[2 * (size_t)i] = uv[2 * (size_t)i];
+    hp.uv[2 * (size_t)i + 1] = uv[2 * (size_t)i + 1];
+    opt_index[point_vertex[i]] = i;
+  }
+  hp.kf_begin = {0, n};
+
+  // ---- regulariser selection (:251-336). A pair is owned by the first endpoint that reaches it.
+  std::vector<int> pair_stamp(g->n_edges, 0);  // spatial_connections_ids de-duplication, keyed by graph edge
+  std::set<int> lost_ordered;                  // absl::btree_set<ID> (:222)
+  std::vector<int> ent;
+  for (int idx = 0; idx < n; idx++) {
+    ent.clear();
+    graph_sorted_entries(g, point_vertex[idx], min_w, ent);
+    int n_regularizers = 0;
+    for (int pe : ent) {
+      const int other = g->col[pe], ge = g->eid[pe];
+      if (n_regularizers > regularizers_per_point || g->status[ge] == NRSLAM_EDGE_BAD) break;  // :258-261
+      if (vfs[other] < 0 || vfs[other] != NRSLAM_TRACKED_WITH_3D) {                             // :264-273
+        if (vfs[other] >= 0 && vfs[other] != NRSLAM_JUST_TRIANGULATED) lost_ordered.insert(other);
+        continue;
+      }
+      const int idx_other = opt_index[other];
+      if (idx_other < 0) continue;   // inconsistent input: TRACKED_WITH_3D in the frame but not optimised
+      if (pair_stamp[ge]) continue;  // :277-279
+      pair_stamp[ge] = 1;
+      hp.pair_i.push_back(idx);
+      hp.pair_j.push_back(idx_other);
+      hp.pair_w.push_back((double)g->weight[ge]);
+      hp.pair_d0.push_back((double)g->first_distance[ge]);
+      n_regularizers++;
+    }
+  }
+  // ---- lost neighbours (:476-537): one extra vertex each, unary SpatialRegularizerFixed edges to at most 11
+  // optimised neighbours. They are rows of the same staged problem but only take part in the second launch.
+  // (The graph is only modified by UpdateVertex below, whose weights / statuses the reference does see when it
+  // queries GetEdges for the lost points — so the unary edge list is built after the refresh.)
+  const std::vector<int> lost_list(lost_ordered.begin(), lost_ordered.end());
+  const int n_lost = (int)lost_list.size();
+  const int Vtot = n + n_lost;
+  hp.V = Vtot;
+  hp.x_seed.resize(4 * (size_t)Vtot, 0.0);
+  hp.rest.resize(4 * (size_t)Vtot, 0.0);
+  hp.uv.resize(2 * (size_t)Vtot, 0.0);
+  hp.pt_kf.resize(Vtot, -1);
+  hp.kf_begin = {0, Vtot};
+  hp.want_fixed_flags = n_lost > 0;
+  if (n_lost > 0) {
+    // capacity for the unary edges (filled after the graph refresh): at most 11 per lost point
+    hp.un_ptr.assign(Vtot + 1, 0);
+    hp.un_w.assign(11 * (size_t)n_lost, 0.0);
+    hp.un_ref.assign(11 * (size_t)n_lost, 0);
+  }
+  hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM,
+            OP_FINAL_CHI2};
+  hp.op_args = {0, 0, opt.pose_deform_iterations[0], 0, 0, opt.pose_deform_iterations[1], 0, 0};
+
+  Staged& st = ctx->staged[1];
+  int rc = stage_problem(ctx, st, hp);
+  if (rc) return rc;
+  const double t1 = wall_ms();
+  rc = run_staged(ctx, st, stats);
+  if (rc) return rc;
+
+  const double* pose = st.out.h<double>(st.o_pose);
+  for (int i = 0; i < 7; i++)
+    if (!std::isfinite(pose[i])) return fail(ctx, NRSLAM_B200_NUM_NONFINITE, "pose_deform: non-finite pose");
+  pose_to_f7(pose, pose_io);  // :398-399
+  const double* xd = st.out.h<double>(st.o_x);
+  const double* chi2d = st.out.h<double>(st.o_chi2);
+
+  // ---- deformation magnitudes, IQR gate (:401-455)
+  std::vector<float> mags(n), def(3 * (size_t)n);
+  for (int idx = 0; idx < n; idx++) {
+    float* d = &def[3 * (size_t)idx];
+    for (int k = 0; k < 3; k++) d[k] = (float)xd[4 * (size_t)idx + k];
+    mags[idx] = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (deformation_out)
+      for (int k = 0; k < 3; k++) deformation_out[3 * (size_t)idx + k] = d[k];
+  }
+  std::vector<float> sorted(mags);
+  std::sort(sorted.begin(), sorted.end());
+  const float q1 = sorted[(int)(sorted.size() * 0.25f)];
+  const float q3 = sorted[(int)(sorted.size() * 0.75f)];
+  const float th_ = 1.5f * (q3 - q1);
+  std::vector<char> inliers(n, 1);
+  std::vector<uint8_t> status(n, NRSLAM_TRACKED_WITH_3D);
+  std::vector<unsigned char> fixed(Vtot, 0);
+  for (int idx = 0; idx < n; idx++) {
+    const float chi_squared = (float)chi2d[idx];
+    if (chi2_out) chi2_out[idx] = chi_squared;
+    if (chi_squared > th2) {
+      inliers[idx] = 0;
+      status[idx] = NRSLAM_TRACKED;
+    }
+    if (X_out)
+      for (int k = 0; k < 3; k++) X_out[3 * (size_t)idx + k] = X_rest[3 * (size_t)idx + k];
+    if (mags[idx] >= q3 + th_) {
+      status[idx] = NRSLAM_TRACKED;
+      continue;
+    }
+    fixed[idx] = 1;  // :439 setFixed(true)
+    for (int k = 0; k < 3; k++) {
+      const float cur = def[3 * (size_t)idx + k] + X_rest[3 * (size_t)idx + k];
+      if (X_out) X_out[3 * (size_t)idx + k] = cur;
+      last_pos[3 * (size_t)point_vertex[idx] + k] = cur;  // :446
+    }
+  }
+  if (median_deformation_out) {
+    std::vector<float> m2(mags);
+    const int median_idx = (int)m2.size() / 2;
+    std::nth_element(m2.begin(), m2.begin() + median_idx, m2.end());
+    *median_deformation_out = m2[median_idx];
+  }
+  // ---- regularisation-graph refresh (:458-474)
+  for (int idx = 0; idx < n; idx++) {
+    if (!inliers[idx]) continue;
+    const int good = graph_update_vertex(g, point_vertex[idx], last_pos);
+    if (good < regularizers_per_point * 0.5) status[idx] = NRSLAM_BAD;
+  }
+  if (status_out) memcpy(status_out, status.data(), n);
+  if (stats) {
+    stats->n_reproj_edges = n;
+    stats->n_pair_edges = (int)hp.pair_i.size();
+    stats->n_points = n;
+    stats->n_poses = 1;
+    stats->stage_ms = (float)(t1 - t0);
+  }
+
+  // ---- lost-point stage (:476-555). The reference re-runs the optimiser on the same graph with the pose and
+  // the accepted deformation vertices fixed: the gated-out deformation vertices stay free and are re-optimised
+  // alongside the lost points (their results are discarded), sharing one lambda / gain-ratio sequence.
+  if (n_lost > 0) {
+    int* un_ptr = st.in.h<int>((size_t)((const char*)st.p.un_ptr - (const char*)st.in.dev()));
+    double* un_w = st.in.h<double>((size_t)((const char*)st.p.un_w - (const char*)st.in.dev()));
+    int* un_ref = st.in.h<int>((size_t)((const char*)st.p.un_ref - (const char*)st.in.dev()));
+    const float min_w2 = graph_min_weight(g);
+    int n_un = 0;
+    for (int i = 0; i <= n; i++) un_ptr[i] = 0;
+    for (int v = 0; v < n_lost; v++) {
+      ent.clear();
+      graph_sorted_entries(g, lost_list[v], min_w2, ent);
+      int n_regularizers = 0;
+      for (int pe : ent) {
+        if (n_regularizers > 10) break;  // :497 literal
+        const int other = g->col[pe];
+        if (opt_index[other] < 0) continue;  // :502-504
+        un_w[n_un] = (double)g->weight[g->eid[pe]];
+        un_ref[n_un] = opt_index[other];
+        n_un++;
+        n_regularizers++;
+      }
+      un_ptr[n + v + 1] = n_un;
+    }
+    if (n_un > 0) {
+      memcpy(st.in.h<unsigned char>(st.o_fixed), fixed.data(), Vtot);
+      // refresh the three unary arrays and the fixed flags on the device (small, contiguous ranges)
+      auto sync_range = [&](const void* dptr, size_t bytes) {
+        const size_t off = (size_t)((const char*)dptr - (const char*)st.in.dev());
+        return cudaMemcpyAsync(st.in.d<char>(off), st.in.h<char>(off), bytes, cudaMemcpyHostToDevice, ctx->stream);
+      };
+      NRS_CUDA(ctx, sync_range(st.p.un_ptr, ((size_t)Vtot + 1) * sizeof(int)));
+      NRS_CUDA(ctx, sync_range(st.p.un_w, (size_t)n_un * sizeof(double)));
+      NRS_CUDA(ctx, sync_range(st.p.un_ref, (size_t)n_un * sizeof(int)));
+      NRS_CUDA(ctx, sync_range(st.in.d<unsigned char>(st.o_fixed), Vtot));
+      Params p2 = st.p;
+      p2.poses_fixed = 1;
+      p2.unary_on = 1;
+      p2.pt_fixed = st.in.d<unsigned char>(st.o_fixed);
+      p2.n_ops = 1;
+      p2.op[0] = OP_OPTIMIZE;
+      p2.op_arg[0] = opt.lost_iterations;
+      rc = run_staged(ctx, st, stats, true, &p2);
+      if (rc) return rc;
+      const double* xl = st.out.h<double>(st.o_x);
+      for (int v = 0; v < n_lost; v++)
+        for (int k = 0; k < 3; k++)
+          last_pos[3 * (size_t)lost_list[v] + k] =
+              (float)xl[4 * (size_t)(n + v) + k] + last_pos[3 * (size_t)lost_list[v] + k];  // :544-552
+    }
+    for (int v = 0; v < n_lost; v++)
+      if (lost_vertex_out) lost_vertex_out[v] = lost_list[v];
+    if (n_lost_out) *n_lost_out = n_lost;
+    if (stats) stats->n_fixed_edges = n_un;
+  }
+  if (stats) stats->host_ms = (float)(wall_ms() - t0);
+  return 0;
+}
+
+// =====================================================================================================
+// LocalDeformableBundleAdjustment — g2o_optimization.cc:880-1161
+// =====================================================================================================
+int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t F, float* kf_pose_io,
+                         int32_t O, const int32_t* obs_kf, const int32_t* obs_vertex, const float* uv,
+                         float* X_io, const nrslam_b200_graph* g, float scale, int32_t iterations,
+                         nrslam_b200_stats* stats) {
+  if (!ctx || !cam || !kf_pose_io || !obs_kf || !obs_vertex || !uv || !X_io || !g || O < 0)
+    return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba: bad argument");
+  const double t0 = wall_ms();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (F < 3) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: fewer than 3 keyframes");  // :922-924
+  if (O == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: no observations");
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const nrslam_b200_options& opt = ctx->opt;
+  if (iterations <= 0) iterations = opt.ba_iterations;
+  const int M = g->n_vertices;
+  const int regularizers_per_point = opt.regularizers_per_point;
+  const float th2 = opt.th_huber_2dof_sq, th3 = opt.th_huber_3dof_sq;
+  const float info_reprojection = 1.0f / (opt.sigma_reprojection * opt.sigma_reprojection);
+  const float info_position = 1.0f / (opt.sigma_position * opt.sigma_position);
+  const float sigma_spatial = (float)((double)opt.sigma_spatial_factor * scale);
+  const float info_spatial = 1.0f / (sigma_spatial * sigma_spatial);
+  const float min_w = graph_min_weight(g);
+
+  HostProblem hp;
+  hp.F = F;
+  hp.V = O;
+  hp.cam = to_cam(cam);
+  hp.spring_kind = SPRING_BA;
+  hp.info_reproj = info_reprojection;
+  hp.delta_reproj = (double)std::sqrt(th2);
+  hp.info_spatial = info_spatial;
+  hp.delta_spatial = (double)std::sqrt(th3);
+  hp.info_spring = info_position;
+  hp.delta_spring = -1;  // :1057-1071 no robust kernel on the springs
+  hp.spring_k = (double)opt.spring_k;
+  hp.th2f = th2;
+  hp.th3f = th3;
+  hp.pose_seed.resize(7 * (size_t)F);
+  for (int k = 0; k < F; k++) pose_from_f7(kf_pose_io + 7 * k, hp.pose_seed.data() + 7 * k);
+  hp.x_seed.resize(4 * (size_t)O);
+  hp.rest.assign(4 * (size_t)O, 0.0);
+  hp.uv.resize(2 * (size_t)O);
+  hp.pt_kf.resize(O);
+  hp.kf_begin.assign(F + 1, 0);
+  for (int o = 0; o < O; o++) {
+    if (obs_kf[o] < 0 || obs_kf[o] >= F || (o > 0 && obs_kf[o] < obs_kf[o - 1]) || obs_vertex[o] < 0 ||
+        obs_vertex[o] >= M)
+      return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba: observations must be grouped by keyframe slot");
+    hp.kf_begin[obs_kf[o] + 1]++;
+    for (int k = 0; k < 3; k++) hp.x_seed[4 * (size_t)o + k] = X_io[3 * (size_t)o + k];
+    hp.x_seed[4 * (size_t)o + 3] = 0;
+    hp.uv[2 * (size_t)o] = uv[2 * (size_t)o];
+    hp.uv[2 * (size_t)o + 1] = uv[2 * (size_t)o + 1];
+    hp.pt_kf[o] = obs_kf[o];
+  }
+  for (int k = 0; k < F; k++) hp.kf_begin[k + 1] += hp.kf_begin[k];
+
+  // ---- springs inside a keyframe, dampers to the next newer keyframe (:982-1136)
+  // sorted neighbour lists are cached per map point; (pair, keyframe) de-duplication is keyed by graph edge
+  std::vector<int> nb_ptr(M + 1, -1), nb_cnt(M, 0), nb_ent;
+  std::vector<int> cur(M, -1), nxt(M, -1);  // inserted_landmarks[k][mappoint] -> row
+  std::vector<int> spring_stamp(g->n_edges, -1), damper_stamp(g->n_edges, -1);
+  for (int o = hp.kf_begin[0]; o < hp.kf_begin[1]; o++) cur[obs_vertex[o]] = o;
+  for (int k = 0; k < F; k++) {
+    const bool has_next = k + 1 < F;
+    if (has_next)
+      for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) nxt[obs_vertex[o]] = o;
+    for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) {
+      const int mp = obs_vertex[o];
+      if (nb_ptr[mp] < 0) {
+        nb_ptr[mp] = (int)nb_ent.size();
+        nb_cnt[mp] = graph_sorted_entries(g, mp, min_w, nb_ent);
+      }
+      const int* ents = nb_ent.data() + nb_ptr[mp];
+      const int ne = nb_cnt[mp];
+      int n_regularizers = 0;
+      for (int t = 0; t < ne; t++) {
+        const int other = g->col[ents[t]], ge = g->eid[ents[t]];
+        if (n_regularizers > regularizers_per_point || g->status[ge] == NRSLAM_EDGE_BAD) break;  // :1035-1037
+        const int oidx = cur[other];
+        if (oidx < 0) continue;
+        if (spring_stamp[ge] == k) {  // :1049-1052 already inserted from the other endpoint
+          n_regularizers++;
+          continue;
+        }
+        spring_stamp[ge] = k;
+        hp.pair_i.push_back(o);
+        hp.pair_j.push_back(oidx);
+        hp.pair_w.push_back(-1.0);
+        hp.pair_d0.push_back((double)g->first_distance[ge]);
+        n_regularizers++;
+      }
+      if (has_next) {
+        const int nlidx = nxt[mp];
+        if (nlidx < 0) continue;
+        int n_reg2 = 0;
+        for (int t = 0; t < ne; t++) {
+          const int other = g->col[ents[t]], ge = g->eid[ents[t]];
+          if (n_reg2 > regularizers_per_point || g->status[ge] == NRSLAM_EDGE_BAD) break;
+          const int oidx = cur[other], noidx = nxt[other];
+          if (oidx < 0 || noidx < 0) continue;
+          if (damper_stamp[ge] == k) {
+            n_reg2++;
+            continue;
+          }
+          damper_stamp[ge] = k;
+          hp.dmp_v.push_back(o);
+          hp.dmp_v.push_back(oidx);
+          hp.dmp_v.push_back(nlidx);
+          hp.dmp_v.push_back(noidx);
+          hp.dmp_w.push_back((double)g->weight[ge]);
+          n_reg2++;
+        }
+      }
+    }
+    // slide: cur <- nxt
+    for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) cur[obs_vertex[o]] = -1;
+    if (has_next) {
+      for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) {
+        cur[obs_vertex[o]] = o;
+        nxt[obs_vertex[o]] = -1;
+      }
+    }
+  }
+  hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE};
+  hp.op_args = {0, 0, iterations};
+
+  Staged& st = ctx->staged[2];
+  int rc = stage_problem(ctx, st, hp);
+  if (rc) return rc;
+  const double t1 = wall_ms();
+  rc = run_staged(ctx, st, stats);
+  if (rc) return rc;
+  const double* pose = st.out.h<double>(st.o_pose);
+  const double* xd = st.out.h<double>(st.o_x);
+  for (int i = 0; i < 7 * F; i++)
+    if (!std::isfinite(pose[i])) return fail(ctx, NRSLAM_B200_NUM_NONFINITE, "local_ba: non-finite pose");
+  for (int k = 0; k < F; k++) pose_to_f7(pose + 7 * k, kf_pose_io + 7 * k);  // :1146-1151
+  for (int o = 0; o < O; o++)
+    for (int k = 0; k < 3; k++) X_io[3 * (size_t)o + k] = (float)xd[4 * (size_t)o + k];  // :1153-1160
+  if (stats) {
+    stats->n_reproj_edges = O;
+    stats->n_spring_edges = (int)hp.pair_i.size();
+    stats->n_damper_edges = (int)hp.dmp_w.size();
+    stats->n_points = O;
+    stats->n_poses = F;
+    stats->stage_ms = (float)(t1 - t0);
+    stats->host_ms = (float)(wall_ms() - t0);
+  }
+  return 0;
+}
+
+int nrslam_b200_resolve(nrslam_b200_ctx* ctx, int32_t which, nrslam_b200_stats* stats) {
+  if (!ctx || which < 0 || which > 2) return fail(ctx, NRSLAM_B200_ERR_ARG, "resolve: bad argument");
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  const double t0 = wall_ms();
+  const int rc = run_staged(ctx, ctx->staged[which], stats, /*copy_back=*/false);
+  if (stats) stats->host_ms = (float)(wall_ms() - t0);
+  return rc;
+}
+
+}  // extern "C"

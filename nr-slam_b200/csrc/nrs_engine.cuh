@@ -1,0 +1,120 @@
+// nrs_engine.cuh — problem description handed to the persistent Levenberg–Marquardt kernel (nrs_engine.cu).
+//
+// One launch executes a whole driver "program" (reset / optimize(n) / re-level / final chi2) on the device:
+// the g2o control flow of third_party/g2o/g2o/core/optimization_algorithm_levenberg.cpp:57-151 and the
+// round / outlier logic of modules/optimization/g2o_optimization.cc run without a host round trip.
+//
+// Unknowns: F camera poses (6-dof, left-multiplicative exp update) and V point vertices (3-dof, additive).
+// Every point vertex owns at most one reprojection edge (true for all three reference drivers: tracking has one
+// deformation vertex per observation, BA one landmark vertex per (keyframe, landmark)), so the whole system is
+// traversed "one row per point": the point's reprojection edge plus the regulariser edges incident to it.
+#pragma once
+#include <stdint.h>
+
+#include "nrs_math.cuh"
+
+namespace nrs {
+
+enum Op : int {
+  OP_RESET = 1,          // estimates <- seeds (g2o_optimization.cc:108-110,341-349)
+  OP_CLEAR_LEVELS = 2,   // all edges to level 0
+  OP_OPTIMIZE = 3,       // SparseOptimizer::optimize(arg) with the LM algorithm
+  OP_RELEVEL_POSE = 4,   // g2o_optimization.cc:113-140 (stale-error semantics for inlier edges)
+  OP_RELEVEL_DEFORM = 5, // g2o_optimization.cc:352-394
+  OP_FINAL_CHI2 = 6      // fresh reprojection chi2 per point (g2o_optimization.cc:419-424)
+};
+
+enum SpringKind : int {
+  SPRING_NONE = 0,
+  SPRING_DEFORM = 1,  // PositionRegularizerWithDeformation: exact Jacobian, Huber
+  SPRING_BA = 2       // PositionRegularizer: Jacobian quirk, no robust kernel
+};
+
+constexpr int kMaxOps = 16;
+constexpr int kTrace = 64;
+constexpr int kSlotVals = 8;     // doubles per CTA per grid reduction
+constexpr int kChunkVals = 28;   // doubles per chunk partial (21 H_pp + 6 b_p, padded)
+
+struct EngineStats {
+  int lm_iterations, lm_trials, pcg_iterations, n_sweeps, n_chi2_passes, n_trace, pcg_fail, barriers;
+  double chi2_trace[kTrace];
+  double lambda_final;
+  long long prof[16];  // clock64 cycles per phase seen by CTA 0 / thread 0 (diagnostics)
+};
+
+struct Params {
+  int F, V, P, D, n_chunks;
+  int poses_fixed, points_fixed, spring_kind;
+  Cam cam;
+  double info_reproj, delta_reproj;    // delta <= 0: no robust kernel
+  double info_spatial, delta_spatial;  // pair "spatial", damper and unary (fixed-reference) edges
+  double info_spring, delta_spring, spring_k;
+  float th2f, th3f;
+  double lm_tau;
+  int lm_max_trials;
+  double pcg_tol;
+  int pcg_max_iter;
+  int n_ops;
+  int op[kMaxOps];
+  int op_arg[kMaxOps];
+
+  // poses: 7 doubles each (q xyzw, t)
+  double* pose;
+  const double* pose_seed;
+  // point vertices, 4-double stride
+  double* x;
+  const double* x_seed;
+  double* x_bak;
+  const double* rest;       // rest position added to the estimate (tracking) — zeros in BA
+  const int* pt_kf;         // pose slot of the point's reprojection edge, -1 if it has none
+  const double* uv;         // [2V] measured pixel
+  unsigned char* rp_level;  // [V] reprojection edge level
+  double* rp_chi2;          // [V] chi2 of the reprojection edge at its last evaluation
+  // pair edges (two point vertices): spatial (weight w >= 0, <0: none) and/or spring (d0)
+  const int* pair_i;
+  const int* pair_j;
+  const double* pair_w;
+  const double* pair_d0;
+  unsigned char* sp_level;  // [P] level of the spatial edge
+  double* pc;               // [8P] linearised coefficients: s, u[3], c
+  const int* inc_ptr;       // [V+1] CSR of pair incidences per point
+  const int* inc_other;     // neighbour vertex
+  const int* inc_ent;       // pair id * 2 + (1 if this vertex is the pair's second endpoint)
+  // damper edges (four point vertices: i_k, j_k, i_k', j_k')
+  const int* dmp_v;         // [4D]
+  const double* dmp_w;      // [D]
+  double* dc;               // [4D] s, g[3]
+  const int* dinc_ptr;      // [V+1]
+  const int* dinc_ent;      // damper id * 4 + role
+  // unary edges to a fixed reference value (SpatialRegularizerFixed)
+  const int* un_ptr;        // [V+1]
+  const double* un_w;       // [U]
+  const int* un_ref;        // [U] vertex whose estimate is the reference value
+  int unary_on;             // unary edges take part (lost-point stage only)
+  const unsigned char* pt_fixed;  // [V] per-vertex setFixed(true), nullptr: none
+  // work partition: chunk = contiguous rows of one pose slot
+  const int* chunk_kf;
+  const int* chunk_begin;
+  const int* chunk_end;
+  const int* kf_chunk_ptr;  // [F+1]
+  // work arrays
+  double* jac;         // [20V] A(2x6) B(2x3) omega
+  double* dg;          // [8V]  sym 3x3 diagonal block (6) + unary s
+  double* bvec;        // [4V]
+  double* minv;        // [8V]
+  double* xcg;         // [4V]
+  double* rvec;        // [4V]
+  double* qvec;        // [4V]
+  double* rec;         // [2][8V] {z, p} records
+  double* chunk_part;  // [2][n_chunks * kChunkVals]
+  double* slots;       // [2][G * kSlotVals]
+  unsigned long long* bar;
+  EngineStats* stats;
+};
+
+// Host-side launch (cooperative). Returns cudaError_t as int. grid/block chosen by the caller.
+int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_t stream);
+size_t engine_smem_bytes(int F, int block);
+int engine_max_grid(int block, size_t smem);
+
+}  // namespace nrs

@@ -1,0 +1,87 @@
+// nrs_host.h — host-side plumbing of libnrslam_b200: context, arenas (one pinned host block mirrored by one
+// device block so a call costs ONE host->device and ONE device->host copy), staged problems.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nrslam_b200.h"
+#include "nrs_engine.cuh"
+
+namespace nrs {
+
+// Bump allocator over a pinned host block and a device block of identical layout.
+class Arena {
+ public:
+  ~Arena() { release(); }
+  void release() {
+    if (host_) cudaFreeHost(host_);
+    if (dev_) cudaFree(dev_);
+    host_ = nullptr;
+    dev_ = nullptr;
+    cap_ = 0;
+  }
+  // Reserve capacity (bytes) — reallocates when too small. Returns false on allocation failure.
+  bool reserve(size_t bytes, bool need_host) {
+    if (bytes <= cap_ && (!need_host || host_)) {
+      used_ = 0;
+      return true;
+    }
+    release();
+    size_t cap = bytes + bytes / 4 + 4096;
+    if (cudaMalloc(&dev_, cap) != cudaSuccess) return false;
+    if (need_host && cudaMallocHost(&host_, cap) != cudaSuccess) return false;
+    cap_ = cap;
+    used_ = 0;
+    return true;
+  }
+  template <typename T>
+  size_t take(size_t n) {
+    used_ = (used_ + 255) & ~size_t(255);
+    const size_t off = used_;
+    used_ += n * sizeof(T);
+    return off;
+  }
+  template <typename T>
+  T* h(size_t off) const { return reinterpret_cast<T*>(static_cast<char*>(host_) + off); }
+  template <typename T>
+  T* d(size_t off) const { return reinterpret_cast<T*>(static_cast<char*>(dev_) + off); }
+  size_t used() const { return used_; }
+  size_t capacity() const { return cap_; }
+  void* host() const { return host_; }
+  void* dev() const { return dev_; }
+
+ private:
+  void* host_ = nullptr;
+  void* dev_ = nullptr;
+  size_t cap_ = 0, used_ = 0;
+};
+
+// A problem staged in HBM: inputs (arena `in`), device-only work arrays (`work`), results (`out`).
+struct Staged {
+  Arena in, work, out;
+  Params p;
+  int grid = 0, block = 0;
+  size_t smem = 0;
+  bool valid = false;
+  // offsets of the results inside `out`
+  size_t o_pose = 0, o_x = 0, o_chi2 = 0, o_rp_level = 0, o_sp_level = 0, o_stats = 0;
+  size_t o_fixed = 0;  // per-vertex fixed flags inside `in` (lost-point stage)
+  size_t h2d_bytes = 0, d2h_bytes = 0;
+};
+
+}  // namespace nrs
+
+struct nrslam_b200_ctx {
+  nrslam_b200_options opt;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  nrs::Staged staged[4];  // 0 pose_only, 1 pose_deform, 2 local_ba, 3 lost-point stage
+  unsigned long long* bar = nullptr;
+};
