@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the NR-SLAM hot path on B200 (contract: see README / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): tracking frames/s on configs[1] — synthetic 640x480 pinhole, 2000 landmarks, REF mode — where
+one frame (= one step) is CameraPoseOptimization (3 x 10 LM iterations) followed by
+CameraPoseAndDeformationOptimization (2 x 10 LM iterations, + 10 for lost points in the end-to-end path). The line
+also carries the second quantity of the metric, deformable-BA LM iterations/s on configs[2]
+(5000 landmarks / 30 keyframes / 50k observations), under "ba".
+
+  value  whole-job frames/s with the staged problem resident in HBM (device time of the LM kernels, CUDA events on
+         the library's launch stream, L2 flushed between steps)
+  e2e    the same frames through the C ABI with HOST buffers: host edge selection, H2D, kernels, D2H, host gating
+  roofline     algorithmic bytes (SURVEY.md §8(d) formulas) / kernel time against the measured HBM peak
+  cpu_baseline the oracle (CPU restatement of the reference algorithm) on one host core, bounded sample
+
+N > 1 (torchrun): the path does not need a collective for tracking — every rank tracks its own camera stream
+(replicas, weak scaling); value = frames of all ranks / max-over-ranks time.
+--impl reference: the CPU restatement on all host cores (one independent frame per core), same metric and config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tracking_frames_per_sec"
+UNIT = "frames/s"
+WORKLOAD = ("configs[1]: synthetic 640x480 pinhole, 2000 landmarks, REF mode (one deformation vertex per landmark, "
+            "symmetric 10-NN regularisation graph), frame = pose_only(3x10 LM) + pose_deform(2x10 LM)")
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(st, n_pose_edges=0):
+    """bytes one launch must move at fp32 storage / int32 indices, independent of implementation.
+    B_sweep = 16 O + 60|48 V + 16 S + 24 D + 16 P + 136 F ; B_mv = 16 O + 36 V + 16 S + 24 D + 16 P + 76 F ;
+    chi2 pass = B_sweep - 36 V. One launch = n_sweeps sweeps + pcg_iterations matvecs + n_chi2 passes."""
+    O = st["n_reproj_edges"]
+    V = st["n_points"]
+    F = max(st["n_poses"], 1)
+    S = st["n_pair_edges"] + st["n_spring_edges"]
+    P = st["n_pair_edges"]
+    D = st["n_damper_edges"]
+    per_v = 60 if st["n_pair_edges"] else 48
+    b_sweep = 16 * O + per_v * V + 16 * S + 24 * D + 16 * P + 136 * F
+    b_mv = 16 * O + 36 * V + 16 * S + 24 * D + 16 * P + 76 * F
+    b_chi = b_sweep - 36 * V
+    return st["n_sweeps"] * b_sweep + st["pcg_iterations"] * b_mv + st["n_chi2_passes"] * b_chi, b_sweep, b_mv
+
+
+def run_reference(args):
+    """CPU arm: the oracle (restatement of the reference algorithm; the reference binary cannot be built here — no
+    Eigen / OpenCV C++ in the image). The reference tracks ONE stream on ONE compute thread (frames are sequential,
+    g2o's OpenMP is off: third_party/g2o/CMakeLists.txt:155), so `value` is single-stream, single-thread; the
+    whole-box figure with one independent stream per host core is reported beside it under "multi_stream"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    oracle_lib.build()
+    for _ in range(min(args.warmup, 1)):
+        _ref_frame(0)
+    t0 = time.time()
+    for s in range(args.steps):
+        _ref_frame(s)
+    dt = time.time() - t0
+    val = args.steps / dt
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_ref_frame, range(cores))
+        t1 = time.time()
+        pool.map(_ref_frame, range(cores))
+        dt_all = time.time() - t1
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp32 camera model)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d frames of configs[1], one stream on one thread like the reference; "
+                                       "restatement of the reference algorithm (g2o LM + exact sparse Cholesky), "
+                                       "not the reference binary" % args.steps},
+            "multi_stream": {"value": cores / dt_all, "unit": UNIT, "cores": cores,
+                             "sample": "one independent stream per host core, one frame each"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def _ref_frame(i):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from nrslam_b200 import synth
+    p = synth.tracking_problem("c2", seed=1235 + (i % 4))
+    o = oracle_lib.Oracle()
+    r = o.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
+    o.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"], p["graph"].copy(),
+                  p["scale"], r["pose"], p["last_world_position"])
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-ba", action="store_true", help="skip the secondary BA measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = min(args.steps, 10)  # bounded sample (~0.5 s of CPU work per frame)
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import nrslam_b200  # noqa: F401
+    from nrslam_b200 import api, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    opt = api.default_options()
+    opt.device = local_rank
+    core = api.Core(opt)
+    # every rank tracks its own stream: a different seeded frame of the same shape (replicas, weak scaling)
+    p = synth.tracking_problem("c2", seed=1235 + rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def frame_e2e():
+        r0 = core.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
+        r1 = core.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
+                              p["graph"].copy(), p["scale"], r0["pose"], p["last_world_position"])
+        return r0, r1
+
+    # ---- end-to-end through the C ABI (host buffers in, host results out)
+    for _ in range(args.warmup):
+        frame_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r0, r1 = frame_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = r0["stats"]["h2d_bytes"] + r1["stats"]["h2d_bytes"]
+    d2h = r0["stats"]["d2h_bytes"] + r1["stats"]["d2h_bytes"]
+    e2e_launches = r0["stats"]["kernel_launches"] + r1["stats"]["kernel_launches"]
+
+    # ---- device-resident: re-run the staged programs (pose_only, pose_deform main rounds) on HBM-resident inputs
+    for _ in range(args.warmup):
+        core.resolve(0)
+        core.resolve(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = 0.0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        s0 = core.resolve(0)
+        s1 = core.resolve(1)
+        dev_ms += s0["gpu_ms"] + s1["gpu_ms"]
+    barrier()
+    wall_s = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    value = world * args.steps / (dev_ms_max * 1e-3)
+    e2e_value = world * args.steps / (e2e_ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (the pose+deformation LM launch)
+    pk, pk_kind = peaks()
+    st = dict(s1)
+    st.update(n_reproj_edges=r1["stats"]["n_reproj_edges"], n_points=r1["stats"]["n_points"], n_poses=1,
+              n_pair_edges=r1["stats"]["n_pair_edges"], n_spring_edges=0, n_damper_edges=0)
+    alg, b_sweep, b_mv = algorithmic_bytes(st)
+    ach = alg / (s1["gpu_ms"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "nrs_lm_kernel (pose+deformation launch)", "achieved": ach,
+                "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": None, "algorithmic_bytes_per_launch": alg, "launch_ms": s1["gpu_ms"],
+                "bytes_per_sweep": b_sweep, "bytes_per_matvec": b_mv, "sweeps": s1["n_sweeps"],
+                "matvecs": s1["pcg_iterations"], "chi2_passes": s1["n_chi2_passes"],
+                "note": "working set (<4 MB) is L2-resident inside the launch; the kernel is bound by barrier/"
+                        "gather latency, not HBM (SURVEY.md §0.9)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp32 camera model)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "seed": 1235, "landmarks": int(p["n"]),
+                       "pair_edges": int(r1["stats"]["n_pair_edges"]), "l2_flush_between_steps": True,
+                       "pcg_rel_tol": opt.pcg_rel_tol, "parallelism": "replicas x%d" % world,
+                       "grid_ctas": s1["grid_ctas"], "block_threads": s1["block_threads"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms_max / args.steps, "launches_per_step": e2e_launches},
+            "gpu_launches": 2 * args.steps, "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "lm_iterations_per_step": s0["lm_iterations"] + s1["lm_iterations"],
+            "pcg_iterations_per_step": s0["pcg_iterations"] + s1["pcg_iterations"],
+            "roofline": roofline, "clocks": clocks}
+
+    # ---- second quantity of the metric: deformable-BA LM iterations/s (configs[2], one GPU)
+    if not args.no_ba:
+        q = synth.ba_problem("c3")
+        b = core.local_ba(q["cam"], q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
+        t0 = time.perf_counter()
+        b = core.local_ba(q["cam"], q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
+        ba_e2e_ms = 1e3 * (time.perf_counter() - t0)
+        ks = max(2, min(args.steps, 5))
+        ms = 0.0
+        for _ in range(ks):
+            flush.zero_()
+            torch.cuda.synchronize()
+            sb = core.resolve(2)
+            ms += sb["gpu_ms"]
+        stb = dict(sb)
+        stb.update({k: b["stats"][k] for k in ("n_reproj_edges", "n_points", "n_poses", "n_pair_edges",
+                                                "n_spring_edges", "n_damper_edges")})
+        alg_b, bsw, bmv = algorithmic_bytes(stb)
+        line["ba"] = {"metric": "deformable_ba_lm_iterations_per_sec", "unit": "iters/s",
+                      "value": world * ks * sb["lm_iterations"] / (ms * 1e-3),
+                      "e2e_value": world * b["stats"]["lm_iterations"] / (ba_e2e_ms * 1e-3),
+                      "workload": "configs[2]: 640x480 pinhole, 5000 landmarks / 30 keyframes / %d observations, "
+                                  "%d springs, %d dampers, optimize(5)" % (b["stats"]["n_reproj_edges"],
+                                                                           b["stats"]["n_spring_edges"],
+                                                                           b["stats"]["n_damper_edges"]),
+                      "launch_ms": ms / ks, "pcg_iterations": sb["pcg_iterations"],
+                      "roofline": {"bound": "hbm", "achieved": alg_b / (ms / ks * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                                   "unit": "GB/s", "frac": alg_b / (ms / ks * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                   "bytes_per_sweep": bsw, "bytes_per_matvec": bmv}}
+
+    # ---- CPU baseline: the oracle on one host core, bounded sample (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        orc = oracle_lib.Oracle()
+        n_frames = 0
+        t0 = time.perf_counter()
+        while n_frames < 3 or (time.perf_counter() - t0 < 10.0 and n_frames < 20):
+            a0 = orc.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
+            orc.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
+                            p["graph"].copy(), p["scale"], a0["pose"], p["last_world_position"])
+            n_frames += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n_frames / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%d frames of the same configs[1] problem, single thread (the reference "
+                                          "is single-threaded: g2o OpenMP off); restatement of the reference "
+                                          "algorithm, not the reference binary" % n_frames,
+                                "host_cores_available": len(os.sched_getaffinity(0))}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    core.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

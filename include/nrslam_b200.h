@@ -120,6 +120,9 @@ typedef struct nrslam_b200_stats {
   float gpu_ms;               /* device time of the solve stage (CUDA events on the ctx stream) */
   float host_ms;              /* wall time of the whole call */
   float stage_ms;             /* host edge selection + H2D */
+  int64_t h2d_bytes;          /* bytes copied host -> device by this call */
+  int64_t d2h_bytes;          /* bytes copied device -> host by this call */
+  int32_t grid_ctas, block_threads; /* launch geometry of the LM kernel */
 } nrslam_b200_stats;
 
 typedef struct nrslam_b200_ctx nrslam_b200_ctx;

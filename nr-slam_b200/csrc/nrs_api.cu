@@ -321,6 +321,9 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
     stats->n_sweeps += es->n_sweeps;
     stats->n_chi2_passes += es->n_chi2_passes;
     stats->kernel_launches += 1;
+    stats->grid_ctas = st.grid;
+    stats->block_threads = st.block;
+    stats->d2h_bytes += copy_back ? (int64_t)st.out.used() : (int64_t)sizeof(EngineStats);
     for (int i = 0; i < es->n_trace && stats->n_trace < NRSLAM_B200_TRACE; i++)
       stats->chi2_trace[stats->n_trace++] = es->chi2_trace[i];
     stats->lambda_final = es->lambda_final;
@@ -482,6 +485,7 @@ int nrslam_b200_pose_only(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, i
   int rc = stage_problem(ctx, st, hp);
   if (rc) return rc;
   const double t1 = wall_ms();
+  if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes;
   rc = run_staged(ctx, st, stats);
   if (rc) return rc;
   const double* pose = st.out.h<double>(st.o_pose);
@@ -614,6 +618,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   int rc = stage_problem(ctx, st, hp);
   if (rc) return rc;
   const double t1 = wall_ms();
+  if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes;
   rc = run_staged(ctx, st, stats);
   if (rc) return rc;
 
@@ -718,6 +723,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
       NRS_CUDA(ctx, sync_range(st.p.un_w, (size_t)n_un * sizeof(double)));
       NRS_CUDA(ctx, sync_range(st.p.un_ref, (size_t)n_un * sizeof(int)));
       NRS_CUDA(ctx, sync_range(st.in.d<unsigned char>(st.o_fixed), Vtot));
+      if (stats) stats->h2d_bytes += ((int64_t)Vtot + 1) * 4 + (int64_t)n_un * 12 + Vtot;
       Params p2 = st.p;
       p2.poses_fixed = 1;
       p2.unary_on = 1;
@@ -875,6 +881,7 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
   int rc = stage_problem(ctx, st, hp);
   if (rc) return rc;
   const double t1 = wall_ms();
+  if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes;
   rc = run_staged(ctx, st, stats);
   if (rc) return rc;
   const double* pose = st.out.h<double>(st.o_pose);
