@@ -77,8 +77,12 @@ def test_pose_deform(core, oracle, cfg, n, kw):
     assert a["stats"]["n_pair_edges"] == b["stats"]["n_pair_edges"]
     if not kb8:
         assert a["stats"]["n_fixed_edges"] == b["stats"]["n_fixed_edges"]
-    assert np.allclose(ga.weight, gb.weight, rtol=1e-4, atol=1e-6)
-    assert np.allclose(ga.max_distance, gb.max_distance, rtol=1e-4) and np.allclose(ga.min_distance, gb.min_distance, rtol=1e-4)
+    # graph attributes are fp32 functions of positions that agree to PT_TOL each: distances to 2 PT_TOL absolute,
+    # weights exp(-d^2 / 2 sigma^2) to |dw| <= d / sigma^2 * 2 PT_TOL
+    dtol = 2 * (PT_TOL if not kb8 else 2e-4)
+    assert np.allclose(ga.weight, gb.weight, rtol=1e-4, atol=dtol)
+    assert np.allclose(ga.max_distance, gb.max_distance, rtol=0, atol=dtol)
+    assert np.allclose(ga.min_distance, gb.min_distance, rtol=0, atol=dtol)
 
 
 def test_pose_deform_with_bad_graph_edges(core, oracle):
