@@ -112,6 +112,8 @@ struct HostProblem {
   std::vector<double> un_w;             // U
   std::vector<int> un_ref;              // U
   bool want_fixed_flags = false;        // reserve a per-vertex fixed-flag array (filled later)
+  int n_sort = 0;                       // leading rows of every pose-slot group that may be re-ordered spatially
+  int n_stage1 = 0;                     // rows of the first launch (tracking: without the lost-point rows); 0 = all
   std::vector<int> kf_begin;            // F+1: rows of pose slot k are [kf_begin[k], kf_begin[k+1]) (rows w/o pose: slot 0)
   std::vector<int> ops, op_args;
 };
@@ -124,34 +126,192 @@ size_t put(Arena& a, const std::vector<T>& v, size_t min_elems = 1) {
   return off;
 }
 
-int pick_block(const nrslam_b200_ctx* ctx, int V) {
-  const char* env = getenv("NRSLAM_B200_BLOCK");
-  if (env) {
-    int b = atoi(env);
-    if (b >= 64 && b <= 256 && b % 32 == 0) return b;
-  }
-  (void)ctx;
-  if (V <= 8192) return 128;
-  return 256;
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
-int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
+// 30-bit Morton code of a point inside the bounding box [lo, lo + ext]
+inline uint32_t morton3(const double* p, const double* lo, const double* inv_ext) {
+  uint32_t code = 0;
+  uint32_t q[3];
+  for (int a = 0; a < 3; a++) {
+    double t = (p[a] - lo[a]) * inv_ext[a];
+    t = std::min(std::max(t, 0.0), 1.0);
+    q[a] = (uint32_t)(t * 1023.0);
+  }
+  for (int b = 9; b >= 0; b--)
+    for (int a = 0; a < 3; a++) code = (code << 1) | ((q[a] >> b) & 1u);
+  return code;
+}
+
+// Re-order the first hp.n_sort rows of every pose-slot group along a Morton curve of their positions and rewrite
+// every row index of the problem. row_of[old] = new.
+void sort_rows(HostProblem& hp, std::vector<int>& row_of) {
+  const int V = hp.V;
+  row_of.resize(V);
+  std::iota(row_of.begin(), row_of.end(), 0);
+  if (hp.n_sort <= 1 || hp.points_fixed) return;
+  std::vector<int> old_of_new(V);
+  std::iota(old_of_new.begin(), old_of_new.end(), 0);
+  std::vector<std::pair<uint32_t, int>> keyed;
+  for (int k = 0; k < hp.F; k++) {
+    const int b = hp.kf_begin[k], e = std::min(hp.kf_begin[k + 1], hp.n_sort);
+    if (e - b < 2) continue;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    auto pos = [&](int i, int a) { return hp.rest[4 * (size_t)i + a] + hp.x_seed[4 * (size_t)i + a]; };
+    for (int i = b; i < e; i++)
+      for (int a = 0; a < 3; a++) {
+        lo[a] = std::min(lo[a], pos(i, a));
+        hi[a] = std::max(hi[a], pos(i, a));
+      }
+    // one common scale for the three axes keeps the curve isotropic
+    double ext = 0;
+    for (int a = 0; a < 3; a++) ext = std::max(ext, hi[a] - lo[a]);
+    const double inv = ext > 0 ? 1.0 / ext : 0.0;
+    const double inv_ext[3] = {inv, inv, inv};
+    keyed.clear();
+    for (int i = b; i < e; i++) {
+      const double p[3] = {pos(i, 0), pos(i, 1), pos(i, 2)};
+      keyed.emplace_back(morton3(p, lo, inv_ext), i);
+    }
+    std::sort(keyed.begin(), keyed.end());
+    for (int t = 0; t < e - b; t++) old_of_new[b + t] = keyed[t].second;
+  }
+  for (int nw = 0; nw < V; nw++) row_of[old_of_new[nw]] = nw;
+  auto permute = [&](std::vector<double>& v, int stride) {
+    std::vector<double> o(v.size());
+    for (int nw = 0; nw < V; nw++)
+      for (int a = 0; a < stride; a++) o[(size_t)stride * nw + a] = v[(size_t)stride * old_of_new[nw] + a];
+    v.swap(o);
+  };
+  permute(hp.x_seed, 4);
+  permute(hp.rest, 4);
+  permute(hp.uv, 2);
+  {
+    std::vector<int> o(V);
+    for (int nw = 0; nw < V; nw++) o[nw] = hp.pt_kf[old_of_new[nw]];
+    hp.pt_kf.swap(o);
+  }
+  for (auto& v : hp.pair_i) v = row_of[v];
+  for (auto& v : hp.pair_j) v = row_of[v];
+  for (auto& v : hp.dmp_v) v = row_of[v];
+}
+
+// Launch plan of one engine launch over the rows [0, kf_begin[F]).
+struct Plan {
+  int V = 0, n_chunks = 0, grid = 0, block = 0, cluster_mode = 0, resident = 0, res_rows = 0, res_inc = 0,
+      block_prec = 0;
+  size_t smem = 0;
+  std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr;
+  const int *d_chunk_kf = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_kf_chunk_ptr = nullptr;
+};
+
+// The path is bound by synchronisation latency: prefer ONE thread-block cluster (hardware barrier) whenever the
+// rows fit a cluster's threads; otherwise a cooperative grid with the atomics barrier.
+int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int>& kf_begin,
+              const std::vector<int>& inc_ptr, Plan& pl) {
+  const int F = hp.F;
+  pl.V = kf_begin[F];
+  if (ctx->max_cluster < 0) ctx->max_cluster = engine_max_cluster(kMaxBlock, 200 * 1024);
+  int ncl = env_int("NRSLAM_B200_CLUSTER", ctx->max_cluster);
+  ncl = std::min(ncl, ctx->max_cluster);
+  auto count_chunks = [&](int rows) {
+    int n = 0;
+    for (int k = 0; k < F; k++) n += (kf_begin[k + 1] - kf_begin[k] + rows - 1) / rows;
+    return n;
+  };
+  int chunk_rows = kMaxRows, cluster_mode = 0;
+  if (ncl >= 2) {
+    for (int rows = 32; rows <= kMaxRows; rows += 8) {
+      if (count_chunks(rows) <= ncl) {
+        chunk_rows = rows;
+        cluster_mode = 1;
+        break;
+      }
+    }
+  }
+  // kTPR threads per row inside the CG loop; pose-only problems (no CG) run one thread per row
+  int block = hp.points_fixed ? std::max((chunk_rows + 31) / 32 * 32, 128) : kTPR * chunk_rows;
+  block = std::min(kMaxBlock, (block + 31) / 32 * 32);
+  // chunks: contiguous rows of one pose slot, at most chunk_rows rows each
+  pl.kf_chunk_ptr.assign(F + 1, 0);
+  for (int k = 0; k < F; k++) {
+    pl.kf_chunk_ptr[k] = (int)pl.chunk_kf.size();
+    for (int b = kf_begin[k]; b < kf_begin[k + 1]; b += chunk_rows) {
+      pl.chunk_kf.push_back(k);
+      pl.chunk_begin.push_back(b);
+      pl.chunk_end.push_back(std::min(b + chunk_rows, kf_begin[k + 1]));
+    }
+  }
+  pl.kf_chunk_ptr[F] = (int)pl.chunk_kf.size();
+  const int n_chunks = (int)pl.chunk_kf.size();
+  // resident mode: one chunk per CTA and the chunk state fits shared memory
+  int res_rows = 0, res_inc = 0;
+  for (int c = 0; c < n_chunks; c++) {
+    res_rows = std::max(res_rows, pl.chunk_end[c] - pl.chunk_begin[c]);
+    res_inc = std::max(res_inc, inc_ptr[pl.chunk_end[c]] - inc_ptr[pl.chunk_begin[c]]);
+  }
+  res_rows = (res_rows + kPrecBlock - 1) / kPrecBlock * kPrecBlock;
+  res_inc = std::max(res_inc, 1);
+  int resident = 0, block_prec = 0, grid = 0;
+  size_t smem = engine_smem_bytes(F, 0, 0, 0);
+  if (smem > 200 * 1024) return fail(ctx, NRSLAM_B200_ERR_ARG, "too many poses for the shared-memory pose blocks");
+  const size_t kSmemBudget = 220 * 1024;
+  if (!hp.points_fixed && env_int("NRSLAM_B200_RESIDENT", 1)) {
+    const size_t s1 = engine_smem_bytes(F, res_rows, res_inc, 1), s0 = engine_smem_bytes(F, res_rows, res_inc, 0);
+    const bool want_prec = env_int("NRSLAM_B200_BLOCKPREC", 1) != 0;
+    const size_t s = (want_prec && s1 <= kSmemBudget) ? s1 : s0;
+    if (s <= kSmemBudget) {
+      const int mg = cluster_mode ? n_chunks : engine_max_grid(block, s);
+      if (n_chunks <= mg) {
+        resident = 1;
+        block_prec = (s == s1 && want_prec) ? 1 : 0;
+        smem = s;
+        grid = n_chunks;
+      }
+    }
+  }
+  if (!resident) {
+    if (cluster_mode) {
+      grid = n_chunks;
+    } else {
+      const int max_grid = engine_max_grid(block, smem);
+      if (max_grid <= 0) return fail(ctx, NRSLAM_B200_ERR_CUDA, "kernel cannot be made resident");
+      grid = std::max(1, std::min(n_chunks, max_grid));
+      if (ctx->opt.grid_ctas > 0) grid = std::min(grid, ctx->opt.grid_ctas);
+      const int g = env_int("NRSLAM_B200_GRID", 0);
+      if (g > 0) grid = std::min(max_grid, g);
+    }
+  }
+  if (cluster_mode) {
+    // the cluster must be schedulable with this shared-memory size; otherwise fall back to the cooperative grid
+    const int mc = engine_max_cluster(block, smem);
+    if (mc < grid) {
+      cluster_mode = 0;
+      const int max_grid = engine_max_grid(block, smem);
+      if (max_grid < grid) return fail(ctx, NRSLAM_B200_ERR_CUDA, "kernel cannot be made resident");
+    }
+  }
+  pl.n_chunks = n_chunks; pl.grid = grid; pl.block = block; pl.cluster_mode = cluster_mode; pl.resident = resident;
+  pl.res_rows = res_rows; pl.res_inc = res_inc; pl.block_prec = block_prec; pl.smem = smem;
+  return 0;
+}
+
+void apply_plan(Params& p, const Plan& pl) {
+  p.V = pl.V; p.n_chunks = pl.n_chunks;
+  p.cluster_mode = pl.cluster_mode; p.resident = pl.resident; p.res_rows = pl.res_rows; p.res_inc = pl.res_inc;
+  p.block_prec = pl.block_prec;
+  p.chunk_kf = pl.d_chunk_kf; p.chunk_begin = pl.d_chunk_begin; p.chunk_end = pl.d_chunk_end;
+  p.kf_chunk_ptr = pl.d_kf_chunk_ptr;
+}
+
+int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   const int F = hp.F, V = hp.V, P = (int)hp.pair_i.size(), D = (int)hp.dmp_w.size();
   const int U = (int)hp.un_w.size();
   st.valid = false;
-  const int block = pick_block(ctx, V);
-  // chunks: contiguous rows of one pose slot, at most `block` rows each
-  std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr(F + 1, 0);
-  for (int k = 0; k < F; k++) {
-    kf_chunk_ptr[k] = (int)chunk_kf.size();
-    for (int b = hp.kf_begin[k]; b < hp.kf_begin[k + 1]; b += block) {
-      chunk_kf.push_back(k);
-      chunk_begin.push_back(b);
-      chunk_end.push_back(std::min(b + block, hp.kf_begin[k + 1]));
-    }
-  }
-  kf_chunk_ptr[F] = (int)chunk_kf.size();
-  const int n_chunks = (int)chunk_kf.size();
+  sort_rows(hp, st.row_of);
+
   // incidence lists
   std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P);
   for (int e = 0; e < P; e++) {
@@ -178,6 +338,23 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
     for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ent[w[hp.dmp_v[t]]++] = (int)t;  // id*4 + role
   }
 
+  // ---- launch plans. Tracking stages its lost-point rows behind the optimised ones: the main rounds run on the
+  // first hp.n_stage1 rows only (plan A), the lost-point stage on all rows (plan B).
+  const int V1 = (hp.n_stage1 > 0 && hp.n_stage1 < V && F == 1) ? hp.n_stage1 : V;
+  Plan planA, planB;
+  {
+    std::vector<int> kfb(hp.kf_begin);
+    kfb[F] = V1;
+    const int rc = make_plan(ctx, hp, kfb, inc_ptr, planA);
+    if (rc) return rc;
+    if (V1 < V) {
+      const int rc2 = make_plan(ctx, hp, hp.kf_begin, inc_ptr, planB);
+      if (rc2) return rc2;
+    }
+  }
+  const int n_chunks = planA.n_chunks;
+  const int max_chunks = std::max(planA.n_chunks, planB.n_chunks), max_grid_used = std::max(planA.grid, planB.grid);
+
   // ---- input arena
   size_t need = 0;
   auto sz = [&](size_t bytes) { need += ((bytes + 255) & ~size_t(255)) + 256; };
@@ -186,13 +363,13 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
   sz(((size_t)V + 1) * 4); sz(2 * (size_t)P * 4); sz(2 * (size_t)P * 4);
   sz(4 * (size_t)D * 4); sz((size_t)D * 8); sz(((size_t)V + 1) * 4); sz(4 * (size_t)D * 4);
   sz(((size_t)V + 1) * 4); sz((size_t)U * 8); sz((size_t)U * 4); sz((size_t)V);
-  sz((size_t)n_chunks * 4 * 3); sz(((size_t)F + 1) * 4);
+  sz((size_t)max_chunks * 4 * 3 * 2); sz(((size_t)F + 1) * 4 * 2);
   need += 8192;
   if (!st.in.reserve(need, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "input arena allocation failed");
   Arena& in = st.in;
   Params& p = st.p;
   memset(&p, 0, sizeof(p));
-  p.F = F; p.V = V; p.P = P; p.D = D; p.n_chunks = n_chunks;
+  p.F = F; p.V = V; p.P = P; p.D = D; p.n_chunks = n_chunks;  // V / chunks: overwritten by apply_plan below
   p.poses_fixed = hp.poses_fixed; p.points_fixed = hp.points_fixed; p.spring_kind = hp.spring_kind;
   p.cam = hp.cam;
   p.info_reproj = hp.info_reproj; p.delta_reproj = hp.delta_reproj;
@@ -201,6 +378,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
   p.th2f = hp.th2f; p.th3f = hp.th3f;
   p.lm_tau = ctx->opt.lm_tau; p.lm_max_trials = ctx->opt.lm_max_trials;
   p.pcg_tol = ctx->opt.pcg_rel_tol; p.pcg_max_iter = ctx->opt.pcg_max_iterations;
+  p.no_dsmem = env_int("NRSLAM_B200_NO_DSMEM", 0);
   p.n_ops = (int)hp.ops.size();
   if (p.n_ops > kMaxOps) return fail(ctx, NRSLAM_B200_ERR_ARG, "program too long");
   for (int i = 0; i < p.n_ops; i++) {
@@ -232,23 +410,24 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
     st.o_fixed = in.take<unsigned char>(V);
     memset(in.h<unsigned char>(st.o_fixed), 0, V);
   }
-  p.chunk_kf = in.d<int>(put(in, chunk_kf));
-  p.chunk_begin = in.d<int>(put(in, chunk_begin));
-  p.chunk_end = in.d<int>(put(in, chunk_end));
-  p.kf_chunk_ptr = in.d<int>(put(in, kf_chunk_ptr));
+  for (Plan* pl : {&planA, &planB}) {
+    if (pl->n_chunks == 0) continue;
+    pl->d_chunk_kf = in.d<int>(put(in, pl->chunk_kf));
+    pl->d_chunk_begin = in.d<int>(put(in, pl->chunk_begin));
+    pl->d_chunk_end = in.d<int>(put(in, pl->chunk_end));
+    pl->d_kf_chunk_ptr = in.d<int>(put(in, pl->kf_chunk_ptr));
+  }
+  apply_plan(p, planA);
   st.h2d_bytes = in.used();
-
-  // ---- launch geometry
-  st.block = block;
-  st.smem = engine_smem_bytes(F, block);
-  if (st.smem > 200 * 1024) return fail(ctx, NRSLAM_B200_ERR_ARG, "too many poses for the shared-memory pose blocks");
-  int max_grid = engine_max_grid(block, st.smem);
-  if (max_grid <= 0) return fail(ctx, NRSLAM_B200_ERR_CUDA, "kernel cannot be made resident");
-  int grid = std::max(1, std::min(n_chunks, max_grid));
-  if (ctx->opt.grid_ctas > 0) grid = std::min(grid, ctx->opt.grid_ctas);
-  const char* genv = getenv("NRSLAM_B200_GRID");
-  if (genv && atoi(genv) > 0) grid = std::min(max_grid, atoi(genv));
-  st.grid = grid;
+  st.block = planA.block;
+  st.smem = planA.smem;
+  st.grid = planA.grid;
+  st.has_plan2 = planB.n_chunks > 0;
+  if (st.has_plan2) {
+    st.block2 = planB.block;
+    st.smem2 = planB.smem;
+    st.grid2 = planB.grid;
+  }
 
   // ---- results + work arrays
   Arena& out = st.out;
@@ -269,8 +448,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
   p.stats = out.d<EngineStats>(st.o_stats);
 
   Arena& wk = st.work;
-  size_t wneed = (size_t)V * 8 * (4 + 20 + 8 + 4 + 8 + 4 + 4 + 4 + 16) + (size_t)P * 64 + (size_t)D * 32 +
-                 2 * (size_t)n_chunks * kChunkVals * 8 + 2 * (size_t)grid * kSlotVals * 8 + 32 * 256 + 4096;
+  size_t wneed = (size_t)V * 8 * (4 + 20 + 8 + 4 + 8 + 4 * 5) + (size_t)P * 40 + (size_t)D * 32 +
+                 2 * (size_t)max_chunks * kChunkVals * 8 + 2 * (size_t)max_grid_used * kSlotVals * 8 + 32 * 256 + 4096;
   if (!wk.reserve(wneed, false)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "work arena allocation failed");
   p.x_bak = wk.d<double>(wk.take<double>(4 * (size_t)V));
   p.jac = wk.d<double>(wk.take<double>(20 * (size_t)V));
@@ -279,13 +458,19 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
   p.minv = wk.d<double>(wk.take<double>(8 * (size_t)V));
   p.xcg = wk.d<double>(wk.take<double>(4 * (size_t)V));
   p.rvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
+  p.pvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
   p.qvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
-  p.rec = wk.d<double>(wk.take<double>(16 * (size_t)V));
-  p.pc = wk.d<double>(wk.take<double>(8 * (size_t)std::max(P, 1)));
+  p.zvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
+  p.pc = wk.d<double>(wk.take<double>(4 * (size_t)std::max(P, 1)));
+  p.pcc = wk.d<double>(wk.take<double>((size_t)std::max(P, 1)));
   p.dc = wk.d<double>(wk.take<double>(4 * (size_t)std::max(D, 1)));
-  p.chunk_part = wk.d<double>(wk.take<double>(2 * (size_t)n_chunks * kChunkVals));
-  p.slots = wk.d<double>(wk.take<double>(2 * (size_t)grid * kSlotVals));
+  p.chunk_part = wk.d<double>(wk.take<double>(2 * (size_t)max_chunks * kChunkVals));
+  p.slots = wk.d<double>(wk.take<double>(2 * (size_t)max_grid_used * kSlotVals));
   p.bar = ctx->bar;
+  if (st.has_plan2) {
+    st.p2 = p;
+    apply_plan(st.p2, planB);
+  }
 
   NRS_CUDA(ctx, cudaMemcpyAsync(in.dev(), in.host(), in.used(), cudaMemcpyHostToDevice, ctx->stream));
   // dg[.][6] (unary diagonal weight) is read by the matvec even when no unary edges exist
@@ -297,10 +482,11 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, const HostProblem& hp) {
 
 // Launch the staged program, bring the results back, fill stats. Blocks until done.
 int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool copy_back = true,
-               const Params* override_params = nullptr) {
+               const Params* override_params = nullptr, bool plan2 = false) {
   if (!st.valid) return fail(ctx, NRSLAM_B200_ERR_ARG, "no staged problem");
   NRS_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  const int rc = launch_engine(override_params ? *override_params : st.p, st.grid, st.block, st.smem, ctx->stream);
+  const int rc = launch_engine(override_params ? *override_params : st.p, plan2 ? st.grid2 : st.grid,
+                               plan2 ? st.block2 : st.block, plan2 ? st.smem2 : st.smem, ctx->stream);
   if (rc != 0)
     return fail(ctx, NRSLAM_B200_ERR_CUDA, std::string("engine launch: ") + cudaGetErrorString((cudaError_t)rc));
   NRS_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -321,8 +507,10 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
     stats->n_sweeps += es->n_sweeps;
     stats->n_chi2_passes += es->n_chi2_passes;
     stats->kernel_launches += 1;
-    stats->grid_ctas = st.grid;
-    stats->block_threads = st.block;
+    if (!plan2) {
+      stats->grid_ctas = st.grid;
+      stats->block_threads = st.block;
+    }
     stats->d2h_bytes += copy_back ? (int64_t)st.out.used() : (int64_t)sizeof(EngineStats);
     for (int i = 0; i < es->n_trace && stats->n_trace < NRSLAM_B200_TRACE; i++)
       stats->chi2_trace[stats->n_trace++] = es->chi2_trace[i];
@@ -603,6 +791,8 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   hp.uv.resize(2 * (size_t)Vtot, 0.0);
   hp.pt_kf.resize(Vtot, -1);
   hp.kf_begin = {0, Vtot};
+  hp.n_sort = n;  // the lost rows stay behind the optimised ones
+  hp.n_stage1 = n;
   hp.want_fixed_flags = n_lost > 0;
   if (n_lost > 0) {
     // capacity for the unary edges (filled after the graph refresh): at most 11 per lost point
@@ -628,12 +818,13 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   pose_to_f7(pose, pose_io);  // :398-399
   const double* xd = st.out.h<double>(st.o_x);
   const double* chi2d = st.out.h<double>(st.o_chi2);
+  const std::vector<int>& row_of = st.row_of;  // caller row -> engine row
 
   // ---- deformation magnitudes, IQR gate (:401-455)
   std::vector<float> mags(n), def(3 * (size_t)n);
   for (int idx = 0; idx < n; idx++) {
     float* d = &def[3 * (size_t)idx];
-    for (int k = 0; k < 3; k++) d[k] = (float)xd[4 * (size_t)idx + k];
+    for (int k = 0; k < 3; k++) d[k] = (float)xd[4 * (size_t)row_of[idx] + k];
     mags[idx] = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     if (deformation_out)
       for (int k = 0; k < 3; k++) deformation_out[3 * (size_t)idx + k] = d[k];
@@ -647,7 +838,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   std::vector<uint8_t> status(n, NRSLAM_TRACKED_WITH_3D);
   std::vector<unsigned char> fixed(Vtot, 0);
   for (int idx = 0; idx < n; idx++) {
-    const float chi_squared = (float)chi2d[idx];
+    const float chi_squared = (float)chi2d[row_of[idx]];
     if (chi2_out) chi2_out[idx] = chi_squared;
     if (chi_squared > th2) {
       inliers[idx] = 0;
@@ -659,7 +850,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
       status[idx] = NRSLAM_TRACKED;
       continue;
     }
-    fixed[idx] = 1;  // :439 setFixed(true)
+    fixed[row_of[idx]] = 1;  // :439 setFixed(true)
     for (int k = 0; k < 3; k++) {
       const float cur = def[3 * (size_t)idx + k] + X_rest[3 * (size_t)idx + k];
       if (X_out) X_out[3 * (size_t)idx + k] = cur;
@@ -706,7 +897,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
         const int other = g->col[pe];
         if (opt_index[other] < 0) continue;  // :502-504
         un_w[n_un] = (double)g->weight[g->eid[pe]];
-        un_ref[n_un] = opt_index[other];
+        un_ref[n_un] = row_of[opt_index[other]];
         n_un++;
         n_regularizers++;
       }
@@ -724,14 +915,14 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
       NRS_CUDA(ctx, sync_range(st.p.un_ref, (size_t)n_un * sizeof(int)));
       NRS_CUDA(ctx, sync_range(st.in.d<unsigned char>(st.o_fixed), Vtot));
       if (stats) stats->h2d_bytes += ((int64_t)Vtot + 1) * 4 + (int64_t)n_un * 12 + Vtot;
-      Params p2 = st.p;
+      Params p2 = st.has_plan2 ? st.p2 : st.p;
       p2.poses_fixed = 1;
       p2.unary_on = 1;
       p2.pt_fixed = st.in.d<unsigned char>(st.o_fixed);
       p2.n_ops = 1;
       p2.op[0] = OP_OPTIMIZE;
       p2.op_arg[0] = opt.lost_iterations;
-      rc = run_staged(ctx, st, stats, true, &p2);
+      rc = run_staged(ctx, st, stats, true, &p2, st.has_plan2);
       if (rc) return rc;
       const double* xl = st.out.h<double>(st.o_x);
       for (int v = 0; v < n_lost; v++)
@@ -876,6 +1067,7 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
   }
   hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE};
   hp.op_args = {0, 0, iterations};
+  hp.n_sort = O;
 
   Staged& st = ctx->staged[2];
   int rc = stage_problem(ctx, st, hp);
@@ -890,7 +1082,7 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
     if (!std::isfinite(pose[i])) return fail(ctx, NRSLAM_B200_NUM_NONFINITE, "local_ba: non-finite pose");
   for (int k = 0; k < F; k++) pose_to_f7(pose + 7 * k, kf_pose_io + 7 * k);  // :1146-1151
   for (int o = 0; o < O; o++)
-    for (int k = 0; k < 3; k++) X_io[3 * (size_t)o + k] = (float)xd[4 * (size_t)o + k];  // :1153-1160
+    for (int k = 0; k < 3; k++) X_io[3 * (size_t)o + k] = (float)xd[4 * (size_t)st.row_of[o] + k];  // :1153-1160
   if (stats) {
     stats->n_reproj_edges = O;
     stats->n_spring_edges = (int)hp.pair_i.size();

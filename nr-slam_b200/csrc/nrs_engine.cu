@@ -1,4 +1,4 @@
-// nrs_engine.cu — persistent, cooperative Levenberg–Marquardt kernel for sm_100a.
+// nrs_engine.cu — persistent Levenberg–Marquardt kernel for sm_100a.
 //
 // What it replaces (reference paths relative to /root/reference):
 //   SparseOptimizer::optimize / computeActiveErrors / update / push / pop   third_party/g2o/g2o/core/sparse_optimizer.cpp:62-114,392-470
@@ -8,16 +8,25 @@
 //   the ten edge types of modules/optimization/*.cc (cited at each formula)
 //   the round / re-levelling logic of modules/optimization/g2o_optimization.cc:100-140,338-395
 //
-// Design: one launch runs a whole driver program. Each CTA owns "chunks" of point rows; a row is a
+// Design. One launch runs a whole driver program. Each CTA owns "chunks" of point rows; a row is a
 // point vertex with its reprojection edge and the regulariser edges incident to it, so the normal equations are
 // applied matrix-free, row by row, without atomics and in a fixed summation order. The reference factorises
-// H + lambda*I exactly (sparse LL^T); here the damped system is solved by block-Jacobi preconditioned CG whose
-// vectors stay in HBM/L2 and whose 6-dof pose blocks are replicated in every CTA's shared memory. CTAs meet at a
-// global-memory barrier (release/acquire on one counter); reductions go through per-CTA slots summed in a fixed
-// order, so every CTA derives bit-identical scalars and takes the same branches.
+// H + lambda*I exactly (sparse LL^T); here the damped system is solved by preconditioned CG. The path is bound by
+// synchronisation latency, not bandwidth, so the kernel is organised around the cost of a sync:
+//   - small problems (a tracking frame, the reference's 5-keyframe BA window) run as ONE thread-block cluster of up
+//     to 16 CTAs and synchronise with the hardware cluster barrier (0.35 us measured) instead of a global-memory
+//     barrier (0.9-1.3 us, profiles/r01_barrier_latency.txt);
+//   - in "resident" mode every CTA keeps the Jacobians, the regulariser coefficients, the CG vectors and a dense
+//     16-row block-Jacobi preconditioner of its chunk in shared memory for the duration of a solve; the only
+//     vector that crosses CTAs (z = M^-1 r) is exchanged through L2;
+//   - one CG iteration costs two synchronisations and one batched gather;
+//   - grid reductions go through per-CTA slots summed in a fixed order, so every CTA derives bit-identical scalars
+//     and takes the same branches; the 6-dof pose blocks are replicated in every CTA's shared memory.
 #include <cooperative_groups.h>
 #include <float.h>
 #include <stdio.h>
+
+#include <algorithm>
 
 #include "nrs_engine.cuh"
 
@@ -37,7 +46,8 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsig
 struct V3 {
   double x, y, z;
 };
-__device__ __forceinline__ V3 ld3(const double* base, int i) {  // L2-coherent (data written by other CTAs)
+// data written by other CTAs during the launch: L2-coherent loads
+__device__ __forceinline__ V3 ld3(const double* base, int i) {
   const double2 a = __ldcg(reinterpret_cast<const double2*>(base + 4 * (size_t)i));
   const double b = __ldcg(base + 4 * (size_t)i + 2);
   return V3{a.x, a.y, b};
@@ -46,51 +56,89 @@ __device__ __forceinline__ void st3(double* base, int i, const V3& v) {
   *reinterpret_cast<double2*>(base + 4 * (size_t)i) = make_double2(v.x, v.y);
   base[4 * (size_t)i + 2] = v.z;
 }
-__device__ __forceinline__ V3 ld3c(const double* base, int i) {  // read-only input
+// read-only inputs
+__device__ __forceinline__ V3 ld3c(const double* base, int i) {
   const double2 a = __ldg(reinterpret_cast<const double2*>(base + 4 * (size_t)i));
   const double b = __ldg(base + 4 * (size_t)i + 2);
   return V3{a.x, a.y, b};
+}
+// plain (generic) access: CTA-private data in shared memory or in this CTA's own rows of a global array
+__device__ __forceinline__ V3 ld3p(const double* base, int i) {
+  const double2 a = *reinterpret_cast<const double2*>(base + 4 * (size_t)i);
+  return V3{a.x, a.y, base[4 * (size_t)i + 2]};
 }
 
 __device__ __forceinline__ int sym6(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  // a <= c
 
 // Inverse of the SPD 6x6 (upper-packed H + lambda I) by Cholesky; out = full 36. Returns false if not SPD.
+// Fully unrolled (everything stays in registers) with one reciprocal per pivot.
 __device__ bool invert6(const double* Hu, double lambda, double* out) {
-  double L[36];
-  for (int i = 0; i < 36; i++) L[i] = 0;
+  double L[6][6], id[6];
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; j++) {
     double s = Hu[sym6(j, j)] + lambda;
-    for (int k = 0; k < j; k++) s -= L[j * 6 + k] * L[j * 6 + k];
-    if (!(s > 0)) return false;
-    const double d = sqrt(s);
-    L[j * 6 + j] = d;
+#pragma unroll
+    for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+    if (!(s > 0)) ok = false;
+    const double r = rsqrt(s);
+    id[j] = r;  // 1 / L_jj
+    L[j][j] = s * r;
+#pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double t = Hu[sym6(j, i)];
-      for (int k = 0; k < j; k++) t -= L[i * 6 + k] * L[j * 6 + k];
-      L[i * 6 + j] = t / d;
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+      L[i][j] = t * r;
     }
   }
+  if (!ok) return false;
+  // W = L^-1 (lower), then H^-1 = W^T W
+  double W[6][6];
+#pragma unroll
   for (int c = 0; c < 6; c++) {
-    double y[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = 0; k < i; k++) s -= L[i * 6 + k] * y[k];
-      y[i] = s / L[i * 6 + i];
+      if (i < c) {
+        W[i][c] = 0;
+      } else {
+        double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = c; k < i; k++) s -= L[i][k] * W[k][c];
+        W[i][c] = s * id[i];
+      }
     }
-    for (int i = 5; i >= 0; i--) {
-      double s = y[i];
-      for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * y[k];
-      y[i] = s / L[i * 6 + i];
-    }
-    for (int i = 0; i < 6; i++) out[i * 6 + c] = y[i];
   }
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int c = a; c < 6; c++) {
+      double s = 0;
+#pragma unroll
+      for (int k = c; k < 6; k++) s += W[k][a] * W[k][c];
+      out[a * 6 + c] = s;
+      out[c * 6 + a] = s;
+    }
   return true;
 }
+
+
+#define NRS_SHARED(p) __builtin_assume(__isShared(p))
+constexpr int kPB = kPrecBlock;      // rows per dense preconditioner block
+constexpr int kPN = 3 * kPrecBlock;  // its dimension
+constexpr int kPS = kPN + 4;         // padded row stride (floats): 16-byte aligned rows, conflict-free float4 row reads
 
 struct Engine {
   const Params& P;
   // shared memory
   double *s_pose, *s_pose_bak, *s_H, *s_M, *s_bp, *s_xp, *s_rp, *s_zp, *s_pp, *s_qp, *s_red, *s_scal;
+  double *s_jac, *s_x, *s_r, *s_p, *s_q, *s_z, *s_minv, *s_coef;  // resident chunk state
+  double* s_pr;             // per-row pose partials of the CG matvec (6 per row)
+  double* s_rowA;           // per-row pose-block records of the linearisation (16 per row)
+  const double** s_zptr;    // per incidence: where the neighbour's z lives (shared memory or L2)
+  float* s_rf;              // residual as fp32 for the block preconditioner
+  float* s_binv;  // dense block inverses (fp32, symmetric): a preconditioner need not be exact
+  int* s_oth;
   int* s_flag;
   unsigned gen;
   int tid, nthr;
@@ -115,7 +163,35 @@ struct Engine {
     s_qp = sm;              sm += 6 * F;
     s_red = sm;             sm += 32 * kChunkVals;
     s_scal = sm;            sm += 32;
-    s_flag = reinterpret_cast<int*>(sm);
+    s_pr = sm;              sm += 6 * kMaxRows;
+    s_flag = reinterpret_cast<int*>(sm);  sm += 2;
+    sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));  // double2 accesses below
+    // the pose-block records of the linearisation and the Jacobian cache of the CG loop are never live together
+    s_rowA = sm;
+    if (!p.resident) sm += 16 * kMaxRows;
+    if (p.resident) {
+      const int R = p.res_rows, CI = p.res_inc;
+      s_jac = sm;           sm += (20 * (size_t)R > 16 * (size_t)kMaxRows) ? 20 * (size_t)R : 16 * (size_t)kMaxRows;
+      s_x = sm;             sm += 4 * (size_t)R;
+      s_r = sm;             sm += 4 * (size_t)R;
+      s_p = sm;             sm += 4 * (size_t)R;
+      s_q = sm;             sm += 4 * (size_t)R;
+      s_z = sm;             sm += 4 * (size_t)R;
+      s_minv = sm;          if (!p.block_prec) sm += 8 * (size_t)R;
+      s_coef = sm;          sm += 4 * (size_t)CI;
+      s_zptr = reinterpret_cast<const double**>(sm);  sm += CI;
+      s_oth = nullptr;
+      sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));
+      s_rf = reinterpret_cast<float*>(sm);  sm += (3 * (size_t)R + 1) / 2;
+      sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));
+      s_binv = reinterpret_cast<float*>(sm);
+    } else {
+      s_jac = s_x = s_r = s_p = s_q = s_z = s_minv = s_coef = nullptr;
+      s_zptr = nullptr;
+      s_oth = nullptr;
+      s_rf = nullptr;
+      s_binv = nullptr;
+    }
     gen = 0;
     lambda = -1;
     ni = 2;
@@ -123,21 +199,24 @@ struct Engine {
     for (int i = 0; i < 16; i++) prof[i] = 0;
   }
 
-  // ---- grid-wide barrier: release-add on one counter, acquire-poll until every CTA of this generation arrived
+  // ---- grid-wide barrier. Cluster mode: hardware barrier with release/acquire semantics at cluster scope.
+  // Grid mode: release-add on one counter, acquire-poll until every CTA of this generation arrived; bar.sync on both
+  // sides extends the ordering to every thread of the CTA (no separate fences: profiles/r01_barrier_latency.txt).
   __device__ __forceinline__ void barrier() {
-    __syncthreads();
     gen++;
-    if (tid == 0) {
-      const long long t0 = clock64();
-      __threadfence();
-      red_release_add_u64(P.bar, 1ULL);
-      const unsigned long long target = (unsigned long long)gen * gridDim.x;
-      while (ld_acquire_u64(P.bar) < target) {
+    if (P.cluster_mode) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+      __syncthreads();
+      if (tid == 0) {
+        red_release_add_u64(P.bar, 1ULL);
+        const unsigned long long target = (unsigned long long)gen * gridDim.x;
+        while (ld_acquire_u64(P.bar) < target) {
+        }
       }
-      __threadfence();
-      prof[0] += clock64() - t0;
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   // ---- block reduction of NV per-thread values (fixed order); result in dst[0..NV)
@@ -167,7 +246,6 @@ struct Engine {
   template <int N>
   __device__ __forceinline__ void grid_reduce(double (&v)[N], unsigned maxmask) {
     const int par = gen & 1;
-    // block level
 #pragma unroll
     for (int k = 0; k < N; k++) {
 #pragma unroll
@@ -264,10 +342,10 @@ struct Engine {
         }
       }
       if (LIN) {
-        double2* o = reinterpret_cast<double2*>(P.pc + 8 * (size_t)e);
+        double2* o = reinterpret_cast<double2*>(P.pc + 4 * (size_t)e);
         o[0] = make_double2(s, u0);
         o[1] = make_double2(u1, u2);
-        o[2] = make_double2(c, 0.0);
+        P.pcc[e] = c;
       }
     }
     for (int e = blockIdx.x * nthr + tid; e < P.D; e += gsz) {
@@ -288,6 +366,43 @@ struct Engine {
         o[1] = make_double2(g * e1, g * e2);
       }
     }
+  }
+
+  // Fixed-order reduction of the chunk's pose-block records (s_rowA: A 2x6, omega, weighted error) into the 21
+  // upper-triangular entries of H_pp and the 6 of b_p: 27 x 8 threads sum strided row groups, 27 threads finish.
+  __device__ __forceinline__ void reduce_pose_block(int nrows, double* dst) {
+    __syncthreads();
+    for (int tt = tid; tt < 27 * 8; tt += nthr) {
+      const int v = tt % 27, g = tt / 27;
+      int a = 0, c = 0;
+      if (v < 21) {
+        int t = v;
+        while (t >= 6 - a) {
+          t -= 6 - a;
+          a++;
+        }
+        c = a + t;
+      } else {
+        a = v - 21;
+      }
+      double s = 0;
+      for (int r = g; r < nrows; r += 8) {
+        const double* rec = s_rowA + 16 * (size_t)r;
+        if (v < 21)
+          s += rec[12] * (rec[a] * rec[c] + rec[6 + a] * rec[6 + c]);
+        else
+          s += rec[a] * rec[14] + rec[6 + a] * rec[15];
+      }
+      s_red[tt] = s;
+    }
+    __syncthreads();
+    if (tid < 27) {
+      double s = 0;
+#pragma unroll
+      for (int g = 0; g < 8; g++) s += s_red[27 * g + tid];
+      dst[tid] = s;
+    }
+    __syncthreads();
   }
 
   // Reprojection error of point row i at the current estimate; returns chi2 (info * |e|^2).
@@ -315,11 +430,7 @@ struct Engine {
     for (int c = blockIdx.x; c < P.n_chunks; c += gridDim.x) {
       const int i = P.chunk_begin[c] + tid;
       const bool valid = i < P.chunk_end[c];
-      double red[27];
-      if (LIN) {
-#pragma unroll
-        for (int k = 0; k < 27; k++) red[k] = 0;
-      }
+      bool pose_rec = false;  // this row stored a pose-block record (A, omega, weighted error)
       if (valid) {
         const V3 xi = ld3(P.x, i);
         const int kf = P.pt_kf[i];
@@ -356,13 +467,14 @@ struct Engine {
             omega = drho * P.info_reproj;
             const double we0 = -omega * err[0], we1 = -omega * err[1];
             if (!P.poses_fixed) {
-              int t = 0;
+              // pose block H_pp += omega A^T A, b_p += A^T we: the row record goes to shared memory and is reduced
+              // over the chunk in a fixed order below (keeps 27 accumulators out of the registers)
+              double2* rec = reinterpret_cast<double2*>(s_rowA + 16 * (size_t)tid);
 #pragma unroll
-              for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int cc = a; cc < 6; cc++) red[t++] = omega * (A[a] * A[cc] + A[6 + a] * A[6 + cc]);
-#pragma unroll
-              for (int a = 0; a < 6; a++) red[21 + a] = A[a] * we0 + A[6 + a] * we1;
+              for (int k = 0; k < 6; k++) rec[k] = make_double2(A[2 * k], A[2 * k + 1]);
+              rec[6] = make_double2(omega, 0.0);
+              rec[7] = make_double2(we0, we1);
+              pose_rec = true;
             }
             if (var) {
               double R[9];
@@ -429,23 +541,43 @@ struct Engine {
             }
           }
           if (LIN) {
-            for (int a = P.inc_ptr[i]; a < P.inc_ptr[i + 1]; a++) {
-              const int other = P.inc_other[a], ent = P.inc_ent[a];
-              const double2* cf = reinterpret_cast<const double2*>(P.pc + 8 * (size_t)(ent >> 1));
-              const double2 c0 = __ldcg(cf), c1 = __ldcg(cf + 1);
-              const double cc = __ldcg(P.pc + 8 * (size_t)(ent >> 1) + 4);
-              const double s = c0.x, u0 = c0.y, u1 = c1.x, u2 = c1.y;
-              const V3 xo = ld3(P.x, other);
-              D[0] += s + u0 * u0;
-              D[1] += u0 * u1;
-              D[2] += u0 * u2;
-              D[3] += s + u1 * u1;
-              D[4] += u1 * u2;
-              D[5] += s + u2 * u2;
-              const double sg = (ent & 1) ? -cc : cc;
-              b[0] -= s * (xi.x - xo.x) + sg * u0;
-              b[1] -= s * (xi.y - xo.y) + sg * u1;
-              b[2] -= s * (xi.z - xo.z) + sg * u2;
+            const int a1 = P.inc_ptr[i + 1];
+            for (int a0 = P.inc_ptr[i]; a0 < a1; a0 += 4) {
+              // batch of up to 4 incidences: issue every load before the first use
+              int other[4], ent[4];
+              double2 c0[4], c1[4];
+              double cc[4];
+              V3 xo[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int a = min(a0 + k, a1 - 1);
+                other[k] = P.inc_other[a];
+                ent[k] = P.inc_ent[a];
+              }
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const double2* cf = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(ent[k] >> 1));
+                c0[k] = __ldcg(cf);
+                c1[k] = __ldcg(cf + 1);
+                cc[k] = __ldcg(P.pcc + (ent[k] >> 1));
+                xo[k] = ld3(P.x, other[k]);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if (a0 + k < a1) {
+                  const double s = c0[k].x, u0 = c0[k].y, u1 = c1[k].x, u2 = c1[k].y;
+                  D[0] += s + u0 * u0;
+                  D[1] += u0 * u1;
+                  D[2] += u0 * u2;
+                  D[3] += s + u1 * u1;
+                  D[4] += u1 * u2;
+                  D[5] += s + u2 * u2;
+                  const double sg = (ent[k] & 1) ? -cc[k] : cc[k];
+                  b[0] -= s * (xi.x - xo[k].x) + sg * u0;
+                  b[1] -= s * (xi.y - xo[k].y) + sg * u1;
+                  b[2] -= s * (xi.z - xo[k].z) + sg * u2;
+                }
+              }
             }
             if (P.D > 0) {
               for (int a = P.dinc_ptr[i]; a < P.dinc_ptr[i + 1]; a++) {
@@ -476,9 +608,34 @@ struct Engine {
         }
       }
       if (LIN && !P.poses_fixed) {
-        block_reduce<27>(red, P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals);
+        if (tid < kMaxRows && !pose_rec) {
+          double2* rec = reinterpret_cast<double2*>(s_rowA + 16 * (size_t)tid);
+#pragma unroll
+          for (int k = 0; k < 8; k++) rec[k] = make_double2(0.0, 0.0);
+        }
+        reduce_pose_block(P.chunk_end[c] - P.chunk_begin[c],
+                          P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals);
       }
     }
+  }
+
+  // Sum of value v over the chunk partials of pose slot k in chunk order; the loads of a batch are issued together
+  // (a plain `s += load` loop serialises one L2 round trip per chunk).
+  __device__ __forceinline__ double sum_chunk_partials(int k, int v, int par) {
+    const int c1 = P.kf_chunk_ptr[k + 1];
+    double s = 0;
+    for (int c0 = P.kf_chunk_ptr[k]; c0 < c1; c0 += 8) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int c = min(c0 + u, c1 - 1);
+        t[u] = __ldcg(P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals + v);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (c0 + u < c1) s += t[u];
+    }
+    return s;
   }
 
   // own-row iteration helper
@@ -491,61 +648,282 @@ struct Engine {
   }
 
   // ================================================================================================
-  // Block-Jacobi preconditioned CG on (H + lambda I) delta = b.  Result: xcg rows, s_xp poses.
+  // Dense block-Jacobi preconditioner (resident mode): blocks of kPB consecutive rows of the chunk. The block of
+  // H + lambda I (3x3 diagonal blocks + the pair couplings inside the block) is assembled in fp32 and inverted in
+  // place with the symmetric sweep operator; it is applied as a dense 48x48 product in the CG loop.
+  // ================================================================================================
+  __device__ void build_block_prec(int rb, int re, int ab) {
+    NRS_SHARED(s_binv);
+    NRS_SHARED(s_coef);
+    const int nrows = re - rb;
+    const int nblk = (nrows + kPB - 1) / kPB;
+    const int total = nblk * kPN * kPS;
+    for (int t = tid; t < total; t += nthr) s_binv[t] = 0.f;
+    __syncthreads();
+    // diagonal 3x3 blocks (+ lambda); rows without unknowns and the padding of the last block get the identity
+    for (int lr = tid; lr < nblk * kPB; lr += nthr) {
+      const int i = rb + lr;
+      float* M = s_binv + (size_t)(lr / kPB) * kPN * kPS;
+      const int o = 3 * (lr % kPB);
+      const bool live = lr < nrows && !(P.pt_fixed && P.pt_fixed[i]);
+      if (live) {
+        const double2* d = reinterpret_cast<const double2*>(P.dg + 8 * (size_t)i);
+        const double2 d0 = d[0], d1 = d[1], d2 = d[2];
+        M[(o + 0) * kPS + o + 0] = (float)(d0.x + lambda);
+        M[(o + 0) * kPS + o + 1] = M[(o + 1) * kPS + o + 0] = (float)d0.y;
+        M[(o + 0) * kPS + o + 2] = M[(o + 2) * kPS + o + 0] = (float)d1.x;
+        M[(o + 1) * kPS + o + 1] = (float)(d1.y + lambda);
+        M[(o + 1) * kPS + o + 2] = M[(o + 2) * kPS + o + 1] = (float)d2.x;
+        M[(o + 2) * kPS + o + 2] = (float)(d2.y + lambda);
+      } else {
+        M[(o + 0) * kPS + o + 0] = M[(o + 1) * kPS + o + 1] = M[(o + 2) * kPS + o + 2] = 1.f;
+      }
+    }
+    __syncthreads();
+    // pair couplings inside a block: -(s I + u u^T), written once per incidence (both incidences of a pair write
+    // the two mirrored 3x3 blocks, each from its own side)
+    for (int lr = tid; lr < nrows; lr += nthr) {
+      const int i = rb + lr;
+      if (P.pt_fixed && P.pt_fixed[i]) continue;
+      float* M = s_binv + (size_t)(lr / kPB) * kPN * kPS;
+      const int oi = 3 * (lr % kPB);
+      for (int a = P.inc_ptr[i]; a < P.inc_ptr[i + 1]; a++) {
+        const int other = P.inc_other[a];
+        const int lo = other - rb;
+        if (lo < 0 || lo >= nrows || lo / kPB != lr / kPB) continue;
+        if (P.pt_fixed && P.pt_fixed[other]) continue;
+        const double* cf = s_coef + 4 * (size_t)(a - ab);
+        const float s = (float)cf[0], u0 = (float)cf[1], u1 = (float)cf[2], u2 = (float)cf[3];
+        const int oj = 3 * (lo % kPB);
+        const float u[3] = {u0, u1, u2};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) M[(oi + r) * kPS + oj + c] = -((r == c ? s : 0.f) + u[r] * u[c]);
+      }
+    }
+    __syncthreads();
+    // symmetric sweep of every pivot: A -> -A^-1. One warp per block, lanes own columns.
+    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+    for (int bk = warp; bk < nblk; bk += nw) {
+      float* M = s_binv + (size_t)bk * kPN * kPS;
+      for (int j = 0; j < kPN; j++) {
+        const float d = M[j * kPS + j];
+        const float id = 1.f / d;
+        // row j (pivot row) values for the columns of this lane
+        const int k0 = lane, k1 = lane + 32;
+        const float pj0 = M[j * kPS + k0];
+        const float pj1 = (k1 < kPN) ? M[j * kPS + k1] : 0.f;
+        __syncwarp();
+        for (int i = 0; i < kPN; i++) {
+          if (i == j) continue;
+          const float f = M[i * kPS + j] * id;  // broadcast read
+          if (k0 != j) M[i * kPS + k0] -= f * pj0;
+          if (k1 < kPN && k1 != j) M[i * kPS + k1] -= f * pj1;
+        }
+        __syncwarp();
+        // pivot column and row: a_ij / d ; pivot: -1/d
+        for (int i = lane; i < kPN; i += 32) {
+          if (i != j) {
+            const float v = M[i * kPS + j] * id;
+            M[i * kPS + j] = v;
+            M[j * kPS + i] = v;
+          }
+        }
+        if (lane == 0) M[j * kPS + j] = -id;
+        __syncwarp();
+      }
+      // the two triangles differ by rounding ((a/d) b vs (b/d) a): mirror the lower one so M is exactly symmetric
+      for (int t = lane; t < kPN * kPN; t += 32) {
+        const int i = t / kPN, k = t % kPN;
+        if (k > i) M[i * kPS + k] = M[k * kPS + i];
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+
+  // Reduce the per-row pose partials (6 doubles per row, written to s_pr by lane 0 of every quad) of a chunk in a
+  // fixed order: 48 threads sum strided row groups, 6 threads finish. dst: chunk partial (global).
+  __device__ __forceinline__ void reduce_pose_partials(int nrows, double* dst) {
+    __syncthreads();
+    for (int tt = tid; tt < 48; tt += nthr) {
+      const int a = tt % 6, g = tt / 6;
+      double s = 0;
+      for (int r = g; r < nrows; r += 8) s += s_pr[6 * r + a];
+      s_red[tt] = s;
+    }
+    __syncthreads();
+    if (tid < 6) {
+      double s = 0;
+#pragma unroll
+      for (int g = 0; g < 8; g++) s += s_red[6 * g + tid];
+      dst[tid] = s;
+    }
+    __syncthreads();
+  }
+
+  // z = Minv_block r for the resident chunk: lane l < 3 of the row's quad produces component l as a 48-term fp32 dot
+  // product (r was stored as fp32 in s_rf by the caller, followed by __syncthreads). A preconditioner only has to be
+  // a fixed SPD operator, so fp32 is enough; everything that defines the solution (r, x, A) stays fp64.
+  // Publishes z to shared and global memory; returns this thread's r_l z_l.
+  __device__ __forceinline__ double prec_apply_quads(int rb, int re, bool publish = true) {
+    NRS_SHARED(s_binv);
+    NRS_SHARED(s_rf);
+    NRS_SHARED(s_z);
+    NRS_SHARED(s_r);
+    const int lr = tid / kTPR;
+    if (lr >= re - rb) return 0.0;
+    const int i = rb + lr;
+    if (P.pt_fixed && P.pt_fixed[i]) return 0.0;
+    const int bk = lr / kPB;
+    const float4* rf = reinterpret_cast<const float4*>(s_rf + (size_t)bk * kPN);
+    double part = 0;
+    for (int l = tid % kTPR; l < 3; l += kTPR) {
+      const float4* M =
+          reinterpret_cast<const float4*>(s_binv + (size_t)bk * kPN * kPS + (size_t)(3 * (lr % kPB) + l) * kPS);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < kPN / 4; j++) {
+        const float4 m = M[j], r = rf[j];
+        s0 = fmaf(m.x, r.x, s0);
+        s1 = fmaf(m.y, r.y, s1);
+        s2 = fmaf(m.z, r.z, s2);
+        s3 = fmaf(m.w, r.w, s3);
+      }
+      const double z = -(double)((s0 + s1) + (s2 + s3));  // the sweep leaves -A^-1
+      s_z[4 * (size_t)lr + l] = z;
+      if (publish) P.zvec[4 * (size_t)i + l] = z;
+      part += s_r[4 * (size_t)lr + l] * z;
+    }
+    return part;
+  }
+
+  // ================================================================================================
+  // Preconditioned CG on (H + lambda I) delta = b.  Result: xcg rows (global), s_xp poses.
+  // The matvec is applied to z = M^-1 r and p, q = A p follow by recurrence (q = A z + beta q), so one iteration is
+  //   [gather z of the neighbours, w = A z, p, q, partial p.q] sync [alpha; x, r, z = M^-1 r, partial r.z] sync.
+  // Thread organisation inside the loop: a quad of kTPR = 4 consecutive lanes per point row. Phase 1: the quad
+  // splits the row's regulariser incidences, reduces the three sums with two shuffle steps, lane 0 adds the
+  // reprojection part and runs the recurrences. Phase 2: lanes 0..2 own one component each. The loop is bound by
+  // dependent-issue latency, not by bandwidth (profiles/r01_*), hence 4 threads per row.
   // Returns false on breakdown (treated like g2o's failed linear solve,
   // optimization_algorithm_levenberg.cpp:102-121).
   // ================================================================================================
   __device__ bool pcg() {
     const int F = P.F;
     const bool pts = !P.points_fixed, pos = !P.poses_fixed;
-    // ---- preconditioner
+    const bool res = P.resident != 0;
     if (tid == 0) *s_flag = 0;
     __syncthreads();
     if (pos) {
       for (int k = tid; k < F; k += nthr)
         if (!invert6(s_H + 21 * k, lambda, s_M + 36 * k)) *s_flag = 1;
     }
-    double rz_part[1] = {0};
-    if (pts) {
-      for_rows([&](int i) {
-        if (P.pt_fixed && P.pt_fixed[i]) {  // no unknowns: keep p = z = 0 for this row
-          double2* mo = reinterpret_cast<double2*>(P.minv + 8 * (size_t)i);
-          mo[0] = mo[1] = mo[2] = make_double2(0.0, 0.0);
-          st3(P.rvec, i, V3{0, 0, 0});
-          st3(P.xcg, i, V3{0, 0, 0});
-          st3(P.rec + 8 * (size_t)P.V, i * 2, V3{0, 0, 0});
-          return;
-        }
-        const double2* d = reinterpret_cast<const double2*>(P.dg + 8 * (size_t)i);
-        const double2 d0 = d[0], d1 = d[1], d2 = d[2];
-        const double a = d0.x + lambda, b = d0.y, c = d1.x, e = d1.y + lambda, f = d2.x, g = d2.y + lambda;
-        // symmetric 3x3 inverse by cofactors
-        const double C00 = e * g - f * f, C01 = c * f - b * g, C02 = b * f - c * e;
-        const double det = a * C00 + b * C01 + c * C02;
-        const double id = 1.0 / det;
-        const double m00 = C00 * id, m01 = C01 * id, m02 = C02 * id;
-        const double m11 = (a * g - c * c) * id, m12 = (b * c - a * f) * id, m22 = (a * e - b * b) * id;
-        double2* mo = reinterpret_cast<double2*>(P.minv + 8 * (size_t)i);
-        mo[0] = make_double2(m00, m01);
-        mo[1] = make_double2(m02, m11);
-        mo[2] = make_double2(m12, m22);
-        const V3 r = ld3(P.bvec, i);
-        const V3 z{m00 * r.x + m01 * r.y + m02 * r.z, m01 * r.x + m11 * r.y + m12 * r.z,
-                   m02 * r.x + m12 * r.y + m22 * r.z};
-        st3(P.rvec, i, r);
-        st3(P.xcg, i, V3{0, 0, 0});
-        st3(P.rec + 8 * (size_t)P.V, i * 2, z);  // rec[1][i].z  (record stride 8 = 2 x 4)
-        rz_part[0] += r.x * z.x + r.y * z.y + r.z * z.z;
-      });
-    }
     __syncthreads();
     if (*s_flag) return false;  // uniform: every CTA inverts the same blocks
+    if (!pts) {
+      // pose-only system: F independent 6x6 solves (LinearSolverDense, solvers/dense/linear_solver_dense.h:56-104)
+      for (int t = tid; t < 6 * F; t += nthr) {
+        const int k = t / 6, a = t % 6;
+        double s = 0;
+        for (int c = 0; c < 6; c++) s += s_M[36 * k + a * 6 + c] * s_bp[6 * k + c];
+        s_xp[t] = s;
+      }
+      __syncthreads();
+      return true;
+    }
+    // ---- chunk-resident state
+    const int c0 = blockIdx.x;  // resident: exactly one chunk per CTA (or none)
+    const bool has = res && c0 < P.n_chunks;
+    const int rb = has ? P.chunk_begin[c0] : 0, re = has ? P.chunk_end[c0] : 0;
+    const int ab = has ? P.inc_ptr[rb] : 0, ae = has ? P.inc_ptr[re] : 0;
+    const bool bprec = res && P.block_prec;
+    if (has) {
+      for (int t = tid; t < 10 * (re - rb); t += nthr)
+        reinterpret_cast<double2*>(s_jac)[t] = reinterpret_cast<const double2*>(P.jac + 20 * (size_t)rb)[t];
+      for (int a = ab + tid; a < ae; a += nthr) {
+        const int ent = P.inc_ent[a];
+        const double2* cf = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(ent >> 1));
+        reinterpret_cast<double2*>(s_coef)[2 * (a - ab)] = cf[0];
+        reinterpret_cast<double2*>(s_coef)[2 * (a - ab) + 1] = cf[1];
+        const int other = P.inc_other[a];
+        // where the neighbour's z lives: this chunk's shared memory, or L2
+        s_zptr[a - ab] = (other >= rb && other < re) ? s_z + 4 * (size_t)(other - rb) : P.zvec + 4 * (size_t)other;
+      }
+      __syncthreads();
+      if (bprec) build_block_prec(rb, re, ab);
+    }
+    // vectors: shared memory (indexed from the chunk's first row) or global
+    double* X = res ? s_x : P.xcg;
+    double* R = res ? s_r : P.rvec;
+    double* Pv = res ? s_p : P.pvec;
+    double* Q = res ? s_q : P.qvec;
+    double* MI = res ? s_minv : P.minv;
+    const int vb = res ? rb : 0;
+
+    if (bprec && has) {  // rows of the last block past the chunk end: zero residual
+      const int padded = ((re - rb + kPB - 1) / kPB) * kPB;
+      for (int lr = re - rb + tid; lr < padded; lr += nthr) {
+        st3(s_r, lr, V3{0, 0, 0});
+        s_rf[3 * lr] = s_rf[3 * lr + 1] = s_rf[3 * lr + 2] = 0.f;
+      }
+    }
+    // ---- initial residual, z = M^-1 r (one thread per row)
+    double rz_part[1] = {0};
+    for_rows([&](int i) {
+      const int li = i - vb;
+      if (P.pt_fixed && P.pt_fixed[i]) {  // no unknowns: keep z = 0 for this row
+        if (!bprec) {
+          double2* mo = reinterpret_cast<double2*>(MI + 8 * (size_t)li);
+          mo[0] = mo[1] = mo[2] = make_double2(0.0, 0.0);
+        }
+        st3(R, li, V3{0, 0, 0});
+        st3(X, li, V3{0, 0, 0});
+        st3(P.zvec, i, V3{0, 0, 0});
+        if (res) st3(s_z, li, V3{0, 0, 0});
+        if (bprec) s_rf[3 * li] = s_rf[3 * li + 1] = s_rf[3 * li + 2] = 0.f;
+        return;
+      }
+      const V3 r = ld3p(P.bvec, i);
+      st3(R, li, r);
+      st3(X, li, V3{0, 0, 0});
+      if (bprec) {
+        s_rf[3 * li] = (float)r.x;
+        s_rf[3 * li + 1] = (float)r.y;
+        s_rf[3 * li + 2] = (float)r.z;
+        return;
+      }
+      const double2* d = reinterpret_cast<const double2*>(P.dg + 8 * (size_t)i);
+      const double2 d0 = d[0], d1 = d[1], d2 = d[2];
+      const double a = d0.x + lambda, b = d0.y, c = d1.x, e = d1.y + lambda, f = d2.x, g = d2.y + lambda;
+      // symmetric 3x3 inverse by cofactors
+      const double C00 = e * g - f * f, C01 = c * f - b * g, C02 = b * f - c * e;
+      const double det = a * C00 + b * C01 + c * C02;
+      const double id = 1.0 / det;
+      const double m00 = C00 * id, m01 = C01 * id, m02 = C02 * id;
+      const double m11 = (a * g - c * c) * id, m12 = (b * c - a * f) * id, m22 = (a * e - b * b) * id;
+      double2* mo = reinterpret_cast<double2*>(MI + 8 * (size_t)li);
+      mo[0] = make_double2(m00, m01);
+      mo[1] = make_double2(m02, m11);
+      mo[2] = make_double2(m12, m22);
+      const V3 z{m00 * r.x + m01 * r.y + m02 * r.z, m01 * r.x + m11 * r.y + m12 * r.z,
+                 m02 * r.x + m12 * r.y + m22 * r.z};
+      st3(P.zvec, i, z);
+      if (res) st3(s_z, li, z);
+      rz_part[0] += r.x * z.x + r.y * z.y + r.z * z.z;
+    });
+    if (bprec) {
+      __syncthreads();
+      if (has) rz_part[0] += prec_apply_quads(rb, re);
+    }
     double rz_pose = 0;
     if (pos) {
       for (int t = tid; t < 6 * F; t += nthr) {
         s_rp[t] = s_bp[t];
         s_xp[t] = 0;
         s_pp[t] = 0;
+        s_qp[t] = 0;
       }
       __syncthreads();
       for (int t = tid; t < 6 * F; t += nthr) {
@@ -560,44 +938,125 @@ struct Engine {
     grid_reduce<1>(rz_part, 0);
     double rz = s_scal[0] + rz_pose;
     const double rz0 = rz;
-    if (!(rz0 > 0)) return isfinite(rz0);  // b == 0: delta = 0
+    if (!(rz0 > 0)) {  // b == 0: delta = 0
+      if (res) for_rows([&](int i) { st3(P.xcg, i, V3{0, 0, 0}); });
+      return isfinite(rz0);
+    }
     const double stop = P.pcg_tol * P.pcg_tol * rz0;
     double beta = 0;
     bool ok = true;
     int it = 0;
+    // quad mapping of the loop and the per-row constants, kept in registers when this CTA owns at most one chunk
+    const int qr = tid / kTPR, ql = tid % kTPR;
+    const bool single = P.n_chunks <= (int)gridDim.x;
+    bool my_fixed = false;
+    int my_kf = -1, my_a0 = 0, my_a1 = 0, my_cb = 0, my_ce = 0, my_kc0 = 0, my_kc1 = 0;
+    double my_su = 0;
+    if (single && tid >= 32 && tid - 32 < 6 * F) {
+      my_kc0 = P.kf_chunk_ptr[(tid - 32) / 6];
+      my_kc1 = P.kf_chunk_ptr[(tid - 32) / 6 + 1];
+    }
+    if (single && (int)blockIdx.x < P.n_chunks) {
+      my_cb = P.chunk_begin[blockIdx.x];
+      my_ce = P.chunk_end[blockIdx.x];
+      const int i = my_cb + qr;
+      if (i < my_ce) {
+        my_fixed = P.pt_fixed && P.pt_fixed[i];
+        my_kf = P.pt_kf[i];
+        my_a0 = P.inc_ptr[i];
+        my_a1 = P.inc_ptr[i + 1];
+        my_su = P.dg[8 * (size_t)i + 6];
+      }
+    }
     for (; it < P.pcg_max_iter; it++) {
-      const int bufR = (it & 1) ^ 1, bufW = it & 1;
-      const double* recR = P.rec + (size_t)bufR * 8 * P.V;
-      double* recW = P.rec + (size_t)bufW * 8 * P.V;
       const bool first = (it == 0);
       const int par = gen & 1;
-      if (pos) {
-        for (int t = tid; t < 6 * F; t += nthr) s_pp[t] = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
-        __syncthreads();
-      }
-      // ---- q = (H + lambda I) p, row by row
+      // ---- phase 1: w = (H + lambda I) z ; p = z + beta p ; q = w + beta q ; partial p.q
       const long long tm0 = clock64();
       double pq_part[1] = {0};
       for (int c = blockIdx.x; c < P.n_chunks; c += gridDim.x) {
-        const int i = P.chunk_begin[c] + tid;
-        const bool valid = i < P.chunk_end[c];
-        double red[6] = {0, 0, 0, 0, 0, 0};
+        const int cb = single ? my_cb : P.chunk_begin[c], ce = single ? my_ce : P.chunk_end[c];
+        const int i = cb + qr;
+        const bool valid = i < ce;
+        const int li = i - vb;
+        double w0 = 0, w1 = 0, w2 = 0;
+        V3 zi{0, 0, 0};
+        bool fixed = true;
+        int kf = -1;
+        double su = 0;
         if (valid) {
-          V3 pi{0, 0, 0};
-          if (pts) {
-            const V3 zi = ld3(recR, 2 * i);
-            if (first) {
-              pi = zi;
-            } else {
-              const V3 po = ld3(recR, 2 * i + 1);
-              pi = V3{zi.x + beta * po.x, zi.y + beta * po.y, zi.z + beta * po.z};
+          fixed = single ? my_fixed : (P.pt_fixed && P.pt_fixed[i]);
+          kf = single ? my_kf : P.pt_kf[i];
+          su = single ? my_su : P.dg[8 * (size_t)i + 6];
+          zi = res ? ld3p(s_z, li) : ld3p(P.zvec, i);
+          if (!fixed) {
+            const int a_beg = single ? my_a0 : P.inc_ptr[i];
+            const int a1 = single ? my_a1 : P.inc_ptr[i + 1];
+            // lane l takes incidences a_beg + l, + 4, + 8 (one batch covers 12 incidences of the row): addresses
+            // first, then every load, then the arithmetic
+            for (int a0 = a_beg + ql; a0 < a1; a0 += 3 * kTPR) {
+              const double* zp[3];
+              const double2* cp[3];
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                const int a = min(a0 + kTPR * k, a1 - 1);
+                if (res) {
+                  cp[k] = reinterpret_cast<const double2*>(s_coef) + 2 * (a - ab);
+                  zp[k] = s_zptr[a - ab];
+                } else {
+                  cp[k] = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(P.inc_ent[a] >> 1));
+                  zp[k] = P.zvec + 4 * (size_t)P.inc_other[a];
+                }
+              }
+              double2 c0v[3], c1v[3], za[3];
+              double zb[3];
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                c0v[k] = cp[k][0];
+                c1v[k] = cp[k][1];
+                za[k] = *reinterpret_cast<const double2*>(zp[k]);
+                zb[k] = zp[k][2];
+              }
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                if (a0 + kTPR * k < a1) {
+                  const double dx = zi.x - za[k].x, dy = zi.y - za[k].y, dz = zi.z - zb[k];
+                  const double ud = c0v[k].y * dx + c1v[k].x * dy + c1v[k].y * dz;
+                  w0 += c0v[k].x * dx + c0v[k].y * ud;
+                  w1 += c0v[k].x * dy + c1v[k].x * ud;
+                  w2 += c0v[k].x * dz + c1v[k].y * ud;
+                }
+              }
             }
-            st3(recW, 2 * i + 1, pi);
+            if (P.D > 0) {
+              for (int a = P.dinc_ptr[i] + ql; a < P.dinc_ptr[i + 1]; a += kTPR) {
+                const int ent = P.dinc_ent[a];
+                const int4 v = *reinterpret_cast<const int4*>(P.dmp_v + 4 * (size_t)(ent >> 2));
+                const double s = P.dc[4 * (size_t)(ent >> 2)];
+                const V3 z0 = ld3p(P.zvec, v.x), z1 = ld3p(P.zvec, v.y), z2 = ld3p(P.zvec, v.z),
+                         z3 = ld3p(P.zvec, v.w);
+                const int role = ent & 3;
+                const double sg = ((role == 1 || role == 2) ? 1.0 : -1.0) * s;
+                w0 += sg * (-z0.x + z1.x + z2.x - z3.x);
+                w1 += sg * (-z0.y + z1.y + z2.y - z3.y);
+                w2 += sg * (-z0.z + z1.z + z2.z - z3.z);
+              }
+            }
           }
-          double q0 = lambda * pi.x, q1 = lambda * pi.y, q2 = lambda * pi.z;
-          const int kf = P.pt_kf[i];
+        }
+        // quad reduction (whole warp participates; lanes of invalid rows carry zeros)
+        #pragma unroll
+        for (int o = 1; o < kTPR; o <<= 1) {
+          w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+          w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+          w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+        }
+        if (valid && ql == 0) {
+          double red[6] = {0, 0, 0, 0, 0, 0};
+          double q0 = w0 + (lambda + su) * zi.x, q1 = w1 + (lambda + su) * zi.y, q2 = w2 + (lambda + su) * zi.z;
           if (kf >= 0) {
-            const double2* jo = reinterpret_cast<const double2*>(P.jac + 20 * (size_t)i);
+            const double2* jo =
+                reinterpret_cast<const double2*>(res ? s_jac + 20 * (size_t)li : P.jac + 20 * (size_t)i);
             const double omega = jo[9].x;
             if (omega != 0) {
               double A[12], B[6];
@@ -615,116 +1074,152 @@ struct Engine {
               }
               double jp0 = 0, jp1 = 0;
               if (pos) {
-                const double* pk = s_pp + 6 * kf;
+                const double* pk = s_zp + 6 * kf;
 #pragma unroll
                 for (int a = 0; a < 6; a++) {
                   jp0 += A[a] * pk[a];
                   jp1 += A[6 + a] * pk[a];
                 }
               }
-              const double t0 = omega * (jp0 + B[0] * pi.x + B[1] * pi.y + B[2] * pi.z);
-              const double t1 = omega * (jp1 + B[3] * pi.x + B[4] * pi.y + B[5] * pi.z);
-              q0 += B[0] * t0 + B[3] * t1;
-              q1 += B[1] * t0 + B[4] * t1;
-              q2 += B[2] * t0 + B[5] * t1;
+              const double t0 = omega * (jp0 + B[0] * zi.x + B[1] * zi.y + B[2] * zi.z);
+              const double t1 = omega * (jp1 + B[3] * zi.x + B[4] * zi.y + B[5] * zi.z);
+              if (!fixed) {
+                q0 += B[0] * t0 + B[3] * t1;
+                q1 += B[1] * t0 + B[4] * t1;
+                q2 += B[2] * t0 + B[5] * t1;
+              }
               if (pos) {
 #pragma unroll
                 for (int a = 0; a < 6; a++) red[a] = A[a] * t0 + A[6 + a] * t1;
-                pq_part[0] += jp0 * t0 + jp1 * t1;
               }
             }
           }
-          if (pts) {
-            for (int a = P.inc_ptr[i]; a < P.inc_ptr[i + 1]; a++) {
-              const int other = P.inc_other[a], ent = P.inc_ent[a];
-              const double2* cf = reinterpret_cast<const double2*>(P.pc + 8 * (size_t)(ent >> 1));
-              const double2 c0 = cf[0], c1 = cf[1];
-              const V3 zo = ld3(recR, 2 * other);
-              V3 po = zo;
-              if (!first) {
-                const V3 pp = ld3(recR, 2 * other + 1);
-                po = V3{zo.x + beta * pp.x, zo.y + beta * pp.y, zo.z + beta * pp.z};
-              }
-              const double dx = pi.x - po.x, dy = pi.y - po.y, dz = pi.z - po.z;
-              const double ud = c0.y * dx + c1.x * dy + c1.y * dz;
-              q0 += c0.x * dx + c0.y * ud;
-              q1 += c0.x * dy + c1.x * ud;
-              q2 += c0.x * dz + c1.y * ud;
+          if (!fixed) {
+            V3 pn = zi, qn{q0, q1, q2};
+            if (!first) {
+              const V3 po = ld3p(Pv, li), qo = ld3p(Q, li);
+              pn = V3{zi.x + beta * po.x, zi.y + beta * po.y, zi.z + beta * po.z};
+              qn = V3{q0 + beta * qo.x, q1 + beta * qo.y, q2 + beta * qo.z};
             }
-            if (P.D > 0) {
-              for (int a = P.dinc_ptr[i]; a < P.dinc_ptr[i + 1]; a++) {
-                const int ent = P.dinc_ent[a];
-                const int4 v = *reinterpret_cast<const int4*>(P.dmp_v + 4 * (size_t)(ent >> 2));
-                const double s = P.dc[4 * (size_t)(ent >> 2)];
-                const int vv[4] = {v.x, v.y, v.z, v.w};
-                double r0 = 0, r1 = 0, r2 = 0;
+            st3(Pv, li, pn);
+            st3(Q, li, qn);
+            pq_part[0] += pn.x * qn.x + pn.y * qn.y + pn.z * qn.z;
+          } else {
+            st3(Pv, li, V3{0, 0, 0});
+            st3(Q, li, V3{0, 0, 0});
+          }
+          if (pos) {
 #pragma unroll
-                for (int m = 0; m < 4; m++) {
-                  const V3 zo = ld3(recR, 2 * vv[m]);
-                  V3 po = zo;
-                  if (!first) {
-                    const V3 pp = ld3(recR, 2 * vv[m] + 1);
-                    po = V3{zo.x + beta * pp.x, zo.y + beta * pp.y, zo.z + beta * pp.z};
-                  }
-                  const double sg = (m == 1 || m == 2) ? 1.0 : -1.0;
-                  r0 += sg * po.x;
-                  r1 += sg * po.y;
-                  r2 += sg * po.z;
-                }
-                const int role = ent & 3;
-                const double sg = ((role == 1 || role == 2) ? 1.0 : -1.0) * s;
-                q0 += sg * r0;
-                q1 += sg * r1;
-                q2 += sg * r2;
-              }
-            }
-            const double su = P.dg[8 * (size_t)i + 6];
-            q0 += su * pi.x;
-            q1 += su * pi.y;
-            q2 += su * pi.z;
-            st3(P.qvec, i, V3{q0, q1, q2});
-            pq_part[0] += pi.x * q0 + pi.y * q1 + pi.z * q2;
+            for (int a = 0; a < 6; a++) s_pr[6 * qr + a] = red[a];
           }
         }
-        if (pos) block_reduce<6>(red, P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals);
+        // single-chunk CTAs send the pose partials through their reduction slot (one exchange with p.q)
+        if (pos)
+          reduce_pose_partials(ce - cb, single ? s_scal + 8 : P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals);
       }
       const long long tm1 = clock64();
-      grid_reduce<1>(pq_part, 0);
-      const long long tm2 = clock64();
-      double pq = s_scal[0];
-      if (pos) {
-        for (int t = tid; t < 6 * F; t += nthr) {
-          const int k = t / 6, a = t % 6;
-          double s = lambda * s_pp[t];
-          for (int c = P.kf_chunk_ptr[k]; c < P.kf_chunk_ptr[k + 1]; c++)
-            s += __ldcg(P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals + a);
-          s_qp[t] = s;
+      double pq;
+      if (pos && single) {
+        // block-level p.q, then slot = [p.q, pose partials]; after the barrier warp 0 sums p.q over the CTAs while
+        // 6 F threads of the other warps sum the pose partials of their pose slot: one L2 round trip in total
+        double v = pq_part[0];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        double* slot = P.slots + ((size_t)par * gridDim.x + blockIdx.x) * kSlotVals;
+        if (tid == 0) {
+          double t = s_red[0];
+          for (int w = 1; w < nw; w++) t += s_red[w];
+          slot[0] = t;
+        } else if (tid >= 32 && tid < 38) {
+          slot[1 + tid - 32] = ((int)blockIdx.x < P.n_chunks) ? s_scal[8 + tid - 32] : 0.0;
+        }
+        barrier();
+        if (tid < 32) {
+          double t = 0;
+          for (int c = lane; c < (int)gridDim.x; c += 32) t += __ldcg(P.slots + ((size_t)par * gridDim.x + c) * kSlotVals);
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+          if (lane == 0) s_scal[0] = t;
+        } else {
+         for (int t = tid - 32; t < 6 * F; t += nthr - 32) {
+          const int a = t % 6;
+          const bool mine = t == tid - 32;
+          const int c1 = mine ? my_kc1 : P.kf_chunk_ptr[t / 6 + 1];
+          double sum = 0;
+          for (int cc = mine ? my_kc0 : P.kf_chunk_ptr[t / 6]; cc < c1; cc += 8) {
+            double tv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              tv[u] = __ldcg(P.slots + ((size_t)par * gridDim.x + min(cc + u, c1 - 1)) * kSlotVals + 1 + a);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              if (cc + u < c1) sum += tv[u];
+          }
+          const double w = lambda * s_zp[t] + sum;
+          s_pp[t] = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+          s_qp[t] = first ? w : w + beta * s_qp[t];
+         }
         }
         __syncthreads();
-        for (int t = 0; t < 6 * F; t++) pq += lambda * s_pp[t] * s_pp[t];
+        pq = s_scal[0];
+        for (int t = 0; t < 6 * F; t++) pq += s_pp[t] * s_qp[t];
+      } else {
+        grid_reduce<1>(pq_part, 0);
+        pq = s_scal[0];
+        if (pos) {
+          // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (replicated per CTA)
+          for (int t = tid; t < 6 * F; t += nthr) {
+            const int k = t / 6, a = t % 6;
+            const double w = lambda * s_zp[t] + sum_chunk_partials(k, a, par);
+            s_pp[t] = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+            s_qp[t] = first ? w : w + beta * s_qp[t];
+          }
+          __syncthreads();
+          for (int t = 0; t < 6 * F; t++) pq += s_pp[t] * s_qp[t];
+        }
       }
+      const long long tm2 = clock64();
       if (!(pq > 0) || !isfinite(pq)) {
         ok = false;
         break;
       }
       const double alpha = rz / pq;
+      // ---- phase 2: x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z   (lane l < 3 of a quad: component l)
       double rzn_part[1] = {0};
-      if (pts) {
-        for_rows([&](int i) {
-          const V3 pi = ld3(recW, 2 * i + 1);
-          const V3 qi = ld3(P.qvec, i);
-          V3 xi = ld3(P.xcg, i), ri = ld3(P.rvec, i);
-          xi.x += alpha * pi.x; xi.y += alpha * pi.y; xi.z += alpha * pi.z;
-          ri.x -= alpha * qi.x; ri.y -= alpha * qi.y; ri.z -= alpha * qi.z;
-          const double2* mo = reinterpret_cast<const double2*>(P.minv + 8 * (size_t)i);
-          const double2 m0 = mo[0], m1 = mo[1], m2 = mo[2];
-          const V3 z{m0.x * ri.x + m0.y * ri.y + m1.x * ri.z, m0.y * ri.x + m1.y * ri.y + m2.x * ri.z,
-                     m1.x * ri.x + m2.x * ri.y + m2.y * ri.z};
-          st3(P.xcg, i, xi);
-          st3(P.rvec, i, ri);
-          st3(recW, 2 * i, z);
-          rzn_part[0] += ri.x * z.x + ri.y * z.y + ri.z * z.z;
-        });
+      for (int c = blockIdx.x; c < P.n_chunks; c += gridDim.x) {
+        const int i = (single ? my_cb : P.chunk_begin[c]) + qr;
+        const bool valid = i < (single ? my_ce : P.chunk_end[c]);
+        const int li = i - vb;
+        const bool act = valid && !(single ? my_fixed : (P.pt_fixed && P.pt_fixed[i]));
+        if (act) {
+          for (int cmp = ql; cmp < 3; cmp += kTPR) {
+            const size_t o = 4 * (size_t)li + cmp;
+            X[o] += alpha * Pv[o];
+            const double rc = R[o] - alpha * Q[o];
+            R[o] = rc;
+            if (bprec) s_rf[3 * li + cmp] = (float)rc;
+          }
+        }
+        if (!bprec) {
+          __syncwarp();  // the lanes of the quad wrote one component each
+          if (act && ql == 0) {
+            const V3 ri = ld3p(R, li);
+            const double2* mo = reinterpret_cast<const double2*>(MI + 8 * (size_t)li);
+            const double2 m0 = mo[0], m1 = mo[1], m2 = mo[2];
+            const V3 z{m0.x * ri.x + m0.y * ri.y + m1.x * ri.z, m0.y * ri.x + m1.y * ri.y + m2.x * ri.z,
+                       m1.x * ri.x + m2.x * ri.y + m2.y * ri.z};
+            st3(P.zvec, i, z);
+            if (res) st3(s_z, li, z);
+            rzn_part[0] += ri.x * z.x + ri.y * z.y + ri.z * z.z;
+          }
+        }
+      }
+      if (bprec) {
+        __syncthreads();
+        if (has) rzn_part[0] += prec_apply_quads(rb, re);
       }
       double rzn_pose = 0;
       if (pos) {
@@ -763,6 +1258,429 @@ struct Engine {
       }
     }
     pcg_iters += it;
+    if (res) for_rows([&](int i) { st3(P.xcg, i, ld3p(s_x, i - vb)); });
+    return ok;
+  }
+
+  // ================================================================================================
+  // Cluster-native CG loop for a tracking frame (cluster mode, resident, one chunk per CTA, one pose, no dampers).
+  // Nothing in the loop touches global memory: the neighbours' z is read from the owning CTA's shared memory
+  // (distributed shared memory) and the reduction slots live in shared memory too, so the release fence of the
+  // cluster barrier has no global stores to drain (the L2 exchange cost 1.8 us per barrier, profiles/r01_*).
+  // Per iteration: 5 CTA barriers + 2 cluster barriers; warp 0 does the small serial parts while the rest wait.
+  // ================================================================================================
+  __device__ bool pcg_cluster() {
+    NRS_SHARED(s_jac); NRS_SHARED(s_x); NRS_SHARED(s_r); NRS_SHARED(s_p); NRS_SHARED(s_q); NRS_SHARED(s_z);
+    NRS_SHARED(s_minv); NRS_SHARED(s_coef); NRS_SHARED(s_zptr); NRS_SHARED(s_rf); NRS_SHARED(s_pr);
+    NRS_SHARED(s_red); NRS_SHARED(s_scal); NRS_SHARED(s_zp); NRS_SHARED(s_pp); NRS_SHARED(s_qp); NRS_SHARED(s_rp);
+    NRS_SHARED(s_xp); NRS_SHARED(s_M); NRS_SHARED(s_bp);
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const bool pos = !P.poses_fixed;
+    const int G = gridDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+    if (tid == 0) *s_flag = 0;
+    __syncthreads();
+    if (pos && tid == 0)
+      if (!invert6(s_H, lambda, s_M)) *s_flag = 1;
+    __syncthreads();
+    if (*s_flag) return false;  // uniform: every CTA inverts the same block
+    const int c0 = blockIdx.x;
+    const int rb = P.chunk_begin[c0], re = P.chunk_end[c0], nrows = re - rb;
+    const int ab = P.inc_ptr[rb], ae = P.inc_ptr[re];
+    const bool bprec = P.block_prec != 0;
+    for (int t = tid; t < 10 * nrows; t += nthr)
+      reinterpret_cast<double2*>(s_jac)[t] = reinterpret_cast<const double2*>(P.jac + 20 * (size_t)rb)[t];
+    for (int a = ab + tid; a < ae; a += nthr) {
+      const int ent = P.inc_ent[a];
+      const double2* cf = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(ent >> 1));
+      reinterpret_cast<double2*>(s_coef)[2 * (a - ab)] = cf[0];
+      reinterpret_cast<double2*>(s_coef)[2 * (a - ab) + 1] = cf[1];
+      const int other = P.inc_other[a];
+      if (other >= rb && other < re) {
+        s_zptr[a - ab] = s_z + 4 * (size_t)(other - rb);
+      } else {
+        // owning chunk == owning CTA: binary search over the chunk starts, then map its s_z into this CTA's view
+        int lo = 0, hi = P.n_chunks - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (P.chunk_begin[mid] <= other) lo = mid; else hi = mid - 1;
+        }
+        const double* remote = cluster.map_shared_rank(s_z, lo);
+        s_zptr[a - ab] = remote + 4 * (size_t)(other - P.chunk_begin[lo]);
+      }
+    }
+    __syncthreads();
+    if (bprec) build_block_prec(rb, re, ab);
+    if (bprec) {  // rows of the last block past the chunk end: zero residual
+      const int padded = ((nrows + kPB - 1) / kPB) * kPB;
+      for (int lr = nrows + tid; lr < padded; lr += nthr) {
+        st3(s_r, lr, V3{0, 0, 0});
+        s_rf[3 * lr] = s_rf[3 * lr + 1] = s_rf[3 * lr + 2] = 0.f;
+      }
+    }
+    // ---- initial residual, z = M^-1 r (one thread per row)
+    double rz_part = 0;
+    if (tid < nrows) {
+      const int li = tid, i = rb + tid;
+      if (P.pt_fixed && P.pt_fixed[i]) {
+        if (!bprec) {
+          double2* mo = reinterpret_cast<double2*>(s_minv + 8 * (size_t)li);
+          mo[0] = mo[1] = mo[2] = make_double2(0.0, 0.0);
+        }
+        st3(s_r, li, V3{0, 0, 0});
+        st3(s_x, li, V3{0, 0, 0});
+        st3(s_z, li, V3{0, 0, 0});
+        if (bprec) s_rf[3 * li] = s_rf[3 * li + 1] = s_rf[3 * li + 2] = 0.f;
+      } else {
+        const V3 r = ld3p(P.bvec, i);
+        st3(s_r, li, r);
+        st3(s_x, li, V3{0, 0, 0});
+        if (bprec) {
+          s_rf[3 * li] = (float)r.x;
+          s_rf[3 * li + 1] = (float)r.y;
+          s_rf[3 * li + 2] = (float)r.z;
+        } else {
+          const double2* d = reinterpret_cast<const double2*>(P.dg + 8 * (size_t)i);
+          const double2 d0 = d[0], d1 = d[1], d2 = d[2];
+          const double a = d0.x + lambda, b = d0.y, c = d1.x, e = d1.y + lambda, f = d2.x, g = d2.y + lambda;
+          const double C00 = e * g - f * f, C01 = c * f - b * g, C02 = b * f - c * e;
+          const double det = a * C00 + b * C01 + c * C02;
+          const double id = 1.0 / det;
+          const double m00 = C00 * id, m01 = C01 * id, m02 = C02 * id;
+          const double m11 = (a * g - c * c) * id, m12 = (b * c - a * f) * id, m22 = (a * e - b * b) * id;
+          double2* mo = reinterpret_cast<double2*>(s_minv + 8 * (size_t)li);
+          mo[0] = make_double2(m00, m01);
+          mo[1] = make_double2(m02, m11);
+          mo[2] = make_double2(m12, m22);
+          const V3 z{m00 * r.x + m01 * r.y + m02 * r.z, m01 * r.x + m11 * r.y + m12 * r.z,
+                     m02 * r.x + m12 * r.y + m22 * r.z};
+          st3(s_z, li, z);
+          rz_part += r.x * z.x + r.y * z.y + r.z * z.z;
+        }
+      }
+    }
+    if (bprec) {
+      __syncthreads();
+      rz_part += prec_apply_quads(rb, re, false);
+    }
+    if (pos && tid < 6) {
+      s_rp[tid] = s_bp[tid];
+      s_xp[tid] = 0;
+      s_pp[tid] = 0;
+      s_qp[tid] = 0;
+      double s = 0;
+      for (int c = 0; c < 6; c++) s += s_M[tid * 6 + c] * s_bp[c];
+      s_zp[tid] = s;
+    }
+    // slots (shared memory, double-buffered): [par][8]; broadcast scalars s_bc[4]
+    double* s_slot = s_scal + 8;  // 16 doubles
+    double* s_bc = s_scal + 24;   // alpha / beta / flags
+    // ---- reduction helper pieces are inlined below; initial r.z
+    {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) rz_part += __shfl_xor_sync(0xffffffffu, rz_part, off);
+      if (lane == 0) s_red[warp] = rz_part;
+      __syncthreads();
+      if (warp == 0) {
+        double t = 0;
+        for (int w = lane; w < nw; w += 32) t += s_red[w];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) s_slot[15] = t;
+      }
+      barrier();
+      if (warp == 0) {
+        double t = 0;
+        if (lane < G) t = cluster.map_shared_rank(s_slot, lane)[15];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        double rzp = 0;
+        if (pos)
+          for (int a = 0; a < 6; a++) rzp += s_rp[a] * s_zp[a];
+        if (lane == 0) s_bc[0] = t + rzp;
+      }
+      __syncthreads();
+    }
+    double rz = s_bc[0];
+    const double rz0 = rz;
+    if (!(rz0 > 0)) {  // b == 0: delta = 0
+      if (tid < nrows) st3(P.xcg, rb + tid, V3{0, 0, 0});
+      barrier();  // nobody leaves while its slot may still be read
+      return isfinite(rz0);
+    }
+    const double stop = P.pcg_tol * P.pcg_tol * rz0;
+    double beta = 0;
+    bool ok = true;
+    int it = 0;
+    const int qr = tid / kTPR, ql = tid % kTPR;
+    const bool valid = qr < nrows;
+    const int i = rb + qr, li = qr;
+    bool fixed = true;
+    int kf = -1, a_beg = 0, a1 = 0;
+    double su = 0;
+    if (valid) {
+      fixed = P.pt_fixed && P.pt_fixed[i];
+      kf = P.pt_kf[i];
+      a_beg = P.inc_ptr[i];
+      a1 = P.inc_ptr[i + 1];
+      su = P.dg[8 * (size_t)i + 6];
+    }
+    for (; it < P.pcg_max_iter; it++) {
+      const bool first = (it == 0);
+      // four slot buffers: phase 1 of even / odd iterations [0..6] / [8..14], phase 2 [7] / [15]; a buffer is
+      // rewritten only after two further cluster barriers, when every reader has moved on
+      const int par = (it & 1) ? 8 : 0;
+      // ---- phase 1: w = (H + lambda I) z ; p = z + beta p ; q = w + beta q ; partial p.q
+      const long long tm0 = clock64();
+      double pq_part = 0;
+      double w0 = 0, w1 = 0, w2 = 0;
+      V3 zi{0, 0, 0};
+      if (valid) {
+        zi = ld3p(s_z, li);
+        if (!fixed) {
+          for (int a0 = a_beg + ql; a0 < a1; a0 += 3 * kTPR) {
+            const double* zp[3];
+            const double2* cp[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const int a = min(a0 + kTPR * k, a1 - 1);
+              cp[k] = reinterpret_cast<const double2*>(s_coef) + 2 * (a - ab);
+              zp[k] = s_zptr[a - ab];
+            }
+            double2 c0v[3], c1v[3], za[3];
+            double zb[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              c0v[k] = cp[k][0];
+              c1v[k] = cp[k][1];
+              za[k] = *reinterpret_cast<const double2*>(zp[k]);
+              zb[k] = zp[k][2];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              if (a0 + kTPR * k < a1) {
+                const double dx = zi.x - za[k].x, dy = zi.y - za[k].y, dz = zi.z - zb[k];
+                const double ud = c0v[k].y * dx + c1v[k].x * dy + c1v[k].y * dz;
+                w0 += c0v[k].x * dx + c0v[k].y * ud;
+                w1 += c0v[k].x * dy + c1v[k].x * ud;
+                w2 += c0v[k].x * dz + c1v[k].y * ud;
+              }
+            }
+          }
+        }
+      }
+      #pragma unroll
+      for (int o = 1; o < kTPR; o <<= 1) {
+        w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+        w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+      }
+      if (valid && ql == 0) {
+        double red[6] = {0, 0, 0, 0, 0, 0};
+        double q0 = w0 + (lambda + su) * zi.x, q1 = w1 + (lambda + su) * zi.y, q2 = w2 + (lambda + su) * zi.z;
+        if (kf >= 0) {
+          const double2* jo = reinterpret_cast<const double2*>(s_jac + 20 * (size_t)li);
+          const double omega = jo[9].x;
+          if (omega != 0) {
+            double A[12], B[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+              const double2 t = jo[k];
+              A[2 * k] = t.x;
+              A[2 * k + 1] = t.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const double2 t = jo[6 + k];
+              B[2 * k] = t.x;
+              B[2 * k + 1] = t.y;
+            }
+            double jp0 = 0, jp1 = 0;
+            if (pos) {
+#pragma unroll
+              for (int a = 0; a < 6; a++) {
+                jp0 += A[a] * s_zp[a];
+                jp1 += A[6 + a] * s_zp[a];
+              }
+            }
+            const double t0 = omega * (jp0 + B[0] * zi.x + B[1] * zi.y + B[2] * zi.z);
+            const double t1 = omega * (jp1 + B[3] * zi.x + B[4] * zi.y + B[5] * zi.z);
+            if (!fixed) {
+              q0 += B[0] * t0 + B[3] * t1;
+              q1 += B[1] * t0 + B[4] * t1;
+              q2 += B[2] * t0 + B[5] * t1;
+            }
+            if (pos) {
+#pragma unroll
+              for (int a = 0; a < 6; a++) red[a] = A[a] * t0 + A[6 + a] * t1;
+            }
+          }
+        }
+        if (!fixed) {
+          V3 pn = zi, qn{q0, q1, q2};
+          if (!first) {
+            const V3 po = ld3p(s_p, li), qo = ld3p(s_q, li);
+            pn = V3{zi.x + beta * po.x, zi.y + beta * po.y, zi.z + beta * po.z};
+            qn = V3{q0 + beta * qo.x, q1 + beta * qo.y, q2 + beta * qo.z};
+          }
+          st3(s_p, li, pn);
+          st3(s_q, li, qn);
+          pq_part = pn.x * qn.x + pn.y * qn.y + pn.z * qn.z;
+        }
+        if (pos) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) s_pr[6 * li + a] = red[a];
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) pq_part += __shfl_xor_sync(0xffffffffu, pq_part, off);
+      if (lane == 0) s_red[warp] = pq_part;
+      __syncthreads();  // S1
+      if (warp == 0) {
+        double t = 0;
+        for (int w = lane; w < nw; w += 32) t += s_red[w];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) s_slot[par] = t;
+        if (pos) {
+          // pose partials: lane = a + 6 g (g < 5): rows g, g + 5, ...; then the 5 groups per a in order
+          double v = 0;
+          if (lane < 30) {
+            const int a = lane % 6, g = lane / 6;
+            for (int r = g; r < nrows; r += 5) v += s_pr[6 * r + a];
+          }
+          const double v1 = __shfl_down_sync(0xffffffffu, v, 6), v2 = __shfl_down_sync(0xffffffffu, v, 12),
+                       v3 = __shfl_down_sync(0xffffffffu, v, 18), v4 = __shfl_down_sync(0xffffffffu, v, 24);
+          if (lane < 6) s_slot[par + 1 + lane] = (((v + v1) + v2) + v3) + v4;
+        }
+      }
+      const long long tm1 = clock64();
+      barrier();  // B1
+      if (warp == 0) {
+        const double* rs = cluster.map_shared_rank(s_slot, lane < G ? lane : 0) + par;
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) t[k] = (lane < G && (k == 0 || pos)) ? rs[k] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], off);
+        }
+        double pq = t[0];
+        if (pos) {
+          // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (lanes 0..5)
+          double ppv = 0, qpv = 0;
+          if (lane < 6) {
+            double wsum = t[1];
+#pragma unroll
+            for (int k = 2; k < 7; k++)
+              if (lane == k - 1) wsum = t[k];
+            const double w = lambda * s_zp[lane] + wsum;
+            ppv = first ? s_zp[lane] : s_zp[lane] + beta * s_pp[lane];
+            qpv = first ? w : w + beta * s_qp[lane];
+            s_pp[lane] = ppv;
+            s_qp[lane] = qpv;
+          }
+          double d = ppv * qpv;
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          pq += __shfl_sync(0xffffffffu, d, 0);
+        }
+        if (lane == 0) s_bc[0] = pq;
+      }
+      __syncthreads();  // S2
+      const long long tm2 = clock64();
+      const double pq = s_bc[0];
+      if (!(pq > 0) || !isfinite(pq)) {
+        ok = false;
+        break;
+      }
+      const double alpha = rz / pq;
+      // ---- phase 2: x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z   (lane l < 3 of a quad: component l)
+      double rzn_part = 0;
+      const bool act = valid && !fixed;
+      if (act) {
+        for (int cmp = ql; cmp < 3; cmp += kTPR) {
+          const size_t o = 4 * (size_t)li + cmp;
+          s_x[o] += alpha * s_p[o];
+          const double rc = s_r[o] - alpha * s_q[o];
+          s_r[o] = rc;
+          if (bprec) s_rf[3 * li + cmp] = (float)rc;
+        }
+      }
+      if (pos && tid < 6) {  // pose rows (replicated): x, r, z = M r
+        s_xp[tid] += alpha * s_pp[tid];
+        s_rp[tid] -= alpha * s_qp[tid];
+      }
+      if (!bprec) {
+        __syncwarp();  // the lanes of the quad wrote one component each
+        if (act && ql == 0) {
+          const V3 ri = ld3p(s_r, li);
+          const double2* mo = reinterpret_cast<const double2*>(s_minv + 8 * (size_t)li);
+          const double2 m0 = mo[0], m1 = mo[1], m2 = mo[2];
+          const V3 z{m0.x * ri.x + m0.y * ri.y + m1.x * ri.z, m0.y * ri.x + m1.y * ri.y + m2.x * ri.z,
+                     m1.x * ri.x + m2.x * ri.y + m2.y * ri.z};
+          st3(s_z, li, z);
+          rzn_part = ri.x * z.x + ri.y * z.y + ri.z * z.z;
+        }
+        __syncthreads();  // S3 (pose r complete)
+      } else {
+        __syncthreads();  // S3 (rf and pose r complete)
+        rzn_part = prec_apply_quads(rb, re, false);
+      }
+      if (pos && tid < 6) {
+        double s = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) s += s_M[tid * 6 + c] * s_rp[c];
+        s_zp[tid] = s;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) rzn_part += __shfl_xor_sync(0xffffffffu, rzn_part, off);
+      if (lane == 0) s_red[warp] = rzn_part;
+      __syncthreads();  // S4
+      if (warp == 0) {
+        double t = 0;
+        for (int w = lane; w < nw; w += 32) t += s_red[w];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) s_slot[par + 7] = t;
+      }
+      const long long tm3 = clock64();
+      barrier();  // B2
+      if (warp == 0) {
+        double t = 0;
+        if (lane < G) t = cluster.map_shared_rank(s_slot, lane)[par + 7];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        double rzp = 0;
+        if (pos)
+          for (int a = 0; a < 6; a++) rzp += s_rp[a] * s_zp[a];
+        if (lane == 0) s_bc[1] = t + rzp;
+      }
+      __syncthreads();  // S5
+      const long long tm4 = clock64();
+      prof[1] += tm1 - tm0;  // matvec pass
+      prof[2] += tm2 - tm1;  // pq exchange
+      prof[3] += tm3 - tm2;  // update pass
+      prof[4] += tm4 - tm3;  // rz exchange
+      const double rzn = s_bc[1];
+      if (!isfinite(rzn)) {
+        ok = false;
+        it++;
+        break;
+      }
+      beta = rzn / rz;
+      rz = rzn;
+      if (rz <= stop) {
+        it++;
+        break;
+      }
+    }
+    pcg_iters += it;
+    if (tid < nrows) st3(P.xcg, rb + tid, ld3p(s_x, tid));
+    barrier();  // every remote read of this CTA's shared memory has completed; s_xp is complete
     return ok;
   }
 
@@ -772,10 +1690,13 @@ struct Engine {
   __device__ bool lm_iteration(int iteration) {
     const int F = P.F;
     const bool pts = !P.points_fixed, pos = !P.poses_fixed;
-    barrier();  // estimates written by other CTAs (restore / reset) are visible
+    const long long tl0 = clock64();
+    if (pts) barrier();  // estimates written by other CTAs (restore / reset) are visible
     double acc[2] = {0, 0};  // chi2, max diagonal
-    edges_pass<true>(acc[0]);
-    barrier();
+    if (P.P > 0 || P.D > 0) {
+      edges_pass<true>(acc[0]);
+      barrier();
+    }
     const int par = gen & 1;
     rows_pass<true>(acc[0], acc[1], par);
     grid_reduce<2>(acc, 2u);
@@ -785,9 +1706,7 @@ struct Engine {
     if (pos) {
       for (int t = tid; t < 27 * F; t += nthr) {
         const int k = t / 27, v = t % 27;
-        double s = 0;
-        for (int c = P.kf_chunk_ptr[k]; c < P.kf_chunk_ptr[k + 1]; c++)
-          s += __ldcg(P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals + v);
+        const double s = sum_chunk_partials(k, v, par);
         if (v < 21)
           s_H[21 * k + v] = s;
         else
@@ -802,10 +1721,16 @@ struct Engine {
       lambda = P.lm_tau * maxDiag;
       ni = 2;
     }
+    prof[5] += clock64() - tl0;  // linearisation
     double rho = 0;
     int qmax = 0;
     do {
-      const bool solved = pcg();
+      const long long ts0 = clock64();
+      const bool native = P.cluster_mode && P.resident && P.F == 1 && P.D == 0 && !P.points_fixed &&
+                          P.n_chunks == (int)gridDim.x && !P.no_dsmem;
+      const bool solved = native ? pcg_cluster() : pcg();
+      const long long ts1 = clock64();
+      prof[6] += ts1 - ts0;  // solve
       lm_trials++;
       if (!solved) pcg_fail++;
       // push + update (sparse_optimizer.cpp:457-470), scale = delta^T (lambda delta + b)
@@ -813,8 +1738,8 @@ struct Engine {
       if (solved) {
         if (pts) {
           for_rows([&](int i) {
-            const V3 d = ld3(P.xcg, i), bb = ld3(P.bvec, i);
-            V3 x = ld3(P.x, i);
+            const V3 d = ld3p(P.xcg, i), bb = ld3p(P.bvec, i);
+            V3 x = ld3p(P.x, i);
             st3(P.x_bak, i, x);
             x.x += d.x; x.y += d.y; x.z += d.z;
             st3(P.x, i, x);
@@ -827,8 +1752,8 @@ struct Engine {
           for (int k = tid; k < F; k += nthr) pose_oplus(s_pose + 7 * k, s_xp + 6 * k);
           __syncthreads();
         }
-        barrier();
-        edges_pass<false>(acc2[0]);
+        if (pts) barrier();  // updated point estimates are read across CTAs by the regulariser edges
+        if (P.P > 0 || P.D > 0) edges_pass<false>(acc2[0]);
         double dummy = 0;
         rows_pass<false>(acc2[0], dummy, 0);
         n_chi2++;
@@ -841,7 +1766,8 @@ struct Engine {
       scale += 1e-3;
       rho = (currentChi - tempChi) / scale;
       if (rho > 0 && isfinite(tempChi)) {
-        double alpha = 1. - pow((2 * rho - 1), 3);
+        const double t3 = 2 * rho - 1;
+        double alpha = 1. - t3 * t3 * t3;
         alpha = fmin(alpha, 2. / 3.);
         const double scaleFactor = fmax(1. / 3., alpha);
         lambda *= scaleFactor;
@@ -851,7 +1777,7 @@ struct Engine {
         lambda *= ni;
         ni *= 2;
         if (solved) {  // pop
-          if (pts) for_rows([&](int i) { st3(P.x, i, ld3(P.x_bak, i)); });
+          if (pts) for_rows([&](int i) { st3(P.x, i, ld3p(P.x_bak, i)); });
           if (pos) {
             __syncthreads();
             for (int t = tid; t < 7 * F; t += nthr) s_pose[t] = s_pose_bak[t];
@@ -860,6 +1786,7 @@ struct Engine {
         }
         if (!isfinite(lambda)) break;
       }
+      prof[7] += clock64() - ts1;  // update + chi2
       qmax++;
     } while (rho < 0 && qmax < P.lm_max_trials);
     lm_iters++;
@@ -963,40 +1890,99 @@ struct Engine {
         for (int i = 0; i < 16; i++) st->prof[i] = prof[i];
       }
     }
+    // a cluster must not retire CTAs while others may still arrive at the hardware barrier
+    if (P.cluster_mode) barrier();
   }
 };
 
-__global__ void __launch_bounds__(256, 1) nrs_lm_kernel(const __grid_constant__ Params p) {
-  extern __shared__ double nrs_smem[];
+__global__ void __launch_bounds__(kMaxBlock, 1) nrs_lm_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) double nrs_smem[];
   Engine eng(p, nrs_smem);
   eng.run();
 }
 
 }  // namespace
 
-size_t engine_smem_bytes(int F, int block) {
-  (void)block;
-  return sizeof(double) * ((size_t)F * (7 + 7 + 21 + 36 + 6 * 6) + 32 * kChunkVals + 32) + 16;
+size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec) {
+  size_t d = (size_t)F * (7 + 7 + 21 + 36 + 6 * 6) + 32 * kChunkVals + 32 + 6 * kMaxRows + 2 + 6;  // + alignment slack
+  if (res_rows == 0) d += 16 * kMaxRows;
+  if (res_rows > 0) {
+    d += std::max(20 * (size_t)res_rows, 16 * (size_t)kMaxRows) + (size_t)res_rows * (4 * 5 + (block_prec ? 0 : 8)) +
+         5 * (size_t)res_inc + (3 * (size_t)res_rows + 1) / 2 + 4;
+    size_t bytes = d * sizeof(double);
+    if (block_prec) bytes += (size_t)((res_rows + kPrecBlock - 1) / kPrecBlock) * kPN * kPS * sizeof(float);
+    return bytes + 16;
+  }
+  return d * sizeof(double) + 16;
+}
+
+static bool set_smem(size_t smem) {
+  static size_t current = 0;
+  if (smem > 48 * 1024 && smem > current) {
+    if (cudaFuncSetAttribute(nrs_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    current = smem;
+  }
+  return true;
 }
 
 int engine_max_grid(int block, size_t smem) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(nrs_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nrs_lm_kernel, block, smem);
+  if (!set_smem(smem)) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nrs_lm_kernel, block, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
   return sms * per_sm;
 }
 
+int engine_max_cluster(int block, size_t smem) {
+  if (!set_smem(smem)) return 0;
+  cudaFuncSetAttribute(nrs_lm_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaGetLastError();
+  for (int cs = 16; cs >= 2; cs >>= 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, nrs_lm_kernel, &cfg) == cudaSuccess && n >= 1) return cs;
+    cudaGetLastError();
+  }
+  return 0;
+}
+
 int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_t stream) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(nrs_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+  if (!set_smem(smem)) return (int)cudaErrorInvalidValue;
+  void* args[] = {const_cast<Params*>(&p)};
+  if (p.cluster_mode) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = grid;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelExC(&cfg, (const void*)nrs_lm_kernel, args);
   }
   cudaError_t e = cudaMemsetAsync(p.bar, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return (int)e;
-  void* args[] = {const_cast<Params*>(&p)};
   e = cudaLaunchCooperativeKernel((const void*)nrs_lm_kernel, dim3(grid), dim3(block), args, smem, stream);
   return (int)e;
 }

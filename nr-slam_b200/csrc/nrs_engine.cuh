@@ -34,6 +34,13 @@ constexpr int kMaxOps = 16;
 constexpr int kTrace = 64;
 constexpr int kSlotVals = 8;     // doubles per CTA per grid reduction
 constexpr int kChunkVals = 28;   // doubles per chunk partial (21 H_pp + 6 b_p, padded)
+#ifndef NRS_TPR
+#define NRS_TPR 2
+#endif
+constexpr int kTPR = NRS_TPR;    // threads per point row inside the CG loop (a group of adjacent lanes, 2 or 4)
+constexpr int kMaxRows = 128;    // point rows per chunk
+constexpr int kMaxBlock = kTPR * kMaxRows;  // threads per CTA (544)
+constexpr int kPrecBlock = 16;   // rows per dense preconditioner block (resident mode)
 
 struct EngineStats {
   int lm_iterations, lm_trials, pcg_iterations, n_sweeps, n_chi2_passes, n_trace, pcg_fail, barriers;
@@ -58,6 +65,15 @@ struct Params {
   int op[kMaxOps];
   int op_arg[kMaxOps];
 
+  // execution mode (chosen by the host from the problem size, nrs_api.cu: plan_launch)
+  int cluster_mode;   // 1: the grid is ONE thread-block cluster -> hardware cluster barrier instead of the atomics one
+  int resident;       // 1: one chunk per CTA; Jacobians, edge coefficients and the CG vectors of the chunk live in
+                      //    shared memory for the duration of a solve, only the exchanged vector goes through L2
+  int res_rows;       // shared-memory capacity: rows per chunk
+  int res_inc;        // shared-memory capacity: pair incidences per chunk
+  int block_prec;     // 1: dense kPrecBlock-row block-Jacobi preconditioner (resident mode only), else 3x3 blocks
+  int no_dsmem;       // 1: keep the general CG loop (exchange through L2) even where the cluster-native loop applies
+
   // poses: 7 doubles each (q xyzw, t)
   double* pose;
   const double* pose_seed;
@@ -76,7 +92,8 @@ struct Params {
   const double* pair_w;
   const double* pair_d0;
   unsigned char* sp_level;  // [P] level of the spatial edge
-  double* pc;               // [8P] linearised coefficients: s, u[3], c
+  double* pc;               // [4P] linearised coefficients: s, u[3]   (H_ij = -(s I + u u^T))
+  double* pcc;              // [P]  spring residual term c (gradient)
   const int* inc_ptr;       // [V+1] CSR of pair incidences per point
   const int* inc_other;     // neighbour vertex
   const int* inc_ent;       // pair id * 2 + (1 if this vertex is the pair's second endpoint)
@@ -92,7 +109,7 @@ struct Params {
   const int* un_ref;        // [U] vertex whose estimate is the reference value
   int unary_on;             // unary edges take part (lost-point stage only)
   const unsigned char* pt_fixed;  // [V] per-vertex setFixed(true), nullptr: none
-  // work partition: chunk = contiguous rows of one pose slot
+  // work partition: chunk = contiguous rows of one pose slot, at most blockDim.x rows
   const int* chunk_kf;
   const int* chunk_begin;
   const int* chunk_end;
@@ -104,17 +121,21 @@ struct Params {
   double* minv;        // [8V]
   double* xcg;         // [4V]
   double* rvec;        // [4V]
+  double* pvec;        // [4V]
   double* qvec;        // [4V]
-  double* rec;         // [2][8V] {z, p} records
+  double* zvec;        // [4V] preconditioned residual — the one vector neighbours read during the CG loop
   double* chunk_part;  // [2][n_chunks * kChunkVals]
   double* slots;       // [2][G * kSlotVals]
   unsigned long long* bar;
   EngineStats* stats;
 };
 
-// Host-side launch (cooperative). Returns cudaError_t as int. grid/block chosen by the caller.
+// Host-side launch. Returns cudaError_t as int. grid/block/smem chosen by the caller (plan_launch).
 int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_t stream);
-size_t engine_smem_bytes(int F, int block);
+// Shared memory needed for F poses (+ the resident chunk state when res_rows > 0).
+size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec);
+// Largest co-resident grid for a cooperative launch / largest cluster that can be scheduled (0 if none).
 int engine_max_grid(int block, size_t smem);
+int engine_max_cluster(int block, size_t smem);
 
 }  // namespace nrs

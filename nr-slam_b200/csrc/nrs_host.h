@@ -66,11 +66,19 @@ struct Staged {
   Params p;
   int grid = 0, block = 0;
   size_t smem = 0;
+  // second launch plan over all rows (tracking: the lost-point stage adds rows behind the optimised ones)
+  bool has_plan2 = false;
+  Params p2;
+  int grid2 = 0, block2 = 0;
+  size_t smem2 = 0;
   bool valid = false;
   // offsets of the results inside `out`
   size_t o_pose = 0, o_x = 0, o_chi2 = 0, o_rp_level = 0, o_sp_level = 0, o_stats = 0;
   size_t o_fixed = 0;  // per-vertex fixed flags inside `in` (lost-point stage)
   size_t h2d_bytes = 0, d2h_bytes = 0;
+  // rows are re-ordered along a space-filling curve before staging (locality for the resident chunks and the
+  // dense block preconditioner): row_of[caller row] = engine row
+  std::vector<int> row_of;
 };
 
 }  // namespace nrs
@@ -84,4 +92,5 @@ struct nrslam_b200_ctx {
   std::string err;
   nrs::Staged staged[4];  // 0 pose_only, 1 pose_deform, 2 local_ba, 3 lost-point stage
   unsigned long long* bar = nullptr;
+  int max_cluster = -1;   // largest schedulable thread-block cluster of the LM kernel (queried lazily)
 };
