@@ -236,3 +236,42 @@ def ba_problem(config="c1", seed=None, n=None, n_kf=None, run=None, knn=10, defo
                 obs_vertex=np.concatenate(obs_vertex), uv=np.concatenate(uv_l), X=np.concatenate(X_l),
                 graph=graph, scale=float(scale), config=config, seed=seed, n=n,
                 poses_true=np.stack(poses_true).astype(np.float32))
+
+
+def _texture(rng, h, w):
+    """Band-limited random texture in [0, 1] (separable box smoothing of white noise at two scales; numpy only)."""
+    def smooth(a, r):
+        k = np.ones(2 * r + 1) / (2 * r + 1)
+        for _ in range(3):  # three box passes ~ Gaussian
+            a = np.apply_along_axis(lambda v: np.convolve(np.pad(v, r, mode="reflect"), k, mode="valid"), 0, a)
+            a = np.apply_along_axis(lambda v: np.convolve(np.pad(v, r, mode="reflect"), k, mode="valid"), 1, a)
+        return a
+    n = rng.normal(size=(h, w))
+    t = smooth(n, 1) * 3 + smooth(n, 4) * 8
+    return (t - t.min()) / (t.max() - t.min())
+
+
+def klt_pair(seed=1, size=(640, 480), n_points=500, shift=(2.6, -1.7), gain=1.1, bias=-8.0, noise=1.0, margin=40):
+    """A reference / current image pair for the KLT tracker: band-limited texture, the current
+    image is the reference translated by a sub-pixel shift (bilinear resampling), with affine gain/bias and noise.
+    Returns ref, cur (uint8 HxW), pts (reference keypoints), pts_true, status (all TRACKED)."""
+    from .abi import TRACKED
+    rng = np.random.default_rng(seed)
+    w, h = size
+    pad = 16
+    big = _texture(rng, h + 2 * pad, w + 2 * pad) * 200 + 25
+    ref = big[pad:pad + h, pad:pad + w]
+    dx, dy = shift
+    # cur(x, y) = ref(x - dx, y - dy): a point at p in ref appears at p + shift in cur
+    xs = np.arange(w) - dx + pad
+    ys = np.arange(h) - dy + pad
+    x0, y0 = np.floor(xs).astype(int), np.floor(ys).astype(int)
+    fx, fy = (xs - x0)[None, :], (ys - y0)[:, None]
+    g = big
+    cur = ((1 - fy) * ((1 - fx) * g[np.ix_(y0, x0)] + fx * g[np.ix_(y0, x0 + 1)]) +
+           fy * ((1 - fx) * g[np.ix_(y0 + 1, x0)] + fx * g[np.ix_(y0 + 1, x0 + 1)]))
+    cur = gain * cur + bias + rng.normal(scale=noise, size=cur.shape) if noise > 0 else gain * cur + bias
+    pts = np.stack([rng.uniform(margin, w - margin, n_points), rng.uniform(margin, h - margin, n_points)], 1)
+    return dict(ref=np.clip(np.rint(ref), 0, 255).astype(np.uint8), cur=np.clip(np.rint(cur), 0, 255).astype(np.uint8),
+                pts=pts.astype(np.float32), pts_true=(pts + np.array([dx, dy])).astype(np.float32),
+                status=np.full(n_points, TRACKED, np.uint8), shift=shift)

@@ -106,3 +106,82 @@ class Oracle:
         g = graph.struct()
         positions = np.ascontiguousarray(positions, np.float32)
         return self.L.orc_graph_update_vertex(C.byref(g), int(vertex), ptr(positions, C.c_float))
+
+
+class OracleKLT:
+    """LucasKanadeTracker restatement (oracle/orc_klt.cc). Same method names as nrslam_b200.api.KLT."""
+
+    def __init__(self, win=21, max_level=4, max_iters=10, eps=1e-4, min_eig=1e-4):
+        self.L = lib()
+        self.L.orc_klt_create.restype = C.c_void_p
+        self.win, self.max_level = win, max_level
+        self.h = C.c_void_p(self.L.orc_klt_create(win, max_level, max_iters, C.c_float(eps), C.c_float(min_eig)))
+
+    def close(self):
+        if self.h:
+            self.L.orc_klt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def num_points(self):
+        return self.L.orc_klt_num_points(self.h)
+
+    def set_reference(self, image, pts, mask=None):
+        image = np.ascontiguousarray(image, np.uint8)
+        pts = np.ascontiguousarray(pts, np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        return self.L.orc_klt_set_reference(self.h, ptr(image, C.c_uint8), image.shape[1], image.shape[0],
+                                            image.strides[0], len(pts), ptr(pts, C.c_float), ptr(m, C.c_uint8),
+                                            0 if m is None else m.strides[0])
+
+    def track(self, image, pts, status, use_initial_flow=False, min_ssim=0.7, mask=None):
+        image = np.ascontiguousarray(image, np.uint8)
+        pts = np.array(pts, np.float32)
+        status = np.array(status, np.uint8)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        nt = C.c_int32(0)
+        rc = self.L.orc_klt_track(self.h, ptr(image, C.c_uint8), image.shape[1], image.shape[0], image.strides[0],
+                                  len(pts), ptr(pts, C.c_float), ptr(status, C.c_uint8), int(use_initial_flow),
+                                  C.c_float(min_ssim), ptr(m, C.c_uint8), 0 if m is None else m.strides[0],
+                                  C.byref(nt))
+        return dict(rc=rc, pts=pts, status=status, n_tracked=nt.value)
+
+    def get_patch(self, idx):
+        nl, a = self.max_level + 1, self.win * self.win
+        gray = np.zeros((nl, a), np.int16)
+        grad = np.zeros((nl, a, 2), np.int16)
+        mean = np.zeros(nl, np.float32)
+        mean2 = np.zeros(nl, np.float32)
+        valid = np.zeros(nl, np.uint8)
+        rc = self.L.orc_klt_get_patch(self.h, int(idx), ptr(gray, C.c_int16), ptr(grad, C.c_int16),
+                                      ptr(mean, C.c_float), ptr(mean2, C.c_float), ptr(valid, C.c_uint8))
+        return dict(rc=rc, gray=gray, grad=grad, mean=mean, mean2=mean2, valid=valid)
+
+    def insert_patch(self, x, y, patch):
+        return self.L.orc_klt_insert_patch(self.h, C.c_float(x), C.c_float(y), ptr(patch["gray"], C.c_int16),
+                                           ptr(patch["grad"], C.c_int16), ptr(patch["mean"], C.c_float),
+                                           ptr(patch["mean2"], C.c_float), ptr(patch["valid"], C.c_uint8))
+
+    def clear(self):
+        return self.L.orc_klt_clear(self.h)
+
+
+def klt_pyramid(image, win, max_level, level):
+    """Bordered level image / derivative of the oracle's pyramid restatement (pinning hook)."""
+    image = np.ascontiguousarray(image, np.uint8)
+    h, w = image.shape
+    lw, lh = w, h
+    for _ in range(level):
+        lw, lh = (lw + 1) // 2, (lh + 1) // 2
+    img = np.zeros((lh + 2 * win, lw + 2 * win), np.uint8)
+    der = np.zeros((lh + 2 * win, lw + 2 * win, 2), np.int16)
+    ow, oh = C.c_int(0), C.c_int(0)
+    n = lib().orc_klt_pyramid(ptr(image, C.c_uint8), w, h, image.strides[0], win, max_level, level, ptr(img, C.c_uint8),
+                              ptr(der, C.c_int16), C.byref(ow), C.byref(oh))
+    assert n > level and (ow.value, oh.value) == (lw, lh)
+    return img, der
