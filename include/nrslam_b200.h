@@ -194,6 +194,7 @@ int32_t nrslam_b200_graph_update_vertex(nrslam_b200_graph* g, int32_t vertex, co
 
 /* ---- LucasKanadeTracker (matching/lucas_kanade_tracker.h:55-92) -------------------------------
  * One tracker object per reference image. Images are 8-bit single channel, `pitch` bytes per row.
+ * win_size must be 21 (the only window the reference uses, modules/SLAM/system.cc:78-83).
  * Point i of every call is point i of SetReferenceImage (+ inserted ones): KLT index == frame index. */
 typedef struct nrslam_b200_klt nrslam_b200_klt;
 int nrslam_b200_klt_create(nrslam_b200_ctx* ctx, int32_t win_size, int32_t max_level, int32_t max_iters,
@@ -218,8 +219,14 @@ int nrslam_b200_klt_insert_patch(nrslam_b200_klt* klt, float x, float y, const i
                                  const uint8_t* valid);
 int nrslam_b200_klt_clear(nrslam_b200_klt* klt);
 int32_t nrslam_b200_klt_num_points(const nrslam_b200_klt* klt);
-/* Re-run the last Track on the device-resident image/points (benchmark hook); device ms out. */
+/* Re-run the last Track (pyramid of the device-resident current image + tracking kernel) on the device-resident
+ * inputs (benchmark hook); device ms out. */
 int nrslam_b200_klt_retrack(nrslam_b200_klt* klt, float* gpu_ms_out);
+/* Diagnostics: read back one level of the reference (which = 0) or current (1) pyramid WITH its winSize border,
+ * as cv::buildOpticalFlowPyramid lays it out (lucas_kanade_tracker.cc:50,184): img_out (h+2*win) x (w+2*win) u8,
+ * deriv_out same size x 2 int16. Used by the bit-exact pyramid parity test. */
+int nrslam_b200_klt_debug_level(nrslam_b200_klt* klt, int32_t which, int32_t level, uint8_t* img_out,
+                                int16_t* deriv_out, int32_t* w_out, int32_t* h_out);
 
 #ifdef __cplusplus
 }

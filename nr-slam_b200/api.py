@@ -61,12 +61,18 @@ class Core:
         self.L = load()
         self.opt = opt or default_options()
         self._ctx = C.c_void_p()
+        self._children = []  # weak references to the KLT trackers living on this context
         rc = self.L.nrslam_b200_create(C.byref(self.opt), C.byref(self._ctx))
         if rc != 0:
             raise NrslamError(rc, "nrslam_b200_create failed")
 
     def close(self):
         if self._ctx:
+            for ref in self._children:  # trackers hold a pointer to the context: destroy them first
+                k = ref()
+                if k is not None:
+                    k.close()
+            self._children = []
             self.L.nrslam_b200_destroy(self._ctx)
             self._ctx = C.c_void_p()
 
@@ -154,3 +160,102 @@ class Core:
         g = graph.struct()
         positions = _f32(positions)
         return self.L.nrslam_b200_graph_update_vertex(C.byref(g), int(vertex), ptr(positions, C.c_float))
+
+
+class KLT:
+    """LucasKanadeTracker (modules/matching/lucas_kanade_tracker.h:55-70) on the GPU: SetReferenceImage, Track,
+    Get/InsertPhotometricInformation, clear. One object per reference image; point i of every call is point i of
+    set_reference (+ inserted ones), exactly like the reference (KLT index == frame index)."""
+
+    def __init__(self, core, win=21, max_level=4, max_iters=10, eps=1e-4, min_eig=1e-4):
+        self.core = core
+        self.L = core.L
+        self.win, self.max_level = win, max_level
+        self._h = C.c_void_p()
+        rc = self.L.nrslam_b200_klt_create(core._ctx, win, max_level, max_iters, C.c_float(eps), C.c_float(min_eig),
+                                           C.byref(self._h))
+        if rc != 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
+        import weakref
+        core._children.append(weakref.ref(self))
+
+    def close(self):
+        if self._h:
+            if self.core._ctx:  # the context is still alive
+                self.L.nrslam_b200_klt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(self.core._ctx) or b"").decode())
+        return rc
+
+    def num_points(self):
+        return self.L.nrslam_b200_klt_num_points(self._h)
+
+    def set_reference(self, image, pts, mask=None):
+        image = np.ascontiguousarray(image, np.uint8)
+        pts = _f32(pts)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        return self._check(self.L.nrslam_b200_klt_set_reference(
+            self._h, ptr(image, C.c_uint8), image.shape[1], image.shape[0], image.strides[0], len(pts),
+            ptr(pts, C.c_float), ptr(m, C.c_uint8), 0 if m is None else m.strides[0]))
+
+    def track(self, image, pts, status, use_initial_flow=False, min_ssim=0.7, mask=None):
+        image = np.ascontiguousarray(image, np.uint8)
+        pts = np.array(pts, np.float32)
+        status = np.array(status, np.uint8)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        nt = C.c_int32(0)
+        rc = self._check(self.L.nrslam_b200_klt_track(
+            self._h, ptr(image, C.c_uint8), image.shape[1], image.shape[0], image.strides[0], len(pts),
+            ptr(pts, C.c_float), ptr(status, C.c_uint8), int(use_initial_flow), C.c_float(min_ssim),
+            ptr(m, C.c_uint8), 0 if m is None else m.strides[0], C.byref(nt)))
+        return dict(rc=rc, pts=pts, status=status, n_tracked=nt.value)
+
+    def retrack(self):
+        ms = C.c_float(0)
+        self._check(self.L.nrslam_b200_klt_retrack(self._h, C.byref(ms)))
+        return ms.value
+
+    def get_patch(self, idx):
+        nl, a = self.max_level + 1, self.win * self.win
+        gray = np.zeros((nl, a), np.int16)
+        grad = np.zeros((nl, a, 2), np.int16)
+        mean = np.zeros(nl, np.float32)
+        mean2 = np.zeros(nl, np.float32)
+        valid = np.zeros(nl, np.uint8)
+        rc = self._check(self.L.nrslam_b200_klt_get_patch(self._h, int(idx), ptr(gray, C.c_int16),
+                                                          ptr(grad, C.c_int16), ptr(mean, C.c_float),
+                                                          ptr(mean2, C.c_float), ptr(valid, C.c_uint8)))
+        return dict(rc=rc, gray=gray, grad=grad, mean=mean, mean2=mean2, valid=valid)
+
+    def insert_patch(self, x, y, patch):
+        return self._check(self.L.nrslam_b200_klt_insert_patch(
+            self._h, C.c_float(x), C.c_float(y), ptr(np.ascontiguousarray(patch["gray"], np.int16), C.c_int16),
+            ptr(np.ascontiguousarray(patch["grad"], np.int16), C.c_int16),
+            ptr(np.ascontiguousarray(patch["mean"], np.float32), C.c_float),
+            ptr(np.ascontiguousarray(patch["mean2"], np.float32), C.c_float),
+            ptr(np.ascontiguousarray(patch["valid"], np.uint8), C.c_uint8)))
+
+    def clear(self):
+        return self._check(self.L.nrslam_b200_klt_clear(self._h))
+
+    def debug_level(self, which, level, shape_hw):
+        """Bordered pyramid level (diagnostics): returns (image u8, derivative int16 x2)."""
+        h, w = shape_hw
+        for _ in range(level):
+            w, h = (w + 1) // 2, (h + 1) // 2
+        img = np.zeros((h + 2 * self.win, w + 2 * self.win), np.uint8)
+        der = np.zeros((h + 2 * self.win, w + 2 * self.win, 2), np.int16)
+        ow, oh = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.nrslam_b200_klt_debug_level(self._h, int(which), int(level), ptr(img, C.c_uint8),
+                                                       ptr(der, C.c_int16), C.byref(ow), C.byref(oh)))
+        assert (ow.value, oh.value) == (w, h)
+        return img, der

@@ -1,0 +1,140 @@
+"""Parity of the CUDA KLT tracker (through the C ABI) against the CPU oracle and the OpenCV golden vectors.
+
+Bars: integer work (pyramid levels, Scharr derivatives, reference patches) BIT-EXACT; reference means 1e-6 / mean squares 1e-5
+relative (the reference accumulates 441 fp32 terms row-major, the kernel sums exact integers and rounds once); tracked positions
+within 0.02 px for >= 99 % of the points whose status agrees (fp32 sums in a different order), statuses may flip only on
+threshold ties: flip rate <= 1 %; index bookkeeping (which points are touched, counts) exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from nrslam_b200 import abi, api, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "klt_pyramid.npz")
+
+
+@pytest.mark.parametrize("name", ["even", "odd"])
+def test_pyramid_bit_exact_vs_opencv_golden(core, name):
+    g = np.load(GOLD)
+    img = g[name + "_image"]
+    k = api.KLT(core, max_level=2)
+    k.set_reference(img, np.zeros((0, 2), np.float32))
+    win = 21
+    for lv in range(3):
+        di, dd = k.debug_level(0, lv, img.shape)
+        gi, gd = g["%s_L%d_img" % (name, lv)], g["%s_L%d_deriv" % (name, lv)]
+        assert np.array_equal(di, np.pad(gi, win, mode="reflect")), "level %d image" % lv
+        assert np.array_equal(dd, np.pad(gd, ((win, win), (win, win), (0, 0)))), "level %d derivative" % lv
+    k.close()
+
+
+def test_reference_patches_bit_exact(core, oracle):
+    p = synth.klt_pair(seed=11, n_points=300, margin=4)   # includes points whose window leaves the image
+    p["pts"][0] = (-14.0, 30.0)   # no level has a reference window for this point
+    p["pts"][3] = (637.0, 478.5)
+    mask = np.full(p["ref"].shape, 255, np.uint8)
+    mask[100:140, 200:260] = 0
+    for m in (None, mask):
+        a = oracle_lib.OracleKLT()
+        a.set_reference(p["ref"], p["pts"], m)
+        b = api.KLT(core)
+        b.set_reference(p["ref"], p["pts"], m)
+        n_invalid = 0
+        for i in range(0, 300, 3):
+            pa, pb = a.get_patch(i), b.get_patch(i)
+            assert np.array_equal(pa["valid"], pb["valid"])
+            assert np.array_equal(pa["gray"], pb["gray"]) and np.array_equal(pa["grad"], pb["grad"])
+            v = pa["valid"] > 0
+            assert np.allclose(pa["mean"][v], pb["mean"][v], rtol=1e-6) and np.allclose(pa["mean2"][v], pb["mean2"][v], rtol=1e-5)
+            assert np.all(pb["mean"][~v] == -1)
+            n_invalid += int((~v).sum())
+        assert n_invalid > 0
+        b.close()
+
+
+def compare_track(ra, rb, status_in):
+    usable = np.isin(status_in, [abi.TRACKED_WITH_3D, abi.TRACKED, abi.JUST_TRIANGULATED])
+    # untouched points: identical
+    assert np.array_equal(ra["status"][~usable], rb["status"][~usable])
+    assert np.array_equal(ra["pts"][~usable], rb["pts"][~usable])
+    same = ra["status"] == rb["status"]
+    flip = 1.0 - same[usable].mean()
+    assert flip <= 0.01, "status flip rate %.4f" % flip
+    ok = same & usable & (ra["status"] == status_in)
+    err = np.abs(ra["pts"][ok] - rb["pts"][ok]).max(axis=1)
+    assert (err < 0.02).mean() >= 0.99, "position agreement %.4f, max %.4f" % ((err < 0.02).mean(), err.max())
+    assert abs(ra["n_tracked"] - rb["n_tracked"]) <= max(1, int(0.01 * usable.sum()))
+    return flip, err
+
+
+@pytest.mark.parametrize("kw", [dict(seed=21), dict(seed=22, shift=(6.2, 4.9), gain=0.85, bias=14.0),
+                                dict(seed=23, shift=(0.0, 0.0), gain=1.0, bias=0.0, noise=0.0),
+                                dict(seed=24, size=(352, 368), n_points=300, margin=6)])
+def test_track_parity(core, kw):
+    p = synth.klt_pair(**{**dict(n_points=600), **kw})
+    st = p["status"].copy()
+    st[::17] = abi.BAD                 # not usable: must stay untouched
+    st[1::19] = abi.TRACKED_WITH_3D
+    a = oracle_lib.OracleKLT()
+    a.set_reference(p["ref"], p["pts"])
+    b = api.KLT(core)
+    b.set_reference(p["ref"], p["pts"])
+    ra = a.track(p["cur"], p["pts"], st)
+    rb = b.track(p["cur"], p["pts"], st)
+    compare_track(ra, rb, st)
+    good = (rb["status"] == st) & np.isin(st, [abi.TRACKED, abi.TRACKED_WITH_3D])
+    if kw.get("margin", 40) >= 40:
+        assert good.mean() > 0.75
+        assert np.median(np.abs(rb["pts"][good] - p["pts_true"][good])) < 0.1
+    # deterministic
+    rb2 = b.track(p["cur"], p["pts"], st)
+    assert np.array_equal(rb["pts"], rb2["pts"]) and np.array_equal(rb["status"], rb2["status"])
+    b.close()
+
+
+def test_track_with_initial_flow_and_inserted_points(core):
+    """use_initial_flow (tracking.cc:447,460 PointReuse) and InsertPhotometricInformation round trip."""
+    p = synth.klt_pair(seed=31, n_points=200, shift=(9.0, -7.5))
+    a = oracle_lib.OracleKLT()
+    b = api.KLT(core)
+    a.set_reference(p["ref"], p["pts"][:150])
+    b.set_reference(p["ref"], p["pts"][:150])
+    donor = api.KLT(core)
+    donor.set_reference(p["ref"], p["pts"][150:])
+    for i in range(50):
+        patch = donor.get_patch(i)
+        a.insert_patch(p["pts"][150 + i, 0], p["pts"][150 + i, 1], patch)
+        b.insert_patch(p["pts"][150 + i, 0], p["pts"][150 + i, 1], patch)
+    assert a.num_points() == b.num_points() == 200
+    guess = p["pts_true"] + np.float32(0.8)
+    ra = a.track(p["cur"], guess, p["status"], use_initial_flow=True, min_ssim=0.75)
+    rb = b.track(p["cur"], guess, p["status"], use_initial_flow=True, min_ssim=0.75)
+    compare_track(ra, rb, p["status"])
+    ok = rb["status"] == abi.TRACKED
+    assert ok.mean() > 0.8 and np.median(np.abs(rb["pts"][ok] - p["pts_true"][ok])) < 0.1
+    b.clear()
+    assert b.num_points() == 0
+    b.close()
+    donor.close()
+
+
+def test_full_size_properties(core):
+    """configs[1] size (640x480, 2000 points): identity tracking returns the reference points; counts consistent."""
+    p = synth.klt_pair(seed=41, n_points=2000, shift=(0.0, 0.0), gain=1.0, bias=0.0, noise=0.0)
+    b = api.KLT(core)
+    b.set_reference(p["ref"], p["pts"])
+    r = b.track(p["ref"], p["pts"], p["status"])
+    ok = r["status"] == abi.TRACKED
+    assert ok.mean() > 0.95 and np.abs(r["pts"][ok] - p["pts"][ok]).max() < 1e-3
+    assert r["n_tracked"] == int(ok.sum())
+    ms = b.retrack()
+    assert ms > 0
+    b.close()
+
+
+def test_rejects_unsupported_window(core):
+    with pytest.raises(api.NrslamError):
+        api.KLT(core, win=15)
