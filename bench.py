@@ -4,10 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Metric (BASELINE.json): tracking frames/s on configs[1] — synthetic 640x480 pinhole, 2000 landmarks, REF mode — where
-one frame (= one step) is CameraPoseOptimization (3 x 10 LM iterations) followed by
-CameraPoseAndDeformationOptimization (2 x 10 LM iterations, + 10 for lost points in the end-to-end path). The line
-also carries the second quantity of the metric, deformable-BA LM iterations/s on configs[2]
-(5000 landmarks / 30 keyframes / 50k observations), under "ba".
+one frame (= one step) is what Tracking::TrackCameraAndDeformation runs per image (tracking.cc:291-330):
+LucasKanadeTracker::Track of the 2000 points on a synthetic 640x480 image pair, CameraPoseOptimization (3 x 10 LM
+iterations) and CameraPoseAndDeformationOptimization (2 x 10 LM iterations, + 10 for lost points in the end-to-end
+path). The same frame without the KLT stage is reported under "without_klt". The line also carries the second quantity
+of the metric, deformable-BA LM iterations/s on configs[2] (5000 landmarks / 30 keyframes / 50k observations), under
+"ba".
 
   value  whole-job frames/s with the staged problem resident in HBM (device time of the LM kernels, CUDA events on
          the library's launch stream, L2 flushed between steps)
@@ -33,7 +35,8 @@ sys.path.insert(0, ROOT)
 METRIC = "tracking_frames_per_sec"
 UNIT = "frames/s"
 WORKLOAD = ("configs[1]: synthetic 640x480 pinhole, 2000 landmarks, REF mode (one deformation vertex per landmark, "
-            "symmetric 10-NN regularisation graph), frame = pose_only(3x10 LM) + pose_deform(2x10 LM)")
+            "symmetric 10-NN regularisation graph), frame = KLT track (2000 points, 640x480 pair) + pose_only(3x10 LM) "
+            "+ pose_deform(2x10 LM)")
 
 
 def peaks():
@@ -148,12 +151,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+_REF_KLT = {}
+
+
 def _ref_frame(i):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from nrslam_b200 import synth
     p = synth.tracking_problem("c2", seed=1235 + (i % 4))
     o = oracle_lib.Oracle()
+    if "k" not in _REF_KLT:  # the reference image is set once per keyframe, not per frame (tracking.cc:361-367)
+        im = synth.klt_pair(seed=77, n_points=2000)
+        k = oracle_lib.OracleKLT()
+        k.set_reference(im["ref"], im["pts"])
+        _REF_KLT.update(k=k, im=im)
+    im = _REF_KLT["im"]
+    _REF_KLT["k"].track(im["cur"], im["pts"], im["status"])
     r = o.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
     o.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"], p["graph"].copy(),
                   p["scale"], r["pose"], p["last_world_position"])
@@ -200,7 +213,12 @@ def main():
     p = synth.tracking_problem("c2", seed=1235 + rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    im = synth.klt_pair(seed=77 + rank, n_points=2000)
+    klt = api.KLT(core)
+    klt.set_reference(im["ref"], im["pts"])
+
     def frame_e2e():
+        klt.track(im["cur"], im["pts"], im["status"])
         r0 = core.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
         r1 = core.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
                               p["graph"].copy(), p["scale"], r0["pose"], p["last_world_position"])
@@ -221,26 +239,39 @@ def main():
 
     # ---- device-resident: re-run the staged programs (pose_only, pose_deform main rounds) on HBM-resident inputs
     for _ in range(args.warmup):
+        klt.retrack()
         core.resolve(0)
         core.resolve(1)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     dev_ms = 0.0
+    klt_ms = 0.0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
+        kms = klt.retrack()   # pyramid of the resident image + track kernel
         s0 = core.resolve(0)
         s1 = core.resolve(1)
-        dev_ms += s0["gpu_ms"] + s1["gpu_ms"]
+        klt_ms += kms
+        dev_ms += kms + s0["gpu_ms"] + s1["gpu_ms"]
     barrier()
     wall_s = time.perf_counter() - wall0
     clocks = sampler.stop()
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # the same frames without the KLT stage (optimisation only), end to end
+    def frame_opt_only():
+        r0 = core.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
+        core.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
+                         p["graph"].copy(), p["scale"], r0["pose"], p["last_world_position"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame_opt_only()
+    opt_e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s * 1e3, dev_ms - klt_ms, opt_e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    dev_ms_max, e2e_ms_max, dev_opt_ms_max, e2e_opt_ms_max = (float(v) for v in t)
 
     value = world * args.steps / (dev_ms_max * 1e-3)
     e2e_value = world * args.steps / (e2e_ms_max * 1e-3)
@@ -252,13 +283,18 @@ def main():
               n_pair_edges=r1["stats"]["n_pair_edges"], n_spring_edges=0, n_damper_edges=0)
     alg, b_sweep, b_mv = algorithmic_bytes(st)
     ach = alg / (s1["gpu_ms"] * 1e-3) / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_lm_track_ncu_summary.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "nrs_lm_kernel (pose+deformation launch)", "achieved": ach,
                 "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": None, "algorithmic_bytes_per_launch": alg, "launch_ms": s1["gpu_ms"],
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_ms": s1["gpu_ms"],
                 "bytes_per_sweep": b_sweep, "bytes_per_matvec": b_mv, "sweeps": s1["n_sweeps"],
                 "matvecs": s1["pcg_iterations"], "chi2_passes": s1["n_chi2_passes"],
-                "note": "working set (<4 MB) is L2-resident inside the launch; the kernel is bound by barrier/"
-                        "gather latency, not HBM (SURVEY.md §0.9)"}
+                "note": "working set (<4 MB) lives in shared memory / L2 inside the launch; the kernel is bound by "
+                        "synchronisation and dependent-issue latency, not HBM (SURVEY.md 0.9, DESIGN.md 3)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -269,7 +305,12 @@ def main():
                        "grid_ctas": s1["grid_ctas"], "block_threads": s1["block_threads"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / args.steps, "launches_per_step": e2e_launches},
-            "gpu_launches": 2 * args.steps, "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            # per step: KLT pyramid (1 level-0 + 4 pyrDown + 5 Scharr) + 1 track kernel, 2 LM kernels
+            "gpu_launches": (11 + 2) * args.steps, "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "klt": {"device_ms_per_step": klt_ms / args.steps, "points": 2000, "image": "640x480",
+                    "kernels_per_step": 11},
+            "without_klt": {"value": world * args.steps / (dev_opt_ms_max * 1e-3),
+                            "e2e_value": world * args.steps / (e2e_opt_ms_max * 1e-3), "unit": UNIT},
             "lm_iterations_per_step": s0["lm_iterations"] + s1["lm_iterations"],
             "pcg_iterations_per_step": s0["pcg_iterations"] + s1["pcg_iterations"],
             "roofline": roofline, "clocks": clocks}
@@ -309,9 +350,12 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
         orc = oracle_lib.Oracle()
+        oklt = oracle_lib.OracleKLT()
+        oklt.set_reference(im["ref"], im["pts"])
         n_frames = 0
         t0 = time.perf_counter()
         while n_frames < 3 or (time.perf_counter() - t0 < 10.0 and n_frames < 20):
+            oklt.track(im["cur"], im["pts"], im["status"])
             a0 = orc.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
             orc.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
                             p["graph"].copy(), p["scale"], a0["pose"], p["last_world_position"])
@@ -324,6 +368,7 @@ def main():
                                 "host_cores_available": len(os.sched_getaffinity(0))}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    klt.close()
     core.close()
     if dist is not None:
         dist.destroy_process_group()
