@@ -210,7 +210,8 @@ def main():
     opt.device = local_rank
     core = api.Core(opt)
     # every rank tracks its own stream: a different seeded frame of the same shape (replicas, weak scaling)
-    p = synth.tracking_problem("c2", seed=1235 + rank)
+    from nrslam_b200 import dist as nrs_dist
+    p = synth.tracking_problem("c2", seed=nrs_dist.stream_seed(1235, rank))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     im = synth.klt_pair(seed=77 + rank, n_points=2000)
