@@ -551,6 +551,7 @@ void nrslam_b200_default_options(nrslam_b200_options* o) {
   o->lm_max_trials = 10;
   o->lm_tau = 1e-5;
   o->pcg_rel_tol = 1e-8;
+  if (const char* e = getenv("NRSLAM_B200_PCG_TOL")) o->pcg_rel_tol = atof(e);  // experiments only
   o->pcg_max_iterations = 2000;
   const char* lr = getenv("LOCAL_RANK");
   o->device = lr ? atoi(lr) : 0;
