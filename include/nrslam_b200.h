@@ -228,6 +228,22 @@ int nrslam_b200_klt_retrack(nrslam_b200_klt* klt, float* gpu_ms_out);
 int nrslam_b200_klt_debug_level(nrslam_b200_klt* klt, int32_t which, int32_t level, uint8_t* img_out,
                                 int16_t* deriv_out, int32_t* w_out, int32_t* h_out);
 
+/* ---- ShiTomasi (features/shi_tomasi.h:30-60, features/feature.h:34 Feature::Extract) ------------------------
+ * One extractor object carries the running class-id counter (shi_tomasi.cc:81). extract(): 8-bit image; existing_xy
+ * = keypoints already in the frame (their rounded pixel is excluded with a 15-px window, :89-99); out: the NEW
+ * keypoints in raster order (x, y as floats, octave size 1) with consecutive class ids. n_out = number found (may
+ * exceed capacity: only `capacity` are written, the counter advances by n_out like the reference's). Scores within
+ * 4 rows / 1 column of the image border are defined as 0 (the reference leaves row-rotation artefacts there,
+ * DESIGN.md 7b). */
+typedef struct nrslam_b200_shi nrslam_b200_shi;
+int nrslam_b200_shi_create(nrslam_b200_ctx* ctx, int32_t nms_window, nrslam_b200_shi** out);
+void nrslam_b200_shi_destroy(nrslam_b200_shi* shi);
+int nrslam_b200_shi_extract(nrslam_b200_shi* shi, const uint8_t* image, int32_t width, int32_t height, int32_t pitch,
+                            const float* existing_xy, int32_t n_existing, float* out_xy, int32_t* out_class_id,
+                            int32_t capacity, int32_t* n_out);
+/* Diagnostics: the score map of the last extract (height x width floats, -1 marks included). */
+int nrslam_b200_shi_debug_scores(nrslam_b200_shi* shi, float* scores_out);
+
 #ifdef __cplusplus
 }
 #endif

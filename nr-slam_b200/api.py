@@ -259,3 +259,105 @@ class KLT:
                                                        ptr(der, C.c_int16), C.byref(ow), C.byref(oh)))
         assert (ow.value, oh.value) == (w, h)
         return img, der
+
+
+def project_points(cam, pose, X):
+    """CameraModel::Project of world points through a Sophus::SE3f pose, in fp32 like the reference
+    (tracking.cc:401-407: `CameraTransformationWorld() * landmark` then `calibration_->Project`)."""
+    pose = np.asarray(pose, np.float32)
+    q, t = pose[:4], pose[4:]
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], np.float32)
+    Pc = (np.asarray(X, np.float32) @ R.T + t).astype(np.float32)
+    p = np.array(cam.params[:], np.float32)
+    if cam.model == 0:
+        uv = np.stack([p[0] * Pc[:, 0] / Pc[:, 2] + p[2], p[1] * Pc[:, 1] / Pc[:, 2] + p[3]], 1)
+    else:
+        r2 = Pc[:, 0] * Pc[:, 0] + Pc[:, 1] * Pc[:, 1]
+        th = np.arctan2(np.sqrt(r2), Pc[:, 2]).astype(np.float32)
+        psi = np.arctan2(Pc[:, 1], Pc[:, 0]).astype(np.float32)
+        t2 = th * th
+        r = th + p[4] * th * t2 + p[5] * th * t2 * t2 + p[6] * th * t2 * t2 * t2 + p[7] * th * t2 * t2 * t2 * t2
+        uv = np.stack([p[0] * r * np.cos(psi) + p[2], p[1] * r * np.sin(psi) + p[3]], 1)
+    return uv.astype(np.float32), Pc
+
+
+def point_reuse(make_klt, cam, pose, image, X_world, patches, in_frame, klt_max_iters=10, klt_eps=1e-4,
+                klt_min_eig=1e-4):
+    """Tracking::PointReuse (modules/tracking/tracking.cc:394-506) as a composition of the C-ABI pieces: project the
+    map points that are not in the frame, keep those inside the image with positive depth, track them with a fresh
+    2-level KLT fed from their stored patches (InsertPhotometricInformation, initial flow = projection, SSIM 0.75) and
+    gate by the squared reprojection error (> 5.99 rejected). `make_klt(max_level, max_iters, eps, min_eig)` builds the
+    tracker (api.KLT on the GPU, OracleKLT in the tests); `patches[i]` is the map point's PhotometricInformation
+    (levels 0..1 are used). Returns the candidate indices, their tracked keypoints and the accepted mask."""
+    from .abi import TRACKED_WITH_3D
+    h, w = image.shape
+    uv, Pc = project_points(cam, pose, X_world)
+    cand = [i for i in range(len(X_world))
+            if not in_frame[i] and Pc[i, 2] >= 0 and 0 <= uv[i, 0] < w and 0 <= uv[i, 1] < h]
+    if not cand:
+        return np.zeros(0, np.int64), np.zeros((0, 2), np.float32), np.zeros(0, bool)
+    klt = make_klt(1, klt_max_iters, klt_eps, klt_min_eig)
+    for i in cand:
+        pt = patches[i]
+        klt.insert_patch(uv[i, 0], uv[i, 1], dict(gray=np.ascontiguousarray(pt["gray"][:2]),
+                                                   grad=np.ascontiguousarray(pt["grad"][:2]),
+                                                   mean=np.ascontiguousarray(pt["mean"][:2]),
+                                                   mean2=np.ascontiguousarray(pt["mean2"][:2]),
+                                                   valid=np.ascontiguousarray(pt["valid"][:2])))
+    seeds = uv[cand]
+    r = klt.track(image, seeds, np.full(len(cand), TRACKED_WITH_3D, np.uint8), use_initial_flow=True, min_ssim=0.75)
+    klt.close()
+    d = r["pts"] - seeds                     # SquaredReprojectionError(projected_landmark, keypoint.pt)
+    err2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
+    accepted = (r["status"] == TRACKED_WITH_3D) & ~(err2 > np.float32(5.99))
+    return np.array(cand, np.int64), r["pts"], accepted
+
+
+class ShiTomasi:
+    """ShiTomasi feature extractor (modules/features/shi_tomasi.h:30-60; Feature::Extract, features/feature.h:34)."""
+
+    def __init__(self, core, nms_window=7):
+        self.core = core
+        self.L = core.L
+        self._h = C.c_void_p()
+        rc = self.L.nrslam_b200_shi_create(core._ctx, int(nms_window), C.byref(self._h))
+        if rc != 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
+        import weakref
+        core._children.append(weakref.ref(self))
+        self._shape = None
+
+    def close(self):
+        if self._h:
+            if self.core._ctx:
+                self.L.nrslam_b200_shi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, image, existing=None, capacity=20000, want_scores=False):
+        """Returns the NEW keypoints (raster order) and their class ids, like ShiTomasi::Extract appends them."""
+        image = np.ascontiguousarray(image, np.uint8)
+        ex = np.zeros((0, 2), np.float32) if existing is None else _f32(existing)
+        xy = np.zeros((capacity, 2), np.float32)
+        ids = np.zeros(capacity, np.int32)
+        n = C.c_int32(0)
+        rc = self.L.nrslam_b200_shi_extract(self._h, ptr(image, C.c_uint8), image.shape[1], image.shape[0],
+                                            image.strides[0], ptr(ex, C.c_float), len(ex), ptr(xy, C.c_float),
+                                            ptr(ids, C.c_int32), capacity, C.byref(n))
+        if rc < 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(self.core._ctx) or b"").decode())
+        m = min(n.value, capacity)
+        out = dict(n=n.value, xy=xy[:m].copy(), ids=ids[:m].copy(), scores=None)
+        if want_scores:
+            sc = np.zeros(image.shape, np.float32)
+            self.L.nrslam_b200_shi_debug_scores(self._h, ptr(sc, C.c_float))
+            out["scores"] = sc
+        return out

@@ -684,8 +684,12 @@ int nrslam_b200_klt_track(nrslam_b200_klt* k, const uint8_t* image, int32_t widt
   if (!k || !image || !pts_io || !status_io || pitch < width)
     return kfail(k, NRSLAM_B200_ERR_ARG, "klt_track: bad argument");
   if (n_points != k->n) return kfail(k, NRSLAM_B200_ERR_ARG, "klt_track: point count differs from the reference set");
-  if (width != k->w || height != k->h) return kfail(k, NRSLAM_B200_ERR_ARG, "klt_track: image size differs from the reference image");
   KLT_CUDA(k, cudaSetDevice(k->ctx->device));
+  if (k->w == 0) {  // a tracker fed only through InsertPhotometricInformation (Tracking::PointReuse, tracking.cc:421-447)
+    const int rc0 = ensure_image(k, width, height);
+    if (rc0) return rc0;
+  }
+  if (width != k->w || height != k->h) return kfail(k, NRSLAM_B200_ERR_ARG, "klt_track: image size differs from the reference image");
   if (n_tracked_out) *n_tracked_out = 0;
   int rc = build_pyramid(k, k->cur, image, pitch);
   if (rc) return rc;

@@ -185,3 +185,36 @@ def klt_pyramid(image, win, max_level, level):
                               ptr(der, C.c_int16), C.byref(ow), C.byref(oh))
     assert n > level and (ow.value, oh.value) == (lw, lh)
     return img, der
+
+
+class OracleShiTomasi:
+    """ShiTomasi restatement (oracle/orc_shi.cc). literal=True simulates the reference's border behaviour, False is the
+    clean definition the CUDA kernel implements."""
+
+    def __init__(self, nms_window=7):
+        self.L = lib()
+        self.L.orc_shi_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.orc_shi_create(int(nms_window)))
+
+    def close(self):
+        if self.h:
+            self.L.orc_shi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, image, existing=None, literal=False, capacity=20000, want_scores=False):
+        image = np.ascontiguousarray(image, np.uint8)
+        ex = np.zeros((0, 2), np.float32) if existing is None else np.ascontiguousarray(existing, np.float32)
+        xy = np.zeros((capacity, 2), np.float32)
+        ids = np.zeros(capacity, np.int32)
+        sc = np.zeros(image.shape, np.float32) if want_scores else None
+        n = self.L.orc_shi_extract(self.h, ptr(image, C.c_uint8), image.shape[1], image.shape[0], image.strides[0],
+                                   ptr(ex, C.c_float), len(ex), int(literal), ptr(xy, C.c_float), ptr(ids, C.c_int32),
+                                   capacity, ptr(sc, C.c_float))
+        assert 0 <= n <= capacity
+        return dict(n=n, xy=xy[:n].copy(), ids=ids[:n].copy(), scores=sc)
