@@ -134,6 +134,7 @@ struct Engine {
   double *s_pose, *s_pose_bak, *s_H, *s_M, *s_bp, *s_xp, *s_rp, *s_zp, *s_pp, *s_qp, *s_red, *s_scal;
   double *s_jac, *s_x, *s_r, *s_p, *s_q, *s_z, *s_minv, *s_coef;  // resident chunk state
   double* s_pr;             // per-row pose partials of the CG matvec (6 per row)
+  double* s_gather;         // [2][16][8] reduction values PUSHED here by every CTA of the cluster (cluster-native CG)
   double* s_rowA;           // per-row pose-block records of the linearisation (16 per row)
   const double** s_zptr;    // per incidence: where the neighbour's z lives (shared memory or L2)
   float* s_rf;              // residual as fp32 for the block preconditioner
@@ -164,6 +165,7 @@ struct Engine {
     s_red = sm;             sm += 32 * kChunkVals;
     s_scal = sm;            sm += 32;
     s_pr = sm;              sm += 6 * kMaxRows;
+    s_gather = sm;          sm += 2 * 16 * 8;
     s_flag = reinterpret_cast<int*>(sm);  sm += 2;
     sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));  // double2 accesses below
     // the pose-block records of the linearisation and the Jacobian cache of the CG loop are never live together
@@ -1376,6 +1378,17 @@ struct Engine {
     // slots (shared memory, double-buffered): [par][8]; broadcast scalars s_bc[4]
     double* s_slot = s_scal + 8;  // 16 doubles
     double* s_bc = s_scal + 24;   // alpha / beta / flags
+    const int my_rank = blockIdx.x;
+    // Exchange by PUSH: warp 0 stores this CTA's values into every CTA's gather buffer (remote stores are fire and
+    // forget); after the cluster barrier everybody sums its LOCAL copy. Remote LOADS after the barrier cost a DSMEM
+    // round trip on the critical path and contend for the owner's shared-memory port.
+    auto push = [&](int buf, int k0, int nk) {  // called by warp 0 after its values sit in s_slot[k0 .. k0 + nk)
+      __syncwarp();
+      if (lane < G) {
+        double* dst = cluster.map_shared_rank(s_gather, lane) + (size_t)(buf * 16 + my_rank) * 8;
+        for (int k = 0; k < nk; k++) dst[k0 + k] = s_slot[k0 + k];
+      }
+    };
     // ---- reduction helper pieces are inlined below; initial r.z
     {
 #pragma unroll
@@ -1387,12 +1400,13 @@ struct Engine {
         for (int w = lane; w < nw; w += 32) t += s_red[w];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        if (lane == 0) s_slot[15] = t;
+        if (lane == 0) s_slot[7] = t;
+        push(1, 7, 1);
       }
       barrier();
       if (warp == 0) {
         double t = 0;
-        if (lane < G) t = cluster.map_shared_rank(s_slot, lane)[15];
+        if (lane < G) t = s_gather[(size_t)(1 * 16 + lane) * 8 + 7];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
         double rzp = 0;
@@ -1428,9 +1442,9 @@ struct Engine {
     }
     for (; it < P.pcg_max_iter; it++) {
       const bool first = (it == 0);
-      // four slot buffers: phase 1 of even / odd iterations [0..6] / [8..14], phase 2 [7] / [15]; a buffer is
-      // rewritten only after two further cluster barriers, when every reader has moved on
-      const int par = (it & 1) ? 8 : 0;
+      // two gather buffers (iteration parity): entries [0..6] carry phase 1, [7] phase 2; a buffer is rewritten only
+      // after two further cluster barriers, when every reader has moved on
+      const int par = it & 1;
       // ---- phase 1: w = (H + lambda I) z ; p = z + beta p ; q = w + beta q ; partial p.q
       const long long tm0 = clock64();
       double pq_part = 0;
@@ -1542,7 +1556,7 @@ struct Engine {
         for (int w = lane; w < nw; w += 32) t += s_red[w];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        if (lane == 0) s_slot[par] = t;
+        if (lane == 0) s_slot[0] = t;
         if (pos) {
           // pose partials: lane = a + 6 g (g < 5): rows g, g + 5, ...; then the 5 groups per a in order
           double v = 0;
@@ -1552,13 +1566,14 @@ struct Engine {
           }
           const double v1 = __shfl_down_sync(0xffffffffu, v, 6), v2 = __shfl_down_sync(0xffffffffu, v, 12),
                        v3 = __shfl_down_sync(0xffffffffu, v, 18), v4 = __shfl_down_sync(0xffffffffu, v, 24);
-          if (lane < 6) s_slot[par + 1 + lane] = (((v + v1) + v2) + v3) + v4;
+          if (lane < 6) s_slot[1 + lane] = (((v + v1) + v2) + v3) + v4;
         }
+        push(par, 0, pos ? 7 : 1);
       }
       const long long tm1 = clock64();
       barrier();  // B1
       if (warp == 0) {
-        const double* rs = cluster.map_shared_rank(s_slot, lane < G ? lane : 0) + par;
+        const double* rs = s_gather + (size_t)(par * 16 + (lane < G ? lane : 0)) * 8;
         double t[7];
 #pragma unroll
         for (int k = 0; k < 7; k++) t[k] = (lane < G && (k == 0 || pos)) ? rs[k] : 0.0;
@@ -1645,13 +1660,14 @@ struct Engine {
         for (int w = lane; w < nw; w += 32) t += s_red[w];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        if (lane == 0) s_slot[par + 7] = t;
+        if (lane == 0) s_slot[7] = t;
+        push(par, 7, 1);
       }
       const long long tm3 = clock64();
       barrier();  // B2
       if (warp == 0) {
         double t = 0;
-        if (lane < G) t = cluster.map_shared_rank(s_slot, lane)[par + 7];
+        if (lane < G) t = s_gather[(size_t)(par * 16 + lane) * 8 + 7];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
         double rzp = 0;
@@ -1904,7 +1920,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) nrs_lm_kernel(const __grid_const
 }  // namespace
 
 size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec) {
-  size_t d = (size_t)F * (7 + 7 + 21 + 36 + 6 * 6) + 32 * kChunkVals + 32 + 6 * kMaxRows + 2 + 6;  // + alignment slack
+  size_t d = (size_t)F * (7 + 7 + 21 + 36 + 6 * 6) + 32 * kChunkVals + 32 + 6 * kMaxRows + 2 * 16 * 8 + 2 + 6;  // + alignment slack
   if (res_rows == 0) d += 16 * kMaxRows;
   if (res_rows > 0) {
     d += std::max(20 * (size_t)res_rows, 16 * (size_t)kMaxRows) + (size_t)res_rows * (4 * 5 + (block_prec ? 0 : 8)) +
