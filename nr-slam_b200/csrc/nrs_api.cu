@@ -205,7 +205,48 @@ struct Plan {
   size_t smem = 0;
   std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr;
   const int *d_chunk_kf = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_kf_chunk_ptr = nullptr;
+  // halo push lists of the cluster-native CG loop (built when the plan qualifies for it)
+  int halo_rows = 0;
+  std::vector<int> inc_halo, push_ptr, push_row, push_dst;
+  const int *d_inc_halo = nullptr, *d_push_ptr = nullptr, *d_push_row = nullptr, *d_push_dst = nullptr;
 };
+
+// For every chunk: the out-of-chunk rows its incidences read (its halo) and, for every owner chunk, which rows to push
+// where. Deterministic (sorted) so that runs are reproducible.
+void build_halo(Plan& pl, const std::vector<int>& inc_ptr, const std::vector<int>& inc_other) {
+  const int nc = pl.n_chunks;
+  pl.inc_halo.assign(inc_other.size(), -1);
+  std::vector<int> chunk_of(pl.V, 0);
+  for (int c = 0; c < nc; c++)
+    for (int i = pl.chunk_begin[c]; i < pl.chunk_end[c]; i++) chunk_of[i] = c;
+  std::vector<std::vector<std::pair<int, int>>> pushes(nc);  // owner -> (row, target * 65536 + slot)
+  pl.halo_rows = 0;
+  for (int c = 0; c < nc; c++) {
+    std::vector<int> rows;
+    for (int a = inc_ptr[pl.chunk_begin[c]]; a < inc_ptr[pl.chunk_end[c]]; a++) {
+      const int o = inc_other[a];
+      if (o < pl.chunk_begin[c] || o >= pl.chunk_end[c]) rows.push_back(o);
+    }
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    pl.halo_rows = std::max(pl.halo_rows, (int)rows.size());
+    for (int a = inc_ptr[pl.chunk_begin[c]]; a < inc_ptr[pl.chunk_end[c]]; a++) {
+      const int o = inc_other[a];
+      if (o < pl.chunk_begin[c] || o >= pl.chunk_end[c])
+        pl.inc_halo[a] = (int)(std::lower_bound(rows.begin(), rows.end(), o) - rows.begin());
+    }
+    for (size_t k = 0; k < rows.size(); k++) pushes[chunk_of[rows[k]]].emplace_back(rows[k], c * 65536 + (int)k);
+  }
+  pl.push_ptr.assign(nc + 1, 0);
+  for (int c = 0; c < nc; c++) {
+    std::sort(pushes[c].begin(), pushes[c].end());
+    pl.push_ptr[c + 1] = pl.push_ptr[c] + (int)pushes[c].size();
+    for (auto& pr : pushes[c]) {
+      pl.push_row.push_back(pr.first);
+      pl.push_dst.push_back(pr.second);
+    }
+  }
+}
 
 // The path is bound by synchronisation latency: prefer ONE thread-block cluster (hardware barrier) whenever the
 // rows fit a cluster's threads; otherwise a cooperative grid with the atomics barrier.
@@ -304,6 +345,8 @@ void apply_plan(Params& p, const Plan& pl) {
   p.block_prec = pl.block_prec;
   p.chunk_kf = pl.d_chunk_kf; p.chunk_begin = pl.d_chunk_begin; p.chunk_end = pl.d_chunk_end;
   p.kf_chunk_ptr = pl.d_kf_chunk_ptr;
+  p.halo_rows = pl.halo_rows; p.inc_halo = pl.d_inc_halo; p.push_ptr = pl.d_push_ptr; p.push_row = pl.d_push_row;
+  p.push_dst = pl.d_push_dst;
 }
 
 int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
@@ -354,6 +397,18 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   }
   const int n_chunks = planA.n_chunks;
   const int max_chunks = std::max(planA.n_chunks, planB.n_chunks), max_grid_used = std::max(planA.grid, planB.grid);
+  for (Plan* pl : {&planA, &planB}) {
+    // the cluster-native CG loop (nrs_engine.cu: pcg_cluster) exchanges z through pushed halos
+    if (pl->n_chunks == 0 || !pl->cluster_mode || !pl->resident || F != 1 || D != 0 || hp.points_fixed) continue;
+    if (!env_int("NRSLAM_B200_HALO_PUSH", 1) || pl->n_chunks >= 65536) continue;
+    build_halo(*pl, inc_ptr, inc_other);
+    const size_t extra = 4 * sizeof(double) * (size_t)pl->halo_rows;
+    if (pl->halo_rows >= 65536 || pl->smem + extra > 224 * 1024) {
+      pl->halo_rows = 0;  // does not fit: pull through distributed shared memory
+      continue;
+    }
+    pl->smem += extra;
+  }
 
   // ---- input arena
   size_t need = 0;
@@ -364,6 +419,9 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   sz(4 * (size_t)D * 4); sz((size_t)D * 8); sz(((size_t)V + 1) * 4); sz(4 * (size_t)D * 4);
   sz(((size_t)V + 1) * 4); sz((size_t)U * 8); sz((size_t)U * 4); sz((size_t)V);
   sz((size_t)max_chunks * 4 * 3 * 2); sz(((size_t)F + 1) * 4 * 2);
+  for (Plan* pl : {&planA, &planB}) {
+    sz(pl->inc_halo.size() * 4); sz(pl->push_ptr.size() * 4); sz(pl->push_row.size() * 4); sz(pl->push_dst.size() * 4);
+  }
   need += 8192;
   if (!st.in.reserve(need, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "input arena allocation failed");
   Arena& in = st.in;
@@ -416,6 +474,12 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     pl->d_chunk_begin = in.d<int>(put(in, pl->chunk_begin));
     pl->d_chunk_end = in.d<int>(put(in, pl->chunk_end));
     pl->d_kf_chunk_ptr = in.d<int>(put(in, pl->kf_chunk_ptr));
+    if (pl->halo_rows > 0) {
+      pl->d_inc_halo = in.d<int>(put(in, pl->inc_halo));
+      pl->d_push_ptr = in.d<int>(put(in, pl->push_ptr));
+      pl->d_push_row = in.d<int>(put(in, pl->push_row));
+      pl->d_push_dst = in.d<int>(put(in, pl->push_dst));
+    }
   }
   apply_plan(p, planA);
   st.h2d_bytes = in.used();

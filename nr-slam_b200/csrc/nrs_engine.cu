@@ -138,6 +138,7 @@ struct Engine {
   double* s_rowA;           // per-row pose-block records of the linearisation (16 per row)
   const double** s_zptr;    // per incidence: where the neighbour's z lives (shared memory or L2)
   float* s_rf;              // residual as fp32 for the block preconditioner
+  double* s_halo;           // z of the out-of-chunk neighbours, pushed by their owners (4 doubles per halo row)
   float* s_binv;  // dense block inverses (fp32, symmetric): a preconditioner need not be exact
   int* s_oth;
   int* s_flag;
@@ -186,12 +187,14 @@ struct Engine {
       sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));
       s_rf = reinterpret_cast<float*>(sm);  sm += (3 * (size_t)R + 1) / 2;
       sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));
+      s_halo = sm;          sm += 4 * (size_t)p.halo_rows;
       s_binv = reinterpret_cast<float*>(sm);
     } else {
       s_jac = s_x = s_r = s_p = s_q = s_z = s_minv = s_coef = nullptr;
       s_zptr = nullptr;
       s_oth = nullptr;
       s_rf = nullptr;
+      s_halo = nullptr;
       s_binv = nullptr;
     }
     gen = 0;
@@ -1301,6 +1304,8 @@ struct Engine {
       const int other = P.inc_other[a];
       if (other >= rb && other < re) {
         s_zptr[a - ab] = s_z + 4 * (size_t)(other - rb);
+      } else if (P.halo_rows > 0) {
+        s_zptr[a - ab] = s_halo + 4 * (size_t)P.inc_halo[a];
       } else {
         // owning chunk == owning CTA: binary search over the chunk starts, then map its s_z into this CTA's view
         int lo = 0, hi = P.n_chunks - 1;
@@ -1389,12 +1394,25 @@ struct Engine {
         for (int k = 0; k < nk; k++) dst[k0 + k] = s_slot[k0 + k];
       }
     };
+    // halo push: every thread takes entries of this chunk's push list (row -> target chunk, slot)
+    const int hp0 = P.halo_rows > 0 ? P.push_ptr[c0] : 0, hp1 = P.halo_rows > 0 ? P.push_ptr[c0 + 1] : 0;
+    auto push_halo = [&]() {  // after a CTA barrier that follows the z update
+      for (int e = hp0 + tid; e < hp1; e += nthr) {
+        const int row = P.push_row[e], dst = P.push_dst[e];
+        double* h = cluster.map_shared_rank(s_halo, dst >> 16) + 4 * (size_t)(dst & 65535);
+        const V3 z = ld3p(s_z, row - rb);
+        h[0] = z.x;
+        h[1] = z.y;
+        h[2] = z.z;
+      }
+    };
     // ---- reduction helper pieces are inlined below; initial r.z
     {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) rz_part += __shfl_xor_sync(0xffffffffu, rz_part, off);
       if (lane == 0) s_red[warp] = rz_part;
       __syncthreads();
+      push_halo();
       if (warp == 0) {
         double t = 0;
         for (int w = lane; w < nw; w += 32) t += s_red[w];
@@ -1655,6 +1673,7 @@ struct Engine {
       for (int off = 16; off > 0; off >>= 1) rzn_part += __shfl_xor_sync(0xffffffffu, rzn_part, off);
       if (lane == 0) s_red[warp] = rzn_part;
       __syncthreads();  // S4
+      push_halo();
       if (warp == 0) {
         double t = 0;
         for (int w = lane; w < nw; w += 32) t += s_red[w];

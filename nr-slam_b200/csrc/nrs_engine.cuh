@@ -73,6 +73,13 @@ struct Params {
   int res_inc;        // shared-memory capacity: pair incidences per chunk
   int block_prec;     // 1: dense kPrecBlock-row block-Jacobi preconditioner (resident mode only), else 3x3 blocks
   int no_dsmem;       // 1: keep the general CG loop (exchange through L2) even where the cluster-native loop applies
+  // halo exchange of the cluster-native CG loop: after every z = M^-1 r the owner of a row PUSHES it into the halo
+  // buffer of every chunk whose regulariser edges read it (remote shared-memory stores, no remote loads)
+  int halo_rows;            // shared-memory capacity: halo rows per chunk (0: pull through distributed shared memory)
+  const int* inc_halo;      // [2P] per incidence: halo slot of the neighbour in this chunk's buffer, -1 if in-chunk
+  const int* push_ptr;      // [n_chunks + 1]
+  const int* push_row;      // row (global index) to push
+  const int* push_dst;      // target chunk * 65536 + slot
 
   // poses: 7 doubles each (q xyzw, t)
   double* pose;

@@ -1,0 +1,95 @@
+"""Edge cases of the C ABI on the GPU: empty / tiny / ragged inputs, argument errors, problems without regulariser
+edges — each against the oracle where it computes, and against the documented error convention where it does not."""
+import numpy as np
+import pytest
+
+from nrslam_b200 import abi, api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_inputs_return_too_few_and_leave_outputs_alone(core):
+    p = synth.tracking_problem("c1", n=50)
+    z2, z3 = np.zeros((0, 2), np.float32), np.zeros((0, 3), np.float32)
+    r = core.pose_only(p["cam"], z2, z3, p["seed_pose"])
+    assert r["rc"] == 1 and np.array_equal(r["pose"], p["seed_pose"])
+    g = p["graph"].copy()
+    r = core.pose_deform(p["cam"], z2, z3, np.zeros(0, np.int32), p["vertex_frame_status"], g, p["scale"],
+                         p["seed_pose"], p["last_world_position"])
+    assert r["rc"] == 1 and np.array_equal(r["pose"], p["seed_pose"]) and len(r["lost"]) == 0
+    assert np.array_equal(g.weight, p["graph"].weight) and np.array_equal(g.status, p["graph"].status)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 33])
+def test_tiny_pose_only(core, oracle, n):
+    p = synth.tracking_problem("c1", n=40, outlier_frac=0.0)
+    uv, X = p["uv"][:n], p["X_rest"][:n]
+    a = oracle.pose_only(p["cam"], uv, X, p["seed_pose"])
+    b = core.pose_only(p["cam"], uv, X, p["seed_pose"])
+    assert a["rc"] == b["rc"]
+    if n >= 7:   # with fewer than 3 points the 6x6 system is singular up to lambda: compare well-posed sizes only
+        assert np.abs(a["pose"] - b["pose"]).max() < 2e-5
+        assert np.array_equal(a["inliers"], b["inliers"])
+    assert np.isfinite(b["pose"]).all()
+
+
+def test_pose_deform_without_regulariser_edges(core, oracle):
+    """Isolated points (empty graph rows): every deformation vertex is constrained by its reprojection edge only."""
+    p = synth.tracking_problem("c1", n=120, extra_frac=0.0)
+    g = p["graph"]
+    empty = abi.GraphArrays(np.zeros(g.n_vertices + 1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                            np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32),
+                            np.zeros(0, np.float32), np.zeros(0, np.uint8), g.weight_sigma)
+    args = (p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"])
+    a = oracle.pose_deform(*args, empty.copy(), p["scale"], p["seed_pose"], p["last_world_position"])
+    b = core.pose_deform(*args, empty.copy(), p["scale"], p["seed_pose"], p["last_world_position"])
+    assert a["stats"]["n_pair_edges"] == b["stats"]["n_pair_edges"] == 0
+    assert np.abs(a["pose"] - b["pose"]).max() < 2e-6
+    assert np.abs(a["deformation"] - b["deformation"]).max() < 2e-5
+    assert np.array_equal(a["status"], b["status"]) and len(b["lost"]) == 0
+
+
+def test_argument_errors(core):
+    p = synth.tracking_problem("c1", n=40)
+    bad = p["point_vertex"].copy()
+    bad[3] = p["graph"].n_vertices + 5
+    with pytest.raises(api.NrslamError) as e:
+        core.pose_deform(p["cam"], p["uv"], p["X_rest"], bad, p["vertex_frame_status"], p["graph"].copy(), p["scale"],
+                         p["seed_pose"], p["last_world_position"])
+    assert e.value.code == -3
+    q = synth.ba_problem("c1", n=60)
+    shuffled = q["obs_kf"][::-1].copy()     # observations must be grouped by keyframe slot
+    with pytest.raises(api.NrslamError) as e:
+        core.local_ba(q["cam"], q["kf_pose"], shuffled, q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
+    assert e.value.code == -3
+
+
+def test_ragged_keyframes(core, oracle):
+    """Keyframes with very different numbers of observations, one of them nearly empty."""
+    q = synth.ba_problem("c1", n=240, n_kf=5, run=3)
+    keep = np.ones(len(q["obs_kf"]), bool)
+    idx = np.nonzero(q["obs_kf"] == 2)[0]
+    keep[idx[3:]] = False                    # keyframe 2 keeps 3 observations
+    args = (q["cam"], q["kf_pose"], q["obs_kf"][keep], q["obs_vertex"][keep], q["uv"][keep], q["X"][keep], q["graph"],
+            q["scale"])
+    a = oracle.local_ba(*args)
+    b = core.local_ba(*args)
+    assert a["stats"]["n_spring_edges"] == b["stats"]["n_spring_edges"]
+    assert a["stats"]["n_damper_edges"] == b["stats"]["n_damper_edges"]
+    assert np.abs(a["kf_pose"] - b["kf_pose"]).max() < 2e-6 and np.abs(a["X"] - b["X"]).max() < 2e-5
+
+
+def test_full_size_c4_ba_properties(core):
+    """BASELINE configs[3] at full size: KannalaBrandt8 1440x1080, 20k landmarks / 100 keyframes / 200k observations.
+    Size-independent properties: the accepted chi2 never increases, poses stay unit quaternions, the result is finite
+    and reproducible."""
+    q = synth.ba_problem("c4")
+    args = (q["cam"], q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
+    b = core.local_ba(*args)
+    tr = np.array(b["stats"]["chi2_trace"])
+    assert len(tr) == 5 and np.all(np.diff(tr) <= 0)
+    assert b["stats"]["n_reproj_edges"] == len(q["obs_kf"]) >= 190000
+    assert np.allclose(np.linalg.norm(b["kf_pose"][:, :4], axis=1), 1.0, atol=1e-6)
+    assert np.isfinite(b["X"]).all()
+    b2 = core.local_ba(*args)
+    assert np.array_equal(b["X"], b2["X"]) and np.array_equal(b["kf_pose"], b2["kf_pose"])
