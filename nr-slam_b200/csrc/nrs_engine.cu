@@ -1389,9 +1389,10 @@ struct Engine {
     // round trip on the critical path and contend for the owner's shared-memory port.
     auto push = [&](int buf, int k0, int nk) {  // called by warp 0 after its values sit in s_slot[k0 .. k0 + nk)
       __syncwarp();
-      if (lane < G) {
-        double* dst = cluster.map_shared_rank(s_gather, lane) + (size_t)(buf * 16 + my_rank) * 8;
-        for (int k = 0; k < nk; k++) dst[k0 + k] = s_slot[k0 + k];
+      const int target = lane & 15, half = lane >> 4;  // two lanes per target CTA share the values
+      if (target < G) {
+        double* dst = cluster.map_shared_rank(s_gather, target) + (size_t)(buf * 16 + my_rank) * 8;
+        for (int k = half; k < nk; k += 2) dst[k0 + k] = s_slot[k0 + k];
       }
     };
     // halo push: every thread takes entries of this chunk's push list (row -> target chunk, slot)
@@ -1467,6 +1468,7 @@ struct Engine {
       const long long tm0 = clock64();
       double pq_part = 0;
       double w0 = 0, w1 = 0, w2 = 0;
+      double redw[6] = {0, 0, 0, 0, 0, 0};  // this row's pose partial (lane 0 of the row's lane group)
       V3 zi{0, 0, 0};
       if (valid) {
         zi = ld3p(s_z, li);
@@ -1562,34 +1564,44 @@ struct Engine {
         }
         if (pos) {
 #pragma unroll
-          for (int a = 0; a < 6; a++) s_pr[6 * li + a] = red[a];
+          for (int a = 0; a < 6; a++) redw[a] = red[a];
+        }
+      }
+      if (pos) {
+        // pose partials: every warp reduces its own rows by shuffle (lanes that own no row carry zeros); warp 0 only
+        // adds the per-warp sums after the barrier — keeps the serial section in front of the cluster barrier short
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+          for (int off = 16; off >= kTPR; off >>= 1) redw[a] += __shfl_xor_sync(0xffffffffu, redw[a], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) s_red[32 + 6 * warp + a] = redw[a];
         }
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) pq_part += __shfl_xor_sync(0xffffffffu, pq_part, off);
       if (lane == 0) s_red[warp] = pq_part;
+      const long long tq0 = clock64();
       __syncthreads();  // S1
+      const long long tq1 = clock64();
       if (warp == 0) {
         double t = 0;
         for (int w = lane; w < nw; w += 32) t += s_red[w];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
         if (lane == 0) s_slot[0] = t;
-        if (pos) {
-          // pose partials: lane = a + 6 g (g < 5): rows g, g + 5, ...; then the 5 groups per a in order
+        if (pos && lane < 6) {
           double v = 0;
-          if (lane < 30) {
-            const int a = lane % 6, g = lane / 6;
-            for (int r = g; r < nrows; r += 5) v += s_pr[6 * r + a];
-          }
-          const double v1 = __shfl_down_sync(0xffffffffu, v, 6), v2 = __shfl_down_sync(0xffffffffu, v, 12),
-                       v3 = __shfl_down_sync(0xffffffffu, v, 18), v4 = __shfl_down_sync(0xffffffffu, v, 24);
-          if (lane < 6) s_slot[1 + lane] = (((v + v1) + v2) + v3) + v4;
+          for (int w = 0; w < nw; w++) v += s_red[32 + 6 * w + lane];
+          s_slot[1 + lane] = v;
         }
         push(par, 0, pos ? 7 : 1);
       }
       const long long tm1 = clock64();
       barrier();  // B1
+      const long long tq2 = clock64();
       if (warp == 0) {
         const double* rs = s_gather + (size_t)(par * 16 + (lane < G ? lane : 0)) * 8;
         double t[7];
@@ -1661,6 +1673,7 @@ struct Engine {
         __syncthreads();  // S3 (pose r complete)
       } else {
         __syncthreads();  // S3 (rf and pose r complete)
+        const long long tq4 = clock64(); prof[11] += tq4 - tm2;  // phase 2a: x, r, rf + S3
         rzn_part = prec_apply_quads(rb, re, false);
       }
       if (pos && tid < 6) {
@@ -1673,6 +1686,7 @@ struct Engine {
       for (int off = 16; off > 0; off >>= 1) rzn_part += __shfl_xor_sync(0xffffffffu, rzn_part, off);
       if (lane == 0) s_red[warp] = rzn_part;
       __syncthreads();  // S4
+      const long long tq5 = clock64();
       push_halo();
       if (warp == 0) {
         double t = 0;
@@ -1684,6 +1698,7 @@ struct Engine {
       }
       const long long tm3 = clock64();
       barrier();  // B2
+      const long long tq6 = clock64();
       if (warp == 0) {
         double t = 0;
         if (lane < G) t = s_gather[(size_t)(par * 16 + lane) * 8 + 7];
@@ -1697,6 +1712,12 @@ struct Engine {
       __syncthreads();  // S5
       const long long tm4 = clock64();
       prof[1] += tm1 - tm0;  // matvec pass
+      prof[8] += tq0 - tm0;   // phase 1 row work up to the block reduction
+      prof[9] += tq1 - tq0;   // S1 wait
+      prof[10] += tm1 - tq1;  // warp 0: reduce + push (other warps: nothing)
+      prof[12] += tq2 - tm1;  // B1
+      prof[13] += tq5 - tm2;  // phase 2 up to S4 (incl. S3, prec apply)
+      prof[14] += tq6 - tm3;  // B2
       prof[2] += tm2 - tm1;  // pq exchange
       prof[3] += tm3 - tm2;  // update pass
       prof[4] += tm4 - tm3;  // rz exchange
