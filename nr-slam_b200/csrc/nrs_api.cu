@@ -402,9 +402,13 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     if (pl->n_chunks == 0 || !pl->cluster_mode || !pl->resident || F != 1 || D != 0 || hp.points_fixed) continue;
     if (!env_int("NRSLAM_B200_HALO_PUSH", 1) || pl->n_chunks >= 65536) continue;
     build_halo(*pl, inc_ptr, inc_other);
-    const size_t extra = 4 * sizeof(double) * (size_t)pl->halo_rows;
+    const size_t extra = sizeof(double) * (3 * (size_t)pl->halo_rows + 2);
     if (pl->halo_rows >= 65536 || pl->smem + extra > 224 * 1024) {
-      pl->halo_rows = 0;  // does not fit: pull through distributed shared memory
+      pl->halo_rows = 0;  // does not fit: the general CG loop (exchange through L2) runs instead
+      pl->inc_halo.clear();
+      pl->push_ptr.clear();
+      pl->push_row.clear();
+      pl->push_dst.clear();
       continue;
     }
     pl->smem += extra;
@@ -474,7 +478,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     pl->d_chunk_begin = in.d<int>(put(in, pl->chunk_begin));
     pl->d_chunk_end = in.d<int>(put(in, pl->chunk_end));
     pl->d_kf_chunk_ptr = in.d<int>(put(in, pl->kf_chunk_ptr));
-    if (pl->halo_rows > 0) {
+    if (!pl->push_ptr.empty()) {
       pl->d_inc_halo = in.d<int>(put(in, pl->inc_halo));
       pl->d_push_ptr = in.d<int>(put(in, pl->push_ptr));
       pl->d_push_row = in.d<int>(put(in, pl->push_row));

@@ -68,6 +68,19 @@ __device__ __forceinline__ V3 ld3p(const double* base, int i) {
   return V3{a.x, a.y, base[4 * (size_t)i + 2]};
 }
 
+// 3-double packed rows (shared-memory copies of z): a 32-byte row stride touches only half of the banks when lanes
+// gather random rows; 24-byte rows spread over all of them
+__device__ __forceinline__ V3 ld3s(const double* base, int i) {
+  const double* p = base + 3 * (size_t)i;
+  return V3{p[0], p[1], p[2]};
+}
+__device__ __forceinline__ void st3s(double* base, int i, const V3& v) {
+  double* p = base + 3 * (size_t)i;
+  p[0] = v.x;
+  p[1] = v.y;
+  p[2] = v.z;
+}
+
 __device__ __forceinline__ int sym6(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  // a <= c
 
 // Inverse of the SPD 6x6 (upper-packed H + lambda I) by Cholesky; out = full 36. Returns false if not SPD.
@@ -126,7 +139,9 @@ __device__ bool invert6(const double* Hu, double lambda, double* out) {
 #define NRS_SHARED(p) __builtin_assume(__isShared(p))
 constexpr int kPB = kPrecBlock;      // rows per dense preconditioner block
 constexpr int kPN = 3 * kPrecBlock;  // its dimension
+constexpr int kJS = 22;              // shared-memory stride of a Jacobian row (20 doubles + 2: spreads rows over the banks)
 constexpr int kPS = kPN + 4;         // padded row stride (floats): 16-byte aligned rows, conflict-free float4 row reads
+static_assert((kPN / 4) % kTPR == 0, "the lanes of a row split the float4 columns of the block preconditioner evenly");
 
 struct Engine {
   const Params& P;
@@ -174,12 +189,12 @@ struct Engine {
     if (!p.resident) sm += 16 * kMaxRows;
     if (p.resident) {
       const int R = p.res_rows, CI = p.res_inc;
-      s_jac = sm;           sm += (20 * (size_t)R > 16 * (size_t)kMaxRows) ? 20 * (size_t)R : 16 * (size_t)kMaxRows;
+      s_jac = sm;           sm += (kJS * (size_t)R > 16 * (size_t)kMaxRows) ? kJS * (size_t)R : 16 * (size_t)kMaxRows;
       s_x = sm;             sm += 4 * (size_t)R;
       s_r = sm;             sm += 4 * (size_t)R;
       s_p = sm;             sm += 4 * (size_t)R;
       s_q = sm;             sm += 4 * (size_t)R;
-      s_z = sm;             sm += 4 * (size_t)R;
+      s_z = sm;             sm += (3 * (size_t)R + 1) & ~(size_t)1;
       s_minv = sm;          if (!p.block_prec) sm += 8 * (size_t)R;
       s_coef = sm;          sm += 4 * (size_t)CI;
       s_zptr = reinterpret_cast<const double**>(sm);  sm += CI;
@@ -187,7 +202,7 @@ struct Engine {
       sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));
       s_rf = reinterpret_cast<float*>(sm);  sm += (3 * (size_t)R + 1) / 2;
       sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));
-      s_halo = sm;          sm += 4 * (size_t)p.halo_rows;
+      s_halo = sm;          sm += (3 * (size_t)p.halo_rows + 1) & ~(size_t)1;
       s_binv = reinterpret_cast<float*>(sm);
     } else {
       s_jac = s_x = s_r = s_p = s_q = s_z = s_minv = s_coef = nullptr;
@@ -777,29 +792,49 @@ struct Engine {
     NRS_SHARED(s_rf);
     NRS_SHARED(s_z);
     NRS_SHARED(s_r);
-    const int lr = tid / kTPR;
-    if (lr >= re - rb) return 0.0;
-    const int i = rb + lr;
-    if (P.pt_fixed && P.pt_fixed[i]) return 0.0;
-    const int bk = lr / kPB;
-    const float4* rf = reinterpret_cast<const float4*>(s_rf + (size_t)bk * kPN);
-    double part = 0;
-    for (int l = tid % kTPR; l < 3; l += kTPR) {
-      const float4* M =
-          reinterpret_cast<const float4*>(s_binv + (size_t)bk * kPN * kPS + (size_t)(3 * (lr % kPB) + l) * kPS);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int lr = tid / kTPR, l = tid % kTPR;
+    const bool act = lr < re - rb && !(P.pt_fixed && P.pt_fixed[rb + lr]);
+    // the lanes of a row split the 48 columns; every lane accumulates its slice of all three components (the residual
+    // slice is loaded once for the three rows of M), then the lane group adds up by shuffle
+    float acc[3] = {0.f, 0.f, 0.f};
+    if (act) {
+      const int bk = lr / kPB;
+      constexpr int kQ = kPN / 4 / kTPR;  // float4 columns per lane
+      const float4* rf = reinterpret_cast<const float4*>(s_rf + (size_t)bk * kPN) + l * kQ;
+      const float4* M0 =
+          reinterpret_cast<const float4*>(s_binv + (size_t)bk * kPN * kPS + (size_t)(3 * (lr % kPB)) * kPS) + l * kQ;
+      float4 rv[kQ];
 #pragma unroll
-      for (int j = 0; j < kPN / 4; j++) {
-        const float4 m = M[j], r = rf[j];
-        s0 = fmaf(m.x, r.x, s0);
-        s1 = fmaf(m.y, r.y, s1);
-        s2 = fmaf(m.z, r.z, s2);
-        s3 = fmaf(m.w, r.w, s3);
+      for (int j = 0; j < kQ; j++) rv[j] = rf[j];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4* M = M0 + (size_t)c * (kPS / 4);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kQ; j++) {
+          const float4 m = M[j];
+          s0 = fmaf(m.x, rv[j].x, s0);
+          s1 = fmaf(m.y, rv[j].y, s1);
+          s0 = fmaf(m.z, rv[j].z, s0);
+          s1 = fmaf(m.w, rv[j].w, s1);
+        }
+        acc[c] = s0 + s1;
       }
-      const double z = -(double)((s0 + s1) + (s2 + s3));  // the sweep leaves -A^-1
-      s_z[4 * (size_t)lr + l] = z;
-      if (publish) P.zvec[4 * (size_t)i + l] = z;
-      part += s_r[4 * (size_t)lr + l] * z;
+    }
+#pragma unroll
+    for (int o = 1; o < kTPR; o <<= 1) {
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+      acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o);
+      acc[2] += __shfl_xor_sync(0xffffffffu, acc[2], o);
+    }
+    double part = 0;
+    if (act) {
+      for (int c = l; c < 3; c += kTPR) {
+        const double z = -(double)acc[c];  // the sweep leaves -A^-1
+        s_z[3 * (size_t)lr + c] = z;
+        if (publish) P.zvec[4 * (size_t)(rb + lr) + c] = z;
+        part += s_r[4 * (size_t)lr + c] * z;
+      }
     }
     return part;
   }
@@ -846,7 +881,8 @@ struct Engine {
     const bool bprec = res && P.block_prec;
     if (has) {
       for (int t = tid; t < 10 * (re - rb); t += nthr)
-        reinterpret_cast<double2*>(s_jac)[t] = reinterpret_cast<const double2*>(P.jac + 20 * (size_t)rb)[t];
+        reinterpret_cast<double2*>(s_jac + kJS * (size_t)(t / 10))[t % 10] =
+            reinterpret_cast<const double2*>(P.jac + 20 * (size_t)rb)[t];
       for (int a = ab + tid; a < ae; a += nthr) {
         const int ent = P.inc_ent[a];
         const double2* cf = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(ent >> 1));
@@ -854,7 +890,7 @@ struct Engine {
         reinterpret_cast<double2*>(s_coef)[2 * (a - ab) + 1] = cf[1];
         const int other = P.inc_other[a];
         // where the neighbour's z lives: this chunk's shared memory, or L2
-        s_zptr[a - ab] = (other >= rb && other < re) ? s_z + 4 * (size_t)(other - rb) : P.zvec + 4 * (size_t)other;
+        s_zptr[a - ab] = (other >= rb && other < re) ? s_z + 3 * (size_t)(other - rb) : P.zvec + 4 * (size_t)other;
       }
       __syncthreads();
       if (bprec) build_block_prec(rb, re, ab);
@@ -886,7 +922,7 @@ struct Engine {
         st3(R, li, V3{0, 0, 0});
         st3(X, li, V3{0, 0, 0});
         st3(P.zvec, i, V3{0, 0, 0});
-        if (res) st3(s_z, li, V3{0, 0, 0});
+        if (res) st3s(s_z, li, V3{0, 0, 0});
         if (bprec) s_rf[3 * li] = s_rf[3 * li + 1] = s_rf[3 * li + 2] = 0.f;
         return;
       }
@@ -915,7 +951,7 @@ struct Engine {
       const V3 z{m00 * r.x + m01 * r.y + m02 * r.z, m01 * r.x + m11 * r.y + m12 * r.z,
                  m02 * r.x + m12 * r.y + m22 * r.z};
       st3(P.zvec, i, z);
-      if (res) st3(s_z, li, z);
+      if (res) st3s(s_z, li, z);
       rz_part[0] += r.x * z.x + r.y * z.y + r.z * z.z;
     });
     if (bprec) {
@@ -993,7 +1029,7 @@ struct Engine {
           fixed = single ? my_fixed : (P.pt_fixed && P.pt_fixed[i]);
           kf = single ? my_kf : P.pt_kf[i];
           su = single ? my_su : P.dg[8 * (size_t)i + 6];
-          zi = res ? ld3p(s_z, li) : ld3p(P.zvec, i);
+          zi = res ? ld3s(s_z, li) : ld3p(P.zvec, i);
           if (!fixed) {
             const int a_beg = single ? my_a0 : P.inc_ptr[i];
             const int a1 = single ? my_a1 : P.inc_ptr[i + 1];
@@ -1013,19 +1049,20 @@ struct Engine {
                   zp[k] = P.zvec + 4 * (size_t)P.inc_other[a];
                 }
               }
-              double2 c0v[3], c1v[3], za[3];
-              double zb[3];
+              double2 c0v[3], c1v[3];
+              double zx[3], zy[3], zb[3];
 #pragma unroll
               for (int k = 0; k < 3; k++) {
                 c0v[k] = cp[k][0];
                 c1v[k] = cp[k][1];
-                za[k] = *reinterpret_cast<const double2*>(zp[k]);
+                zx[k] = zp[k][0];
+                zy[k] = zp[k][1];
                 zb[k] = zp[k][2];
               }
 #pragma unroll
               for (int k = 0; k < 3; k++) {
                 if (a0 + kTPR * k < a1) {
-                  const double dx = zi.x - za[k].x, dy = zi.y - za[k].y, dz = zi.z - zb[k];
+                  const double dx = zi.x - zx[k], dy = zi.y - zy[k], dz = zi.z - zb[k];
                   const double ud = c0v[k].y * dx + c1v[k].x * dy + c1v[k].y * dz;
                   w0 += c0v[k].x * dx + c0v[k].y * ud;
                   w1 += c0v[k].x * dy + c1v[k].x * ud;
@@ -1061,7 +1098,7 @@ struct Engine {
           double q0 = w0 + (lambda + su) * zi.x, q1 = w1 + (lambda + su) * zi.y, q2 = w2 + (lambda + su) * zi.z;
           if (kf >= 0) {
             const double2* jo =
-                reinterpret_cast<const double2*>(res ? s_jac + 20 * (size_t)li : P.jac + 20 * (size_t)i);
+                reinterpret_cast<const double2*>(res ? s_jac + kJS * (size_t)li : P.jac + 20 * (size_t)i);
             const double omega = jo[9].x;
             if (omega != 0) {
               double A[12], B[6];
@@ -1217,7 +1254,7 @@ struct Engine {
             const V3 z{m0.x * ri.x + m0.y * ri.y + m1.x * ri.z, m0.y * ri.x + m1.y * ri.y + m2.x * ri.z,
                        m1.x * ri.x + m2.x * ri.y + m2.y * ri.z};
             st3(P.zvec, i, z);
-            if (res) st3(s_z, li, z);
+            if (res) st3s(s_z, li, z);
             rzn_part[0] += ri.x * z.x + ri.y * z.y + ri.z * z.z;
           }
         }
@@ -1295,7 +1332,8 @@ struct Engine {
     const int ab = P.inc_ptr[rb], ae = P.inc_ptr[re];
     const bool bprec = P.block_prec != 0;
     for (int t = tid; t < 10 * nrows; t += nthr)
-      reinterpret_cast<double2*>(s_jac)[t] = reinterpret_cast<const double2*>(P.jac + 20 * (size_t)rb)[t];
+      reinterpret_cast<double2*>(s_jac + kJS * (size_t)(t / 10))[t % 10] =
+          reinterpret_cast<const double2*>(P.jac + 20 * (size_t)rb)[t];
     for (int a = ab + tid; a < ae; a += nthr) {
       const int ent = P.inc_ent[a];
       const double2* cf = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(ent >> 1));
@@ -1303,18 +1341,9 @@ struct Engine {
       reinterpret_cast<double2*>(s_coef)[2 * (a - ab) + 1] = cf[1];
       const int other = P.inc_other[a];
       if (other >= rb && other < re) {
-        s_zptr[a - ab] = s_z + 4 * (size_t)(other - rb);
-      } else if (P.halo_rows > 0) {
-        s_zptr[a - ab] = s_halo + 4 * (size_t)P.inc_halo[a];
+        s_zptr[a - ab] = s_z + 3 * (size_t)(other - rb);
       } else {
-        // owning chunk == owning CTA: binary search over the chunk starts, then map its s_z into this CTA's view
-        int lo = 0, hi = P.n_chunks - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (P.chunk_begin[mid] <= other) lo = mid; else hi = mid - 1;
-        }
-        const double* remote = cluster.map_shared_rank(s_z, lo);
-        s_zptr[a - ab] = remote + 4 * (size_t)(other - P.chunk_begin[lo]);
+        s_zptr[a - ab] = s_halo + 3 * (size_t)P.inc_halo[a];  // pushed by the owner after every z update
       }
     }
     __syncthreads();
@@ -1337,7 +1366,7 @@ struct Engine {
         }
         st3(s_r, li, V3{0, 0, 0});
         st3(s_x, li, V3{0, 0, 0});
-        st3(s_z, li, V3{0, 0, 0});
+        st3s(s_z, li, V3{0, 0, 0});
         if (bprec) s_rf[3 * li] = s_rf[3 * li + 1] = s_rf[3 * li + 2] = 0.f;
       } else {
         const V3 r = ld3p(P.bvec, i);
@@ -1362,7 +1391,7 @@ struct Engine {
           mo[2] = make_double2(m12, m22);
           const V3 z{m00 * r.x + m01 * r.y + m02 * r.z, m01 * r.x + m11 * r.y + m12 * r.z,
                      m02 * r.x + m12 * r.y + m22 * r.z};
-          st3(s_z, li, z);
+          st3s(s_z, li, z);
           rz_part += r.x * z.x + r.y * z.y + r.z * z.z;
         }
       }
@@ -1396,12 +1425,12 @@ struct Engine {
       }
     };
     // halo push: every thread takes entries of this chunk's push list (row -> target chunk, slot)
-    const int hp0 = P.halo_rows > 0 ? P.push_ptr[c0] : 0, hp1 = P.halo_rows > 0 ? P.push_ptr[c0 + 1] : 0;
+    const int hp0 = P.push_ptr[c0], hp1 = P.push_ptr[c0 + 1];
     auto push_halo = [&]() {  // after a CTA barrier that follows the z update
       for (int e = hp0 + tid; e < hp1; e += nthr) {
         const int row = P.push_row[e], dst = P.push_dst[e];
-        double* h = cluster.map_shared_rank(s_halo, dst >> 16) + 4 * (size_t)(dst & 65535);
-        const V3 z = ld3p(s_z, row - rb);
+        double* h = cluster.map_shared_rank(s_halo, dst >> 16) + 3 * (size_t)(dst & 65535);
+        const V3 z = ld3s(s_z, row - rb);
         h[0] = z.x;
         h[1] = z.y;
         h[2] = z.z;
@@ -1471,7 +1500,7 @@ struct Engine {
       double redw[6] = {0, 0, 0, 0, 0, 0};  // this row's pose partial (lane 0 of the row's lane group)
       V3 zi{0, 0, 0};
       if (valid) {
-        zi = ld3p(s_z, li);
+        zi = ld3s(s_z, li);
         if (!fixed) {
           for (int a0 = a_beg + ql; a0 < a1; a0 += 3 * kTPR) {
             const double* zp[3];
@@ -1481,20 +1510,22 @@ struct Engine {
               const int a = min(a0 + kTPR * k, a1 - 1);
               cp[k] = reinterpret_cast<const double2*>(s_coef) + 2 * (a - ab);
               zp[k] = s_zptr[a - ab];
+              __builtin_assume(__isShared(zp[k]));  // own rows or the pushed halo: never a remote address
             }
-            double2 c0v[3], c1v[3], za[3];
-            double zb[3];
+            double2 c0v[3], c1v[3];
+            double zx[3], zy[3], zb[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
               c0v[k] = cp[k][0];
               c1v[k] = cp[k][1];
-              za[k] = *reinterpret_cast<const double2*>(zp[k]);
+              zx[k] = zp[k][0];
+              zy[k] = zp[k][1];
               zb[k] = zp[k][2];
             }
 #pragma unroll
             for (int k = 0; k < 3; k++) {
               if (a0 + kTPR * k < a1) {
-                const double dx = zi.x - za[k].x, dy = zi.y - za[k].y, dz = zi.z - zb[k];
+                const double dx = zi.x - zx[k], dy = zi.y - zy[k], dz = zi.z - zb[k];
                 const double ud = c0v[k].y * dx + c1v[k].x * dy + c1v[k].y * dz;
                 w0 += c0v[k].x * dx + c0v[k].y * ud;
                 w1 += c0v[k].x * dy + c1v[k].x * ud;
@@ -1514,7 +1545,7 @@ struct Engine {
         double red[6] = {0, 0, 0, 0, 0, 0};
         double q0 = w0 + (lambda + su) * zi.x, q1 = w1 + (lambda + su) * zi.y, q2 = w2 + (lambda + su) * zi.z;
         if (kf >= 0) {
-          const double2* jo = reinterpret_cast<const double2*>(s_jac + 20 * (size_t)li);
+          const double2* jo = reinterpret_cast<const double2*>(s_jac + kJS * (size_t)li);
           const double omega = jo[9].x;
           if (omega != 0) {
             double A[12], B[6];
@@ -1667,7 +1698,7 @@ struct Engine {
           const double2 m0 = mo[0], m1 = mo[1], m2 = mo[2];
           const V3 z{m0.x * ri.x + m0.y * ri.y + m1.x * ri.z, m0.y * ri.x + m1.y * ri.y + m2.x * ri.z,
                      m1.x * ri.x + m2.x * ri.y + m2.y * ri.z};
-          st3(s_z, li, z);
+          st3s(s_z, li, z);
           rzn_part = ri.x * z.x + ri.y * z.y + ri.z * z.z;
         }
         __syncthreads();  // S3 (pose r complete)
@@ -1783,7 +1814,7 @@ struct Engine {
     do {
       const long long ts0 = clock64();
       const bool native = P.cluster_mode && P.resident && P.F == 1 && P.D == 0 && !P.points_fixed &&
-                          P.n_chunks == (int)gridDim.x && !P.no_dsmem;
+                          P.n_chunks == (int)gridDim.x && !P.no_dsmem && P.push_ptr != nullptr;
       const bool solved = native ? pcg_cluster() : pcg();
       const long long ts1 = clock64();
       prof[6] += ts1 - ts0;  // solve
@@ -1963,8 +1994,8 @@ size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec) {
   size_t d = (size_t)F * (7 + 7 + 21 + 36 + 6 * 6) + 32 * kChunkVals + 32 + 6 * kMaxRows + 2 * 16 * 8 + 2 + 6;  // + alignment slack
   if (res_rows == 0) d += 16 * kMaxRows;
   if (res_rows > 0) {
-    d += std::max(20 * (size_t)res_rows, 16 * (size_t)kMaxRows) + (size_t)res_rows * (4 * 5 + (block_prec ? 0 : 8)) +
-         5 * (size_t)res_inc + (3 * (size_t)res_rows + 1) / 2 + 4;
+    d += std::max((size_t)kJS * res_rows, 16 * (size_t)kMaxRows) + (size_t)res_rows * (4 * 4 + 3 + (block_prec ? 0 : 8)) +
+         5 * (size_t)res_inc + (3 * (size_t)res_rows + 1) / 2 + 6;
     size_t bytes = d * sizeof(double);
     if (block_prec) bytes += (size_t)((res_rows + kPrecBlock - 1) / kPrecBlock) * kPN * kPS * sizeof(float);
     return bytes + 16;
