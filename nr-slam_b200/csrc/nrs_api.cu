@@ -206,9 +206,10 @@ struct Plan {
   std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr;
   const int *d_chunk_kf = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_kf_chunk_ptr = nullptr;
   // halo push lists of the cluster-native CG loop (built when the plan qualifies for it)
-  int halo_rows = 0;
-  std::vector<int> inc_halo, push_ptr, push_row, push_dst;
+  int halo_rows = 0, coarse = 0;
+  std::vector<int> inc_halo, push_ptr, push_row, push_dst, xinc_ptr, xinc_idx;
   const int *d_inc_halo = nullptr, *d_push_ptr = nullptr, *d_push_row = nullptr, *d_push_dst = nullptr;
+  const int *d_xinc_ptr = nullptr, *d_xinc_idx = nullptr;
 };
 
 // For every chunk: the out-of-chunk rows its incidences read (its halo) and, for every owner chunk, which rows to push
@@ -236,6 +237,13 @@ void build_halo(Plan& pl, const std::vector<int>& inc_ptr, const std::vector<int
         pl.inc_halo[a] = (int)(std::lower_bound(rows.begin(), rows.end(), o) - rows.begin());
     }
     for (size_t k = 0; k < rows.size(); k++) pushes[chunk_of[rows[k]]].emplace_back(rows[k], c * 65536 + (int)k);
+  }
+  pl.xinc_ptr.assign(nc + 1, 0);
+  pl.xinc_idx.clear();
+  for (int c = 0; c < nc; c++) {
+    for (int a = inc_ptr[pl.chunk_begin[c]]; a < inc_ptr[pl.chunk_end[c]]; a++)
+      if (pl.inc_halo[a] >= 0) pl.xinc_idx.push_back(a);
+    pl.xinc_ptr[c + 1] = (int)pl.xinc_idx.size();
   }
   pl.push_ptr.assign(nc + 1, 0);
   for (int c = 0; c < nc; c++) {
@@ -345,8 +353,10 @@ void apply_plan(Params& p, const Plan& pl) {
   p.block_prec = pl.block_prec;
   p.chunk_kf = pl.d_chunk_kf; p.chunk_begin = pl.d_chunk_begin; p.chunk_end = pl.d_chunk_end;
   p.kf_chunk_ptr = pl.d_kf_chunk_ptr;
+  p.coarse = pl.coarse;
   p.halo_rows = pl.halo_rows; p.inc_halo = pl.d_inc_halo; p.push_ptr = pl.d_push_ptr; p.push_row = pl.d_push_row;
   p.push_dst = pl.d_push_dst;
+  p.xinc_ptr = pl.d_xinc_ptr; p.xinc_idx = pl.d_xinc_idx;
 }
 
 int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
@@ -356,7 +366,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   sort_rows(hp, st.row_of);
 
   // incidence lists
-  std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P);
+  std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P), inc_row(2 * (size_t)P);
   for (int e = 0; e < P; e++) {
     inc_ptr[hp.pair_i[e] + 1]++;
     inc_ptr[hp.pair_j[e] + 1]++;
@@ -368,9 +378,11 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
       int a = w[hp.pair_i[e]]++;
       inc_other[a] = hp.pair_j[e];
       inc_ent[a] = 2 * e;
+      inc_row[a] = hp.pair_i[e];
       a = w[hp.pair_j[e]]++;
       inc_other[a] = hp.pair_i[e];
       inc_ent[a] = 2 * e + 1;
+      inc_row[a] = hp.pair_j[e];
     }
   }
   std::vector<int> dinc_ptr(V + 1, 0), dinc_ent(4 * (size_t)D);
@@ -402,13 +414,23 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     if (pl->n_chunks == 0 || !pl->cluster_mode || !pl->resident || F != 1 || D != 0 || hp.points_fixed) continue;
     if (!env_int("NRSLAM_B200_HALO_PUSH", 1) || pl->n_chunks >= 65536) continue;
     build_halo(*pl, inc_ptr, inc_other);
-    const size_t extra = sizeof(double) * (3 * (size_t)pl->halo_rows + 2);
-    if (pl->halo_rows >= 65536 || pl->smem + extra > 224 * 1024) {
+    // the coarse level needs the dense block preconditioner's layout and at most 16 aggregates
+    int coarse = env_int("NRSLAM_B200_COARSE", 1) && pl->block_prec && pl->n_chunks <= 16 && pl->halo_rows < 255 * 256;
+    size_t extra = engine_smem_extra(pl->res_inc, pl->halo_rows, coarse);
+    if (coarse && pl->smem + extra > 226 * 1024) {
+      coarse = 0;
+      extra = engine_smem_extra(pl->res_inc, pl->halo_rows, 0);
+    }
+    pl->coarse = coarse;
+    if (pl->halo_rows >= 65536 || pl->smem + extra > 226 * 1024) {
+      pl->coarse = 0;
       pl->halo_rows = 0;  // does not fit: the general CG loop (exchange through L2) runs instead
       pl->inc_halo.clear();
       pl->push_ptr.clear();
       pl->push_row.clear();
       pl->push_dst.clear();
+      pl->xinc_ptr.clear();
+      pl->xinc_idx.clear();
       continue;
     }
     pl->smem += extra;
@@ -419,12 +441,12 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   auto sz = [&](size_t bytes) { need += ((bytes + 255) & ~size_t(255)) + 256; };
   sz(7 * F * 8); sz(4 * (size_t)V * 8); sz(4 * (size_t)V * 8); sz(2 * (size_t)V * 8); sz((size_t)V * 4);
   sz((size_t)P * 4); sz((size_t)P * 4); sz((size_t)P * 8); sz((size_t)P * 8);
-  sz(((size_t)V + 1) * 4); sz(2 * (size_t)P * 4); sz(2 * (size_t)P * 4);
+  sz(((size_t)V + 1) * 4); sz(2 * (size_t)P * 4); sz(2 * (size_t)P * 4); sz(2 * (size_t)P * 4);
   sz(4 * (size_t)D * 4); sz((size_t)D * 8); sz(((size_t)V + 1) * 4); sz(4 * (size_t)D * 4);
   sz(((size_t)V + 1) * 4); sz((size_t)U * 8); sz((size_t)U * 4); sz((size_t)V);
   sz((size_t)max_chunks * 4 * 3 * 2); sz(((size_t)F + 1) * 4 * 2);
   for (Plan* pl : {&planA, &planB}) {
-    sz(pl->inc_halo.size() * 4); sz(pl->push_ptr.size() * 4); sz(pl->push_row.size() * 4); sz(pl->push_dst.size() * 4);
+    sz(pl->inc_halo.size() * 4); sz(pl->push_ptr.size() * 4); sz(pl->push_row.size() * 4); sz(pl->push_dst.size() * 4); sz(pl->xinc_ptr.size() * 4); sz(pl->xinc_idx.size() * 4);
   }
   need += 8192;
   if (!st.in.reserve(need, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "input arena allocation failed");
@@ -459,6 +481,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   p.inc_ptr = in.d<int>(put(in, inc_ptr));
   p.inc_other = in.d<int>(put(in, inc_other));
   p.inc_ent = in.d<int>(put(in, inc_ent));
+  p.inc_row = in.d<int>(put(in, inc_row));
   p.dmp_v = in.d<int>(put(in, hp.dmp_v, 4));
   p.dmp_w = in.d<double>(put(in, hp.dmp_w));
   p.dinc_ptr = in.d<int>(put(in, dinc_ptr));
@@ -483,6 +506,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
       pl->d_push_ptr = in.d<int>(put(in, pl->push_ptr));
       pl->d_push_row = in.d<int>(put(in, pl->push_row));
       pl->d_push_dst = in.d<int>(put(in, pl->push_dst));
+      pl->d_xinc_ptr = in.d<int>(put(in, pl->xinc_ptr));
+      pl->d_xinc_idx = in.d<int>(put(in, pl->xinc_idx));
     }
   }
   apply_plan(p, planA);

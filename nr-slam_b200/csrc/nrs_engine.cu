@@ -153,7 +153,11 @@ struct Engine {
   double* s_rowA;           // per-row pose-block records of the linearisation (16 per row)
   const double** s_zptr;    // per incidence: where the neighbour's z lives (shared memory or L2)
   float* s_rf;              // residual as fp32 for the block preconditioner
-  double* s_halo;           // z of the out-of-chunk neighbours, pushed by their owners (4 doubles per halo row)
+  double* s_halo;           // z of the out-of-chunk neighbours, pushed by their owners (3 doubles per halo row)
+  // coarse level of the cluster-native loop
+  unsigned char *s_cid, *s_hcid;  // aggregate (= chunk) of every incidence's neighbour / of every halo row (255: fixed row)
+  float *s_Aall, *s_Ac, *s_rcv;   // published row blocks [16][kRowBlk], coarse matrix -> -inverse [54][kCoarseS], residual
+  double* s_y;                    // coarse correction [kCoarseN]
   float* s_binv;  // dense block inverses (fp32, symmetric): a preconditioner need not be exact
   int* s_oth;
   int* s_flag;
@@ -181,7 +185,7 @@ struct Engine {
     s_red = sm;             sm += 32 * kChunkVals;
     s_scal = sm;            sm += 32;
     s_pr = sm;              sm += 6 * kMaxRows;
-    s_gather = sm;          sm += 2 * 16 * 8;
+    s_gather = sm;          sm += 2 * 16 * kGatherVals;
     s_flag = reinterpret_cast<int*>(sm);  sm += 2;
     sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));  // double2 accesses below
     // the pose-block records of the linearisation and the Jacobian cache of the CG loop are never live together
@@ -204,6 +208,18 @@ struct Engine {
       sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));
       s_halo = sm;          sm += (3 * (size_t)p.halo_rows + 1) & ~(size_t)1;
       s_binv = reinterpret_cast<float*>(sm);
+      s_cid = s_hcid = nullptr;
+      s_Aall = s_Ac = s_rcv = nullptr;
+      s_y = nullptr;
+      if (p.coarse) {  // behind the block inverses
+        float* f = s_binv + (size_t)(R / kPB) * kPN * kPS;
+        s_Aall = f;         f += 16 * kRowBlk;
+        s_Ac = f;           f += kCoarseN * kCoarseS;
+        s_rcv = f;          f += kCoarseS;
+        s_y = reinterpret_cast<double*>(f);  f += 2 * kCoarseS;
+        s_cid = reinterpret_cast<unsigned char*>(f);
+        s_hcid = s_cid + ((CI + 15) & ~15);
+      }
     } else {
       s_jac = s_x = s_r = s_p = s_q = s_z = s_minv = s_coef = nullptr;
       s_zptr = nullptr;
@@ -211,6 +227,9 @@ struct Engine {
       s_rf = nullptr;
       s_halo = nullptr;
       s_binv = nullptr;
+      s_cid = s_hcid = nullptr;
+      s_Aall = s_Ac = s_rcv = nullptr;
+      s_y = nullptr;
     }
     gen = 0;
     lambda = -1;
@@ -732,14 +751,28 @@ struct Engine {
         const float id = 1.f / d;
         // row j (pivot row) values for the columns of this lane
         const int k0 = lane, k1 = lane + 32;
-        const float pj0 = M[j * kPS + k0];
-        const float pj1 = (k1 < kPN) ? M[j * kPS + k1] : 0.f;
+        const bool has1 = k1 < kPN;
+        const float pj0 = (k0 == j) ? 0.f : M[j * kPS + k0];        // column j itself is rewritten below
+        const float pj1 = (has1 && k1 != j) ? M[j * kPS + k1] : 0.f;
         __syncwarp();
-        for (int i = 0; i < kPN; i++) {
-          if (i == j) continue;
-          const float f = M[i * kPS + j] * id;  // broadcast read
-          if (k0 != j) M[i * kPS + k0] -= f * pj0;
-          if (k1 < kPN && k1 != j) M[i * kPS + k1] -= f * pj1;
+        // eliminate in groups of 8 rows: all loads of a group first (independent chains for the scheduler); the
+        // pivot row takes f = 0 and is rewritten afterwards
+#pragma unroll 1
+        for (int i0 = 0; i0 < kPN; i0 += 8) {
+          float f[8], a0[8], a1[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int i = i0 + u;
+            f[u] = (i == j) ? 0.f : M[i * kPS + j] * id;  // broadcast read
+            a0[u] = M[i * kPS + k0];
+            a1[u] = has1 ? M[i * kPS + k1] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int i = i0 + u;
+            if (k0 != j) M[i * kPS + k0] = fmaf(-f[u], pj0, a0[u]);
+            if (has1 && k1 != j) M[i * kPS + k1] = fmaf(-f[u], pj1, a1[u]);
+          }
         }
         __syncwarp();
         // pivot column and row: a_ij / d ; pivot: -1/d
@@ -1306,27 +1339,32 @@ struct Engine {
 
   // ================================================================================================
   // Cluster-native CG loop for a tracking frame (cluster mode, resident, one chunk per CTA, one pose, no dampers).
-  // Nothing in the loop touches global memory: the neighbours' z is read from the owning CTA's shared memory
-  // (distributed shared memory) and the reduction slots live in shared memory too, so the release fence of the
-  // cluster barrier has no global stores to drain (the L2 exchange cost 1.8 us per barrier, profiles/r01_*).
-  // Per iteration: 5 CTA barriers + 2 cluster barriers; warp 0 does the small serial parts while the rest wait.
+  // Nothing in the loop touches global memory: z of the out-of-chunk neighbours and the reduction values are PUSHED
+  // into the consumers' shared memory (remote stores before the cluster barrier, local loads after it).
+  // Preconditioner: dense 16-row blocks + (P.coarse) an additive coarse level with one 3-dof aggregate per CTA and the
+  // 6 pose unknowns — the pose / common-mode deformation gauge direction is only held by lambda, and a 54 x 54 Galerkin
+  // system solved redundantly by every CTA removes it from the CG spectrum (about 1.6x fewer iterations).
+  // Per iteration: 5-6 CTA barriers + 2 cluster barriers; warp 0 does the small serial parts while the rest wait.
   // ================================================================================================
   __device__ bool pcg_cluster() {
     NRS_SHARED(s_jac); NRS_SHARED(s_x); NRS_SHARED(s_r); NRS_SHARED(s_p); NRS_SHARED(s_q); NRS_SHARED(s_z);
     NRS_SHARED(s_minv); NRS_SHARED(s_coef); NRS_SHARED(s_zptr); NRS_SHARED(s_rf); NRS_SHARED(s_pr);
     NRS_SHARED(s_red); NRS_SHARED(s_scal); NRS_SHARED(s_zp); NRS_SHARED(s_pp); NRS_SHARED(s_qp); NRS_SHARED(s_rp);
-    NRS_SHARED(s_xp); NRS_SHARED(s_M); NRS_SHARED(s_bp);
+    NRS_SHARED(s_xp); NRS_SHARED(s_M); NRS_SHARED(s_bp); NRS_SHARED(s_halo); NRS_SHARED(s_gather);
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const bool pos = !P.poses_fixed;
+    const bool coarse = P.coarse != 0 && (blockDim.x >> 5) >= 8;  // the sweep splits the 54 rows over >= 8 warps
+    bool use_coarse = coarse;
     const int G = gridDim.x;
     const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
     if (tid == 0) *s_flag = 0;
     __syncthreads();
-    if (pos && tid == 0)
+    if (pos && !coarse && tid == 0)
       if (!invert6(s_H, lambda, s_M)) *s_flag = 1;
     __syncthreads();
     if (*s_flag) return false;  // uniform: every CTA inverts the same block
+    const long long ts0 = clock64();
     const int c0 = blockIdx.x;
     const int rb = P.chunk_begin[c0], re = P.chunk_end[c0], nrows = re - rb;
     const int ab = P.inc_ptr[rb], ae = P.inc_ptr[re];
@@ -1334,20 +1372,43 @@ struct Engine {
     for (int t = tid; t < 10 * nrows; t += nthr)
       reinterpret_cast<double2*>(s_jac + kJS * (size_t)(t / 10))[t % 10] =
           reinterpret_cast<const double2*>(P.jac + 20 * (size_t)rb)[t];
+    if (coarse) {
+      for (int t = tid; t < P.halo_rows; t += nthr) s_hcid[t] = 255;  // unused halo slots: never corrected
+      __syncthreads();
+    }
     for (int a = ab + tid; a < ae; a += nthr) {
       const int ent = P.inc_ent[a];
       const double2* cf = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(ent >> 1));
       reinterpret_cast<double2*>(s_coef)[2 * (a - ab)] = cf[0];
       reinterpret_cast<double2*>(s_coef)[2 * (a - ab) + 1] = cf[1];
       const int other = P.inc_other[a];
-      if (other >= rb && other < re) {
+      const bool in = other >= rb && other < re;
+      if (in) {
         s_zptr[a - ab] = s_z + 3 * (size_t)(other - rb);
       } else {
         s_zptr[a - ab] = s_halo + 3 * (size_t)P.inc_halo[a];  // pushed by the owner after every z update
       }
+      if (coarse) {
+        int cid = c0;
+        if (!in) {  // owning chunk == aggregate: binary search over the chunk starts
+          int lo = 0, hi = P.n_chunks - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (P.chunk_begin[mid] <= other) lo = mid; else hi = mid - 1;
+          }
+          cid = lo;
+        }
+        const bool ofixed = P.pt_fixed && P.pt_fixed[other];
+        s_cid[a - ab] = ofixed ? 255 : (unsigned char)cid;
+        if (!in) s_hcid[P.inc_halo[a]] = ofixed ? 255 : (unsigned char)cid;
+      }
     }
     __syncthreads();
+    const long long ts1 = clock64();
+    prof[8] += ts1 - ts0;   // setup: copies, pointers
     if (bprec) build_block_prec(rb, re, ab);
+    const long long ts2 = clock64();
+    prof[9] += ts2 - ts1;   // setup: block preconditioner
     if (bprec) {  // rows of the last block past the chunk end: zero residual
       const int padded = ((nrows + kPB - 1) / kPB) * kPB;
       for (int lr = nrows + tid; lr < padded; lr += nthr) {
@@ -1355,8 +1416,335 @@ struct Engine {
         s_rf[3 * lr] = s_rf[3 * lr + 1] = s_rf[3 * lr + 2] = 0.f;
       }
     }
-    // ---- initial residual, z = M^-1 r (one thread per row)
-    double rz_part = 0;
+    double* s_slot = s_scal + 8;   // 16 doubles: staging of this CTA's reduction values
+    double* s_bc = s_scal + 24;    // broadcast scalars
+    const int my_rank = blockIdx.x;
+    // Exchange by PUSH: warp 0 stores this CTA's values into every CTA's gather buffer (remote stores are fire and
+    // forget); after the cluster barrier everybody sums its LOCAL copy.
+    auto push = [&](int buf, int k0, int nk) {  // called by warp 0 after its values sit in s_slot[k0 .. k0 + nk)
+      __syncwarp();
+      const int target = lane & 15, half = lane >> 4;  // two lanes per target CTA share the values
+      if (target < G) {
+        double* dst = cluster.map_shared_rank(s_gather, target) + (size_t)(buf * 16 + my_rank) * kGatherVals;
+        for (int k = half; k < nk; k += 2) dst[k0 + k] = s_slot[k0 + k];
+      }
+    };
+    // halo push: every thread takes entries of this chunk's push list (row -> target chunk, slot)
+    const int hp0 = P.push_ptr[c0], hp1 = P.push_ptr[c0 + 1];
+    auto push_halo = [&]() {  // after a CTA barrier that follows the z update
+      for (int e = hp0 + tid; e < hp1; e += nthr) {
+        const int row = P.push_row[e], dst = P.push_dst[e];
+        double* h = cluster.map_shared_rank(s_halo, dst >> 16) + 3 * (size_t)(dst & 65535);
+        const V3 z = ld3s(s_z, row - rb);
+        h[0] = z.x;
+        h[1] = z.y;
+        h[2] = z.z;
+      }
+    };
+
+    // ---- coarse level: Galerkin matrix Z^T (H + lambda I) Z over [pose ; one 3-dof aggregate per chunk]
+    const long long ts3 = clock64();
+    if (coarse) {
+      NRS_SHARED(s_cid); NRS_SHARED(s_Aall); NRS_SHARED(s_Ac);
+      float* stage = s_Ac;  // the coarse matrix is assembled only after the row blocks have been exchanged
+      // this CTA's row block: 16 x 6 (symmetric 3x3 per target aggregate) + 18 (pose coupling) + [n free rows].
+      // (1) one thread per row: the row's share of the OWN aggregate block (diagonal block + lambda minus the
+      //     in-chunk couplings), of the pose coupling and of the free-row count; fixed-order block reduction.
+      {
+        double v[25];
+#pragma unroll
+        for (int k = 0; k < 25; k++) v[k] = 0;
+        if (tid < nrows && !(P.pt_fixed && P.pt_fixed[rb + tid])) {
+          const int i = rb + tid;
+          const double* d = P.dg + 8 * (size_t)i;  // 00 01 02 11 12 22
+#pragma unroll
+          for (int k = 0; k < 6; k++) v[k] = d[k];
+          v[0] += lambda;
+          v[3] += lambda;
+          v[5] += lambda;
+          for (int a = P.inc_ptr[i]; a < P.inc_ptr[i + 1]; a++) {
+            if (s_cid[a - ab] != c0) continue;
+            const double* cf = s_coef + 4 * (size_t)(a - ab);
+            v[0] -= cf[0] + cf[1] * cf[1];
+            v[1] -= cf[1] * cf[2];
+            v[2] -= cf[1] * cf[3];
+            v[3] -= cf[0] + cf[2] * cf[2];
+            v[4] -= cf[2] * cf[3];
+            v[5] -= cf[0] + cf[3] * cf[3];
+          }
+          if (pos && P.pt_kf[i] >= 0) {
+            const double* jo = s_jac + kJS * (size_t)tid;  // A(2x6) B(2x3) omega
+#pragma unroll
+            for (int a6 = 0; a6 < 6; a6++)
+#pragma unroll
+              for (int b3 = 0; b3 < 3; b3++) v[6 + a6 * 3 + b3] = jo[18] * (jo[a6] * jo[12 + b3] + jo[6 + a6] * jo[15 + b3]);
+          }
+          v[24] = 1.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 25; k++) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 25; k++) s_red[128 + 25 * warp + k] = v[k];
+        }
+      }
+      __syncthreads();
+      for (int t = tid; t < kRowBlk; t += nthr) stage[t] = 0.f;
+      __syncthreads();
+      if (tid < 25) {
+        double s = 0;
+        for (int w = 0; w < nw; w++) s += s_red[128 + 25 * w + tid];
+        if (tid < 6) stage[c0 * 6 + tid] = (float)s;
+        else if (tid < 24) stage[96 + tid - 6] = (float)s;
+        else stage[114] = (float)s;
+      }
+      // (2) couplings to OTHER aggregates: (aggregate, component) threads scan the chunk's cross-chunk incidences
+      if (tid >= 32 && tid < 32 + 96) {
+        const int ct = (tid - 32) / 6, comp = (tid - 32) % 6;
+        if (ct != c0 && ct < G) {
+          const int r = comp < 3 ? 0 : (comp < 5 ? 1 : 2), c = comp < 3 ? comp : (comp < 5 ? comp - 2 : 2);
+          double s = 0;
+          for (int e = P.xinc_ptr[c0]; e < P.xinc_ptr[c0 + 1]; e++) {
+            const int a = P.xinc_idx[e];
+            if (s_cid[a - ab] != ct) continue;
+            if (P.pt_fixed && P.pt_fixed[P.inc_row[a]]) continue;  // rows without unknowns are not in the aggregate
+            const double* cf = s_coef + 4 * (size_t)(a - ab);
+            s -= (r == c ? cf[0] : 0.0) + cf[1 + r] * cf[1 + c];
+          }
+          stage[ct * 6 + comp] = (float)s;
+        }
+      }
+      __syncthreads();
+      for (int t = tid; t < 16 * kRowBlk; t += nthr) {
+        const int target = t / kRowBlk, k = t % kRowBlk;
+        if (target < G) cluster.map_shared_rank(s_Aall, target)[(size_t)my_rank * kRowBlk + k] = stage[k];
+      }
+      const long long ts4 = clock64();
+      prof[10] += ts4 - ts3;  // setup: coarse row block + push
+      barrier();
+      const long long ts5 = clock64();
+      prof[11] += ts5 - ts4;  // setup: coarse exchange barrier
+      // assemble (upper triangle mirrored so that the matrix is exactly symmetric)
+      for (int t = tid; t < kCoarseN * (kCoarseS - kCoarseN); t += nthr)
+        s_Ac[(size_t)(t / (kCoarseS - kCoarseN)) * kCoarseS + kCoarseN + t % (kCoarseS - kCoarseN)] = 0.f;
+      for (int t = tid; t < kCoarseN * kCoarseN; t += nthr) {
+        int I = t / kCoarseN, J = t % kCoarseN;
+        if (I > J) { const int q = I; I = J; J = q; }
+        float v;
+        if (J < 6) {
+          v = pos ? (float)(s_H[sym6(I, J)] + (I == J ? lambda : 0.0)) : (I == J ? 1.f : 0.f);
+        } else {
+          const int cj = (J - 6) / 3, bj = (J - 6) % 3;
+          const bool live_j = cj < G && s_Aall[(size_t)cj * kRowBlk + 114] > 0.5f;
+          if (I < 6) {
+            v = (pos && live_j) ? s_Aall[(size_t)cj * kRowBlk + 96 + I * 3 + bj] : 0.f;
+          } else {
+            const int ci = (I - 6) / 3, bi = (I - 6) % 3;
+            const bool live_i = ci < G && s_Aall[(size_t)ci * kRowBlk + 114] > 0.5f;
+            if (live_i && live_j) {
+              const int r = bi < bj ? bi : bj, c = bi < bj ? bj : bi;
+              const int comp = r == 0 ? c : (r == 1 ? 2 + c : 5);
+              v = s_Aall[(size_t)ci * kRowBlk + cj * 6 + comp];
+            } else {
+              v = (I == J) ? 1.f : 0.f;  // aggregate without unknowns (or beyond the cluster): identity row
+            }
+          }
+        }
+        s_Ac[(size_t)(t / kCoarseN) * kCoarseS + (t % kCoarseN)] = v;
+      }
+      __syncthreads();
+      // symmetric diagonal scaling D^-1/2 A D^-1/2 (the pose block is ~1e9, the aggregates ~1e7, lambda ~1e2: without
+      // it the fp32 sweep loses the small pivots); the scales go where the row blocks were (no longer needed)
+      float* s_ds = s_Aall;
+      if (tid < kCoarseN) {
+        const float d = s_Ac[tid * kCoarseS + tid];
+        s_ds[64 + tid] = d > 0.f ? rsqrtf(d) : 0.f;
+      }
+      __syncthreads();
+      if (tid < kCoarseN) s_ds[tid] = s_ds[64 + tid];
+      for (int t = tid; t < kCoarseN * kCoarseN; t += nthr) {
+        const int I = t / kCoarseN, J = t % kCoarseN;
+        s_Ac[I * kCoarseS + J] *= s_ds[64 + I] * s_ds[64 + J];
+      }
+      __syncthreads();
+      const long long ts6 = clock64();
+      prof[12] += ts6 - ts5;  // setup: coarse assembly + scaling
+      // sweep every pivot: A -> -A^-1. Rows are split over the warps, lanes own columns; a pivot that is not safely
+      // positive disables the coarse level for this solve (identical decision in every CTA: identical inputs)
+      if (tid == 0) *s_flag = 0;
+      __syncthreads();
+      {
+        float* M = s_Ac;
+        for (int j = 0; j < kCoarseN; j++) {
+          const float d = M[j * kCoarseS + j];
+          if (!(d > 1e-5f)) {
+            if (tid == 0) *s_flag = 1;
+            break;  // uniform: every thread reads the same pivot
+          }
+          const float id = 1.f / d;
+          const int k0 = lane, k1 = lane + 32;
+          const float pj0 = M[j * kCoarseS + k0];
+          const float pj1 = (k1 < kCoarseN) ? M[j * kCoarseS + k1] : 0.f;
+          float fcol[(kCoarseN + 7) / 8];  // this warp's rows: the pivot-column entries, read before anything changes
+#pragma unroll
+          for (int q = 0; q < (kCoarseN + 7) / 8; q++) {
+            const int i = warp + nw * q;
+            fcol[q] = (i < kCoarseN) ? M[i * kCoarseS + j] * id : 0.f;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int q = 0; q < (kCoarseN + 7) / 8; q++) {
+            const int i = warp + nw * q;
+            if (i < kCoarseN && i != j) {
+              if (k0 != j) M[i * kCoarseS + k0] -= fcol[q] * pj0;
+              if (k1 < kCoarseN && k1 != j) M[i * kCoarseS + k1] -= fcol[q] * pj1;
+              if (lane == 0) M[i * kCoarseS + j] = fcol[q];  // pivot column: a_ij / d
+            }
+          }
+          if (warp == 0) {  // pivot row: a_ji / d ; pivot: -1 / d   (pj0 / pj1 hold the old row)
+            if (k0 != j) M[j * kCoarseS + k0] = pj0 * id;
+            if (k1 < kCoarseN && k1 != j) M[j * kCoarseS + k1] = pj1 * id;
+            if (lane == 0) M[j * kCoarseS + j] = -id;
+          }
+          __syncthreads();
+        }
+        for (int t = tid; t < kCoarseN * kCoarseN; t += nthr) {
+          const int i = t / kCoarseN, k = t % kCoarseN;
+          if (k > i) M[i * kCoarseS + k] = M[k * kCoarseS + i];
+        }
+      }
+      __syncthreads();
+      prof[13] += clock64() - ts6;  // setup: coarse sweep
+      use_coarse = *s_flag == 0;
+      if (!use_coarse && pos) {  // fall back to the exact 6x6 pose block for this solve
+        __syncthreads();
+        if (tid == 0) {
+          *s_flag = 0;
+          if (!invert6(s_H, lambda, s_M)) *s_flag = 1;
+        }
+        __syncthreads();
+        if (*s_flag) {
+          barrier();
+          return false;
+        }
+      }
+    }
+
+    // ---- z = M^-1 r is finished in two places (initial residual, every iteration): block reduction of r.t and of the
+    // aggregate's residual sum, halo + value push, cluster barrier, coarse solve (warp 0), correction of z.
+    // Returns r.z. rsum: this thread's sum of residual components of its (non-fixed) rows.
+    auto finish_z = [&](int buf, double rz_part, double rs0, double rs1, double rs2) -> double {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) rz_part += __shfl_xor_sync(0xffffffffu, rz_part, off);
+      if (use_coarse) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          rs0 += __shfl_xor_sync(0xffffffffu, rs0, off);
+          rs1 += __shfl_xor_sync(0xffffffffu, rs1, off);
+          rs2 += __shfl_xor_sync(0xffffffffu, rs2, off);
+        }
+      }
+      if (lane == 0) {
+        s_red[warp] = rz_part;
+        if (use_coarse) {
+          s_red[96 + 3 * warp] = rs0;
+          s_red[96 + 3 * warp + 1] = rs1;
+          s_red[96 + 3 * warp + 2] = rs2;
+        }
+      }
+      __syncthreads();  // S4
+      push_halo();
+      if (warp == 0) {
+        double t = 0;
+        for (int w = lane; w < nw; w += 32) t += s_red[w];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) s_slot[7] = t;
+        if (use_coarse && lane < 3) {
+          double v = 0;
+          for (int w = 0; w < nw; w++) v += s_red[96 + 3 * w + lane];
+          s_slot[8 + lane] = v;
+        }
+        push(buf, 7, use_coarse ? 4 : 1);
+      }
+      barrier();  // B2
+      if (warp == 0) {
+        double t = 0;
+        if (lane < G) t = s_gather[(size_t)(buf * 16 + lane) * kGatherVals + 7];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (use_coarse) {
+          // coarse residual [pose ; aggregate sums] (scaled), y = D^-1/2 (D^-1/2 A_c D^-1/2)^-1 D^-1/2 r_c; the sweep
+          // left minus the inverse
+          const float* s_ds = s_Aall;
+          double rfull[2] = {0, 0};
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const int j = lane + 32 * q;
+            if (j < kCoarseN) {
+              if (j < 6)
+                rfull[q] = pos ? s_rp[j] : 0.0;
+              else if ((j - 6) / 3 < G)
+                rfull[q] = s_gather[(size_t)(buf * 16 + (j - 6) / 3) * kGatherVals + 8 + (j - 6) % 3];
+              s_rcv[j] = (float)rfull[q] * s_ds[j];
+            } else if (j < kCoarseS) {
+              s_rcv[j] = 0.f;
+            }
+          }
+          __syncwarp();
+          double dotp = 0;
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const int j = lane + 32 * q;
+            if (j < kCoarseN) {
+              const float4* Mr = reinterpret_cast<const float4*>(s_Ac + (size_t)j * kCoarseS);
+              const float4* rv = reinterpret_cast<const float4*>(s_rcv);
+              float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+              for (int k = 0; k < (kCoarseN + 3) / 4; k++) {
+                const float4 m = Mr[k], r = rv[k];
+                a0 = fmaf(m.x, r.x, a0);
+                a1 = fmaf(m.y, r.y, a1);
+                a0 = fmaf(m.z, r.z, a0);
+                a1 = fmaf(m.w, r.w, a1);
+              }
+              const double y = -(double)((a0 + a1) * s_ds[j]);
+              s_y[j] = y;
+              if (pos && j < 6) s_zp[j] = y;
+              dotp += rfull[q] * y;  // r.z gains (aggregate residual).(correction)
+            }
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) dotp += __shfl_xor_sync(0xffffffffu, dotp, off);
+          t += dotp;
+        } else if (pos) {
+          double rzp = 0;
+          for (int a = 0; a < 6; a++) rzp += s_rp[a] * s_zp[a];
+          t += rzp;
+        }
+        if (lane == 0) s_bc[1] = t;
+      }
+      __syncthreads();  // S5
+      if (use_coarse) {
+        // z += Z y on the own rows and on the halo copies (fixed rows keep z = 0)
+        for (int t = tid; t < 3 * nrows; t += nthr) {
+          const int lr = t / 3, c = t % 3;
+          if (!(P.pt_fixed && P.pt_fixed[rb + lr])) s_z[t] += s_y[6 + 3 * c0 + c];
+        }
+        for (int t = tid; t < 3 * P.halo_rows; t += nthr) {
+          const int cid = s_hcid[t / 3];
+          if (cid != 255) s_halo[t] += s_y[6 + 3 * cid + t % 3];
+        }
+        __syncthreads();  // S6
+      }
+      return s_bc[1];
+    };
+
+    // ---- initial residual, t = M_B^-1 r (one thread per row)
+    double rz_part = 0, rs0 = 0, rs1 = 0, rs2 = 0;
     if (tid < nrows) {
       const int li = tid, i = rb + tid;
       if (P.pt_fixed && P.pt_fixed[i]) {
@@ -1372,6 +1760,9 @@ struct Engine {
         const V3 r = ld3p(P.bvec, i);
         st3(s_r, li, r);
         st3(s_x, li, V3{0, 0, 0});
+        rs0 = r.x;
+        rs1 = r.y;
+        rs2 = r.z;
         if (bprec) {
           s_rf[3 * li] = (float)r.x;
           s_rf[3 * li + 1] = (float)r.y;
@@ -1405,70 +1796,20 @@ struct Engine {
       s_xp[tid] = 0;
       s_pp[tid] = 0;
       s_qp[tid] = 0;
-      double s = 0;
-      for (int c = 0; c < 6; c++) s += s_M[tid * 6 + c] * s_bp[c];
-      s_zp[tid] = s;
+      if (!use_coarse) {
+        double s = 0;
+        for (int c = 0; c < 6; c++) s += s_M[tid * 6 + c] * s_bp[c];
+        s_zp[tid] = s;
+      }
     }
-    // slots (shared memory, double-buffered): [par][8]; broadcast scalars s_bc[4]
-    double* s_slot = s_scal + 8;  // 16 doubles
-    double* s_bc = s_scal + 24;   // alpha / beta / flags
-    const int my_rank = blockIdx.x;
-    // Exchange by PUSH: warp 0 stores this CTA's values into every CTA's gather buffer (remote stores are fire and
-    // forget); after the cluster barrier everybody sums its LOCAL copy. Remote LOADS after the barrier cost a DSMEM
-    // round trip on the critical path and contend for the owner's shared-memory port.
-    auto push = [&](int buf, int k0, int nk) {  // called by warp 0 after its values sit in s_slot[k0 .. k0 + nk)
-      __syncwarp();
-      const int target = lane & 15, half = lane >> 4;  // two lanes per target CTA share the values
-      if (target < G) {
-        double* dst = cluster.map_shared_rank(s_gather, target) + (size_t)(buf * 16 + my_rank) * 8;
-        for (int k = half; k < nk; k += 2) dst[k0 + k] = s_slot[k0 + k];
-      }
-    };
-    // halo push: every thread takes entries of this chunk's push list (row -> target chunk, slot)
-    const int hp0 = P.push_ptr[c0], hp1 = P.push_ptr[c0 + 1];
-    auto push_halo = [&]() {  // after a CTA barrier that follows the z update
-      for (int e = hp0 + tid; e < hp1; e += nthr) {
-        const int row = P.push_row[e], dst = P.push_dst[e];
-        double* h = cluster.map_shared_rank(s_halo, dst >> 16) + 3 * (size_t)(dst & 65535);
-        const V3 z = ld3s(s_z, row - rb);
-        h[0] = z.x;
-        h[1] = z.y;
-        h[2] = z.z;
-      }
-    };
-    // ---- reduction helper pieces are inlined below; initial r.z
-    {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) rz_part += __shfl_xor_sync(0xffffffffu, rz_part, off);
-      if (lane == 0) s_red[warp] = rz_part;
-      __syncthreads();
-      push_halo();
-      if (warp == 0) {
-        double t = 0;
-        for (int w = lane; w < nw; w += 32) t += s_red[w];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        if (lane == 0) s_slot[7] = t;
-        push(1, 7, 1);
-      }
-      barrier();
-      if (warp == 0) {
-        double t = 0;
-        if (lane < G) t = s_gather[(size_t)(1 * 16 + lane) * 8 + 7];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        double rzp = 0;
-        if (pos)
-          for (int a = 0; a < 6; a++) rzp += s_rp[a] * s_zp[a];
-        if (lane == 0) s_bc[0] = t + rzp;
-      }
-      __syncthreads();
-    }
-    double rz = s_bc[0];
+    const long long ts7 = clock64();
+    double rz = finish_z(1, rz_part, rs0, rs1, rs2);
+    prof[14] += clock64() - ts7;  // setup: first z exchange
     const double rz0 = rz;
     if (!(rz0 > 0)) {  // b == 0: delta = 0
       if (tid < nrows) st3(P.xcg, rb + tid, V3{0, 0, 0});
-      barrier();  // nobody leaves while its slot may still be read
+      if (pos && tid < 6) s_xp[tid] = 0;
+      barrier();  // nobody leaves while its buffers may still be written
       return isfinite(rz0);
     }
     const double stop = P.pcg_tol * P.pcg_tol * rz0;
@@ -1490,8 +1831,8 @@ struct Engine {
     }
     for (; it < P.pcg_max_iter; it++) {
       const bool first = (it == 0);
-      // two gather buffers (iteration parity): entries [0..6] carry phase 1, [7] phase 2; a buffer is rewritten only
-      // after two further cluster barriers, when every reader has moved on
+      // two gather buffers (iteration parity): entries [0..6] carry phase 1, [7..10] phase 2; a buffer is rewritten
+      // only after two further cluster barriers, when every reader has moved on
       const int par = it & 1;
       // ---- phase 1: w = (H + lambda I) z ; p = z + beta p ; q = w + beta q ; partial p.q
       const long long tm0 = clock64();
@@ -1535,14 +1876,13 @@ struct Engine {
           }
         }
       }
-      #pragma unroll
+#pragma unroll
       for (int o = 1; o < kTPR; o <<= 1) {
         w0 += __shfl_xor_sync(0xffffffffu, w0, o);
         w1 += __shfl_xor_sync(0xffffffffu, w1, o);
         w2 += __shfl_xor_sync(0xffffffffu, w2, o);
       }
       if (valid && ql == 0) {
-        double red[6] = {0, 0, 0, 0, 0, 0};
         double q0 = w0 + (lambda + su) * zi.x, q1 = w1 + (lambda + su) * zi.y, q2 = w2 + (lambda + su) * zi.z;
         if (kf >= 0) {
           const double2* jo = reinterpret_cast<const double2*>(s_jac + kJS * (size_t)li);
@@ -1578,7 +1918,7 @@ struct Engine {
             }
             if (pos) {
 #pragma unroll
-              for (int a = 0; a < 6; a++) red[a] = A[a] * t0 + A[6 + a] * t1;
+              for (int a = 0; a < 6; a++) redw[a] = A[a] * t0 + A[6 + a] * t1;
             }
           }
         }
@@ -1592,10 +1932,6 @@ struct Engine {
           st3(s_p, li, pn);
           st3(s_q, li, qn);
           pq_part = pn.x * qn.x + pn.y * qn.y + pn.z * qn.z;
-        }
-        if (pos) {
-#pragma unroll
-          for (int a = 0; a < 6; a++) redw[a] = red[a];
         }
       }
       if (pos) {
@@ -1614,9 +1950,7 @@ struct Engine {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) pq_part += __shfl_xor_sync(0xffffffffu, pq_part, off);
       if (lane == 0) s_red[warp] = pq_part;
-      const long long tq0 = clock64();
       __syncthreads();  // S1
-      const long long tq1 = clock64();
       if (warp == 0) {
         double t = 0;
         for (int w = lane; w < nw; w += 32) t += s_red[w];
@@ -1632,9 +1966,8 @@ struct Engine {
       }
       const long long tm1 = clock64();
       barrier();  // B1
-      const long long tq2 = clock64();
       if (warp == 0) {
-        const double* rs = s_gather + (size_t)(par * 16 + (lane < G ? lane : 0)) * 8;
+        const double* rs = s_gather + (size_t)(par * 16 + (lane < G ? lane : 0)) * kGatherVals;
         double t[7];
 #pragma unroll
         for (int k = 0; k < 7; k++) t[k] = (lane < G && (k == 0 || pos)) ? rs[k] : 0.0;
@@ -1652,7 +1985,8 @@ struct Engine {
 #pragma unroll
             for (int k = 2; k < 7; k++)
               if (lane == k - 1) wsum = t[k];
-            const double w = lambda * s_zp[lane] + wsum;
+            double w = lambda * s_zp[lane] + wsum;
+            // H_pp z_p is part of the row sums already (every row adds A^T omega A z_p)
             ppv = first ? s_zp[lane] : s_zp[lane] + beta * s_pp[lane];
             qpv = first ? w : w + beta * s_qp[lane];
             s_pp[lane] = ppv;
@@ -1674,8 +2008,9 @@ struct Engine {
         break;
       }
       const double alpha = rz / pq;
-      // ---- phase 2: x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z   (lane l < 3 of a quad: component l)
+      // ---- phase 2: x += alpha p ; r -= alpha q ; t = M_B^-1 r ; partial r.t and aggregate residual sums
       double rzn_part = 0;
+      rs0 = rs1 = rs2 = 0;
       const bool act = valid && !fixed;
       if (act) {
         for (int cmp = ql; cmp < 3; cmp += kTPR) {
@@ -1684,9 +2019,12 @@ struct Engine {
           const double rc = s_r[o] - alpha * s_q[o];
           s_r[o] = rc;
           if (bprec) s_rf[3 * li + cmp] = (float)rc;
+          if (cmp == 0) rs0 = rc;
+          else if (cmp == 1) rs1 = rc;
+          else rs2 = rc;
         }
       }
-      if (pos && tid < 6) {  // pose rows (replicated): x, r, z = M r
+      if (pos && tid < 6) {  // pose rows (replicated): x, r
         s_xp[tid] += alpha * s_pp[tid];
         s_rp[tid] -= alpha * s_qp[tid];
       }
@@ -1704,55 +2042,21 @@ struct Engine {
         __syncthreads();  // S3 (pose r complete)
       } else {
         __syncthreads();  // S3 (rf and pose r complete)
-        const long long tq4 = clock64(); prof[11] += tq4 - tm2;  // phase 2a: x, r, rf + S3
         rzn_part = prec_apply_quads(rb, re, false);
       }
-      if (pos && tid < 6) {
+      if (pos && !use_coarse && tid < 6) {
         double s = 0;
 #pragma unroll
         for (int c = 0; c < 6; c++) s += s_M[tid * 6 + c] * s_rp[c];
         s_zp[tid] = s;
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) rzn_part += __shfl_xor_sync(0xffffffffu, rzn_part, off);
-      if (lane == 0) s_red[warp] = rzn_part;
-      __syncthreads();  // S4
-      const long long tq5 = clock64();
-      push_halo();
-      if (warp == 0) {
-        double t = 0;
-        for (int w = lane; w < nw; w += 32) t += s_red[w];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        if (lane == 0) s_slot[7] = t;
-        push(par, 7, 1);
-      }
       const long long tm3 = clock64();
-      barrier();  // B2
-      const long long tq6 = clock64();
-      if (warp == 0) {
-        double t = 0;
-        if (lane < G) t = s_gather[(size_t)(par * 16 + lane) * 8 + 7];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        double rzp = 0;
-        if (pos)
-          for (int a = 0; a < 6; a++) rzp += s_rp[a] * s_zp[a];
-        if (lane == 0) s_bc[1] = t + rzp;
-      }
-      __syncthreads();  // S5
+      const double rzn = finish_z(par, rzn_part, rs0, rs1, rs2);
       const long long tm4 = clock64();
       prof[1] += tm1 - tm0;  // matvec pass
-      prof[8] += tq0 - tm0;   // phase 1 row work up to the block reduction
-      prof[9] += tq1 - tq0;   // S1 wait
-      prof[10] += tm1 - tq1;  // warp 0: reduce + push (other warps: nothing)
-      prof[12] += tq2 - tm1;  // B1
-      prof[13] += tq5 - tm2;  // phase 2 up to S4 (incl. S3, prec apply)
-      prof[14] += tq6 - tm3;  // B2
       prof[2] += tm2 - tm1;  // pq exchange
       prof[3] += tm3 - tm2;  // update pass
-      prof[4] += tm4 - tm3;  // rz exchange
-      const double rzn = s_bc[1];
+      prof[4] += tm4 - tm3;  // z exchange (+ coarse level)
       if (!isfinite(rzn)) {
         ok = false;
         it++;
@@ -1767,7 +2071,7 @@ struct Engine {
     }
     pcg_iters += it;
     if (tid < nrows) st3(P.xcg, rb + tid, ld3p(s_x, tid));
-    barrier();  // every remote read of this CTA's shared memory has completed; s_xp is complete
+    barrier();  // every remote write into this CTA's shared memory has landed; s_xp is complete
     return ok;
   }
 
@@ -1991,7 +2295,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) nrs_lm_kernel(const __grid_const
 }  // namespace
 
 size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec) {
-  size_t d = (size_t)F * (7 + 7 + 21 + 36 + 6 * 6) + 32 * kChunkVals + 32 + 6 * kMaxRows + 2 * 16 * 8 + 2 + 6;  // + alignment slack
+  size_t d = (size_t)F * (7 + 7 + 21 + 36 + 6 * 6) + 32 * kChunkVals + 32 + 6 * kMaxRows + 2 * 16 * kGatherVals + 2 + 6;  // + alignment slack
   if (res_rows == 0) d += 16 * kMaxRows;
   if (res_rows > 0) {
     d += std::max((size_t)kJS * res_rows, 16 * (size_t)kMaxRows) + (size_t)res_rows * (4 * 4 + 3 + (block_prec ? 0 : 8)) +
@@ -2001,6 +2305,14 @@ size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec) {
     return bytes + 16;
   }
   return d * sizeof(double) + 16;
+}
+
+size_t engine_smem_extra(int res_inc, int halo_rows, int coarse) {
+  size_t b = sizeof(double) * ((3 * (size_t)halo_rows + 1) & ~(size_t)1);
+  if (coarse)
+    b += sizeof(float) * (16 * kRowBlk + kCoarseN * kCoarseS + kCoarseS + 2 * kCoarseS) + (((size_t)res_inc + 15) & ~(size_t)15) +
+         (((size_t)halo_rows + 15) & ~(size_t)15) + 64;
+  return b;
 }
 
 static bool set_smem(size_t smem) {

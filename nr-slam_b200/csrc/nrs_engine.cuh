@@ -41,6 +41,10 @@ constexpr int kTPR = NRS_TPR;    // threads per point row inside the CG loop (a 
 constexpr int kMaxRows = 128;    // point rows per chunk
 constexpr int kMaxBlock = kTPR * kMaxRows;  // threads per CTA (544)
 constexpr int kPrecBlock = 16;   // rows per dense preconditioner block (resident mode)
+constexpr int kGatherVals = 12;  // doubles per CTA in the pushed reduction buffers of the cluster-native CG loop
+constexpr int kCoarseN = 6 + 3 * 16;   // coarse unknowns: pose + one 3-dof aggregate per CTA of the cluster
+constexpr int kCoarseS = 60;     // row stride of the coarse matrix (floats): float4 rows, conflict-free across lanes
+constexpr int kRowBlk = 116;     // floats a CTA publishes for the coarse matrix: 16 x 6 (sym 3x3) + 18 (pose coupling) + 1 + pad
 
 struct EngineStats {
   int lm_iterations, lm_trials, pcg_iterations, n_sweeps, n_chi2_passes, n_trace, pcg_fail, barriers;
@@ -75,11 +79,14 @@ struct Params {
   int no_dsmem;       // 1: keep the general CG loop (exchange through L2) even where the cluster-native loop applies
   // halo exchange of the cluster-native CG loop: after every z = M^-1 r the owner of a row PUSHES it into the halo
   // buffer of every chunk whose regulariser edges read it (remote shared-memory stores, no remote loads)
-  int halo_rows;            // shared-memory capacity: halo rows per chunk (0: pull through distributed shared memory)
+  int coarse;               // 1: two-level preconditioner in the cluster-native loop (one 3-dof aggregate per chunk + the pose)
+  int halo_rows;            // shared-memory capacity: halo rows per chunk
   const int* inc_halo;      // [2P] per incidence: halo slot of the neighbour in this chunk's buffer, -1 if in-chunk
   const int* push_ptr;      // [n_chunks + 1]
   const int* push_row;      // row (global index) to push
   const int* push_dst;      // target chunk * 65536 + slot
+  const int* xinc_ptr;      // [n_chunks + 1] per chunk: its incidences whose neighbour lives in another chunk ...
+  const int* xinc_idx;      // ... as indices into the incidence arrays, ascending (coarse-matrix assembly)
 
   // poses: 7 doubles each (q xyzw, t)
   double* pose;
@@ -104,6 +111,7 @@ struct Params {
   const int* inc_ptr;       // [V+1] CSR of pair incidences per point
   const int* inc_other;     // neighbour vertex
   const int* inc_ent;       // pair id * 2 + (1 if this vertex is the pair's second endpoint)
+  const int* inc_row;       // the point row an incidence belongs to
   // damper edges (four point vertices: i_k, j_k, i_k', j_k')
   const int* dmp_v;         // [4D]
   const double* dmp_w;      // [D]
@@ -141,6 +149,8 @@ struct Params {
 int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_t stream);
 // Shared memory needed for F poses (+ the resident chunk state when res_rows > 0).
 size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec);
+// Extra shared memory of the cluster-native loop: pushed halo rows and the coarse (aggregate) level.
+size_t engine_smem_extra(int res_inc, int halo_rows, int coarse);
 // Largest co-resident grid for a cooperative launch / largest cluster that can be scheduled (0 if none).
 int engine_max_grid(int block, size_t smem);
 int engine_max_cluster(int block, size_t smem);
