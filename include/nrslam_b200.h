@@ -179,6 +179,40 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
                          const nrslam_b200_graph* g, float scale, int32_t iterations,
                          nrslam_b200_stats* stats);
 
+/* ---- Landmark-sharded LocalDeformableBundleAdjustment over up to 8 GPUs of one NVSwitch domain ----
+ * Same problem and same results (within the stated FP tolerance) as nrslam_b200_local_ba
+ * (g2o_optimization.cc:880-1161); one process and one ctx per GPU. Every rank passes the FULL window and derives the
+ * same partition: landmarks are cut along a Morton curve into `world` ranges of equal observation count, a rank
+ * optimises every per-keyframe copy of its landmarks, keeps read-only halo copies of the neighbours its springs /
+ * dampers reach on other ranks, and the ranks exchange halo rows and partial sums (pose blocks of H and b, chi2,
+ * CG scalars) through peer-mapped buffers inside the persistent kernel — no host round trip per iteration.
+ *   shard_init   allocates this rank's exchange buffer (capacity: max_rows own + halo rows, max_poses keyframes,
+ *                identical on every rank) and returns its CUDA IPC handle;
+ *   shard_attach maps the other ranks' buffers; handles = world x NRSLAM_B200_IPC_HANDLE_BYTES in rank order
+ *                (exchanged by the caller, e.g. torch.distributed.all_gather);
+ *   local_ba_sharded  is collective: every rank must call it with identical arguments. kf_pose_io is updated
+ *                on every rank (bit-identical), X_io only for the observations this rank owns; owner_out[n_obs]
+ *                (optional) names the owner of every observation so the caller can gather the rest.
+ * A rank that fails to arrive makes the others time out (NRSLAM_B200_XTIMEOUT_MS, default 20 s) with
+ * NRSLAM_B200_ERR_CUDA instead of hanging; the sharded state is then unusable until the ctx is re-created. */
+#define NRSLAM_B200_IPC_HANDLE_BYTES 64
+int nrslam_b200_shard_init(nrslam_b200_ctx* ctx, int32_t rank, int32_t world, int32_t max_rows,
+                           int32_t max_poses, unsigned char* handle_out);
+int nrslam_b200_shard_attach(nrslam_b200_ctx* ctx, const unsigned char* handles);
+int nrslam_b200_local_ba_sharded(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n_kf,
+                                 float* kf_pose_io, int32_t n_obs, const int32_t* obs_kf,
+                                 const int32_t* obs_vertex, const float* uv, float* X_io,
+                                 const nrslam_b200_graph* g, float scale, int32_t iterations,
+                                 int32_t* owner_out, nrslam_b200_stats* stats);
+/* Host-only view of that partition (no GPU needed): owner_out[n_obs]; per rank the rows it owns, its halo rows, the
+ * halo copies it refreshes, and n_edges_out[3 world] = (springs, dampers, edges whose chi2 it counts). */
+int nrslam_b200_shard_partition(const nrslam_b200_options* opt, int32_t world, int32_t n_kf,
+                                const float* kf_pose, int32_t n_obs, const int32_t* obs_kf,
+                                const int32_t* obs_vertex, const float* uv, const float* X,
+                                const nrslam_b200_graph* g, float scale, int32_t* owner_out,
+                                int32_t* n_own_out, int32_t* n_halo_out, int32_t* n_push_out,
+                                int32_t* n_edges_out);
+
 /* Re-run the device solve of the most recently staged problem on its HBM-resident inputs (no host<->device
  * copies, no host bookkeeping). which: 0 pose_only, 1 pose_deform (both robust rounds), 2 local_ba.
  * Benchmark / profiler hook: results are identical to the staged call's. */

@@ -23,6 +23,9 @@ ERRORS = {-1: "no sm_100 device", -2: "CUDA error", -3: "bad argument", -4: "all
           -6: "not implemented", 1: "too few points / keyframes", 2: "non-finite result"}
 
 
+IPC_HANDLE_BYTES = 64
+
+
 class NrslamError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("nrslam_b200 error %d (%s): %s" % (code, ERRORS.get(code, "?"), msg))
@@ -144,6 +147,39 @@ class Core:
             ptr(uv, C.c_float), ptr(X, C.c_float), C.byref(g), C.c_float(scale), int(iterations), C.byref(st)))
         return dict(rc=rc, kf_pose=kf_pose, X=X, stats=st.as_dict())
 
+    # ---- landmark-sharded BA over several GPUs (one process + one Core per GPU; include/nrslam_b200.h)
+    def shard_init(self, rank, world, max_rows, max_poses):
+        """Allocates this rank's exchange buffer; returns its 64-byte CUDA IPC handle (bytes)."""
+        h = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        self._check(self.L.nrslam_b200_shard_init(self._ctx, int(rank), int(world), int(max_rows), int(max_poses), h))
+        self._shard = (int(rank), int(world))
+        return bytes(h)
+
+    def shard_attach(self, handles):
+        """handles: the ranks' IPC handles in rank order (e.g. from torch.distributed.all_gather_object)."""
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.L.nrslam_b200_shard_attach(self._ctx, buf))
+
+    def local_ba_sharded(self, cam, kf_pose, obs_kf, obs_vertex, uv, X, graph, scale, iterations=0):
+        """Collective: every rank passes the full window. Returns the poses (identical on every rank), X with this
+        rank's observations optimised (others as passed in) and owner[n_obs]."""
+        F = len(kf_pose)
+        O = len(obs_kf)
+        kf_pose = np.array(kf_pose, np.float32)
+        X = np.array(X, np.float32)
+        ok = np.ascontiguousarray(obs_kf, np.int32)
+        ov = np.ascontiguousarray(obs_vertex, np.int32)
+        uv = _f32(uv)
+        owner = np.zeros(O, np.int32)
+        st = Stats()
+        g = graph.struct()
+        rc = self._check(self.L.nrslam_b200_local_ba_sharded(
+            self._ctx, C.byref(cam), F, ptr(kf_pose, C.c_float), O, ptr(ok, C.c_int32), ptr(ov, C.c_int32),
+            ptr(uv, C.c_float), ptr(X, C.c_float), C.byref(g), C.c_float(scale), int(iterations),
+            ptr(owner, C.c_int32), C.byref(st)))
+        return dict(rc=rc, kf_pose=kf_pose, X=X, owner=owner, stats=st.as_dict())
+
     def resolve(self, which):
         """Re-run the device program of the last staged problem (0 pose_only, 1 pose_deform, 2 local_ba)."""
         st = Stats()
@@ -259,6 +295,29 @@ class KLT:
                                                        ptr(der, C.c_int16), C.byref(ow), C.byref(oh)))
         assert (ow.value, oh.value) == (w, h)
         return img, der
+
+
+def shard_partition(world, kf_pose, obs_kf, obs_vertex, uv, X, graph, scale, opt=None):
+    """Host-only view of the landmark partition local_ba_sharded uses (no GPU): owner[n_obs] and per-rank counts."""
+    L = load()
+    F, O = len(kf_pose), len(obs_kf)
+    kf_pose = _f32(kf_pose)
+    X = _f32(X)
+    ok = np.ascontiguousarray(obs_kf, np.int32)
+    ov = np.ascontiguousarray(obs_vertex, np.int32)
+    uv = _f32(uv)
+    owner = np.zeros(O, np.int32)
+    n_own, n_halo, n_push = (np.zeros(world, np.int32) for _ in range(3))
+    n_edges = np.zeros(3 * world, np.int32)
+    g = graph.struct()
+    rc = L.nrslam_b200_shard_partition(C.byref(opt) if opt is not None else None, int(world), F,
+                                       ptr(kf_pose, C.c_float), O, ptr(ok, C.c_int32), ptr(ov, C.c_int32),
+                                       ptr(uv, C.c_float), ptr(X, C.c_float), C.byref(g), C.c_float(scale),
+                                       ptr(owner, C.c_int32), ptr(n_own, C.c_int32), ptr(n_halo, C.c_int32),
+                                       ptr(n_push, C.c_int32), ptr(n_edges, C.c_int32))
+    if rc != 0:
+        raise NrslamError(rc, "shard_partition")
+    return dict(owner=owner, n_own=n_own, n_halo=n_halo, n_push=n_push, n_edges=n_edges.reshape(world, 3))
 
 
 def project_points(cam, pose, X):

@@ -115,6 +115,8 @@ struct HostProblem {
   int n_sort = 0;                       // leading rows of every pose-slot group that may be re-ordered spatially
   int n_stage1 = 0;                     // rows of the first launch (tracking: without the lost-point rows); 0 = all
   std::vector<int> kf_begin;            // F+1: rows of pose slot k are [kf_begin[k], kf_begin[k+1]) (rows w/o pose: slot 0)
+  int n_halo = 0;                       // landmark-sharded BA: trailing rows owned by other ranks (read-only copies)
+  bool sharded = false;
   std::vector<int> ops, op_args;
 };
 
@@ -271,7 +273,7 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
     return n;
   };
   int chunk_rows = kMaxRows, cluster_mode = 0;
-  if (ncl >= 2) {
+  if (ncl >= 2 && !hp.sharded) {  // a sharded rank synchronises with its peers through the cooperative-grid path
     for (int rows = 32; rows <= kMaxRows; rows += 8) {
       if (count_chunks(rows) <= ncl) {
         chunk_rows = rows;
@@ -307,7 +309,7 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
   size_t smem = engine_smem_bytes(F, 0, 0, 0);
   if (smem > 200 * 1024) return fail(ctx, NRSLAM_B200_ERR_ARG, "too many poses for the shared-memory pose blocks");
   const size_t kSmemBudget = 220 * 1024;
-  if (!hp.points_fixed && env_int("NRSLAM_B200_RESIDENT", 1)) {
+  if (!hp.points_fixed && !hp.sharded && env_int("NRSLAM_B200_RESIDENT", 1)) {
     const size_t s1 = engine_smem_bytes(F, res_rows, res_inc, 1), s0 = engine_smem_bytes(F, res_rows, res_inc, 0);
     const bool want_prec = env_int("NRSLAM_B200_BLOCKPREC", 1) != 0;
     const size_t s = (want_prec && s1 <= kSmemBudget) ? s1 : s0;
@@ -395,14 +397,14 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
 
   // ---- launch plans. Tracking stages its lost-point rows behind the optimised ones: the main rounds run on the
   // first hp.n_stage1 rows only (plan A), the lost-point stage on all rows (plan B).
-  const int V1 = (hp.n_stage1 > 0 && hp.n_stage1 < V && F == 1) ? hp.n_stage1 : V;
+  const int V1 = hp.sharded ? V - hp.n_halo : (hp.n_stage1 > 0 && hp.n_stage1 < V && F == 1) ? hp.n_stage1 : V;
   Plan planA, planB;
   {
     std::vector<int> kfb(hp.kf_begin);
     kfb[F] = V1;
     const int rc = make_plan(ctx, hp, kfb, inc_ptr, planA);
     if (rc) return rc;
-    if (V1 < V) {
+    if (V1 < V && !hp.sharded) {
       const int rc2 = make_plan(ctx, hp, hp.kf_begin, inc_ptr, planB);
       if (rc2) return rc2;
     }
@@ -691,6 +693,10 @@ void nrslam_b200_destroy(nrslam_b200_ctx* ctx) {
     s.work.release();
     s.out.release();
   }
+  for (int r = 0; r < nrs::kMaxWorld; r++)
+    if (ctx->shard.peer[r] && r != ctx->shard.rank) cudaIpcCloseMemHandle(ctx->shard.peer[r]);
+  if (ctx->shard.local) cudaFree(ctx->shard.local);
+  for (auto& s : ctx->staged) s.xin.release();
   if (ctx->bar) cudaFree(ctx->bar);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1036,18 +1042,14 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
 // =====================================================================================================
 // LocalDeformableBundleAdjustment — g2o_optimization.cc:880-1161
 // =====================================================================================================
-int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t F, float* kf_pose_io,
-                         int32_t O, const int32_t* obs_kf, const int32_t* obs_vertex, const float* uv,
-                         float* X_io, const nrslam_b200_graph* g, float scale, int32_t iterations,
-                         nrslam_b200_stats* stats) {
-  if (!ctx || !cam || !kf_pose_io || !obs_kf || !obs_vertex || !uv || !X_io || !g || O < 0)
-    return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba: bad argument");
-  const double t0 = wall_ms();
-  if (stats) memset(stats, 0, sizeof(*stats));
-  if (F < 3) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: fewer than 3 keyframes");  // :922-924
-  if (O == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: no observations");
-  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
-  const nrslam_b200_options& opt = ctx->opt;
+}  // extern "C"
+
+namespace {
+// Graph construction of the BA window (vertices, reprojection edges, springs, dampers) in the reference's order.
+int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const nrslam_b200_camera* cam, int32_t F,
+                     const float* kf_pose_io, int32_t O, const int32_t* obs_kf, const int32_t* obs_vertex,
+                     const float* uv, const float* X_io, const nrslam_b200_graph* g, float scale, int32_t iterations,
+                     HostProblem& hp) {
   if (iterations <= 0) iterations = opt.ba_iterations;
   const int M = g->n_vertices;
   const int regularizers_per_point = opt.regularizers_per_point;
@@ -1058,7 +1060,6 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
   const float info_spatial = 1.0f / (sigma_spatial * sigma_spatial);
   const float min_w = graph_min_weight(g);
 
-  HostProblem hp;
   hp.F = F;
   hp.V = O;
   hp.cam = to_cam(cam);
@@ -1163,6 +1164,378 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
   hp.op_args = {0, 0, iterations};
   hp.n_sort = O;
 
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Landmark sharding of a BA window over `world` ranks. Every rank runs this on the FULL problem and
+// derives the same partition, so no metadata is exchanged at run time:
+//   - landmarks are ordered along a Morton curve of their first observed position and cut into `world` contiguous
+//     ranges of equal observation count; a rank owns every per-keyframe copy of its landmarks;
+//   - a rank's problem = its rows (keyframe-major, Morton order inside a keyframe) + read-only halo copies of the
+//     rows of other ranks that its springs / dampers touch; an edge shared by two ranks is linearised by both and
+//     its chi2 is counted by the owner of its first endpoint;
+//   - push lists tell the owner of a row which halo copies to refresh (rank << 26 | row index on that rank).
+// ---------------------------------------------------------------------------------------------------
+struct ShardPlan {
+  std::vector<int> row_of;           // caller observation -> row of the globally sorted problem
+  std::vector<int> owner;            // [O] owner rank of a sorted row
+  std::vector<int> loc_of;           // [O] index of a sorted row among its owner's rows
+  std::vector<int> n_own;            // [world]
+  std::vector<std::vector<int>> halo;  // [world] sorted rows (global sorted index) held as halo copies
+  std::vector<int> xp_ptr, xp_dst;   // push lists of `rank`
+  std::vector<unsigned char> pair_cnt, dmp_cnt;
+};
+
+int shard_problem(HostProblem& G, const int32_t* obs_vertex, int n_vertices, int rank, int world, HostProblem& L,
+                  ShardPlan& sp) {
+  const int O = G.V, F = G.F;
+  G.n_sort = O;
+  sort_rows(G, sp.row_of);
+  std::vector<int> lm_of_row(O);
+  for (int o = 0; o < O; o++) lm_of_row[sp.row_of[o]] = obs_vertex[o];
+  // ---- landmark order: Morton code of the first (oldest keyframe) observed position, ties by id
+  std::vector<int> first_row(n_vertices, -1), n_obs(n_vertices, 0);
+  for (int r = 0; r < O; r++) {
+    const int m = lm_of_row[r];
+    if (first_row[m] < 0) first_row[m] = r;
+    n_obs[m]++;
+  }
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int m = 0; m < n_vertices; m++) {
+    if (first_row[m] < 0) continue;
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], G.x_seed[4 * (size_t)first_row[m] + a]);
+      hi[a] = std::max(hi[a], G.x_seed[4 * (size_t)first_row[m] + a]);
+    }
+  }
+  double ext = 0;
+  for (int a = 0; a < 3; a++) ext = std::max(ext, hi[a] - lo[a]);
+  const double inv = ext > 0 ? 1.0 / ext : 0.0;
+  const double inv_ext[3] = {inv, inv, inv};
+  std::vector<std::pair<uint32_t, int>> keyed;
+  for (int m = 0; m < n_vertices; m++)
+    if (first_row[m] >= 0) keyed.emplace_back(morton3(&G.x_seed[4 * (size_t)first_row[m]], lo, inv_ext), m);
+  std::sort(keyed.begin(), keyed.end());
+  std::vector<int> lm_owner(n_vertices, -1);
+  {
+    long long seen = 0;
+    for (auto& km : keyed) {
+      // the landmark goes to the rank whose range contains the midpoint of its observations
+      const long long mid = 2 * seen + n_obs[km.second];
+      int r = (int)((mid * world) / (2 * (long long)O));
+      lm_owner[km.second] = std::min(std::max(r, 0), world - 1);
+      seen += n_obs[km.second];
+    }
+  }
+  sp.owner.resize(O);
+  sp.loc_of.resize(O);
+  sp.n_own.assign(world, 0);
+  for (int r = 0; r < O; r++) {
+    sp.owner[r] = lm_owner[lm_of_row[r]];
+    sp.loc_of[r] = sp.n_own[sp.owner[r]]++;
+  }
+  // ---- halo sets of every rank
+  sp.halo.assign(world, {});
+  const int P = (int)G.pair_i.size(), D = (int)G.dmp_w.size();
+  for (int e = 0; e < P; e++) {
+    const int i = G.pair_i[e], j = G.pair_j[e];
+    if (sp.owner[i] != sp.owner[j]) {
+      sp.halo[sp.owner[i]].push_back(j);
+      sp.halo[sp.owner[j]].push_back(i);
+    }
+  }
+  for (int e = 0; e < D; e++) {
+    const int* v = &G.dmp_v[4 * (size_t)e];
+    const int oa = sp.owner[v[0]], ob = sp.owner[v[1]];
+    if (oa != ob) {
+      sp.halo[oa].push_back(v[1]);
+      sp.halo[oa].push_back(v[3]);
+      sp.halo[ob].push_back(v[0]);
+      sp.halo[ob].push_back(v[2]);
+    }
+  }
+  for (auto& h : sp.halo) {
+    std::sort(h.begin(), h.end());
+    h.erase(std::unique(h.begin(), h.end()), h.end());
+  }
+  // ---- this rank's problem
+  const int n_own = sp.n_own[rank], n_halo = (int)sp.halo[rank].size();
+  auto local_of = [&](int row) {
+    if (sp.owner[row] == rank) return sp.loc_of[row];
+    const auto& h = sp.halo[rank];
+    return n_own + (int)(std::lower_bound(h.begin(), h.end(), row) - h.begin());
+  };
+  L = HostProblem();
+  L.F = F;
+  L.V = n_own + n_halo;
+  L.n_halo = n_halo;
+  L.sharded = true;
+  L.poses_fixed = G.poses_fixed;
+  L.points_fixed = G.points_fixed;
+  L.spring_kind = G.spring_kind;
+  L.cam = G.cam;
+  L.info_reproj = G.info_reproj; L.delta_reproj = G.delta_reproj;
+  L.info_spatial = G.info_spatial; L.delta_spatial = G.delta_spatial;
+  L.info_spring = G.info_spring; L.delta_spring = G.delta_spring; L.spring_k = G.spring_k;
+  L.th2f = G.th2f; L.th3f = G.th3f;
+  L.pose_seed = G.pose_seed;
+  L.ops = G.ops;
+  L.op_args = G.op_args;
+  L.n_sort = 0;
+  L.x_seed.assign(4 * (size_t)L.V, 0.0);
+  L.rest.assign(4 * (size_t)L.V, 0.0);
+  L.uv.assign(2 * (size_t)L.V, 0.0);
+  L.pt_kf.assign(L.V, -1);
+  L.kf_begin.assign(F + 1, 0);
+  for (int r = 0; r < O; r++) {
+    if (sp.owner[r] != rank) continue;
+    const int li = sp.loc_of[r];
+    for (int a = 0; a < 4; a++) L.x_seed[4 * (size_t)li + a] = G.x_seed[4 * (size_t)r + a];
+    L.uv[2 * (size_t)li] = G.uv[2 * (size_t)r];
+    L.uv[2 * (size_t)li + 1] = G.uv[2 * (size_t)r + 1];
+    L.pt_kf[li] = G.pt_kf[r];
+    L.kf_begin[G.pt_kf[r] + 1]++;
+  }
+  for (int k = 0; k < F; k++) L.kf_begin[k + 1] += L.kf_begin[k];
+  for (int h = 0; h < n_halo; h++)
+    for (int a = 0; a < 4; a++) L.x_seed[4 * (size_t)(n_own + h) + a] = G.x_seed[4 * (size_t)sp.halo[rank][h] + a];
+  for (int e = 0; e < P; e++) {
+    const int i = G.pair_i[e], j = G.pair_j[e];
+    if (sp.owner[i] != rank && sp.owner[j] != rank) continue;
+    L.pair_i.push_back(local_of(i));
+    L.pair_j.push_back(local_of(j));
+    L.pair_w.push_back(G.pair_w[e]);
+    L.pair_d0.push_back(G.pair_d0[e]);
+    sp.pair_cnt.push_back(sp.owner[i] == rank ? 1 : 0);
+  }
+  for (int e = 0; e < D; e++) {
+    const int* v = &G.dmp_v[4 * (size_t)e];
+    if (sp.owner[v[0]] != rank && sp.owner[v[1]] != rank) continue;
+    for (int a = 0; a < 4; a++) L.dmp_v.push_back(local_of(v[a]));
+    L.dmp_w.push_back(G.dmp_w[e]);
+    sp.dmp_cnt.push_back(sp.owner[v[0]] == rank ? 1 : 0);
+  }
+  // ---- push lists: for every rank r that holds one of my rows as a halo copy
+  std::vector<std::vector<int>> dst(n_own);
+  for (int r = 0; r < world; r++) {
+    if (r == rank) continue;
+    const auto& h = sp.halo[r];
+    for (int s = 0; s < (int)h.size(); s++)
+      if (sp.owner[h[s]] == rank) dst[sp.loc_of[h[s]]].push_back((r << 26) | (sp.n_own[r] + s));
+  }
+  sp.xp_ptr.assign(L.V + 1, 0);
+  sp.xp_dst.clear();
+  for (int i = 0; i < n_own; i++) {
+    for (int d : dst[i]) sp.xp_dst.push_back(d);
+    sp.xp_ptr[i + 1] = (int)sp.xp_dst.size();
+  }
+  for (int i = n_own; i < L.V; i++) sp.xp_ptr[i + 1] = sp.xp_ptr[n_own];
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int nrslam_b200_shard_partition(const nrslam_b200_options* opt_in, int32_t world, int32_t F, const float* kf_pose,
+                                int32_t O, const int32_t* obs_kf, const int32_t* obs_vertex, const float* uv,
+                                const float* X, const nrslam_b200_graph* g, float scale, int32_t* owner_out,
+                                int32_t* n_own_out, int32_t* n_halo_out, int32_t* n_push_out,
+                                int32_t* n_edges_out) {
+  if (!kf_pose || !obs_kf || !obs_vertex || !uv || !X || !g || !owner_out || world < 1 || world > nrs::kMaxWorld ||
+      F < 1 || O < 1)
+    return NRSLAM_B200_ERR_ARG;
+  nrslam_b200_options opt;
+  if (opt_in) opt = *opt_in; else nrslam_b200_default_options(&opt);
+  nrslam_b200_camera cam;
+  memset(&cam, 0, sizeof(cam));
+  for (int r = 0; r < world; r++) {
+    HostProblem G, L;
+    const int rc = build_ba_problem(nullptr, opt, &cam, F, kf_pose, O, obs_kf, obs_vertex, uv, X, g, scale, 0, G);
+    if (rc) return rc;
+    ShardPlan sp;
+    shard_problem(G, obs_vertex, g->n_vertices, r, world, L, sp);
+    if (r == 0)
+      for (int o = 0; o < O; o++) owner_out[o] = sp.owner[sp.row_of[o]];
+    if (n_own_out) n_own_out[r] = sp.n_own[r];
+    if (n_halo_out) n_halo_out[r] = L.n_halo;
+    if (n_push_out) n_push_out[r] = (int)sp.xp_dst.size();
+    if (n_edges_out) {
+      n_edges_out[3 * r] = (int)L.pair_i.size();
+      n_edges_out[3 * r + 1] = (int)L.dmp_w.size();
+      int cnt = 0;
+      for (unsigned char c : sp.pair_cnt) cnt += c;
+      for (unsigned char c : sp.dmp_cnt) cnt += c;
+      n_edges_out[3 * r + 2] = cnt;  // edges whose chi2 this rank counts
+    }
+  }
+  return 0;
+}
+
+int nrslam_b200_shard_init(nrslam_b200_ctx* ctx, int32_t rank, int32_t world, int32_t max_rows, int32_t max_poses,
+                           unsigned char* handle_out) {
+  if (!ctx || !handle_out || world < 2 || world > nrs::kMaxWorld || rank < 0 || rank >= world || max_rows < 1 ||
+      max_poses < 1)
+    return fail(ctx, NRSLAM_B200_ERR_ARG, "shard_init: bad argument");
+  Shard& sh = ctx->shard;
+  if (sh.local) return fail(ctx, NRSLAM_B200_ERR_ARG, "shard_init: already initialised");
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  sh.rank = rank;
+  sh.world = world;
+  sh.max_rows = max_rows;
+  sh.max_poses = max_poses;
+  sh.xstride = 8 + 27 * max_poses;
+  sh.off_abort = 8 * nrs::kMaxWorld;
+  sh.off_red = 256;
+  sh.off_z = sh.off_red + sizeof(double) * 2 * (size_t)world * sh.xstride;
+  sh.off_z = (sh.off_z + 255) & ~size_t(255);
+  sh.off_x = sh.off_z + sizeof(double) * 4 * (size_t)max_rows;
+  sh.bytes = sh.off_x + sizeof(double) * 4 * (size_t)max_rows;
+  NRS_CUDA(ctx, cudaMalloc(&sh.local, sh.bytes));
+  NRS_CUDA(ctx, cudaMemset(sh.local, 0, sh.bytes));
+  NRS_CUDA(ctx, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  NRS_CUDA(ctx, cudaIpcGetMemHandle(&h, sh.local));
+  static_assert(sizeof(h) == NRSLAM_B200_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int nrslam_b200_shard_attach(nrslam_b200_ctx* ctx, const unsigned char* handles) {
+  if (!ctx || !handles || !ctx->shard.local) return fail(ctx, NRSLAM_B200_ERR_ARG, "shard_attach: bad argument");
+  Shard& sh = ctx->shard;
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < sh.world; r++) {
+    if (r == sh.rank) {
+      sh.peer[r] = sh.local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+    NRS_CUDA(ctx, cudaIpcOpenMemHandle(&sh.peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  sh.attached = true;
+  sh.broken = false;
+  sh.epoch = 0;
+  return 0;
+}
+
+int nrslam_b200_local_ba_sharded(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t F, float* kf_pose_io,
+                                 int32_t O, const int32_t* obs_kf, const int32_t* obs_vertex, const float* uv,
+                                 float* X_io, const nrslam_b200_graph* g, float scale, int32_t iterations,
+                                 int32_t* owner_out, nrslam_b200_stats* stats) {
+  if (!ctx || !cam || !kf_pose_io || !obs_kf || !obs_vertex || !uv || !X_io || !g || O < 0)
+    return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba_sharded: bad argument");
+  Shard& sh = ctx->shard;
+  if (!sh.attached) return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba_sharded: call shard_init / shard_attach first");
+  if (sh.broken) return fail(ctx, NRSLAM_B200_ERR_CUDA, "local_ba_sharded: an earlier exchange timed out; re-create the context");
+  const double t0 = wall_ms();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (F < 3) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: fewer than 3 keyframes");
+  if (O == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: no observations");
+  if (F > sh.max_poses) return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba_sharded: more keyframes than shard_init reserved");
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  HostProblem G, hp;
+  {
+    const int brc = build_ba_problem(ctx, ctx->opt, cam, F, kf_pose_io, O, obs_kf, obs_vertex, uv, X_io, g, scale,
+                                     iterations, G);
+    if (brc) return brc;
+  }
+  ShardPlan sp;
+  shard_problem(G, obs_vertex, g->n_vertices, sh.rank, sh.world, hp, sp);
+  const int n_own = sp.n_own[sh.rank];
+  if (hp.V > sh.max_rows) return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba_sharded: more rows than shard_init reserved");
+  if (n_own == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba_sharded: a rank owns no observation");
+  Staged& st = ctx->staged[2];
+  int rc = stage_problem(ctx, st, hp);
+  if (rc) return rc;
+  // ---- this rank's exchange state
+  Arena& xin = st.xin;
+  const size_t xneed = (sp.xp_ptr.size() + sp.xp_dst.size() + 2) * 4 + sp.pair_cnt.size() + sp.dmp_cnt.size() + 8 * 256;
+  if (!xin.reserve(xneed, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "exchange arena allocation failed");
+  Params& p = st.p;
+  p.xp_ptr = xin.d<int>(put(xin, sp.xp_ptr));
+  p.xp_dst = xin.d<int>(put(xin, sp.xp_dst));
+  p.pair_cnt = xin.d<unsigned char>(put(xin, sp.pair_cnt));
+  p.dmp_cnt = xin.d<unsigned char>(put(xin, sp.dmp_cnt));
+  p.world = sh.world;
+  p.rank = sh.rank;
+  p.xstride = sh.xstride;
+  p.xepoch0 = sh.epoch;
+  p.xtimeout_ns = (unsigned long long)env_int("NRSLAM_B200_XTIMEOUT_MS", 20000) * 1000000ULL;
+  for (int r = 0; r < sh.world; r++) {
+    char* base = static_cast<char*>(sh.peer[r]);
+    p.xflag[r] = reinterpret_cast<unsigned long long*>(base);
+    p.xred[r] = reinterpret_cast<double*>(base + sh.off_red);
+    p.xz[r] = reinterpret_cast<double*>(base + sh.off_z);
+    p.xx[r] = reinterpret_cast<double*>(base + sh.off_x);
+  }
+  char* mine = static_cast<char*>(sh.local);
+  p.xabort = reinterpret_cast<int*>(mine + sh.off_abort);
+  p.zvec = p.xz[sh.rank];
+  p.x = p.xx[sh.rank];
+  NRS_CUDA(ctx, cudaMemcpyAsync(xin.dev(), xin.host(), xin.used(), cudaMemcpyHostToDevice, ctx->stream));
+  NRS_CUDA(ctx, cudaMemsetAsync(p.xabort, 0, sizeof(int), ctx->stream));
+  // halo estimates start at their seeds (the owners push every later change); the kernel's RESET seeds the own rows
+  if (hp.n_halo > 0)
+    NRS_CUDA(ctx, cudaMemcpyAsync(p.x + 4 * (size_t)n_own, p.x_seed + 4 * (size_t)n_own,
+                                  sizeof(double) * 4 * (size_t)hp.n_halo, cudaMemcpyDeviceToDevice, ctx->stream));
+  const double t1 = wall_ms();
+  if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes + (int64_t)xin.used();
+  rc = run_staged(ctx, st, stats);
+  st.valid = false;  // the staged program is bound to this call's exchange epoch: no resolve()
+  const EngineStats* es = st.out.h<EngineStats>(st.o_stats);
+  if (rc) {
+    sh.broken = true;
+    return rc;
+  }
+  sh.epoch += (unsigned long long)es->xepochs;
+  if (es->xfail) {
+    sh.broken = true;
+    return fail(ctx, NRSLAM_B200_ERR_CUDA, "local_ba_sharded: a peer rank did not arrive at an exchange (timeout)");
+  }
+  std::vector<double> xd(4 * (size_t)n_own);
+  NRS_CUDA(ctx, cudaMemcpy(xd.data(), p.x, sizeof(double) * 4 * (size_t)n_own, cudaMemcpyDeviceToHost));
+  const double* pose = st.out.h<double>(st.o_pose);
+  for (int i = 0; i < 7 * F; i++)
+    if (!std::isfinite(pose[i])) return fail(ctx, NRSLAM_B200_NUM_NONFINITE, "local_ba: non-finite pose");
+  for (int k = 0; k < F; k++) pose_to_f7(pose + 7 * k, kf_pose_io + 7 * k);
+  for (int o = 0; o < O; o++) {
+    const int row = sp.row_of[o];
+    if (owner_out) owner_out[o] = sp.owner[row];
+    if (sp.owner[row] != sh.rank) continue;  // rows of other ranks stay untouched: the caller gathers them
+    for (int k = 0; k < 3; k++) X_io[3 * (size_t)o + k] = (float)xd[4 * (size_t)sp.loc_of[row] + k];
+  }
+  if (stats) {
+    stats->n_reproj_edges = n_own;
+    stats->n_spring_edges = (int)hp.pair_i.size();
+    stats->n_damper_edges = (int)hp.dmp_w.size();
+    stats->n_points = n_own;
+    stats->n_poses = F;
+    stats->d2h_bytes += (int64_t)(sizeof(double) * 4 * (size_t)n_own);
+    stats->stage_ms = (float)(t1 - t0);
+    stats->host_ms = (float)(wall_ms() - t0);
+  }
+  return 0;
+}
+
+int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t F, float* kf_pose_io,
+                         int32_t O, const int32_t* obs_kf, const int32_t* obs_vertex, const float* uv,
+                         float* X_io, const nrslam_b200_graph* g, float scale, int32_t iterations,
+                         nrslam_b200_stats* stats) {
+  if (!ctx || !cam || !kf_pose_io || !obs_kf || !obs_vertex || !uv || !X_io || !g || O < 0)
+    return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba: bad argument");
+  const double t0 = wall_ms();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (F < 3) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: fewer than 3 keyframes");  // :922-924
+  if (O == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: no observations");
+  NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  HostProblem hp;
+  {
+    const int brc = build_ba_problem(ctx, ctx->opt, cam, F, kf_pose_io, O, obs_kf, obs_vertex, uv, X_io, g, scale,
+                                     iterations, hp);
+    if (brc) return brc;
+  }
   Staged& st = ctx->staged[2];
   int rc = stage_problem(ctx, st, hp);
   if (rc) return rc;

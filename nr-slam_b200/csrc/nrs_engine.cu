@@ -43,6 +43,21 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsig
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// system scope: flags of the multi-GPU exchange live in peer-mapped memory
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct V3 {
   double x, y, z;
 };
@@ -162,6 +177,9 @@ struct Engine {
   int* s_oth;
   int* s_flag;
   unsigned gen;
+  unsigned long long xe;    // multi-GPU: exchanges done by this launch
+  size_t xcur;              // record base (parity) of the last exchange inside this rank's reduction buffer
+  bool xdead;               // a peer timed out: stop waiting, finish the program, report
   int tid, nthr;
   // LM state (uniform)
   double lambda, ni;
@@ -232,6 +250,9 @@ struct Engine {
       s_y = nullptr;
     }
     gen = 0;
+    xe = 0;
+    xcur = 0;
+    xdead = false;
     lambda = -1;
     ni = 2;
     lm_iters = lm_trials = pcg_iters = n_sweeps = n_chi2 = n_trace = pcg_fail = 0;
@@ -283,7 +304,7 @@ struct Engine {
   // ---- grid reduction of n (<= 4) values: v[k] are per-thread partials. maxmask bit k: max instead of sum.
   // Result (identical in every CTA) lands in s_scal[0..n). Includes one grid barrier.
   template <int N>
-  __device__ __forceinline__ void grid_reduce(double (&v)[N], unsigned maxmask) {
+  __device__ __forceinline__ void grid_reduce(double (&v)[N], unsigned maxmask, int xkind = 0) {
     const int par = gen & 1;
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -321,6 +342,75 @@ struct Engine {
       if (lane == 0) s_scal[k] = s;
     }
     __syncthreads();
+    if (P.world > 1) xexchange(N, maxmask, xkind, par);
+  }
+
+  // ---- multi-GPU (landmark-sharded BA). Called by every CTA with this GPU's totals in s_scal[0..n): CTA 0 pushes them
+  // (and, kind 1 / 2, this rank's 6 F CG pose partials / 27 F linearisation pose blocks summed over its chunks) into
+  // the record [parity][rank] of EVERY rank's reduction buffer, signals every rank and waits for every rank's signal;
+  // a second grid barrier releases the other CTAs. All ranks then combine the records in rank order, so every CTA of
+  // every GPU derives bit-identical values and takes the same branches. Halo rows pushed before the call are covered
+  // by the same signal (CTA stores -> grid barrier -> system fence -> flag).
+  __device__ __noinline__ void xexchange(int n, unsigned maxmask, int kind, int par) {
+    xe++;
+    const unsigned long long epoch = P.xepoch0 + xe;
+    const int W = P.world;
+    const size_t half = (size_t)(epoch & 1) * W * P.xstride;
+    const size_t rec = half + (size_t)P.rank * P.xstride;
+    if (blockIdx.x == 0) {
+      for (int t = tid; t < n * W; t += nthr) P.xred[t / n][rec + t % n] = s_scal[t % n];
+      const int per = (kind == 1) ? 6 : 27;
+      const int nx = (kind == 0) ? 0 : per * P.F;
+      for (int t = tid; t < nx; t += nthr) {
+        const double s = sum_chunk_partials(t / per, t % per, par);
+        for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
+      }
+      __syncthreads();
+      if (tid < W) {
+        __threadfence_system();
+        st_release_sys_u64(P.xflag[tid] + P.rank, epoch);
+        if (!xdead) {
+          const unsigned long long t0 = global_timer_ns();
+          while (ld_acquire_sys_u64(P.xflag[P.rank] + tid) < epoch) {
+            if (global_timer_ns() - t0 > P.xtimeout_ns) {
+              *P.xabort = 1;
+              break;
+            }
+          }
+        }
+      }
+    }
+    barrier();
+    if (__ldcg(P.xabort)) xdead = true;  // uniform over the grid: written before the barrier
+    xcur = half;
+    if (tid < n) {
+      const bool mx = (maxmask >> tid) & 1;
+      double s = mx ? -DBL_MAX : 0.0;
+      for (int r = 0; r < W; r++) {
+        const double o = __ldcg(P.xred[P.rank] + half + (size_t)r * P.xstride + tid);
+        s = mx ? fmax(s, o) : s + o;
+      }
+      s_scal[tid] = s;
+    }
+    __syncthreads();
+  }
+  // Value t of the pose records of the last exchange, summed over the ranks in rank order.
+  __device__ __forceinline__ double xextra(int t) {
+    double s = 0;
+    for (int r = 0; r < P.world; r++) s += __ldcg(P.xred[P.rank] + xcur + (size_t)r * P.xstride + 8 + t);
+    return s;
+  }
+  // Refresh the halo copies of owned row i on the ranks that read it.
+  __device__ __forceinline__ void xpush3(double* const* base, int i, const V3& v) {
+    for (int a = P.xp_ptr[i]; a < P.xp_ptr[i + 1]; a++) {
+      const int d = P.xp_dst[a];
+      st3(base[d >> 26], d & 0x3ffffff, v);
+    }
+  }
+  // Grid barrier that also waits for the halo rows pushed by the other ranks.
+  __device__ __forceinline__ void xsync() {
+    double d[1] = {0};
+    grid_reduce<1>(d, 0);
   }
 
   // ================================================================================================
@@ -340,12 +430,13 @@ struct Engine {
       const double w = P.pair_w[e];
       // an edge whose vertices are all fixed is not part of the active set (sparse_optimizer.cpp:232-246)
       const bool live = !(P.pt_fixed && P.pt_fixed[i] && P.pt_fixed[j]);
+      const bool cnt = !P.pair_cnt || P.pair_cnt[e];  // sharded BA: an edge shared with another rank is counted once
       if (live && w >= 0 && P.sp_level[e] == 0) {
         const double e0 = w * (xi.x - xj.x), e1 = w * (xi.y - xj.y), e2 = w * (xi.z - xj.z);
         const double c2 = (e0 * e0 + e1 * e1 + e2 * e2) * P.info_spatial;
         double rho, drho;
         huber(c2, P.delta_spatial, rho, drho);
-        chi += rho;
+        if (cnt) chi += rho;
         s = drho * P.info_spatial * w * w;
       }
       if (live && P.spring_kind != SPRING_NONE) {
@@ -359,7 +450,7 @@ struct Engine {
         const double ch = err * err * P.info_spring;
         double rho, drho;
         huber(ch, P.delta_spring, rho, drho);
-        chi += rho;
+        if (cnt) chi += rho;
         if (LIN) {
           double j0, j1, j2;
           if (P.spring_kind == SPRING_DEFORM) {
@@ -397,7 +488,7 @@ struct Engine {
       const double c2 = (e0 * e0 + e1 * e1 + e2 * e2) * P.info_spatial;
       double rho, drho;
       huber(c2, P.delta_spatial, rho, drho);
-      chi += rho;
+      if (!P.dmp_cnt || P.dmp_cnt[e]) chi += rho;
       if (LIN) {
         const double g = drho * P.info_spatial * w;
         double2* o = reinterpret_cast<double2*>(P.dc + 4 * (size_t)e);
@@ -985,6 +1076,7 @@ struct Engine {
                  m02 * r.x + m12 * r.y + m22 * r.z};
       st3(P.zvec, i, z);
       if (res) st3s(s_z, li, z);
+      if (P.world > 1) xpush3(P.xz, i, z);
       rz_part[0] += r.x * z.x + r.y * z.y + r.z * z.z;
     });
     if (bprec) {
@@ -1022,7 +1114,7 @@ struct Engine {
     int it = 0;
     // quad mapping of the loop and the per-row constants, kept in registers when this CTA owns at most one chunk
     const int qr = tid / kTPR, ql = tid % kTPR;
-    const bool single = P.n_chunks <= (int)gridDim.x;
+    const bool single = P.n_chunks <= (int)gridDim.x && P.world == 1;
     bool my_fixed = false;
     int my_kf = -1, my_a0 = 0, my_a1 = 0, my_cb = 0, my_ce = 0, my_kc0 = 0, my_kc1 = 0;
     double my_su = 0;
@@ -1242,13 +1334,13 @@ struct Engine {
         pq = s_scal[0];
         for (int t = 0; t < 6 * F; t++) pq += s_pp[t] * s_qp[t];
       } else {
-        grid_reduce<1>(pq_part, 0);
+        grid_reduce<1>(pq_part, 0, pos ? 1 : 0);
         pq = s_scal[0];
         if (pos) {
           // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (replicated per CTA)
           for (int t = tid; t < 6 * F; t += nthr) {
             const int k = t / 6, a = t % 6;
-            const double w = lambda * s_zp[t] + sum_chunk_partials(k, a, par);
+            const double w = lambda * s_zp[t] + (P.world > 1 ? xextra(t) : sum_chunk_partials(k, a, par));
             s_pp[t] = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
             s_qp[t] = first ? w : w + beta * s_qp[t];
           }
@@ -1288,6 +1380,7 @@ struct Engine {
                        m1.x * ri.x + m2.x * ri.y + m2.y * ri.z};
             st3(P.zvec, i, z);
             if (res) st3s(s_z, li, z);
+            if (P.world > 1) xpush3(P.xz, i, z);
             rzn_part[0] += ri.x * z.x + ri.y * z.y + ri.z * z.z;
           }
         }
@@ -2082,7 +2175,9 @@ struct Engine {
     const int F = P.F;
     const bool pts = !P.points_fixed, pos = !P.poses_fixed;
     const long long tl0 = clock64();
-    if (pts) barrier();  // estimates written by other CTAs (restore / reset) are visible
+    if (pts) {  // estimates written by other CTAs / ranks (restore, reset) are visible
+      if (P.world > 1) xsync(); else barrier();
+    }
     double acc[2] = {0, 0};  // chi2, max diagonal
     if (P.P > 0 || P.D > 0) {
       edges_pass<true>(acc[0]);
@@ -2090,14 +2185,14 @@ struct Engine {
     }
     const int par = gen & 1;
     rows_pass<true>(acc[0], acc[1], par);
-    grid_reduce<2>(acc, 2u);
+    grid_reduce<2>(acc, 2u, pos ? 2 : 0);
     double currentChi = s_scal[0];
     double maxDiag = s_scal[1];
     n_sweeps++;
     if (pos) {
       for (int t = tid; t < 27 * F; t += nthr) {
         const int k = t / 27, v = t % 27;
-        const double s = sum_chunk_partials(k, v, par);
+        const double s = (P.world > 1) ? xextra(t) : sum_chunk_partials(k, v, par);
         if (v < 21)
           s_H[21 * k + v] = s;
         else
@@ -2134,6 +2229,7 @@ struct Engine {
             st3(P.x_bak, i, x);
             x.x += d.x; x.y += d.y; x.z += d.z;
             st3(P.x, i, x);
+            if (P.world > 1) xpush3(P.xx, i, x);
             acc2[1] += d.x * (lambda * d.x + bb.x) + d.y * (lambda * d.y + bb.y) + d.z * (lambda * d.z + bb.z);
           });
         }
@@ -2143,7 +2239,9 @@ struct Engine {
           for (int k = tid; k < F; k += nthr) pose_oplus(s_pose + 7 * k, s_xp + 6 * k);
           __syncthreads();
         }
-        if (pts) barrier();  // updated point estimates are read across CTAs by the regulariser edges
+        if (pts) {  // updated point estimates are read across CTAs (and ranks) by the regulariser edges
+          if (P.world > 1) xsync(); else barrier();
+        }
         if (P.P > 0 || P.D > 0) edges_pass<false>(acc2[0]);
         double dummy = 0;
         rows_pass<false>(acc2[0], dummy, 0);
@@ -2168,7 +2266,12 @@ struct Engine {
         lambda *= ni;
         ni *= 2;
         if (solved) {  // pop
-          if (pts) for_rows([&](int i) { st3(P.x, i, ld3p(P.x_bak, i)); });
+          if (pts)
+            for_rows([&](int i) {
+              const V3 xb = ld3p(P.x_bak, i);
+              st3(P.x, i, xb);
+              if (P.world > 1) xpush3(P.xx, i, xb);
+            });
           if (pos) {
             __syncthreads();
             for (int t = tid; t < 7 * F; t += nthr) s_pose[t] = s_pose_bak[t];
@@ -2264,6 +2367,7 @@ struct Engine {
       }
     }
     __syncthreads();
+    if (P.world > 1) xsync();  // no push of this launch is in flight when any rank's kernel ends
     if (blockIdx.x == 0) {
       for (int t = tid; t < 7 * F; t += nthr) P.pose[t] = s_pose[t];
       if (tid == 0) {
@@ -2276,6 +2380,8 @@ struct Engine {
         st->n_trace = n_trace < kTrace ? n_trace : kTrace;
         st->pcg_fail = pcg_fail;
         st->barriers = (int)gen;
+        st->xepochs = (int)xe;
+        st->xfail = xdead ? 1 : 0;
         st->lambda_final = lambda;
         prof[15] = clock64() - trun0;
         for (int i = 0; i < 16; i++) st->prof[i] = prof[i];

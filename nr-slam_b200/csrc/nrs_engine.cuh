@@ -31,6 +31,7 @@ enum SpringKind : int {
 };
 
 constexpr int kMaxOps = 16;
+constexpr int kMaxWorld = 8;     // GPUs of one NVSwitch domain a sharded BA can span
 constexpr int kTrace = 64;
 constexpr int kSlotVals = 8;     // doubles per CTA per grid reduction
 constexpr int kChunkVals = 28;   // doubles per chunk partial (21 H_pp + 6 b_p, padded)
@@ -48,6 +49,7 @@ constexpr int kRowBlk = 116;     // floats a CTA publishes for the coarse matrix
 
 struct EngineStats {
   int lm_iterations, lm_trials, pcg_iterations, n_sweeps, n_chi2_passes, n_trace, pcg_fail, barriers;
+  int xepochs, xfail;  // landmark-sharded runs: cross-device exchanges done by this launch / a peer never arrived
   double chi2_trace[kTrace];
   double lambda_final;
   long long prof[16];  // clock64 cycles per phase seen by CTA 0 / thread 0 (diagnostics)
@@ -143,6 +145,23 @@ struct Params {
   double* slots;       // [2][G * kSlotVals]
   unsigned long long* bar;
   EngineStats* stats;
+
+  // ---- landmark-sharded BA over several GPUs (world > 1). Every rank owns the rows of its landmarks
+  // and keeps read-only halo copies of the rows its regulariser edges reach on other ranks. The exchange buffers of
+  // all ranks are peer-mapped (CUDA IPC): owners PUSH the halo values and their partial sums over NVLink, then signal.
+  int world, rank;
+  int xstride;                     // doubles per (parity, source rank) record of the reduction buffer: 8 + 27 F
+  unsigned long long xepoch0;      // exchanges completed by earlier launches (the flags count up monotonically)
+  unsigned long long xtimeout_ns;  // a peer that does not arrive within this time aborts the exchange (no hang)
+  unsigned long long* xflag[kMaxWorld];  // rank r's flags [world], indexed by the signalling rank
+  double* xred[kMaxWorld];         // rank r's reduction records [2][world][xstride]
+  double* xz[kMaxWorld];           // rank r's z vector (its rows, then its halo rows) = that rank's zvec
+  double* xx[kMaxWorld];           // rank r's estimates, same indexing                 = that rank's x
+  const int* xp_ptr;               // [V+1] per owned row: the halo copies to refresh ...
+  const int* xp_dst;               // ... as rank << 26 | row index on that rank
+  const unsigned char* pair_cnt;   // [P] this rank counts the pair edge's chi2 (nullptr: every edge)
+  const unsigned char* dmp_cnt;    // [D]
+  int* xabort;
 };
 
 // Host-side launch. Returns cudaError_t as int. grid/block/smem chosen by the caller (plan_launch).

@@ -79,6 +79,19 @@ struct Staged {
   // rows are re-ordered along a space-filling curve before staging (locality for the resident chunks and the
   // dense block preconditioner): row_of[caller row] = engine row
   std::vector<int> row_of;
+  Arena xin;  // landmark-sharded BA: push lists and edge-count flags of this rank
+};
+
+// Landmark-sharded BA: this rank's exchange buffer and the peer mappings of the other ranks' buffers.
+// Layout (identical on every rank): flags [kMaxWorld] u64 | abort int | reduction records [2][world][xstride] |
+// z [4 max_rows] | x [4 max_rows].
+struct Shard {
+  int rank = 0, world = 1, max_rows = 0, max_poses = 0, xstride = 0;
+  void* local = nullptr;
+  void* peer[kMaxWorld] = {};
+  size_t bytes = 0, off_abort = 0, off_red = 0, off_z = 0, off_x = 0;
+  unsigned long long epoch = 0;  // exchanges completed so far (identical on every rank)
+  bool attached = false, broken = false;
 };
 
 }  // namespace nrs
@@ -93,4 +106,5 @@ struct nrslam_b200_ctx {
   nrs::Staged staged[4];  // 0 pose_only, 1 pose_deform, 2 local_ba, 3 lost-point stage
   unsigned long long* bar = nullptr;
   int max_cluster = -1;   // largest schedulable thread-block cluster of the LM kernel (queried lazily)
+  nrs::Shard shard;
 };

@@ -7,7 +7,9 @@ ranks / max-over-ranks time.
 
 For bundle adjustment the path does shard over landmarks: `shard_landmarks` is the spatially coherent
 partition (Morton order, equal counts) with the halo bookkeeping a landmark-sharded BA needs — the landmarks of another
-shard that a shard's regulariser edges touch. The sharded BA solve itself is not built in round 1.
+shard that a shard's regulariser edges touch. `attach_shards` + `gather_sharded_ba` wrap the landmark-sharded BA of the C ABI
+(nrslam_b200_local_ba_sharded): the ranks exchange halo rows and partial sums inside the persistent kernel through
+peer-mapped buffers; torch.distributed only carries the IPC handles once and gathers the results.
 """
 import numpy as np
 
@@ -59,3 +61,27 @@ def shard_landmarks(positions, rowptr, col, n_shards):
         m = cross & (owner[rows] == s)
         halo.append(np.unique(col[m]).astype(np.int32))
     return owner, halo
+
+
+def attach_shards(core, dist, max_rows, max_poses):
+    """One-time set-up of the sharded BA on an initialised process group: every rank allocates its exchange buffer,
+    the 64-byte CUDA IPC handles are all-gathered, every rank maps its peers' buffers."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    handle = core.shard_init(rank, world, max_rows, max_poses)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    core.shard_attach(handles)
+    dist.barrier()
+
+
+def gather_sharded_ba(result, dist):
+    """Completes X on every rank from the owners' parts (the poses are already identical everywhere)."""
+    import torch
+    world = dist.get_world_size()
+    parts = [None] * world
+    dist.all_gather_object(parts, result["X"])
+    X = result["X"].copy()
+    for r in range(world):
+        m = result["owner"] == r
+        X[m] = parts[r][m]
+    return X

@@ -1,0 +1,53 @@
+"""Host logic of the landmark-sharded BA: the partition every rank derives without communication.
+Runs on CPU: nrslam_b200_shard_partition touches no device."""
+import numpy as np
+import pytest
+
+from nrslam_b200 import api, synth
+
+
+@pytest.fixture(scope="module")
+def window():
+    return synth.ba_problem("c3", n=600, n_kf=8, run=5)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_partition_covers_balances_and_is_coherent(window, world):
+    p = window
+    r = api.shard_partition(world, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"], p["scale"])
+    owner, n_own = r["owner"], r["n_own"]
+    O = len(p["obs_kf"])
+    assert owner.min() >= 0 and owner.max() < world
+    assert np.array_equal(np.bincount(owner, minlength=world), n_own) and n_own.sum() == O
+    # a landmark's copies in every keyframe live on one rank
+    lm_owner = {}
+    for o in range(O):
+        assert lm_owner.setdefault(int(p["obs_vertex"][o]), int(owner[o])) == owner[o]
+    # equal observation counts up to one landmark's run of copies
+    assert n_own.max() - n_own.min() <= 2 * 5 + 2
+    # every halo copy is refreshed by exactly one push of its owner
+    assert r["n_halo"].sum() == r["n_push"].sum()
+    if world == 1:
+        assert r["n_halo"][0] == 0 and r["n_push"][0] == 0
+    elif world <= 4:
+        # spatial coherence: the halo is a boundary layer, smaller than the rows a rank owns even at 150 landmarks / rank
+        assert (r["n_halo"] < 0.8 * n_own).all()
+
+
+def test_every_edge_is_counted_exactly_once(window):
+    p = window
+    one = api.shard_partition(1, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"], p["scale"])
+    total = one["n_edges"][0, 0] + one["n_edges"][0, 1]
+    assert one["n_edges"][0, 2] == total
+    for world in (2, 3, 8):
+        r = api.shard_partition(world, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"],
+                                p["scale"])
+        assert r["n_edges"][:, 2].sum() == total                 # chi2 of a shared edge is counted by one rank
+        assert (r["n_edges"][:, 0] + r["n_edges"][:, 1]).sum() >= total   # ... but linearised by both
+
+
+def test_partition_is_deterministic(window):
+    p = window
+    a = api.shard_partition(4, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"], p["scale"])
+    b = api.shard_partition(4, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"], p["scale"])
+    assert np.array_equal(a["owner"], b["owner"]) and np.array_equal(a["n_halo"], b["n_halo"])
