@@ -30,6 +30,24 @@ double wall_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Host-side phase timer (NRSLAM_B200_HOSTPROF=1): where the end-to-end time of a call goes besides the kernel.
+struct HostProf {
+  bool on = getenv("NRSLAM_B200_HOSTPROF") != nullptr;
+  double t = wall_ms();
+  std::string line;
+  void mark(const char* what) {
+    if (!on) return;
+    const double n = wall_ms();
+    char buf[64];
+    snprintf(buf, sizeof(buf), " %s %.3f", what, n - t);
+    line += buf;
+    t = n;
+  }
+  void print(const char* who) {
+    if (on) fprintf(stderr, "[nrs host] %s:%s\n", who, line.c_str());
+  }
+};
+
 int fail(nrslam_b200_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
@@ -365,7 +383,9 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   const int F = hp.F, V = hp.V, P = (int)hp.pair_i.size(), D = (int)hp.dmp_w.size();
   const int U = (int)hp.un_w.size();
   st.valid = false;
+  HostProf hprof;
   sort_rows(hp, st.row_of);
+  hprof.mark("sort_rows");
 
   // incidence lists
   std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P), inc_row(2 * (size_t)P);
@@ -395,6 +415,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ent[w[hp.dmp_v[t]]++] = (int)t;  // id*4 + role
   }
 
+  hprof.mark("incidences");
   // ---- launch plans. Tracking stages its lost-point rows behind the optimised ones: the main rounds run on the
   // first hp.n_stage1 rows only (plan A), the lost-point stage on all rows (plan B).
   const int V1 = hp.sharded ? V - hp.n_halo : (hp.n_stage1 > 0 && hp.n_stage1 < V && F == 1) ? hp.n_stage1 : V;
@@ -409,6 +430,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
       if (rc2) return rc2;
     }
   }
+  hprof.mark("make_plan");
   const int n_chunks = planA.n_chunks;
   const int max_chunks = std::max(planA.n_chunks, planB.n_chunks), max_grid_used = std::max(planA.grid, planB.grid);
   for (Plan* pl : {&planA, &planB}) {
@@ -438,6 +460,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     pl->smem += extra;
   }
 
+  hprof.mark("build_halo");
   // ---- input arena
   size_t need = 0;
   auto sz = [&](size_t bytes) { need += ((bytes + 255) & ~size_t(255)) + 256; };
@@ -524,6 +547,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     st.grid2 = planB.grid;
   }
 
+  hprof.mark("fill_in_arena");
   // ---- results + work arrays
   Arena& out = st.out;
   size_t oneed = 7 * F * 8 + 4 * (size_t)V * 8 + (size_t)V * 8 + V + P + sizeof(EngineStats) + 8 * 256 + 4096;
@@ -571,6 +595,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   // dg[.][6] (unary diagonal weight) is read by the matvec even when no unary edges exist
   NRS_CUDA(ctx, cudaMemsetAsync(wk.dev(), 0, wk.used(), ctx->stream));
   NRS_CUDA(ctx, cudaMemsetAsync(out.dev(), 0, out.used(), ctx->stream));
+  hprof.mark("enqueue_copies");
+  hprof.print("stage_problem");
   st.valid = true;
   return 0;
 }
@@ -813,6 +839,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   const int M = g->n_vertices;
   for (int i = 0; i < n; i++)
     if (point_vertex[i] < 0 || point_vertex[i] >= M) return fail(ctx, NRSLAM_B200_ERR_ARG, "pose_deform: bad vertex");
+  HostProf hprof;
 
   const int regularizers_per_point = opt.regularizers_per_point;
   const float th2 = opt.th_huber_2dof_sq, th3 = opt.th_huber_3dof_sq;
@@ -852,6 +879,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   }
   hp.kf_begin = {0, n};
 
+  hprof.mark("fill_rows");
   // ---- regulariser selection (:251-336). A pair is owned by the first endpoint that reaches it.
   std::vector<int> pair_stamp(g->n_edges, 0);  // spatial_connections_ids de-duplication, keyed by graph edge
   std::set<int> lost_ordered;                  // absl::btree_set<ID> (:222)
@@ -882,6 +910,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   // optimised neighbours. They are rows of the same staged problem but only take part in the second launch.
   // (The graph is only modified by UpdateVertex below, whose weights / statuses the reference does see when it
   // queries GetEdges for the lost points — so the unary edge list is built after the refresh.)
+  hprof.mark("select_regularisers");
   const std::vector<int> lost_list(lost_ordered.begin(), lost_ordered.end());
   const int n_lost = (int)lost_list.size();
   const int Vtot = n + n_lost;
@@ -907,10 +936,12 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   Staged& st = ctx->staged[1];
   int rc = stage_problem(ctx, st, hp);
   if (rc) return rc;
+  hprof.mark("stage");
   const double t1 = wall_ms();
   if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes;
   rc = run_staged(ctx, st, stats);
   if (rc) return rc;
+  hprof.mark("run1");
 
   const double* pose = st.out.h<double>(st.o_pose);
   for (int i = 0; i < 7; i++)
@@ -963,12 +994,14 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
     std::nth_element(m2.begin(), m2.begin() + median_idx, m2.end());
     *median_deformation_out = m2[median_idx];
   }
+  hprof.mark("gate");
   // ---- regularisation-graph refresh (:458-474)
   for (int idx = 0; idx < n; idx++) {
     if (!inliers[idx]) continue;
     const int good = graph_update_vertex(g, point_vertex[idx], last_pos);
     if (good < regularizers_per_point * 0.5) status[idx] = NRSLAM_BAD;
   }
+  hprof.mark("update_vertex");
   if (status_out) memcpy(status_out, status.data(), n);
   if (stats) {
     stats->n_reproj_edges = n;
@@ -1022,8 +1055,10 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
       p2.n_ops = 1;
       p2.op[0] = OP_OPTIMIZE;
       p2.op_arg[0] = opt.lost_iterations;
+      hprof.mark("lost_setup");
       rc = run_staged(ctx, st, stats, true, &p2, st.has_plan2);
       if (rc) return rc;
+      hprof.mark("run2");
       const double* xl = st.out.h<double>(st.o_x);
       for (int v = 0; v < n_lost; v++)
         for (int k = 0; k < 3; k++)
@@ -1035,6 +1070,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
     if (n_lost_out) *n_lost_out = n_lost;
     if (stats) stats->n_fixed_edges = n_un;
   }
+  hprof.print("pose_deform");
   if (stats) stats->host_ms = (float)(wall_ms() - t0);
   return 0;
 }

@@ -156,6 +156,94 @@ constexpr int kPB = kPrecBlock;      // rows per dense preconditioner block
 constexpr int kPN = 3 * kPrecBlock;  // its dimension
 constexpr int kJS = 22;              // shared-memory stride of a Jacobian row (20 doubles + 2: spreads rows over the banks)
 constexpr int kPS = kPN + 4;         // padded row stride (floats): 16-byte aligned rows, conflict-free float4 row reads
+
+// Sum of value v over the chunk partials of pose slot k in chunk order; the loads of a batch are issued together
+// (a plain `s += load` loop serialises one L2 round trip per chunk).
+__device__ __forceinline__ double sum_chunk_partials_of(const Params& P, int k, int v, int par) {
+  const int c1 = P.kf_chunk_ptr[k + 1];
+  double s = 0;
+  for (int c0 = P.kf_chunk_ptr[k]; c0 < c1; c0 += 8) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int c = min(c0 + u, c1 - 1);
+      t[u] = __ldcg(P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals + v);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (c0 + u < c1) s += t[u];
+  }
+  return s;
+}
+
+// ---- multi-GPU exchange of the landmark-sharded BA (cooperative-grid mode only). Called by every CTA with this
+// GPU's totals in s_scal[0..n): CTA 0 pushes them (and, kind 1 / 2, this rank's 6 F CG pose partials / 27 F
+// linearisation pose blocks summed over its chunks) into the record [parity][rank] of EVERY rank's reduction buffer,
+// signals every rank and waits for every rank's signal; a second grid barrier releases the other CTAs. All ranks
+// then combine the records in rank order, so every CTA of every GPU derives bit-identical values and takes the same
+// branches. Halo rows pushed before the call are covered by the same signal (CTA stores -> grid barrier ->
+// system fence -> flag).
+struct XRet {
+  unsigned long long xe;
+  size_t xcur;
+  unsigned gen;
+  int dead;
+};
+__device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int n, unsigned maxmask, int kind,
+                                            int par, unsigned long long xe, unsigned gen, int dead) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  xe++;
+  const unsigned long long epoch = P.xepoch0 + xe;
+  const int W = P.world;
+  const size_t half = (size_t)(epoch & 1) * W * P.xstride;
+  const size_t rec = half + (size_t)P.rank * P.xstride;
+  if (blockIdx.x == 0) {
+    for (int t = tid; t < n * W; t += nthr) P.xred[t / n][rec + t % n] = s_scal[t % n];
+    const int per = (kind == 1) ? 6 : 27;
+    const int nx = (kind == 0) ? 0 : per * P.F;
+    for (int t = tid; t < nx; t += nthr) {
+      const double s = sum_chunk_partials_of(P, t / per, t % per, par);
+      for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
+    }
+    __syncthreads();
+    if (tid < W) {
+      __threadfence_system();
+      st_release_sys_u64(P.xflag[tid] + P.rank, epoch);
+      if (!dead) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys_u64(P.xflag[P.rank] + tid) < epoch) {
+          if (global_timer_ns() - t0 > P.xtimeout_ns) {
+            *P.xabort = 1;
+            break;
+          }
+        }
+      }
+    }
+  }
+  // grid barrier (release-add / acquire-poll, as Engine::barrier in grid mode)
+  gen++;
+  __syncthreads();
+  if (tid == 0) {
+    red_release_add_u64(P.bar, 1ULL);
+    const unsigned long long target = (unsigned long long)gen * gridDim.x;
+    while (ld_acquire_u64(P.bar) < target) {
+    }
+  }
+  __syncthreads();
+  if (__ldcg(P.xabort)) dead = 1;  // uniform over the grid: written before the barrier
+  if (tid < n) {
+    const bool mx = (maxmask >> tid) & 1;
+    double s = mx ? -DBL_MAX : 0.0;
+    for (int r = 0; r < W; r++) {
+      const double o = __ldcg(P.xred[P.rank] + half + (size_t)r * P.xstride + tid);
+      s = mx ? fmax(s, o) : s + o;
+    }
+    s_scal[tid] = s;
+  }
+  __syncthreads();
+  return XRet{xe, half, gen, dead};
+}
+
 static_assert((kPN / 4) % kTPR == 0, "the lanes of a row split the float4 columns of the block preconditioner evenly");
 
 struct Engine {
@@ -345,54 +433,15 @@ struct Engine {
     if (P.world > 1) xexchange(N, maxmask, xkind, par);
   }
 
-  // ---- multi-GPU (landmark-sharded BA). Called by every CTA with this GPU's totals in s_scal[0..n): CTA 0 pushes them
-  // (and, kind 1 / 2, this rank's 6 F CG pose partials / 27 F linearisation pose blocks summed over its chunks) into
-  // the record [parity][rank] of EVERY rank's reduction buffer, signals every rank and waits for every rank's signal;
-  // a second grid barrier releases the other CTAs. All ranks then combine the records in rank order, so every CTA of
-  // every GPU derives bit-identical values and takes the same branches. Halo rows pushed before the call are covered
-  // by the same signal (CTA stores -> grid barrier -> system fence -> flag).
-  __device__ __noinline__ void xexchange(int n, unsigned maxmask, int kind, int par) {
-    xe++;
-    const unsigned long long epoch = P.xepoch0 + xe;
-    const int W = P.world;
-    const size_t half = (size_t)(epoch & 1) * W * P.xstride;
-    const size_t rec = half + (size_t)P.rank * P.xstride;
-    if (blockIdx.x == 0) {
-      for (int t = tid; t < n * W; t += nthr) P.xred[t / n][rec + t % n] = s_scal[t % n];
-      const int per = (kind == 1) ? 6 : 27;
-      const int nx = (kind == 0) ? 0 : per * P.F;
-      for (int t = tid; t < nx; t += nthr) {
-        const double s = sum_chunk_partials(t / per, t % per, par);
-        for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
-      }
-      __syncthreads();
-      if (tid < W) {
-        __threadfence_system();
-        st_release_sys_u64(P.xflag[tid] + P.rank, epoch);
-        if (!xdead) {
-          const unsigned long long t0 = global_timer_ns();
-          while (ld_acquire_sys_u64(P.xflag[P.rank] + tid) < epoch) {
-            if (global_timer_ns() - t0 > P.xtimeout_ns) {
-              *P.xabort = 1;
-              break;
-            }
-          }
-        }
-      }
-    }
-    barrier();
-    if (__ldcg(P.xabort)) xdead = true;  // uniform over the grid: written before the barrier
-    xcur = half;
-    if (tid < n) {
-      const bool mx = (maxmask >> tid) & 1;
-      double s = mx ? -DBL_MAX : 0.0;
-      for (int r = 0; r < W; r++) {
-        const double o = __ldcg(P.xred[P.rank] + half + (size_t)r * P.xstride + tid);
-        s = mx ? fmax(s, o) : s + o;
-      }
-      s_scal[tid] = s;
-    }
-    __syncthreads();
+  // ---- multi-GPU (landmark-sharded BA): see xexchange_impl. The exchange is a free function that gets the engine
+  // state it needs by value — a non-inlined MEMBER would make `this` escape and push every member of the engine
+  // (shared-memory pointers, lambda, ...) from registers into local memory, also in the single-GPU hot loops.
+  __device__ __forceinline__ void xexchange(int n, unsigned maxmask, int kind, int par) {
+    const XRet r = xexchange_impl(P, s_scal, n, maxmask, kind, par, xe, gen, xdead ? 1 : 0);
+    xe = r.xe;
+    xcur = r.xcur;
+    gen = r.gen;
+    xdead = r.dead != 0;
   }
   // Value t of the pose records of the last exchange, summed over the ranks in rank order.
   __device__ __forceinline__ double xextra(int t) {
@@ -749,23 +798,8 @@ struct Engine {
     }
   }
 
-  // Sum of value v over the chunk partials of pose slot k in chunk order; the loads of a batch are issued together
-  // (a plain `s += load` loop serialises one L2 round trip per chunk).
   __device__ __forceinline__ double sum_chunk_partials(int k, int v, int par) {
-    const int c1 = P.kf_chunk_ptr[k + 1];
-    double s = 0;
-    for (int c0 = P.kf_chunk_ptr[k]; c0 < c1; c0 += 8) {
-      double t[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int c = min(c0 + u, c1 - 1);
-        t[u] = __ldcg(P.chunk_part + ((size_t)par * P.n_chunks + c) * kChunkVals + v);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++)
-        if (c0 + u < c1) s += t[u];
-    }
-    return s;
+    return sum_chunk_partials_of(P, k, v, par);
   }
 
   // own-row iteration helper
