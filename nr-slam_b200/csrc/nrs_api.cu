@@ -130,6 +130,9 @@ struct HostProblem {
   std::vector<double> un_w;             // U
   std::vector<int> un_ref;              // U
   bool want_fixed_flags = false;        // reserve a per-vertex fixed-flag array (filled later)
+  std::vector<unsigned char> fixed0;    // per-vertex setFixed(true) known at staging time (lost-point stage)
+  std::vector<unsigned char> rp_level0, sp_level0;  // edge levels carried over from an earlier program (else 0)
+  bool unary_on = false;                // the unary (fixed-reference) edges take part
   int n_sort = 0;                       // leading rows of every pose-slot group that may be re-ordered spatially
   int n_stage1 = 0;                     // rows of the first launch (tracking: without the lost-point rows); 0 = all
   std::vector<int> kf_begin;            // F+1: rows of pose slot k are [kf_begin[k], kf_begin[k+1]) (rows w/o pose: slot 0)
@@ -469,6 +472,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   sz(((size_t)V + 1) * 4); sz(2 * (size_t)P * 4); sz(2 * (size_t)P * 4); sz(2 * (size_t)P * 4);
   sz(4 * (size_t)D * 4); sz((size_t)D * 8); sz(((size_t)V + 1) * 4); sz(4 * (size_t)D * 4);
   sz(((size_t)V + 1) * 4); sz((size_t)U * 8); sz((size_t)U * 4); sz((size_t)V);
+  sz((size_t)V); sz((size_t)V); sz((size_t)P);
   sz((size_t)max_chunks * 4 * 3 * 2); sz(((size_t)F + 1) * 4 * 2);
   for (Plan* pl : {&planA, &planB}) {
     sz(pl->inc_halo.size() * 4); sz(pl->push_ptr.size() * 4); sz(pl->push_row.size() * 4); sz(pl->push_dst.size() * 4); sz(pl->xinc_ptr.size() * 4); sz(pl->xinc_idx.size() * 4);
@@ -520,6 +524,11 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     st.o_fixed = in.take<unsigned char>(V);
     memset(in.h<unsigned char>(st.o_fixed), 0, V);
   }
+  if (!hp.fixed0.empty()) p.pt_fixed = in.d<unsigned char>(put(in, hp.fixed0));
+  p.unary_on = hp.unary_on ? 1 : 0;
+  const unsigned char *d_rp0 = nullptr, *d_sp0 = nullptr;
+  if (!hp.rp_level0.empty()) d_rp0 = in.d<unsigned char>(put(in, hp.rp_level0));
+  if (!hp.sp_level0.empty()) d_sp0 = in.d<unsigned char>(put(in, hp.sp_level0));
   for (Plan* pl : {&planA, &planB}) {
     if (pl->n_chunks == 0) continue;
     pl->d_chunk_kf = in.d<int>(put(in, pl->chunk_kf));
@@ -595,6 +604,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   // dg[.][6] (unary diagonal weight) is read by the matvec even when no unary edges exist
   NRS_CUDA(ctx, cudaMemsetAsync(wk.dev(), 0, wk.used(), ctx->stream));
   NRS_CUDA(ctx, cudaMemsetAsync(out.dev(), 0, out.used(), ctx->stream));
+  if (d_rp0) NRS_CUDA(ctx, cudaMemcpyAsync(p.rp_level, d_rp0, hp.rp_level0.size(), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (d_sp0) NRS_CUDA(ctx, cudaMemcpyAsync(p.sp_level, d_sp0, hp.sp_level0.size(), cudaMemcpyDeviceToDevice, ctx->stream));
   hprof.mark("enqueue_copies");
   hprof.print("stage_problem");
   st.valid = true;
@@ -907,28 +918,13 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
     }
   }
   // ---- lost neighbours (:476-537): one extra vertex each, unary SpatialRegularizerFixed edges to at most 11
-  // optimised neighbours. They are rows of the same staged problem but only take part in the second launch.
-  // (The graph is only modified by UpdateVertex below, whose weights / statuses the reference does see when it
-  // queries GetEdges for the lost points — so the unary edge list is built after the refresh.)
+  // optimised neighbours; they are optimised by a second, compact problem after the graph refresh below (the
+  // graph is only modified by UpdateVertex, whose weights / statuses the reference does see when it queries
+  // GetEdges for the lost points — so the unary edge list is built after the refresh).
   hprof.mark("select_regularisers");
   const std::vector<int> lost_list(lost_ordered.begin(), lost_ordered.end());
   const int n_lost = (int)lost_list.size();
-  const int Vtot = n + n_lost;
-  hp.V = Vtot;
-  hp.x_seed.resize(4 * (size_t)Vtot, 0.0);
-  hp.rest.resize(4 * (size_t)Vtot, 0.0);
-  hp.uv.resize(2 * (size_t)Vtot, 0.0);
-  hp.pt_kf.resize(Vtot, -1);
-  hp.kf_begin = {0, Vtot};
-  hp.n_sort = n;  // the lost rows stay behind the optimised ones
-  hp.n_stage1 = n;
-  hp.want_fixed_flags = n_lost > 0;
-  if (n_lost > 0) {
-    // capacity for the unary edges (filled after the graph refresh): at most 11 per lost point
-    hp.un_ptr.assign(Vtot + 1, 0);
-    hp.un_w.assign(11 * (size_t)n_lost, 0.0);
-    hp.un_ref.assign(11 * (size_t)n_lost, 0);
-  }
+  hp.n_sort = n;
   hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM,
             OP_FINAL_CHI2};
   hp.op_args = {0, 0, opt.pose_deform_iterations[0], 0, 0, opt.pose_deform_iterations[1], 0, 0};
@@ -967,7 +963,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   const float th_ = 1.5f * (q3 - q1);
   std::vector<char> inliers(n, 1);
   std::vector<uint8_t> status(n, NRSLAM_TRACKED_WITH_3D);
-  std::vector<unsigned char> fixed(Vtot, 0);
+  std::vector<unsigned char> fixed(n, 0);
   for (int idx = 0; idx < n; idx++) {
     const float chi_squared = (float)chi2d[row_of[idx]];
     if (chi2_out) chi2_out[idx] = chi_squared;
@@ -1015,12 +1011,15 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   // the accepted deformation vertices fixed: the gated-out deformation vertices stay free and are re-optimised
   // alongside the lost points (their results are discarded), sharing one lambda / gain-ratio sequence.
   if (n_lost > 0) {
-    int* un_ptr = st.in.h<int>((size_t)((const char*)st.p.un_ptr - (const char*)st.in.dev()));
-    double* un_w = st.in.h<double>((size_t)((const char*)st.p.un_w - (const char*)st.in.dev()));
-    int* un_ref = st.in.h<int>((size_t)((const char*)st.p.un_ref - (const char*)st.in.dev()));
+    // Staged as its own COMPACT problem: only vertices that are still free (gated-out deformation vertices, lost
+    // points) and the fixed vertices their edges read are rows; an edge between two fixed vertices is not part of
+    // g2o's active set (sparse_optimizer.cpp:232-246), so dropping it changes nothing. ~10x fewer rows than the frame.
+    const unsigned char* rp_lvl = st.out.h<unsigned char>(st.o_rp_level);
+    const unsigned char* sp_lvl = st.out.h<unsigned char>(st.o_sp_level);
     const float min_w2 = graph_min_weight(g);
-    int n_un = 0;
-    for (int i = 0; i <= n; i++) un_ptr[i] = 0;
+    // unary edges of the lost points (:476-537), references by engine row of the main problem
+    std::vector<int> un_ptr_l(n_lost + 1, 0), un_ref_row;
+    std::vector<double> un_w_l;
     for (int v = 0; v < n_lost; v++) {
       ent.clear();
       graph_sorted_entries(g, lost_list[v], min_w2, ent);
@@ -1029,41 +1028,104 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
         if (n_regularizers > 10) break;  // :497 literal
         const int other = g->col[pe];
         if (opt_index[other] < 0) continue;  // :502-504
-        un_w[n_un] = (double)g->weight[g->eid[pe]];
-        un_ref[n_un] = row_of[opt_index[other]];
-        n_un++;
+        un_w_l.push_back((double)g->weight[g->eid[pe]]);
+        un_ref_row.push_back(row_of[opt_index[other]]);
         n_regularizers++;
       }
-      un_ptr[n + v + 1] = n_un;
+      un_ptr_l[v + 1] = (int)un_w_l.size();
     }
+    const int n_un = (int)un_w_l.size();
     if (n_un > 0) {
-      memcpy(st.in.h<unsigned char>(st.o_fixed), fixed.data(), Vtot);
-      // refresh the three unary arrays and the fixed flags on the device (small, contiguous ranges)
-      auto sync_range = [&](const void* dptr, size_t bytes) {
-        const size_t off = (size_t)((const char*)dptr - (const char*)st.in.dev());
-        return cudaMemcpyAsync(st.in.d<char>(off), st.in.h<char>(off), bytes, cudaMemcpyHostToDevice, ctx->stream);
+      // compact row numbering: free deformation rows, lost rows, then the fixed rows they touch
+      std::vector<int> crow(n, -1), rows;  // main engine row -> compact row; compact -> main engine row
+      for (int r = 0; r < n; r++)
+        if (!fixed[r]) {
+          crow[r] = (int)rows.size();
+          rows.push_back(r);
+        }
+      const int n_free = (int)rows.size();
+      const int lost0 = n_free;  // compact rows [lost0, lost0 + n_lost) are the lost points
+      auto touch = [&](int r) {
+        if (crow[r] < 0) {
+          crow[r] = n_lost + (int)rows.size();
+          rows.push_back(r);
+        }
       };
-      NRS_CUDA(ctx, sync_range(st.p.un_ptr, ((size_t)Vtot + 1) * sizeof(int)));
-      NRS_CUDA(ctx, sync_range(st.p.un_w, (size_t)n_un * sizeof(double)));
-      NRS_CUDA(ctx, sync_range(st.p.un_ref, (size_t)n_un * sizeof(int)));
-      NRS_CUDA(ctx, sync_range(st.in.d<unsigned char>(st.o_fixed), Vtot));
-      if (stats) stats->h2d_bytes += ((int64_t)Vtot + 1) * 4 + (int64_t)n_un * 12 + Vtot;
-      Params p2 = st.has_plan2 ? st.p2 : st.p;
-      p2.poses_fixed = 1;
-      p2.unary_on = 1;
-      p2.pt_fixed = st.in.d<unsigned char>(st.o_fixed);
-      p2.n_ops = 1;
-      p2.op[0] = OP_OPTIMIZE;
-      p2.op_arg[0] = opt.lost_iterations;
+      const int Pm = (int)hp.pair_i.size();
+      std::vector<int> keep;
+      for (int e = 0; e < Pm; e++) {
+        const int i = hp.pair_i[e], j = hp.pair_j[e];
+        if (fixed[i] && fixed[j]) continue;
+        touch(i);
+        touch(j);
+        keep.push_back(e);
+      }
+      for (int r : un_ref_row) touch(r);
+      // crow of the non-free rows was assigned with the lost block already skipped
+      const int Vc = n_lost + (int)rows.size();
+      auto cidx = [&](int r) { return crow[r]; };
+      HostProblem h2;
+      h2.F = 1;
+      h2.V = Vc;
+      h2.cam = hp.cam;
+      h2.poses_fixed = true;
+      h2.unary_on = true;
+      h2.spring_kind = hp.spring_kind;
+      h2.info_reproj = hp.info_reproj; h2.delta_reproj = hp.delta_reproj;
+      h2.info_spatial = hp.info_spatial; h2.delta_spatial = hp.delta_spatial;
+      h2.info_spring = hp.info_spring; h2.delta_spring = hp.delta_spring; h2.spring_k = hp.spring_k;
+      h2.th2f = hp.th2f; h2.th3f = hp.th3f;
+      h2.pose_seed.assign(pose, pose + 7);
+      h2.x_seed.assign(4 * (size_t)Vc, 0.0);
+      h2.rest.assign(4 * (size_t)Vc, 0.0);
+      h2.uv.assign(2 * (size_t)Vc, 0.0);
+      h2.pt_kf.assign(Vc, -1);
+      h2.fixed0.assign(Vc, 0);
+      h2.rp_level0.assign(Vc, 0);
+      for (size_t t = 0; t < rows.size(); t++) {
+        const int r = rows[t], c = cidx(r);
+        for (int k = 0; k < 4; k++) {
+          h2.x_seed[4 * (size_t)c + k] = xd[4 * (size_t)r + k];
+          h2.rest[4 * (size_t)c + k] = hp.rest[4 * (size_t)r + k];
+        }
+        h2.uv[2 * (size_t)c] = hp.uv[2 * (size_t)r];
+        h2.uv[2 * (size_t)c + 1] = hp.uv[2 * (size_t)r + 1];
+        h2.pt_kf[c] = 0;
+        h2.fixed0[c] = fixed[r];
+        h2.rp_level0[c] = rp_lvl[r];
+      }
+      for (int e : keep) {
+        h2.pair_i.push_back(cidx(hp.pair_i[e]));
+        h2.pair_j.push_back(cidx(hp.pair_j[e]));
+        h2.pair_w.push_back(hp.pair_w[e]);
+        h2.pair_d0.push_back(hp.pair_d0[e]);
+        h2.sp_level0.push_back(sp_lvl[e]);
+      }
+      h2.un_ptr.assign(Vc + 1, 0);
+      for (int c = 0; c < Vc; c++) {
+        const int v = c - lost0;
+        h2.un_ptr[c + 1] = h2.un_ptr[c] + ((v >= 0 && v < n_lost) ? un_ptr_l[v + 1] - un_ptr_l[v] : 0);
+      }
+      h2.un_w = un_w_l;
+      h2.un_ref.resize(n_un);
+      for (int t = 0; t < n_un; t++) h2.un_ref[t] = cidx(un_ref_row[t]);
+      h2.kf_begin = {0, Vc};
+      h2.n_sort = 0;
+      h2.ops = {OP_RESET, OP_OPTIMIZE};
+      h2.op_args = {0, opt.lost_iterations};
+      Staged& st2 = ctx->staged[3];
+      rc = stage_problem(ctx, st2, h2);
+      if (rc) return rc;
+      if (stats) stats->h2d_bytes += (int64_t)st2.h2d_bytes;
       hprof.mark("lost_setup");
-      rc = run_staged(ctx, st, stats, true, &p2, st.has_plan2);
+      rc = run_staged(ctx, st2, stats);
       if (rc) return rc;
       hprof.mark("run2");
-      const double* xl = st.out.h<double>(st.o_x);
+      const double* xl = st2.out.h<double>(st2.o_x);
       for (int v = 0; v < n_lost; v++)
         for (int k = 0; k < 3; k++)
           last_pos[3 * (size_t)lost_list[v] + k] =
-              (float)xl[4 * (size_t)(n + v) + k] + last_pos[3 * (size_t)lost_list[v] + k];  // :544-552
+              (float)xl[4 * (size_t)(lost0 + v) + k] + last_pos[3 * (size_t)lost_list[v] + k];  // :544-552
     }
     for (int v = 0; v < n_lost; v++)
       if (lost_vertex_out) lost_vertex_out[v] = lost_list[v];

@@ -1230,17 +1230,41 @@ struct Engine {
               }
             }
             if (P.D > 0) {
-              for (int a = P.dinc_ptr[i] + ql; a < P.dinc_ptr[i + 1]; a += kTPR) {
-                const int ent = P.dinc_ent[a];
-                const int4 v = *reinterpret_cast<const int4*>(P.dmp_v + 4 * (size_t)(ent >> 2));
-                const double s = P.dc[4 * (size_t)(ent >> 2)];
-                const V3 z0 = ld3p(P.zvec, v.x), z1 = ld3p(P.zvec, v.y), z2 = ld3p(P.zvec, v.z),
-                         z3 = ld3p(P.zvec, v.w);
-                const int role = ent & 3;
-                const double sg = ((role == 1 || role == 2) ? 1.0 : -1.0) * s;
-                w0 += sg * (-z0.x + z1.x + z2.x - z3.x);
-                w1 += sg * (-z0.y + z1.y + z2.y - z3.y);
-                w2 += sg * (-z0.z + z1.z + z2.z - z3.z);
+              // dampers: a row sits in ~16 of them and every incidence is a chain of dependent loads (entry ->
+              // vertices + coefficient -> four z rows). Batches of kDB incidences per lane issue each level of the
+              // chain for the whole batch before the first use.
+              constexpr int kDB = 2;
+              const int d1 = P.dinc_ptr[i + 1];
+              for (int a0 = P.dinc_ptr[i] + ql; a0 < d1; a0 += kDB * kTPR) {
+                int ent[kDB];
+#pragma unroll
+                for (int k = 0; k < kDB; k++) ent[k] = __ldg(P.dinc_ent + min(a0 + kTPR * k, d1 - 1));
+                int4 vv[kDB];
+                double sc[kDB];
+#pragma unroll
+                for (int k = 0; k < kDB; k++) {
+                  vv[k] = __ldg(reinterpret_cast<const int4*>(P.dmp_v) + (ent[k] >> 2));
+                  sc[k] = P.dc[4 * (size_t)(ent[k] >> 2)];
+                }
+                double ax[kDB], ay[kDB], az[kDB];
+#pragma unroll
+                for (int k = 0; k < kDB; k++) {
+                  const V3 z0 = ld3p(P.zvec, vv[k].x), z1 = ld3p(P.zvec, vv[k].y), z2 = ld3p(P.zvec, vv[k].z),
+                           z3 = ld3p(P.zvec, vv[k].w);
+                  ax[k] = -z0.x + z1.x + z2.x - z3.x;
+                  ay[k] = -z0.y + z1.y + z2.y - z3.y;
+                  az[k] = -z0.z + z1.z + z2.z - z3.z;
+                }
+#pragma unroll
+                for (int k = 0; k < kDB; k++) {
+                  if (a0 + kTPR * k < d1) {
+                    const int role = ent[k] & 3;
+                    const double sg = ((role == 1 || role == 2) ? 1.0 : -1.0) * sc[k];
+                    w0 += sg * ax[k];
+                    w1 += sg * ay[k];
+                    w2 += sg * az[k];
+                  }
+                }
               }
             }
           }
