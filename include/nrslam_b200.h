@@ -278,6 +278,40 @@ int nrslam_b200_shi_extract(nrslam_b200_shi* shi, const uint8_t* image, int32_t 
 /* Diagnostics: the score map of the last extract (height x width floats, -1 marks included). */
 int nrslam_b200_shi_debug_scores(nrslam_b200_shi* shi, float* scores_out);
 
+/* ---- Image pre-processing ---------------------------------------------------
+ * pre_image = System::ImageProcessing (SLAM/system.cc:189-201): cv::cvtColor(RGB2GRAY) then cv::CLAHE(clip_limit,
+ * tiles) — the reference uses createCLAHE(3.0, Size(8, 8)) (system.cc:37). rgb: 8-bit interleaved R,G,B rows of
+ * `pitch` bytes. gray_out / clahe_out [width * height] (either may be NULL); both stay resident on the device.
+ * pre_mask = Masker::mask / GetAllMasks()["Global"] (masking/masker.cc:80-92,94-115): AND of the filters' masks,
+ * then erode 10x10. gray == NULL re-uses the gray image of the last pre_image call without a host round trip.
+ *   BRIGHT      threshold(gray, th, 255, THRESH_BINARY_INV), erode(ellipse 11x11), GaussianBlur(11x11, sigma 5,
+ *               REFLECT_101)                                                (masking/bright_filter.cc:24-39)
+ *   BORDER      255 inside [rb, rows - re) x [cb, cols - ce) where gray != 0, erode(rect 21x21)
+ *                                                                           (masking/border_filter.cc:24-40)
+ *   PREDEFINED  a caller-prepared mask (PredefinedFilter loads and erodes it once at start-up,
+ *               masking/predefined_filter.cc:27-41)
+ * Results are bit-exact with OpenCV 4 (tests/golden/preproc.npz). */
+typedef struct nrslam_b200_pre nrslam_b200_pre;
+#define NRSLAM_B200_FILTER_BRIGHT 0
+#define NRSLAM_B200_FILTER_BORDER 1
+#define NRSLAM_B200_FILTER_PREDEFINED 2
+typedef struct nrslam_b200_mask_filter {
+  int32_t kind;
+  int32_t th;               /* BRIGHT */
+  int32_t rb, re, cb, ce;   /* BORDER: rows / columns cut at the beginning / end */
+  const uint8_t* mask;      /* PREDEFINED: [width * height] */
+} nrslam_b200_mask_filter;
+int nrslam_b200_pre_create(nrslam_b200_ctx* ctx, int32_t max_width, int32_t max_height, nrslam_b200_pre** out);
+void nrslam_b200_pre_destroy(nrslam_b200_pre* pre);
+int nrslam_b200_pre_image(nrslam_b200_pre* pre, const uint8_t* rgb, int32_t width, int32_t height, int32_t pitch,
+                          float clip_limit, int32_t tiles_x, int32_t tiles_y, uint8_t* gray_out,
+                          uint8_t* clahe_out);
+int nrslam_b200_pre_mask(nrslam_b200_pre* pre, const uint8_t* gray, int32_t width, int32_t height,
+                         const nrslam_b200_mask_filter* filters, int32_t n_filters, uint8_t* mask_out);
+/* Device time (CUDA events) and kernel count of the last pre_image / pre_mask call. */
+float nrslam_b200_pre_last_ms(const nrslam_b200_pre* pre);
+int32_t nrslam_b200_pre_last_launches(const nrslam_b200_pre* pre);
+
 #ifdef __cplusplus
 }
 #endif

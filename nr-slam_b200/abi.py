@@ -66,6 +66,14 @@ class Stats(C.Structure):
         return d
 
 
+class MaskFilter(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("th", C.c_int32), ("rb", C.c_int32), ("re", C.c_int32), ("cb", C.c_int32),
+                ("ce", C.c_int32), ("mask", C.POINTER(C.c_uint8))]
+
+
+FILTER_BRIGHT, FILTER_BORDER, FILTER_PREDEFINED = range(3)
+
+
 def ptr(a, ctype):
     """numpy array -> typed ctypes pointer (None passes NULL)."""
     if a is None:

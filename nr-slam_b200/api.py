@@ -10,10 +10,12 @@ sm_100 device is present.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
-from .abi import Camera, Graph, Options, Stats, ptr  # noqa: F401
+from .abi import (Camera, FILTER_BORDER, FILTER_BRIGHT, FILTER_PREDEFINED, Graph, MaskFilter, Options, Stats,  # noqa: F401
+                  ptr)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnrslam_b200.so")
@@ -43,6 +45,8 @@ def load():
         lib.nrslam_b200_graph_get_edges.restype = C.c_int32
         lib.nrslam_b200_graph_update_vertex.restype = C.c_int32
         lib.nrslam_b200_klt_num_points.restype = C.c_int32
+        lib.nrslam_b200_pre_last_ms.restype = C.c_float
+        lib.nrslam_b200_pre_last_launches.restype = C.c_int32
         _LIB = lib
     return _LIB
 
@@ -420,3 +424,75 @@ class ShiTomasi:
             self.L.nrslam_b200_shi_debug_scores(self._h, ptr(sc, C.c_float))
             out["scores"] = sc
         return out
+
+
+class Pre:
+    """Per-frame image pre-processing on the GPU: System::ImageProcessing (SLAM/system.cc:189-201: RGB -> gray -> CLAHE)
+    and Masker::mask (masking/masker.cc:80-92). Bit-exact with OpenCV 4."""
+
+    def __init__(self, core, max_width=1440, max_height=1080):
+        self.core = core
+        self.L = core.L
+        self._h = C.c_void_p()
+        rc = self.L.nrslam_b200_pre_create(core._ctx, int(max_width), int(max_height), C.byref(self._h))
+        if rc != 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
+        core._children.append(weakref.ref(self))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if self.core._ctx:
+                self.L.nrslam_b200_pre_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(self.core._ctx) or b"").decode())
+
+    def image(self, rgb, clip_limit=3.0, tiles=(8, 8)):
+        """rgb: (h, w, 3) uint8. Returns (gray, clahe) like ImageProcessing's im_gray and return value."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        h, w = rgb.shape[:2]
+        gray = np.empty((h, w), np.uint8)
+        eq = np.empty((h, w), np.uint8)
+        self._check(self.L.nrslam_b200_pre_image(self._h, ptr(rgb, C.c_uint8), w, h, 3 * w, C.c_float(clip_limit),
+                                                 int(tiles[0]), int(tiles[1]), ptr(gray, C.c_uint8),
+                                                 ptr(eq, C.c_uint8)))
+        return gray, eq
+
+    def mask(self, gray, filters, shape=None):
+        """filters: list of ("bright", th) / ("border", rb, re, cb, ce) / ("predefined", mask). gray=None re-uses the
+        gray image of the last image() call (pass its shape)."""
+        if gray is not None:
+            gray = np.ascontiguousarray(gray, np.uint8)
+            h, w = gray.shape
+        else:
+            h, w = shape
+        arr = (MaskFilter * max(len(filters), 1))()
+        keep = []
+        for i, f in enumerate(filters):
+            if f[0] == "bright":
+                arr[i].kind, arr[i].th = FILTER_BRIGHT, int(f[1])
+            elif f[0] == "border":
+                arr[i].kind = FILTER_BORDER
+                arr[i].rb, arr[i].re, arr[i].cb, arr[i].ce = (int(v) for v in f[1:5])
+            else:
+                m = np.ascontiguousarray(f[1], np.uint8)
+                keep.append(m)
+                arr[i].kind, arr[i].mask = FILTER_PREDEFINED, ptr(m, C.c_uint8)
+        out = np.empty((h, w), np.uint8)
+        self._check(self.L.nrslam_b200_pre_mask(self._h, ptr(gray, C.c_uint8), w, h, arr, len(filters),
+                                                ptr(out, C.c_uint8)))
+        return out
+
+    def last_ms(self):
+        return float(self.L.nrslam_b200_pre_last_ms(self._h))
+
+    def last_launches(self):
+        return int(self.L.nrslam_b200_pre_last_launches(self._h))
