@@ -224,7 +224,7 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of) {
 // Launch plan of one engine launch over the rows [0, kf_begin[F]).
 struct Plan {
   int V = 0, n_chunks = 0, grid = 0, block = 0, cluster_mode = 0, resident = 0, res_rows = 0, res_inc = 0,
-      block_prec = 0;
+      block_prec = 0, wide = 0;
   size_t smem = 0;
   std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr;
   const int *d_chunk_kf = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_kf_chunk_ptr = nullptr;
@@ -303,6 +303,28 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
       }
     }
   }
+  // experiment (off): pick the chunk size that minimises passes x chunk rows of the busiest CTA. Measured on
+  // configs[2]: no gain — a chunk pass is a fixed chain of dependent gathers whatever its row count, so time follows
+  // the number of passes, and smaller chunks add pose-partial records to sum (96-row chunks 67.0 vs 66.1 Mcycles)
+  if (!cluster_mode && !hp.points_fixed && env_int("NRSLAM_B200_BALANCE", 0)) {
+    const size_t smem0 = engine_smem_bytes(F, 0, 0, 0);
+    const int g1 = engine_max_grid(kMaxBlock, smem0, 0), g2 = engine_max_grid(kMaxBlock, smem0, 1);
+    if (count_chunks(kMaxRows) > std::max(std::max(g1, g2), 1)) {
+      const bool want_wide = env_int("NRSLAM_B200_WIDE", 1) != 0;
+      long best = -1;
+      for (int rows = env_int("NRSLAM_B200_BALANCE_MIN", 88); rows <= kMaxRows; rows += 8) {
+        const int nc = count_chunks(rows);
+        const int blk = std::min(kMaxBlock, (kTPR * rows + 31) / 32 * 32);
+        const int G = std::max(1, std::max(engine_max_grid(blk, smem0, 0), want_wide ? engine_max_grid(blk, smem0, 1) : 0));
+        const long passes = (nc + G - 1) / G;
+        const long cost = passes * (rows + 6);  // + a per-pass overhead in row units
+        if (best < 0 || cost < best) {
+          best = cost;
+          chunk_rows = rows;
+        }
+      }
+    }
+  }
   // kTPR threads per row inside the CG loop; pose-only problems (no CG) run one thread per row
   int block = hp.points_fixed ? std::max((chunk_rows + 31) / 32 * 32, 128) : kTPR * chunk_rows;
   block = std::min(kMaxBlock, (block + 31) / 32 * 32);
@@ -326,7 +348,7 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
   }
   res_rows = (res_rows + kPrecBlock - 1) / kPrecBlock * kPrecBlock;
   res_inc = std::max(res_inc, 1);
-  int resident = 0, block_prec = 0, grid = 0;
+  int resident = 0, block_prec = 0, grid = 0, wide = 0;
   size_t smem = engine_smem_bytes(F, 0, 0, 0);
   if (smem > 200 * 1024) return fail(ctx, NRSLAM_B200_ERR_ARG, "too many poses for the shared-memory pose blocks");
   const size_t kSmemBudget = 220 * 1024;
@@ -348,8 +370,16 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
     if (cluster_mode) {
       grid = n_chunks;
     } else {
-      const int max_grid = engine_max_grid(block, smem);
+      int max_grid = engine_max_grid(block, smem);
       if (max_grid <= 0) return fail(ctx, NRSLAM_B200_ERR_CUDA, "kernel cannot be made resident");
+      // more chunks than one CTA per SM can take in one pass: the two-CTAs-per-SM variant hides the gather latency
+      if (!hp.points_fixed && n_chunks > max_grid && env_int("NRSLAM_B200_WIDE", 1)) {
+        const int mg2 = engine_max_grid(block, smem, 1);
+        if (mg2 > max_grid) {
+          wide = 1;
+          max_grid = mg2;
+        }
+      }
       grid = std::max(1, std::min(n_chunks, max_grid));
       if (ctx->opt.grid_ctas > 0) grid = std::min(grid, ctx->opt.grid_ctas);
       const int g = env_int("NRSLAM_B200_GRID", 0);
@@ -366,14 +396,14 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
     }
   }
   pl.n_chunks = n_chunks; pl.grid = grid; pl.block = block; pl.cluster_mode = cluster_mode; pl.resident = resident;
-  pl.res_rows = res_rows; pl.res_inc = res_inc; pl.block_prec = block_prec; pl.smem = smem;
+  pl.res_rows = res_rows; pl.res_inc = res_inc; pl.block_prec = block_prec; pl.smem = smem; pl.wide = wide;
   return 0;
 }
 
 void apply_plan(Params& p, const Plan& pl) {
   p.V = pl.V; p.n_chunks = pl.n_chunks;
   p.cluster_mode = pl.cluster_mode; p.resident = pl.resident; p.res_rows = pl.res_rows; p.res_inc = pl.res_inc;
-  p.block_prec = pl.block_prec;
+  p.block_prec = pl.block_prec; p.wide = pl.wide;
   p.chunk_kf = pl.d_chunk_kf; p.chunk_begin = pl.d_chunk_begin; p.chunk_end = pl.d_chunk_end;
   p.kf_chunk_ptr = pl.d_kf_chunk_ptr;
   p.coarse = pl.coarse;

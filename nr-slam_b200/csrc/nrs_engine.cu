@@ -246,6 +246,10 @@ __device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int
 
 static_assert((kPN / 4) % kTPR == 0, "the lanes of a row split the float4 columns of the block preconditioner evenly");
 
+// WIDE: the variant for large windows (cooperative grid, vectors in global memory): compiled without the
+// shared-memory-resident and cluster-native paths so that it fits 128 registers and TWO CTAs share an SM — the big
+// BA matvec is a chain of dependent L2 gathers per row, and twice the warps hide twice the latency.
+template <bool WIDE>
 struct Engine {
   const Params& P;
   // shared memory
@@ -356,6 +360,7 @@ struct Engine {
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     } else {
+      const long long tb0 = clock64();
       __syncthreads();
       if (tid == 0) {
         red_release_add_u64(P.bar, 1ULL);
@@ -364,7 +369,28 @@ struct Engine {
         }
       }
       __syncthreads();
+      prof[12] += clock64() - tb0;  // grid barriers (arrival skew + latency)
     }
+  }
+
+  // ---- dot product of two replicated pose vectors in shared memory, identical in every thread (and every CTA and
+  // rank: fixed order). Called by all threads after the vectors are complete. Long vectors (BA windows of 30-100
+  // keyframes) are summed by warp 0 — the serial loop cost 6 F dependent DFMAs per thread, twice per CG iteration.
+  __device__ __forceinline__ double pose_dot(const double* a, const double* b, int n) {
+    if (n <= 32) {
+      double s = 0;
+      for (int t = 0; t < n; t++) s += a[t] * b[t];
+      return s;
+    }
+    if (tid < 32) {
+      double s = 0;
+      for (int t = tid; t < n; t += 32) s += a[t] * b[t];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (tid == 0) s_scal[30] = s;
+    }
+    __syncthreads();
+    return s_scal[30];
   }
 
   // ---- block reduction of NV per-thread values (fixed order); result in dst[0..NV)
@@ -418,9 +444,18 @@ struct Engine {
       const int k = tid >> 5;
       const bool mx = (maxmask >> k) & 1;
       double s = mx ? -DBL_MAX : 0.0;
-      for (int c = lane; c < (int)gridDim.x; c += 32) {
-        const double o = __ldcg(P.slots + ((size_t)par * gridDim.x + c) * kSlotVals + k);
-        s = mx ? fmax(s, o) : s + o;
+      // batches of 8 slots per lane: every load of a batch is issued before the first use (a plain accumulate loop
+      // pays one L2 round trip per 32 CTAs)
+      for (int c0 = lane; c0 < (int)gridDim.x; c0 += 8 * 32) {
+        double o[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int c = min(c0 + 32 * u, (int)gridDim.x - 1);
+          o[u] = __ldcg(P.slots + ((size_t)par * gridDim.x + c) * kSlotVals + k);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (c0 + 32 * u < (int)gridDim.x) s = mx ? fmax(s, o[u]) : s + o[u];
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -1011,7 +1046,7 @@ struct Engine {
   __device__ bool pcg() {
     const int F = P.F;
     const bool pts = !P.points_fixed, pos = !P.poses_fixed;
-    const bool res = P.resident != 0;
+    const bool res = !WIDE && P.resident != 0;
     if (tid == 0) *s_flag = 0;
     __syncthreads();
     if (pos) {
@@ -1133,7 +1168,7 @@ struct Engine {
         s_zp[t] = s;
       }
       __syncthreads();
-      for (int t = 0; t < 6 * F; t++) rz_pose += s_rp[t] * s_zp[t];
+      rz_pose = pose_dot(s_rp, s_zp, 6 * F);
     }
     grid_reduce<1>(rz_part, 0);
     double rz = s_scal[0] + rz_pose;
@@ -1148,7 +1183,7 @@ struct Engine {
     int it = 0;
     // quad mapping of the loop and the per-row constants, kept in registers when this CTA owns at most one chunk
     const int qr = tid / kTPR, ql = tid % kTPR;
-    const bool single = P.n_chunks <= (int)gridDim.x && P.world == 1;
+    const bool single = !WIDE && P.n_chunks <= (int)gridDim.x && P.world == 1;
     bool my_fixed = false;
     int my_kf = -1, my_a0 = 0, my_a1 = 0, my_cb = 0, my_ce = 0, my_kc0 = 0, my_kc1 = 0;
     double my_su = 0;
@@ -1390,10 +1425,11 @@ struct Engine {
         }
         __syncthreads();
         pq = s_scal[0];
-        for (int t = 0; t < 6 * F; t++) pq += s_pp[t] * s_qp[t];
+        pq += pose_dot(s_pp, s_qp, 6 * F);
       } else {
         grid_reduce<1>(pq_part, 0, pos ? 1 : 0);
         pq = s_scal[0];
+        const long long tp0 = clock64();
         if (pos) {
           // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (replicated per CTA)
           for (int t = tid; t < 6 * F; t += nthr) {
@@ -1403,8 +1439,9 @@ struct Engine {
             s_qp[t] = first ? w : w + beta * s_qp[t];
           }
           __syncthreads();
-          for (int t = 0; t < 6 * F; t++) pq += s_pp[t] * s_qp[t];
+          pq += pose_dot(s_pp, s_qp, 6 * F);
         }
+        prof[13] += clock64() - tp0;  // pose rows of the matvec (chunk-partial sums, recurrences, serial dot)
       }
       const long long tm2 = clock64();
       if (!(pq > 0) || !isfinite(pq)) {
@@ -1461,7 +1498,7 @@ struct Engine {
           s_zp[t] = s;
         }
         __syncthreads();
-        for (int t = 0; t < 6 * F; t++) rzn_pose += s_rp[t] * s_zp[t];
+        rzn_pose = pose_dot(s_rp, s_zp, 6 * F);
       }
       const long long tm3 = clock64();
       grid_reduce<1>(rzn_part, 0);
@@ -2270,9 +2307,14 @@ struct Engine {
     int qmax = 0;
     do {
       const long long ts0 = clock64();
-      const bool native = P.cluster_mode && P.resident && P.F == 1 && P.D == 0 && !P.points_fixed &&
-                          P.n_chunks == (int)gridDim.x && !P.no_dsmem && P.push_ptr != nullptr;
-      const bool solved = native ? pcg_cluster() : pcg();
+      bool solved;
+      if constexpr (WIDE) {
+        solved = pcg();
+      } else {
+        const bool native = P.cluster_mode && P.resident && P.F == 1 && P.D == 0 && !P.points_fixed &&
+                            P.n_chunks == (int)gridDim.x && !P.no_dsmem && P.push_ptr != nullptr;
+        solved = native ? pcg_cluster() : pcg();
+      }
       const long long ts1 = clock64();
       prof[6] += ts1 - ts0;  // solve
       lm_trials++;
@@ -2452,7 +2494,13 @@ struct Engine {
 
 __global__ void __launch_bounds__(kMaxBlock, 1) nrs_lm_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) double nrs_smem[];
-  Engine eng(p, nrs_smem);
+  Engine<false> eng(p, nrs_smem);
+  eng.run();
+}
+
+__global__ void __launch_bounds__(kMaxBlock, 2) nrs_lm_kernel_wide(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) double nrs_smem[];
+  Engine<true> eng(p, nrs_smem);
   eng.run();
 }
 
@@ -2479,24 +2527,30 @@ size_t engine_smem_extra(int res_inc, int halo_rows, int coarse) {
   return b;
 }
 
-static bool set_smem(size_t smem) {
-  static size_t current = 0;
-  if (smem > 48 * 1024 && smem > current) {
-    if (cudaFuncSetAttribute(nrs_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+static const void* kernel_of(int wide) {
+  return wide ? (const void*)nrs_lm_kernel_wide : (const void*)nrs_lm_kernel;
+}
+
+static bool set_smem(size_t smem, int wide = 0) {
+  static size_t current[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > current[wide]) {
+    if (cudaFuncSetAttribute(kernel_of(wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    current = smem;
+    current[wide] = smem;
   }
   return true;
 }
 
-int engine_max_grid(int block, size_t smem) {
+int engine_max_grid(int block, size_t smem, int wide) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (!set_smem(smem)) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nrs_lm_kernel, block, smem) != cudaSuccess) {
+  if (!set_smem(smem, wide)) return 0;
+  const cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nrs_lm_kernel_wide, block, smem)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nrs_lm_kernel, block, smem);
+  if (e != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -2527,7 +2581,8 @@ int engine_max_cluster(int block, size_t smem) {
 }
 
 int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_t stream) {
-  if (!set_smem(smem)) return (int)cudaErrorInvalidValue;
+  const int wide = (p.wide && !p.cluster_mode) ? 1 : 0;
+  if (!set_smem(smem, wide)) return (int)cudaErrorInvalidValue;
   void* args[] = {const_cast<Params*>(&p)};
   if (p.cluster_mode) {
     cudaLaunchConfig_t cfg = {};
@@ -2546,7 +2601,7 @@ int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_
   }
   cudaError_t e = cudaMemsetAsync(p.bar, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return (int)e;
-  e = cudaLaunchCooperativeKernel((const void*)nrs_lm_kernel, dim3(grid), dim3(block), args, smem, stream);
+  e = cudaLaunchCooperativeKernel(kernel_of(wide), dim3(grid), dim3(block), args, smem, stream);
   return (int)e;
 }
 

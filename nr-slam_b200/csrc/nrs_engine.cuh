@@ -78,6 +78,7 @@ struct Params {
   int res_rows;       // shared-memory capacity: rows per chunk
   int res_inc;        // shared-memory capacity: pair incidences per chunk
   int block_prec;     // 1: dense kPrecBlock-row block-Jacobi preconditioner (resident mode only), else 3x3 blocks
+  int wide;           // 1: launch the two-CTAs-per-SM variant (large windows: cooperative grid, nothing resident)
   int no_dsmem;       // 1: keep the general CG loop (exchange through L2) even where the cluster-native loop applies
   // halo exchange of the cluster-native CG loop: after every z = M^-1 r the owner of a row PUSHES it into the halo
   // buffer of every chunk whose regulariser edges read it (remote shared-memory stores, no remote loads)
@@ -171,7 +172,7 @@ size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec);
 // Extra shared memory of the cluster-native loop: pushed halo rows and the coarse (aggregate) level.
 size_t engine_smem_extra(int res_inc, int halo_rows, int coarse);
 // Largest co-resident grid for a cooperative launch / largest cluster that can be scheduled (0 if none).
-int engine_max_grid(int block, size_t smem);
+int engine_max_grid(int block, size_t smem, int wide = 0);
 int engine_max_cluster(int block, size_t smem);
 
 }  // namespace nrs
