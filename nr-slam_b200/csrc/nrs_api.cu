@@ -133,6 +133,7 @@ struct HostProblem {
   std::vector<unsigned char> fixed0;    // per-vertex setFixed(true) known at staging time (lost-point stage)
   std::vector<unsigned char> rp_level0, sp_level0;  // edge levels carried over from an earlier program (else 0)
   bool unary_on = false;                // the unary (fixed-reference) edges take part
+  bool plain_jacobi = false;            // 3x3 block-Jacobi instead of the dense 16-row blocks (tiny, anchored problems)
   int n_sort = 0;                       // leading rows of every pose-slot group that may be re-ordered spatially
   int n_stage1 = 0;                     // rows of the first launch (tracking: without the lost-point rows); 0 = all
   std::vector<int> kf_begin;            // F+1: rows of pose slot k are [kf_begin[k], kf_begin[k+1]) (rows w/o pose: slot 0)
@@ -354,7 +355,7 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
   const size_t kSmemBudget = 220 * 1024;
   if (!hp.points_fixed && !hp.sharded && env_int("NRSLAM_B200_RESIDENT", 1)) {
     const size_t s1 = engine_smem_bytes(F, res_rows, res_inc, 1), s0 = engine_smem_bytes(F, res_rows, res_inc, 0);
-    const bool want_prec = env_int("NRSLAM_B200_BLOCKPREC", 1) != 0;
+    const bool want_prec = env_int("NRSLAM_B200_BLOCKPREC", 1) != 0 && !hp.plain_jacobi;
     const size_t s = (want_prec && s1 <= kSmemBudget) ? s1 : s0;
     if (s <= kSmemBudget) {
       const int mg = cluster_mode ? n_chunks : engine_max_grid(block, s);
@@ -1100,6 +1101,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
       h2.cam = hp.cam;
       h2.poses_fixed = true;
       h2.unary_on = true;
+      h2.plain_jacobi = env_int("NRSLAM_B200_LOST_JACOBI", 1) != 0;
       h2.spring_kind = hp.spring_kind;
       h2.info_reproj = hp.info_reproj; h2.delta_reproj = hp.delta_reproj;
       h2.info_spatial = hp.info_spatial; h2.delta_spatial = hp.delta_spatial;
