@@ -10,8 +10,8 @@ run() {
   echo "== $name rc=$?"; grep -h '^{' gpurun_out/sharded_${name}_n$N.log | tail -1; grep -v '^{' gpurun_out/sharded_${name}_n$N.log | grep -i "error\|Traceback\|assert" | head -5
 }
 nvidia-smi -L | head -8
-run c1 --config c1
-run c3small --config c3 --landmarks 1500 --keyframes 10 --visible 6
+[ -z "$SKIP_SMALL" ] && run c1 --config c1
+[ -z "$SKIP_SMALL" ] && run c3small --config c3 --landmarks 1500 --keyframes 10 --visible 6
 [ -n "$FULL" ] && run c3 --config c3 --reps 3
 [ -n "$FULL4" ] && run c4 --config c4 --reps 2 --pose-tol 2e-5 --pt-tol 4e-4
 true
