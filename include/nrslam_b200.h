@@ -312,6 +312,70 @@ int nrslam_b200_pre_mask(nrslam_b200_pre* pre, const uint8_t* gray, int32_t widt
 float nrslam_b200_pre_last_ms(const nrslam_b200_pre* pre);
 int32_t nrslam_b200_pre_last_launches(const nrslam_b200_pre* pre);
 
+/* ---- DeformableTriangulation, batched over all candidates of a frame ------------------
+ * Replaces the per-candidate calls of
+ *   absl::StatusOr<Eigen::Vector3f> DeformableTriangulation(TemporalBuffer&, int candidate_id,
+ *                                                           std::shared_ptr<CameraModel>, const float scale)
+ * (modules/optimization/g2o_optimization.h:34-37, .cc:559-814) that Mapping::LandmarkTriangulation issues in a loop
+ * (modules/mapping/mapping.cc:88-113): hundreds of independent small LM problems per non-keyframe frame, one CTA each.
+ * The caller (shim) flattens what the function reads from the TemporalBuffer:
+ *   track_ptr[n_cand + 1]  CSR over track entries; candidate c owns entries track_ptr[c] .. track_ptr[c+1]-1 =
+ *                          TemporalBuffer::GetFeatureTrack(candidate) (ascending frame id: OLDEST FIRST,
+ *                          temporal_buffer.cc:173-183); 1 <= length <= NRSLAM_B200_TRI_MAX_TRACK
+ *   track_uv[2 E]          keypoint.pt of the candidate in that frame
+ *   track_pose[7 E]        TemporalBuffer::GetCameraTransformWorld(frame) (camera_transform_world)
+ *   n_neighbours[n_cand]   size of GetClosestMapPointsToFeature(candidate, 10, 20, 500) (0 .. 11: the loop admits
+ *                          num_neighbors + 1, temporal_buffer.cc:134-140); 0 -> "Feature too close to other ones"
+ *   nb_pos[3 NB E]         GetLandmarkPosition(frame, neighbour k) (world), NB = NRSLAM_B200_TRI_MAX_NB slots per entry
+ *   nb_valid[NB E]         its .ok()
+ * (E = track_ptr[n_cand].) `scale` is accepted and unused, like in the reference body.
+ * Outputs: position_out[3 n_cand] the triangulated world position (valid when status_out == NRSLAM_B200_TRI_OK),
+ * status_out[n_cand] one code per absl::InternalError the reference returns (the StatusOr), lm_iterations_out
+ * (optional) the LM iterations g2o ran. The LM solve is exact (dense LL^T of the (3 T)^2 system in shared memory),
+ * the reprojection edge is differentiated numerically with delta = 1e-9 through the fp32 camera model exactly like
+ * g2o does for ReprojectionErrorOnlyDeformation, which declares no analytic Jacobian
+ * (reprojection_error_only_deformation.h:40, base_fixed_sized_edge.hpp:160-199). */
+#define NRSLAM_B200_TRI_MAX_TRACK 48
+#define NRSLAM_B200_TRI_MAX_NB 12
+enum {
+  NRSLAM_B200_TRI_OK = 0,
+  NRSLAM_B200_TRI_TOO_CLOSE = 1,        /* "Feature too close to other ones."           .cc:569-571 */
+  NRSLAM_B200_TRI_HIGH_REPROJ_FIRST = 2,/* "High reprojection error at first camera."   .cc:618-620 */
+  NRSLAM_B200_TRI_HIGH_REPROJ_SECOND = 3,/* "High reprojection error at second camera." .cc:625-627 */
+  NRSLAM_B200_TRI_LOW_PARALLAX = 4,     /* "Low parallax."                              .cc:633-635 */
+  NRSLAM_B200_TRI_NO_NEIGHBOURS = 5,    /* "Found no neighbours in a temporal point."   .cc:653-655 */
+  NRSLAM_B200_TRI_NEGATIVE_DEPTH = 6,   /* "Negative initial depth."                    .cc:659-661 */
+  NRSLAM_B200_TRI_BAD_NEIGHBOURS = 7,   /* "Triangulation has to many bad neighbors."   .cc:781-783 */
+  NRSLAM_B200_TRI_HIGH_ERROR = 8,       /* "Triangulation has to much error."           .cc:794-796 */
+  NRSLAM_B200_TRI_NAN = 9               /* result.hasNaN() (the caller's check, mapping.cc:98-99) */
+};
+typedef struct nrslam_b200_tri nrslam_b200_tri;
+int nrslam_b200_tri_create(nrslam_b200_ctx* ctx, nrslam_b200_tri** out);
+void nrslam_b200_tri_destroy(nrslam_b200_tri* tri);
+int nrslam_b200_tri_run(nrslam_b200_tri* tri, const nrslam_b200_camera* cam, int32_t n_cand,
+                        const int32_t* track_ptr, const float* track_uv, const float* track_pose,
+                        const int32_t* n_neighbours, const float* nb_pos, const uint8_t* nb_valid, float scale,
+                        float* position_out, int32_t* status_out, int32_t* lm_iterations_out);
+/* Device time (CUDA events on the ctx stream) of the last run's kernel, and a re-run of it on the HBM-resident
+ * staged batch (benchmark hook; results identical). */
+float nrslam_b200_tri_last_ms(const nrslam_b200_tri* tri);
+int nrslam_b200_tri_rerun(nrslam_b200_tri* tri, float* gpu_ms_out);
+
+/* ---- RegularizationGraph::UpdateVertex for all updated vertices of a frame, on the device ----
+ * The loop CameraPoseAndDeformationOptimization runs after the solve (g2o_optimization.cc:458-474):
+ *   for every accepted point i (in frame order): good = graph->UpdateVertex(id_i, positions); if (good < 5) BAD
+ * UpdateVertex (map/regularization_graph.cc:130-146) walks the vertex's edges, and UpdateConnection (:107-128)
+ * updates min/max distance, weight = exp(-d_max^2 / 2 sigma^2) and the BAD status of one edge from the CURRENT
+ * positions of its endpoints. Positions do not change during the loop, so the per-edge update is idempotent and the
+ * loop is order-independent: one thread per undirected edge incident to an updated vertex, then one thread per
+ * updated vertex counting its non-BAD edges. Bit-exact with the sequential host version
+ * (nrslam_b200_graph_update_vertex; the weight is exp() evaluated in fp64 and rounded to fp32, which agrees with
+ * glibc's correctly-rounded expf). vertices[n] = graph vertices to update (each at most once);
+ * positions[3 n_vertices] = MapPoint::GetLastWorldPosition of all graph vertices; good_out[n] = UpdateVertex's
+ * return value. The graph attribute arrays (weight, min/max distance, status) are updated in place. */
+int nrslam_b200_graph_update_vertices(nrslam_b200_ctx* ctx, nrslam_b200_graph* g, int32_t n,
+                                      const int32_t* vertices, const float* positions, int32_t* good_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ def load():
         lib.nrslam_b200_klt_num_points.restype = C.c_int32
         lib.nrslam_b200_pre_last_ms.restype = C.c_float
         lib.nrslam_b200_pre_last_launches.restype = C.c_int32
+        lib.nrslam_b200_tri_last_ms.restype = C.c_float
         _LIB = lib
     return _LIB
 
@@ -200,6 +201,17 @@ class Core:
         g = graph.struct()
         positions = _f32(positions)
         return self.L.nrslam_b200_graph_update_vertex(C.byref(g), int(vertex), ptr(positions, C.c_float))
+
+    def graph_update_vertices(self, graph, vertices, positions):
+        """The UpdateVertex loop of CameraPoseAndDeformationOptimization (g2o_optimization.cc:458-474) on the device:
+        graph attribute arrays updated in place, returns UpdateVertex's good-connection count per vertex."""
+        g = graph.struct()
+        v = np.ascontiguousarray(vertices, np.int32)
+        positions = _f32(positions)
+        good = np.zeros(len(v), np.int32)
+        self._check(self.L.nrslam_b200_graph_update_vertices(self._ctx, C.byref(g), len(v), ptr(v, C.c_int32),
+                                                             ptr(positions, C.c_float), ptr(good, C.c_int32)))
+        return good
 
 
 class KLT:
@@ -496,3 +508,62 @@ class Pre:
 
     def last_launches(self):
         return int(self.L.nrslam_b200_pre_last_launches(self._h))
+
+
+class Triangulator:
+    """Batched DeformableTriangulation (modules/optimization/g2o_optimization.h:34-37, .cc:559-814): one call per frame
+    over all candidates of Mapping::LandmarkTriangulation (mapping/mapping.cc:88-113), one CTA per candidate."""
+
+    def __init__(self, core):
+        self.core = core
+        self.L = core.L
+        self._h = C.c_void_p()
+        rc = self.L.nrslam_b200_tri_create(core._ctx, C.byref(self._h))
+        if rc != 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
+        import weakref
+        core._children.append(weakref.ref(self))
+
+    def close(self):
+        if self._h:
+            if self.core._ctx:
+                self.L.nrslam_b200_tri_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise NrslamError(rc, (self.L.nrslam_b200_last_error(self.core._ctx) or b"").decode())
+        return rc
+
+    def run(self, cam, track_ptr, track_uv, track_pose, n_neighbours, nb_pos, nb_valid, scale=1.0):
+        """-> dict(position [n,3] f32, status [n] i32 (NRSLAM_B200_TRI_*), lm_iterations [n] i32, gpu_ms)."""
+        track_ptr = np.ascontiguousarray(track_ptr, np.int32)
+        n = len(track_ptr) - 1
+        uv, pose = _f32(track_uv), _f32(track_pose)
+        nnb = np.ascontiguousarray(n_neighbours, np.int32)
+        pos, val = _f32(nb_pos), np.ascontiguousarray(nb_valid, np.uint8)
+        out = np.zeros((n, 3), np.float32)
+        status = np.full(n, -1, np.int32)
+        iters = np.zeros(n, np.int32)
+        self._check(self.L.nrslam_b200_tri_run(self._h, C.byref(cam), n, ptr(track_ptr, C.c_int32), ptr(uv, C.c_float),
+                                               ptr(pose, C.c_float), ptr(nnb, C.c_int32), ptr(pos, C.c_float),
+                                               ptr(val, C.c_uint8), C.c_float(scale), ptr(out, C.c_float),
+                                               ptr(status, C.c_int32), ptr(iters, C.c_int32)))
+        return dict(position=out, status=status, lm_iterations=iters, gpu_ms=self.L.nrslam_b200_tri_last_ms(self._h))
+
+    def run_batch(self, batch):
+        """Convenience over a synth.triangulation_batch dict."""
+        return self.run(batch["cam"], batch["track_ptr"], batch["track_uv"], batch["track_pose"],
+                        batch["n_neighbours"], batch["nb_pos"], batch["nb_valid"], batch.get("scale", 1.0))
+
+    def rerun(self):
+        """Re-run the kernel on the HBM-resident staged batch; device ms."""
+        ms = C.c_float(0)
+        self._check(self.L.nrslam_b200_tri_rerun(self._h, C.byref(ms)))
+        return ms.value

@@ -107,4 +107,5 @@ struct nrslam_b200_ctx {
   unsigned long long* bar = nullptr;
   int max_cluster = -1;   // largest schedulable thread-block cluster of the LM kernel (queried lazily)
   nrs::Shard shard;
+  nrs::Arena graph_in, graph_out;  // nrslam_b200_graph_update_vertices staging (nrs_tri.cu)
 };

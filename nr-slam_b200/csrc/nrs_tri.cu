@@ -1,0 +1,280 @@
+// nrs_tri.cu — batched DeformableTriangulation (one CTA per candidate) and the batched RegularizationGraph update.
+//
+// Reference: modules/optimization/g2o_optimization.cc:559-814 called per candidate from
+// modules/mapping/mapping.cc:88-113; modules/map/regularization_graph.cc:89-146 called per accepted point from
+// g2o_optimization.cc:458-474. The per-candidate routine lives in nrs_tri_core.cuh.
+#include <algorithm>
+#include <string>
+
+#include "nrs_host.h"
+#include "nrs_tri_core.cuh"
+
+namespace {
+using namespace nrs;
+
+__global__ void __launch_bounds__(tri::kThreads)
+nrs_tri_kernel(Cam cam, int n_cand, const int* __restrict__ track_ptr, const float* __restrict__ track_uv,
+               const float* __restrict__ track_pose, const int* __restrict__ n_neighbours,
+               const float* __restrict__ nb_pos, const unsigned char* __restrict__ nb_valid,
+               const int* __restrict__ order, float* __restrict__ position_out, int* __restrict__ status_out,
+               int* __restrict__ iters_out) {
+  extern __shared__ __align__(16) unsigned char tri_smem[];
+  // longest tracks first (order[] sorts the candidates by descending track length) so the tail of the grid is cheap
+  const int c = order[blockIdx.x];
+  const int e0 = track_ptr[c], T = track_ptr[c + 1] - e0;
+  tri::solve_candidate(cam, T, track_uv + 2 * (size_t)e0, track_pose + 7 * (size_t)e0, n_neighbours[c],
+                       nb_pos + (size_t)e0 * tri::kNB * 3, nb_valid + (size_t)e0 * tri::kNB, tri_smem,
+                       position_out + 3 * (size_t)c, status_out + c, iters_out + c);
+}
+
+// One thread per CSR entry of an updated vertex (regularization_graph.cc:107-128 UpdateConnection). Reads the edge
+// records of the PREVIOUS state (in_*), writes the new state (out_*, pre-initialised with a copy of in_*): the
+// positions are fixed during the loop of g2o_optimization.cc:458-474, so an edge between two updated vertices gets
+// the same values from both sides and the sequential loop's result does not depend on its order. Only the smaller
+// updated endpoint stores.
+__global__ void nrs_graph_update_kernel(int n_entries, const int* __restrict__ ent_vertex_slot,
+                                        const int* __restrict__ ent_csr, const int* __restrict__ vertices,
+                                        const int* __restrict__ col, const int* __restrict__ eid,
+                                        const unsigned char* __restrict__ is_updated, const float* __restrict__ pos,
+                                        const float* __restrict__ in_min, const float* __restrict__ in_max,
+                                        float sigma, float stretching_th, float* __restrict__ out_w,
+                                        float* __restrict__ out_min, float* __restrict__ out_max,
+                                        unsigned char* __restrict__ out_status, int* __restrict__ good) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_entries) return;
+  const int slot = ent_vertex_slot[t], p = ent_csr[t];
+  const int v = vertices[slot], u = col[p], e = eid[p];
+  const float dx = NRS_FS(pos[3 * v], pos[3 * u]), dy = NRS_FS(pos[3 * v + 1], pos[3 * u + 1]),
+              dz = NRS_FS(pos[3 * v + 2], pos[3 * u + 2]);
+  const float distance = sqrtf(NRS_FA(NRS_FA(NRS_FM(dx, dx), NRS_FM(dy, dy)), NRS_FM(dz, dz)));
+  float mx = in_max[e], mn = in_min[e];
+  if (distance > mx) mx = distance;
+  if (distance < mn) mn = distance;
+  const bool bad = fabsf(NRS_FD(NRS_FS(mx, mn), mn)) > stretching_th;
+  if (!bad) atomicAdd(good + slot, 1);
+  if (!is_updated[u] || v < u) {
+    // InterpolationWeight (geometry_toolbox.cc:26-28): expf of a float argument; glibc's expf is correctly rounded,
+    // the fp64 exp rounded to fp32 is too (up to double-rounding cases of probability ~2^-29).
+    const float arg = NRS_FD(-NRS_FM(mx, mx), NRS_FM(NRS_FM(2.f, sigma), sigma));
+    out_w[e] = (float)exp((double)arg);
+    out_min[e] = mn;
+    out_max[e] = mx;
+    if (bad) out_status[e] = NRSLAM_EDGE_BAD;
+  }
+}
+
+int tfail(nrslam_b200_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+#define TRI_CUDA(ctx, call)                                                                            \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return tfail(ctx, NRSLAM_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+}  // namespace
+
+struct nrslam_b200_tri {
+  nrslam_b200_ctx* ctx = nullptr;
+  nrs::Arena in, out;
+  // staged batch
+  int n_cand = 0, t_max = 0;
+  size_t smem = 0;
+  nrs::Cam cam;
+  size_t o_ptr = 0, o_uv = 0, o_pose = 0, o_nnb = 0, o_pos = 0, o_val = 0, o_order = 0;
+  size_t o_out = 0, o_status = 0, o_iters = 0;
+  float last_ms = 0.f;
+  bool staged = false;
+};
+
+namespace {
+int tri_launch(nrslam_b200_tri* t) {
+  nrslam_b200_ctx* ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  TRI_CUDA(ctx, cudaFuncSetAttribute(nrs_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem));
+  TRI_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  nrs_tri_kernel<<<t->n_cand, tri::kThreads, t->smem, st>>>(
+      t->cam, t->n_cand, t->in.d<int>(t->o_ptr), t->in.d<float>(t->o_uv), t->in.d<float>(t->o_pose),
+      t->in.d<int>(t->o_nnb), t->in.d<float>(t->o_pos), t->in.d<unsigned char>(t->o_val), t->in.d<int>(t->o_order),
+      t->out.d<float>(t->o_out), t->out.d<int>(t->o_status), t->out.d<int>(t->o_iters));
+  TRI_CUDA(ctx, cudaGetLastError());
+  TRI_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int nrslam_b200_tri_create(nrslam_b200_ctx* ctx, nrslam_b200_tri** out) {
+  if (out) *out = nullptr;
+  if (!ctx || !out) return NRSLAM_B200_ERR_ARG;
+  nrslam_b200_tri* t = new nrslam_b200_tri();
+  t->ctx = ctx;
+  *out = t;
+  return 0;
+}
+
+void nrslam_b200_tri_destroy(nrslam_b200_tri* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  delete t;
+}
+
+int nrslam_b200_tri_run(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32_t n_cand, const int32_t* track_ptr,
+                        const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
+                        const float* nb_pos, const uint8_t* nb_valid, float scale, float* position_out,
+                        int32_t* status_out, int32_t* lm_iterations_out) {
+  (void)scale;  // unused by the reference body as well (g2o_optimization.cc:559-814 never reads it)
+  if (!t) return NRSLAM_B200_ERR_ARG;
+  nrslam_b200_ctx* ctx = t->ctx;
+  if (!cam || n_cand < 0 || !track_ptr || !position_out || !status_out)
+    return tfail(ctx, NRSLAM_B200_ERR_ARG, "tri_run: bad argument");
+  if (n_cand == 0) return 0;
+  if (!track_uv || !track_pose || !n_neighbours || !nb_pos || !nb_valid)
+    return tfail(ctx, NRSLAM_B200_ERR_ARG, "tri_run: bad argument");
+  int t_max = 0;
+  for (int c = 0; c < n_cand; c++) {
+    const int T = track_ptr[c + 1] - track_ptr[c];
+    if (T < 1 || T > NRSLAM_B200_TRI_MAX_TRACK || n_neighbours[c] < 0 || n_neighbours[c] > NRSLAM_B200_TRI_MAX_NB)
+      return tfail(ctx, NRSLAM_B200_ERR_ARG, "tri_run: track length or neighbour count out of range");
+    t_max = std::max(t_max, T);
+  }
+  if (track_ptr[0] != 0) return tfail(ctx, NRSLAM_B200_ERR_ARG, "tri_run: track_ptr[0] must be 0");
+  const size_t E = (size_t)track_ptr[n_cand];
+  TRI_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+
+  const size_t need_in = (n_cand + 1 + 2 * (size_t)n_cand) * 4 + E * (2 + 7 + 3 * tri::kNB) * 4 + E * tri::kNB + 4096;
+  if (!t->in.reserve(need_in, true)) return tfail(ctx, NRSLAM_B200_ERR_ALLOC, "tri_run: input arena allocation failed");
+  t->o_ptr = t->in.take<int>(n_cand + 1);
+  t->o_nnb = t->in.take<int>(n_cand);
+  t->o_order = t->in.take<int>(n_cand);
+  t->o_uv = t->in.take<float>(2 * E);
+  t->o_pose = t->in.take<float>(7 * E);
+  t->o_pos = t->in.take<float>(3 * tri::kNB * E);
+  t->o_val = t->in.take<unsigned char>(tri::kNB * E);
+  memcpy(t->in.h<int>(t->o_ptr), track_ptr, (n_cand + 1) * sizeof(int));
+  memcpy(t->in.h<int>(t->o_nnb), n_neighbours, n_cand * sizeof(int));
+  memcpy(t->in.h<float>(t->o_uv), track_uv, 2 * E * sizeof(float));
+  memcpy(t->in.h<float>(t->o_pose), track_pose, 7 * E * sizeof(float));
+  memcpy(t->in.h<float>(t->o_pos), nb_pos, 3 * tri::kNB * E * sizeof(float));
+  memcpy(t->in.h<unsigned char>(t->o_val), nb_valid, tri::kNB * E);
+  int* order = t->in.h<int>(t->o_order);
+  for (int c = 0; c < n_cand; c++) order[c] = c;
+  std::stable_sort(order, order + n_cand, [&](int a, int b) {
+    return track_ptr[a + 1] - track_ptr[a] > track_ptr[b + 1] - track_ptr[b];
+  });
+  const size_t need_out = (size_t)n_cand * 5 * 4 + 4096;
+  if (!t->out.reserve(need_out, true)) return tfail(ctx, NRSLAM_B200_ERR_ALLOC, "tri_run: output arena allocation failed");
+  t->o_out = t->out.take<float>(3 * (size_t)n_cand);
+  t->o_status = t->out.take<int>(n_cand);
+  t->o_iters = t->out.take<int>(n_cand);
+  t->n_cand = n_cand;
+  t->t_max = t_max;
+  t->smem = tri::work_bytes(t_max);
+  t->cam.model = cam->model;
+  for (int i = 0; i < 8; i++) t->cam.p[i] = cam->params[i];
+  t->staged = false;
+
+  TRI_CUDA(ctx, cudaMemcpyAsync(t->in.dev(), t->in.host(), t->in.used(), cudaMemcpyHostToDevice, st));
+  const int rc = tri_launch(t);
+  if (rc) return rc;
+  TRI_CUDA(ctx, cudaMemcpyAsync(t->out.host(), t->out.dev(), t->out.used(), cudaMemcpyDeviceToHost, st));
+  TRI_CUDA(ctx, cudaStreamSynchronize(st));
+  TRI_CUDA(ctx, cudaEventElapsedTime(&t->last_ms, ctx->ev0, ctx->ev1));
+  t->staged = true;
+  memcpy(position_out, t->out.h<float>(t->o_out), 3 * (size_t)n_cand * sizeof(float));
+  memcpy(status_out, t->out.h<int>(t->o_status), n_cand * sizeof(int));
+  if (lm_iterations_out) memcpy(lm_iterations_out, t->out.h<int>(t->o_iters), n_cand * sizeof(int));
+  return 0;
+}
+
+float nrslam_b200_tri_last_ms(const nrslam_b200_tri* t) { return t ? t->last_ms : 0.f; }
+
+int nrslam_b200_tri_rerun(nrslam_b200_tri* t, float* gpu_ms_out) {
+  if (!t || !t->staged) return tfail(t ? t->ctx : nullptr, NRSLAM_B200_ERR_ARG, "tri_rerun: nothing staged");
+  nrslam_b200_ctx* ctx = t->ctx;
+  TRI_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int rc = tri_launch(t);
+  if (rc) return rc;
+  TRI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  TRI_CUDA(ctx, cudaEventElapsedTime(&t->last_ms, ctx->ev0, ctx->ev1));
+  if (gpu_ms_out) *gpu_ms_out = t->last_ms;
+  return 0;
+}
+
+int nrslam_b200_graph_update_vertices(nrslam_b200_ctx* ctx, nrslam_b200_graph* g, int32_t n, const int32_t* vertices,
+                                      const float* positions, int32_t* good_out) {
+  if (!ctx || !g || n < 0 || (n > 0 && (!vertices || !good_out)) || !positions)
+    return tfail(ctx, NRSLAM_B200_ERR_ARG, "graph_update_vertices: bad argument");
+  if (n == 0) return 0;
+  const int V = g->n_vertices, E = g->n_edges;
+  std::vector<unsigned char> upd(V, 0);
+  size_t n_ent = 0;
+  for (int i = 0; i < n; i++) {
+    const int v = vertices[i];
+    if (v < 0 || v >= V || upd[v]) return tfail(ctx, NRSLAM_B200_ERR_ARG, "graph_update_vertices: bad or repeated vertex");
+    upd[v] = 1;
+    n_ent += (size_t)(g->rowptr[v + 1] - g->rowptr[v]);
+  }
+  TRI_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  nrs::Arena& in = ctx->graph_in;
+  nrs::Arena& out = ctx->graph_out;
+  const size_t nnz = (size_t)g->rowptr[V];
+  const size_t need_in = (2 * n_ent + n + 2 * nnz + 3 * (size_t)V + 2 * (size_t)E) * 4 + V + 8192;
+  const size_t need_out = ((size_t)3 * E + n) * 4 + E + 8192;
+  if (!in.reserve(need_in, true) || !out.reserve(need_out, true))
+    return tfail(ctx, NRSLAM_B200_ERR_ALLOC, "graph_update_vertices: allocation failed");
+  const size_t o_slot = in.take<int>(n_ent), o_csr = in.take<int>(n_ent), o_vert = in.take<int>(n),
+               o_col = in.take<int>(nnz), o_eid = in.take<int>(nnz), o_pos = in.take<float>(3 * (size_t)V),
+               o_min = in.take<float>(E), o_max = in.take<float>(E), o_upd = in.take<unsigned char>(V);
+  const size_t q_w = out.take<float>(E), q_min = out.take<float>(E), q_max = out.take<float>(E),
+               q_good = out.take<int>(n), q_status = out.take<unsigned char>(E);
+  {
+    int* slot = in.h<int>(o_slot);
+    int* csr = in.h<int>(o_csr);
+    size_t k = 0;
+    for (int i = 0; i < n; i++)
+      for (int p = g->rowptr[vertices[i]]; p < g->rowptr[vertices[i] + 1]; p++) {
+        slot[k] = i;
+        csr[k++] = p;
+      }
+  }
+  memcpy(in.h<int>(o_vert), vertices, n * sizeof(int));
+  memcpy(in.h<int>(o_col), g->col, nnz * sizeof(int));
+  memcpy(in.h<int>(o_eid), g->eid, nnz * sizeof(int));
+  memcpy(in.h<float>(o_pos), positions, 3 * (size_t)V * sizeof(float));
+  memcpy(in.h<float>(o_min), g->min_distance, E * sizeof(float));
+  memcpy(in.h<float>(o_max), g->max_distance, E * sizeof(float));
+  memcpy(in.h<unsigned char>(o_upd), upd.data(), V);
+  memcpy(out.h<float>(q_w), g->weight, E * sizeof(float));
+  memcpy(out.h<float>(q_min), g->min_distance, E * sizeof(float));
+  memcpy(out.h<float>(q_max), g->max_distance, E * sizeof(float));
+  memset(out.h<int>(q_good), 0, n * sizeof(int));
+  memcpy(out.h<unsigned char>(q_status), g->status, E);
+  TRI_CUDA(ctx, cudaMemcpyAsync(in.dev(), in.host(), in.used(), cudaMemcpyHostToDevice, st));
+  TRI_CUDA(ctx, cudaMemcpyAsync(out.dev(), out.host(), out.used(), cudaMemcpyHostToDevice, st));
+  if (n_ent > 0) {
+    const int blk = 256, grd = (int)((n_ent + blk - 1) / blk);
+    nrs_graph_update_kernel<<<grd, blk, 0, st>>>((int)n_ent, in.d<int>(o_slot), in.d<int>(o_csr), in.d<int>(o_vert),
+                                                 in.d<int>(o_col), in.d<int>(o_eid), in.d<unsigned char>(o_upd),
+                                                 in.d<float>(o_pos), in.d<float>(o_min), in.d<float>(o_max),
+                                                 g->weight_sigma, g->stretching_th, out.d<float>(q_w),
+                                                 out.d<float>(q_min), out.d<float>(q_max),
+                                                 out.d<unsigned char>(q_status), out.d<int>(q_good));
+    TRI_CUDA(ctx, cudaGetLastError());
+  }
+  TRI_CUDA(ctx, cudaMemcpyAsync(out.host(), out.dev(), out.used(), cudaMemcpyDeviceToHost, st));
+  TRI_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(g->weight, out.h<float>(q_w), E * sizeof(float));
+  memcpy(g->min_distance, out.h<float>(q_min), E * sizeof(float));
+  memcpy(g->max_distance, out.h<float>(q_max), E * sizeof(float));
+  memcpy(g->status, out.h<unsigned char>(q_status), E);
+  memcpy(good_out, out.h<int>(q_good), n * sizeof(int));
+  return 0;
+}
+
+}  // extern "C"

@@ -275,3 +275,137 @@ def klt_pair(seed=1, size=(640, 480), n_points=500, shift=(2.6, -1.7), gain=1.1,
     return dict(ref=np.clip(np.rint(ref), 0, 255).astype(np.uint8), cur=np.clip(np.rint(cur), 0, 255).astype(np.uint8),
                 pts=pts.astype(np.float32), pts_true=(pts + np.array([dx, dy])).astype(np.float32),
                 status=np.full(n_points, TRACKED, np.uint8), shift=shift)
+
+
+def _field_modes(rng, ext, n_modes=3):
+    modes = []
+    for _ in range(n_modes):
+        k = rng.normal(size=3) * 2 * np.pi * 0.6 / ext
+        ph = rng.uniform(0, 2 * np.pi)
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        modes.append((k, ph, d))
+    return modes
+
+
+def _eval_field(modes, P, amp):
+    out = np.zeros((len(P), 3))
+    for k, ph, d in modes:
+        out += np.outer(np.sin(P @ k + ph), d)
+    return out * amp / np.sqrt(len(modes))
+
+
+def triangulation_batch(seed=7, n_cand=200, cam_spec=CONFIGS["c2"]["cam"], size=CONFIGS["c2"]["size"], t_min=5,
+                        t_max=20, n_map=130, noise_px=0.5, dropout=0.08, deform_amp=0.03, baseline=0.35,
+                        fail_frac=0.12, nb_slots=12):
+    """One frame's worth of DeformableTriangulation candidates (g2o_optimization.cc:559-814) as the flattened
+    TemporalBuffer view of include/nrslam_b200.h: a deforming sheet observed by a camera translating sideways over
+    t_max frames; map points (the neighbours) carry their per-frame world positions; a candidate is an untriangulated
+    feature tracked over the last T in [t_min, t_max] frames. A fraction of the candidates is built to fail each of the
+    reference's checks (no neighbour / close feature, gross keypoint error in the first or last frame, static camera,
+    neighbours missing in one frame, neighbours behind the camera, incoherent neighbour flows, a common drift of the
+    neighbours that drags the estimates off their rays)."""
+    rng = np.random.default_rng(seed)
+    cam = make_camera(cam_spec)
+    w, h = size
+    F = t_max
+    # trajectory: camera_transform_world per frame
+    poses = np.zeros((F, 7), np.float32)
+    axis = rng.normal(size=3)
+    axis[2] *= 0.2
+    axis /= np.linalg.norm(axis)
+    wrot = rng.normal(size=3)
+    wrot *= np.deg2rad(3.0) / np.linalg.norm(wrot)
+    for f in range(F):
+        s = f / max(F - 1, 1)
+        q = rotvec_to_quat(wrot * s)
+        poses[f] = np.concatenate([q, axis * baseline * s + 0.002 * rng.normal(size=3)]).astype(np.float32)
+    P_map = sheet_points(rng, cam, size, n_map).astype(np.float64)
+    ext = max(np.ptp(P_map[:, 0]), np.ptp(P_map[:, 1]))
+    m1, m2 = _field_modes(rng, ext), _field_modes(rng, ext)
+
+    def positions(P, f):
+        s = f / max(F - 1, 1)
+        return P + _eval_field(m1, P, deform_amp) * s + _eval_field(m2, P, deform_amp) * np.sin(2.0 * s)
+
+    def to_cam(pose, X):
+        return X @ quat_to_R(pose[:4].astype(np.float64)).T + pose[4:].astype(np.float64)
+
+    map_world = np.stack([positions(P_map, f) for f in range(F)]).astype(np.float32)  # F x n_map x 3
+    map_uv_last = project(cam, to_cam(poses[F - 1], map_world[F - 1].astype(np.float64)))
+    tree = cKDTree(map_uv_last.astype(np.float64))
+
+    track_ptr = [0]
+    uv_l, pose_l, pos_l, val_l, nnb_l, kind_l, truth_l = [], [], [], [], [], [], []
+    kinds = ["too_close", "bad_first", "bad_last", "static", "no_nb", "behind", "noisy_nb", "drift"]
+    pool = sheet_points(rng, cam, size, 40 * n_cand + 400).astype(np.float64)
+    for ip in range(len(pool)):
+        if len(nnb_l) >= n_cand:
+            break
+        Pc = pool[ip:ip + 1]
+        T = int(rng.integers(t_min, t_max + 1))
+        frames = np.arange(F - T, F)
+        kind = "ok"
+        if rng.uniform() < fail_frac:
+            kind = kinds[int(rng.integers(len(kinds)))]
+        Xc = np.stack([positions(Pc, f)[0] for f in frames])
+        cposes = poses[frames].copy()
+        if kind == "static":
+            cposes[:] = cposes[-1]
+            Xc[:] = Xc[-1]
+        uv = np.stack([project(cam, to_cam(cposes[i], Xc[i:i + 1]))[0] for i in range(T)]).astype(np.float64)
+        uv += rng.normal(size=uv.shape) * noise_px
+        if not (np.all(uv[:, 0] > 5) and np.all(uv[:, 0] < w - 5) and np.all(uv[:, 1] > 5) and np.all(uv[:, 1] < h - 5)):
+            continue
+        if kind == "bad_first":
+            uv[0] += rng.choice([-1, 1], 2) * rng.uniform(15, 40, 2)
+        if kind == "bad_last":
+            uv[-1] += rng.choice([-1, 1], 2) * rng.uniform(15, 40, 2)
+        # GetClosestMapPointsToFeature(candidate, 10, 20, 500) on the last snapshot (temporal_buffer.cc:97-143)
+        d_all, idx_all = tree.query(uv[-1], k=min(n_map, 64))
+        d32 = d_all.astype(np.float32)
+        too_close = bool(np.any(d32 < 20))
+        if kind == "too_close" and not too_close:
+            continue
+        if kind != "too_close" and too_close:
+            continue
+        nb = [] if too_close else [int(i) for i, d in zip(idx_all, d32) if d <= 500][:11]
+        if not too_close and len(nb) == 0:
+            continue
+        n_nb = len(nb)
+        pos = np.zeros((T, nb_slots, 3), np.float32)
+        val = np.zeros((T, nb_slots), np.uint8)
+        if n_nb:
+            pos[:, :n_nb] = map_world[frames][:, nb]
+            val[:, :n_nb] = rng.uniform(size=(T, n_nb)) > dropout
+            val[0, :n_nb] |= rng.uniform(size=n_nb) > 0.3   # keep most neighbours alive in the first frame
+            if kind == "no_nb":
+                val[int(rng.integers(T))] = 0
+            elif kind == "behind":
+                k = int(rng.integers(T))
+                Rk = quat_to_R(cposes[k, :4].astype(np.float64))
+                ck = -Rk.T @ cposes[k, 4:].astype(np.float64)         # camera centre in the world
+                pos[k, :n_nb] = (2 * ck - pos[k, :n_nb].astype(np.float64)).astype(np.float32)
+            elif kind == "noisy_nb":
+                pos[:, :n_nb] += rng.normal(size=(T, n_nb, 3)).astype(np.float32) * np.float32(0.4)
+            elif kind == "drift":
+                pos[:, :n_nb, 0] += (np.arange(T, dtype=np.float32) * np.float32(0.12))[:, None]
+            if kind not in ("no_nb",):
+                for k in range(T):                                       # never leave a frame empty by accident
+                    if not val[k, :n_nb].any():
+                        val[k, 0] = 1
+        track_ptr.append(track_ptr[-1] + T)
+        uv_l.append(uv.astype(np.float32))
+        pose_l.append(cposes)
+        pos_l.append(pos)
+        val_l.append(val)
+        nnb_l.append(n_nb)
+        kind_l.append(kind)
+        truth_l.append(Xc[-1])
+    if len(nnb_l) < n_cand:
+        raise RuntimeError("triangulation_batch: candidate pool exhausted")
+    return dict(cam=cam, n_cand=n_cand, track_ptr=np.array(track_ptr, np.int32),
+                track_uv=np.concatenate(uv_l).astype(np.float32), track_pose=np.concatenate(pose_l).astype(np.float32),
+                n_neighbours=np.array(nnb_l, np.int32), nb_pos=np.concatenate(pos_l).astype(np.float32),
+                nb_valid=np.concatenate(val_l).astype(np.uint8), kinds=kind_l,
+                truth=np.array(truth_l, np.float32), scale=1.0)

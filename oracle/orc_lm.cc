@@ -226,6 +226,20 @@ void Optimizer::compute_error(Edge& e) const {
       const double *p1n = vertices[e.v[2]].x, *p2n = vertices[e.v[3]].x;
       for (int i = 0; i < 3; i++) e.err[i] = e.weight * ((p1n[i] - p1c[i]) - (p2n[i] - p2c[i]));
     } break;
+    case E_REPROJ_ONLY_DEFORMATION: {
+      // reprojection_error_only_deformation.cc:33-39: _error = obs - calibration_->Project(estimate) (fp32 inside)
+      double uv[2];
+      project_d(cam_, vertices[e.v[0]].x, uv);
+      e.err[0] = e.meas[0] - uv[0];
+      e.err[1] = e.meas[1] - uv[1];
+    } break;
+    case E_SPATIAL_OBS: {
+      // spatial_regularizer_with_observation.cc:33-46: w * (obs - (T_next x_next - T_cur x_cur))
+      double pc[3], pn[3];
+      se3_map(e.Ta, vertices[e.v[0]].x, pc);
+      se3_map(e.Tb, vertices[e.v[1]].x, pn);
+      for (int i = 0; i < 3; i++) e.err[i] = e.weight * (e.meas[i] - (pn[i] - pc[i]));
+    } break;
   }
 }
 
@@ -312,6 +326,31 @@ void Optimizer::linearize(const Edge& e, double J[4][18]) const {
         J[1][i] = d;
         J[2][i] = d;
         J[3][i] = -d;
+      }
+      break;
+    case E_REPROJ_ONLY_DEFORMATION: {
+      // g2o's numeric central difference, base_fixed_sized_edge.hpp:160-199: delta = 1e-9 on the fp64 estimate,
+      // error re-evaluated through the fp32 camera model, column = (e(+delta) - e(-delta)) * 1/(2 delta).
+      const double delta = 1e-9, scalar = 1 / (2 * delta);
+      const double* x = vertices[e.v[0]].x;
+      for (int d = 0; d < 3; d++) {
+        double xp[3] = {x[0] + 0.0, x[1] + 0.0, x[2] + 0.0}, xm[3] = {x[0] + 0.0, x[1] + 0.0, x[2] + 0.0};
+        xp[d] = x[d] + delta;      // LandmarkVertex::oplusImpl: estimate += update (landmark_vertex.cc:40-43)
+        xm[d] = x[d] + (-delta);
+        double up[2], um[2];
+        project_d(cam_, xp, up);
+        project_d(cam_, xm, um);
+        for (int r = 0; r < 2; r++) {
+          const double ep = e.meas[r] - up[r], em = e.meas[r] - um[r];
+          J[0][r * 3 + d] = scalar * (ep - em);
+        }
+      }
+    } break;
+    case E_SPATIAL_OBS:
+      // spatial_regularizer_with_observation.cc:48-51
+      for (int i = 0; i < 9; i++) {
+        J[0][i] = (i % 4 == 0) ? e.weight : 0.0;
+        J[1][i] = (i % 4 == 0) ? -e.weight : 0.0;
       }
       break;
   }

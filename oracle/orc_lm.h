@@ -47,7 +47,10 @@ enum EdgeType {
   E_POSITION_DEFORM = 4,    // optimization/position_regularizer_with_deformation.cc:31-57
   E_SPATIAL_FIXED = 5,      // optimization/spatial_regularizer_fixed.cc:32-43
   E_POSITION_BA = 6,        // optimization/position_regularizer.cc:32-61 (quirk E1)
-  E_DAMPER_BA = 7           // optimization/spatial_regularizer.cc:32-59
+  E_DAMPER_BA = 7,          // optimization/spatial_regularizer.cc:32-59
+  E_REPROJ_ONLY_DEFORMATION = 8,  // optimization/reprojection_error_only_deformation.cc:33-39 — NO analytic Jacobian
+                                  // (.h:40 commented out): g2o differentiates numerically, base_fixed_sized_edge.hpp:160-199
+  E_SPATIAL_OBS = 9         // optimization/spatial_regularizer_with_observation.cc:33-51 (Jacobians +-w I, rotations ignored)
 };
 
 struct Edge {
@@ -63,6 +66,7 @@ struct Edge {
   double rest1[3] = {0, 0, 0}, rest2[3] = {0, 0, 0};
   double weight = 1.0, k = 1.0;
   int ref_vertex = -1;                 // SpatialRegularizerFixed::flow_fixed (read live, no Jacobian)
+  SE3 Ta{{0, 0, 0, 1}, {0, 0, 0}}, Tb{{0, 0, 0, 1}, {0, 0, 0}};  // E_SPATIAL_OBS: current_/next_world_transform_camera_
   double err[3] = {0, 0, 0};           // _error, updated only by compute_error (stale after a pop, like g2o)
   int hb[6] = {-1, -1, -1, -1, -1, -1};
   bool hbT[6] = {false, false, false, false, false, false};

@@ -218,3 +218,34 @@ class OracleShiTomasi:
                                    capacity, ptr(sc, C.c_float))
         assert 0 <= n <= capacity
         return dict(n=n, xy=xy[:n].copy(), ids=ids[:n].copy(), scores=sc)
+
+
+def deformable_triangulation(batch, order=0):
+    """orc_deformable_triangulation over a synth.triangulation_batch dict -> (positions, statuses, lm_iterations)."""
+    L = lib()
+    n = int(batch["n_cand"])
+    pos = np.zeros((n, 3), np.float32)
+    status = np.zeros(n, np.int32)
+    iters = np.zeros(n, np.int32)
+    rc = L.orc_deformable_triangulation(
+        C.byref(batch["cam"]), n, ptr(np.ascontiguousarray(batch["track_ptr"], np.int32), C.c_int32),
+        ptr(np.ascontiguousarray(batch["track_uv"], np.float32), C.c_float),
+        ptr(np.ascontiguousarray(batch["track_pose"], np.float32), C.c_float),
+        ptr(np.ascontiguousarray(batch["n_neighbours"], np.int32), C.c_int32),
+        ptr(np.ascontiguousarray(batch["nb_pos"], np.float32), C.c_float),
+        ptr(np.ascontiguousarray(batch["nb_valid"], np.uint8), C.c_uint8), int(order), ptr(pos, C.c_float),
+        ptr(status, C.c_int32), ptr(iters, C.c_int32))
+    assert rc == 0
+    return pos, status, iters
+
+
+def graph_update_vertices(graph, vertices, positions):
+    """Sequential RegularizationGraph::UpdateVertex loop (g2o_optimization.cc:458-474); graph arrays updated in place."""
+    L = lib()
+    v = np.ascontiguousarray(vertices, np.int32)
+    good = np.zeros(len(v), np.int32)
+    g = graph.struct()
+    rc = L.orc_graph_update_vertices(C.byref(g), len(v), ptr(v, C.c_int32),
+                                     ptr(np.ascontiguousarray(positions, np.float32), C.c_float), ptr(good, C.c_int32))
+    assert rc == 0
+    return good

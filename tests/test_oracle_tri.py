@@ -1,0 +1,105 @@
+"""DeformableTriangulation oracle (oracle/orc_tri.cc, restating g2o_optimization.cc:559-814) and the host emulation
+of the CUDA routine. Parity status: UNPINNED by the reference (it ships no test or golden output for this function);
+the oracle's credibility is traceability plus the properties below.
+
+What is checked without a GPU:
+  * every InternalError branch the synthetic batch is built to hit is returned, successful candidates land near the
+    true surface point, and the result does not depend on the order the spatial edges are created in;
+  * the numeric Jacobian g2o uses for ReprojectionErrorOnlyDeformation (delta = 1e-9 through the fp32 camera) is
+    zero for the overwhelming majority of entries, i.e. the reference's reprojection term barely steers the solve —
+    a property of the reference the restatement must (and does) reproduce rather than "fix";
+  * the per-candidate routine of nr-slam_b200/csrc/nrs_tri_core.cuh, compiled for the host with ONE emulated thread
+    (tests/emul/tri_emul.cc), agrees with the oracle: identical statuses, positions within 2e-6 relative.
+"""
+import ctypes as C
+import os
+import subprocess
+from collections import Counter
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from nrslam_b200 import synth
+from nrslam_b200.abi import ptr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def batch():
+    return synth.triangulation_batch(seed=7, n_cand=160, fail_frac=0.3)
+
+
+def test_statuses_cover_the_reference_error_branches(batch):
+    pos, st, it = O.deformable_triangulation(batch)
+    by_kind = Counter(zip(batch["kinds"], st.tolist()))
+    kinds = np.array(batch["kinds"])
+    assert (st[kinds == "too_close"] == 1).all()
+    pre = {2, 3, 4}   # the two-view checks come first (:618-635) and 0.5 px noise trips them for a few candidates
+    for kind, code in (("no_nb", 5), ("behind", 6), ("noisy_nb", 7)):
+        got = st[kinds == kind]
+        assert set(got.tolist()) <= pre | {code} and (got == code).mean() > 0.6, (kind, got)
+    assert set(st[kinds == "bad_first"].tolist()) <= {2, 3}
+    assert {0, 1, 2, 5, 6, 7} <= set(st.tolist()), by_kind
+    ok = st == 0
+    assert ok.sum() > 0.8 * (kinds == "ok").sum()
+    assert (it[ok] >= 1).all() and (it[ok] <= 10).all() and (it[~ok & (st < 7)] == 0).all()
+    err = np.linalg.norm(pos[ok] - batch["truth"][ok], axis=1)
+    assert np.median(err) < 0.15 and np.isfinite(pos).all()
+
+
+def test_result_is_independent_of_edge_creation_order(batch):
+    p0, s0, _ = O.deformable_triangulation(batch, order=0)
+    p1, s1, _ = O.deformable_triangulation(batch, order=1)
+    assert (s0 == s1).all()
+    ok = s0 == 0
+    assert np.abs(p0[ok] - p1[ok]).max() < 1e-5
+
+
+def test_kb8_camera(batch):
+    b = synth.triangulation_batch(seed=9, n_cand=60, cam_spec=synth.CONFIGS["c4"]["cam"], size=synth.CONFIGS["c4"]["size"])
+    pos, st, _ = O.deformable_triangulation(b)
+    ok = st == 0
+    assert ok.sum() > 30 and np.isfinite(pos).all()
+    # Reference quirk reproduced, not fixed: KannalaBrandt8::Unproject returns a UNIT ray (kannala_brandt_8.cc:81-83)
+    # while the seed `Unproject(kp) * depth_seed` (:663) treats it as a z = 1 ray, so off-axis seeds start at range
+    # (not depth) depth_seed; with the reprojection Jacobian numerically ~0 nothing pulls them back. Accuracy against
+    # the true surface is therefore only loosely bounded for the fisheye model.
+    assert np.median(np.linalg.norm(pos[ok] - b["truth"][ok], axis=1)) < 2.0
+
+
+def _emul_lib():
+    out = os.path.join(ROOT, "tests", "emul", "tri_emul.so")
+    src = os.path.join(ROOT, "tests", "emul", "tri_emul.cc")
+    core = os.path.join(ROOT, "nr-slam_b200", "csrc", "nrs_tri_core.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
+                               "-I/usr/local/cuda/include", "-o", out, src])
+    return C.CDLL(out)
+
+
+def _emulate(b):
+    L = _emul_lib()
+    n = b["n_cand"]
+    pos, st, it = np.zeros((n, 3), np.float32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    rc = L.tri_emul_run(C.byref(b["cam"]), n, ptr(b["track_ptr"], C.c_int32), ptr(b["track_uv"], C.c_float),
+                        ptr(b["track_pose"], C.c_float), ptr(b["n_neighbours"], C.c_int32),
+                        ptr(b["nb_pos"], C.c_float), ptr(b["nb_valid"], C.c_uint8), ptr(pos, C.c_float),
+                        ptr(st, C.c_int32), ptr(it, C.c_int32))
+    assert rc == 0
+    return pos, st, it
+
+
+@pytest.mark.parametrize("seed,kw", [(7, {}), (8, dict(t_min=30, t_max=41)),
+                                     (9, dict(cam_spec=synth.CONFIGS["c4"]["cam"], size=synth.CONFIGS["c4"]["size"]))])
+def test_kernel_routine_emulated_on_the_host_matches_the_oracle(seed, kw):
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("CUDA headers not installed")
+    b = synth.triangulation_batch(seed=seed, n_cand=100, fail_frac=0.3, **kw)
+    po, so, io = O.deformable_triangulation(b)
+    pe, se, ie = _emulate(b)
+    assert (so == se).all()
+    ok = so == 0
+    assert np.abs(po[ok] - pe[ok]).max() <= 2e-6 * 3.0
+    assert (io == ie).mean() > 0.95   # noise-level trial decisions may differ (rho ~ 0 at convergence)
