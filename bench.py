@@ -398,10 +398,53 @@ def main():
                 "pcg_iterations": rs["stats"]["pcg_iterations"],
                 "single_gpu_launch_ms": line["ba"]["launch_ms"]}
 
+    # ---- one frame's batch of DeformableTriangulation candidates (Mapping::FrameMapping,
+    # mapping.cc:60-113) and the RegularizationGraph update loop of the tracking frame (g2o_optimization.cc:458-474)
+    tb = synth.triangulation_batch(seed=21, n_cand=600, fail_frac=0.1)
+    tri = api.Triangulator(core)
+    tri.run_batch(tb)
+    ks = max(3, min(args.steps, 10))
+    tri_dev = sum(tri.rerun() for _ in range(ks)) / ks
+    t0 = time.perf_counter()
+    for _ in range(ks):
+        rt = tri.run_batch(tb)
+    tri_e2e = 1e3 * (time.perf_counter() - t0) / ks
+    line["triangulation"] = {
+        "metric": "deformable_triangulations_per_sec", "unit": "candidates/s",
+        "workload": "600 candidates of one 640x480 frame, tracks of 5..20 frames, <= 11 neighbours, optimize(10) each "
+                    "(%d succeed)" % int((rt["status"] == 0).sum()),
+        "value": world * tb["n_cand"] / (tri_dev * 1e-3), "e2e_value": world * tb["n_cand"] / (tri_e2e * 1e-3),
+        "launch_ms": tri_dev, "e2e_ms": tri_e2e, "lm_iterations": int(rt["lm_iterations"].sum()),
+        "grid_ctas": tb["n_cand"], "block_threads": 128}
+    gq = p["graph"].copy()
+    gverts = np.unique(p["point_vertex"]).astype(np.int32)
+    gpos = p["last_world_position"] + synth.smooth_field(np.random.default_rng(3), p["last_world_position"], 0.05)
+    core.graph_update_vertices(gq.copy(), gverts, gpos)
+    t0 = time.perf_counter()
+    for _ in range(ks):
+        core.graph_update_vertices(gq.copy(), gverts, gpos)
+    gu_e2e = 1e3 * (time.perf_counter() - t0) / ks
+    t0 = time.perf_counter()
+    for _ in range(ks):
+        gh = gq.copy()
+        for v in gverts:
+            core.graph_update_vertex(gh, int(v), gpos)
+    gu_host = 1e3 * (time.perf_counter() - t0) / ks
+    line["graph_update"] = {"vertices": int(len(gverts)), "edges": int(gq.n_edges), "e2e_ms": gu_e2e,
+                            "per_vertex_host_entry_point_ms": gu_host,
+                            "note": "UpdateVertex loop of one tracking frame through the C ABI with host buffers "
+                                    "(H2D of the graph arrays + one kernel + D2H); the second figure is the sequential "
+                                    "host entry point called per vertex from Python (ctypes overhead included)"}
+
     # ---- CPU baseline: the oracle on one host core, bounded sample (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
+        t0 = time.perf_counter()
+        oracle_lib.deformable_triangulation(tb)
+        dtt = time.perf_counter() - t0
+        line["triangulation"]["cpu_baseline"] = {"value": tb["n_cand"] / dtt, "unit": "candidates/s", "cores": 1,
+                                                 "kind": "port", "sample": "the same 600 candidates once (%.2f s)" % dtt}
         orc = oracle_lib.Oracle()
         oklt = oracle_lib.OracleKLT()
         oklt.set_reference(im["ref"], im["pts"])
@@ -432,6 +475,7 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     klt.close()
+    tri.close()
     core.close()
     if dist is not None:
         dist.destroy_process_group()
