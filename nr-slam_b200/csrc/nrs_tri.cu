@@ -53,8 +53,9 @@ __global__ void nrs_graph_update_kernel(int n_entries, const int* __restrict__ e
   const bool bad = fabsf(NRS_FD(NRS_FS(mx, mn), mn)) > stretching_th;
   if (!bad) atomicAdd(good + slot, 1);
   if (!is_updated[u] || v < u) {
-    // InterpolationWeight (geometry_toolbox.cc:26-28): expf of a float argument; glibc's expf is correctly rounded,
-    // the fp64 exp rounded to fp32 is too (up to double-rounding cases of probability ~2^-29).
+    // InterpolationWeight (geometry_toolbox.cc:26-28): expf of a float argument. fp64 exp rounded to fp32 is the
+    // correctly rounded expf (up to double-rounding cases of probability ~2^-29); glibc's expf is faithfully rounded
+    // and differs from it by 1 ulp for 0.07 % of the arguments (measured), which is the stated bar for this attribute.
     const float arg = NRS_FD(-NRS_FM(mx, mx), NRS_FM(NRS_FM(2.f, sigma), sigma));
     out_w[e] = (float)exp((double)arg);
     out_min[e] = mn;

@@ -37,6 +37,15 @@
 #define TRI_DEV __device__ __forceinline__
 #endif
 
+// fp64 product / sum with one rounding each (no FMA contraction) where two code paths must produce identical bits
+#if defined(__CUDA_ARCH__)
+#define TRI_DMUL(a, b) __dmul_rn((a), (b))
+#define TRI_DADD(a, b) __dadd_rn((a), (b))
+#else
+#define TRI_DMUL(a, b) ((a) * (b))
+#define TRI_DADD(a, b) ((a) + (b))
+#endif
+
 namespace nrs {
 namespace tri {
 
@@ -381,6 +390,49 @@ TRI_DEV void solve(const Work& w, int n) {
   TRI_SYNC();
 }
 
+// The same for the decoupled system (every numeric reprojection Jacobian is zero, the usual case): H + lambda I =
+// (omega L + lambda I) (x) I3, so ONE T x T factor serves the x, y and z right-hand sides. The interleaved 3T x 3T
+// factorisation would compute exactly these numbers (its extra terms are products with exact zeros), with three times
+// the dependent steps.
+TRI_DEV void solve3(const Work& w, int T) {
+  const int tid = TRI_TID, nt = TRI_NT;
+  const int n = 3 * T;
+  for (int i = tid; i < n; i += nt) w.r[i] = w.b[i];
+  TRI_SYNC();
+  for (int j = 0; j < T; j++) {
+    const double l = Wel(w, j, j);
+    const double y0 = w.r[3 * j] / l, y1 = w.r[3 * j + 1] / l, y2 = w.r[3 * j + 2] / l;
+    TRI_SYNC();
+    for (int q = 3 * (j + 1) + tid; q < n; q += nt) {
+      const int i = q / 3, c = q - 3 * i;
+      w.r[q] -= Wel(w, i, j) * (c == 0 ? y0 : (c == 1 ? y1 : y2));
+    }
+    if (tid == 0) {
+      w.r[3 * j] = y0;
+      w.r[3 * j + 1] = y1;
+      w.r[3 * j + 2] = y2;
+    }
+    TRI_SYNC();
+  }
+  for (int j = T - 1; j >= 0; j--) {
+    const double l = Wel(w, j, j);
+    const double x0 = w.r[3 * j] / l, x1 = w.r[3 * j + 1] / l, x2 = w.r[3 * j + 2] / l;
+    TRI_SYNC();
+    for (int q = tid; q < 3 * j; q += nt) {
+      const int i = q / 3, c = q - 3 * i;
+      w.r[q] -= Wel(w, j, i) * (c == 0 ? x0 : (c == 1 ? x1 : x2));
+    }
+    if (tid == 0) {
+      w.r[3 * j] = x0;
+      w.r[3 * j + 1] = x1;
+      w.r[3 * j + 2] = x2;
+    }
+    TRI_SYNC();
+  }
+  for (int i = tid; i < n; i += nt) w.dx[i] = w.r[i];
+  TRI_SYNC();
+}
+
 // One candidate. uv [2T], pose [7T], nb_pos [3 kNB T], nb_valid [kNB T] are the candidate's slices (global memory).
 TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float* pose, int n_nb, const float* nb_pos,
                              const unsigned char* nb_valid, void* smem, float* out, int* status_out, int* iters_out) {
@@ -520,13 +572,20 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
       w.Jr[6 * k + d] = scalar * ((mu - (double)upu) - (mu - (double)umu));
       w.Jr[6 * k + 3 + d] = scalar * ((mv - (double)upv) - (mv - (double)umv));
     }
+    if (tid == 0) w.ictl[1] = 0;
     TRI_SYNC();
     for (int k = tid; k < T; k += nt) {
       const double* J = w.Jr + 6 * k;
       double* H = w.Hr + 6 * k;
       int q = 0;
+      bool nz = false;
       for (int a = 0; a < 3; a++)
-        for (int c = a; c < 3; c++) H[q++] = (J[a] * 4.0) * J[c] + (J[3 + a] * 4.0) * J[3 + c];
+        for (int c = a; c < 3; c++) {
+          const double h = (J[a] * 4.0) * J[c] + (J[3 + a] * 4.0) * J[3 + c];
+          H[q++] = h;
+          nz = nz || (h != 0.0);
+        }
+      if (nz) w.ictl[1] = 1;  // some reprojection block couples x, y, z: full 3T x 3T system this iteration
       const double we0 = -4.0 * w.err_r[2 * k], we1 = -4.0 * w.err_r[2 * k + 1];
       for (int c = 0; c < 3; c++) w.b[3 * k + c] += J[c] * we0 + J[3 + c] * we1;
     }
@@ -547,7 +606,15 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
     bool again;
     do {
       for (int i = tid; i < n; i += nt) w.xbak[i] = w.x[i];
+      const bool coupled = w.ictl[1] != 0;
       // H + lambda I, packed lower
+      if (!coupled) {
+        for (int i = tid; i < T; i += nt) {
+          double* row = w.W + (size_t)i * (i + 1) / 2;
+          for (int j = 0; j < i; j++) row[j] = -omega * (double)w.cnt[i * T + j];
+          row[i] = TRI_DADD(TRI_DMUL(omega, (double)w.deg[i]), lambda);
+        }
+      } else
       for (int i = tid; i < n; i += nt) {
         const int a = i / 3, ci = i - 3 * a;
         double* row = w.W + (size_t)i * (i + 1) / 2;
@@ -558,7 +625,7 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
             const int lo = cj, hi = ci;  // cj <= ci inside the diagonal block
             const int q = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
             v = w.Hr[6 * a + q];
-            if (ci == cj) v += omega * (double)w.deg[a] + lambda;
+            if (ci == cj) v += TRI_DADD(TRI_DMUL(omega, (double)w.deg[a]), lambda);  // same roundings as the decoupled path
           } else if (ci == cj) {
             v = -omega * (double)w.cnt[a * T + bq];
           }
@@ -566,9 +633,11 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
         }
       }
       TRI_SYNC();
-      const bool ok2 = cholesky(w, n);
+      const bool ok2 = cholesky(w, coupled ? n : T);
       TRI_SYNC();
-      if (ok2) solve(w, n);
+      if (ok2) {
+        if (coupled) solve(w, n); else solve3(w, T);
+      }
       for (int i = tid; i < n; i += nt) w.x[i] += w.dx[i];
       TRI_SYNC();
       double tempChi = evaluate(cam, w, T, n_nb, uv, omega, false, 1e300, nullptr);
