@@ -377,6 +377,19 @@ int nrslam_b200_tri_rerun(nrslam_b200_tri* tri, float* gpu_ms_out);
 int nrslam_b200_graph_update_vertices(nrslam_b200_ctx* ctx, nrslam_b200_graph* g, int32_t n,
                                       const int32_t* vertices, const float* positions, int32_t* good_out);
 
+/* ---- RegularizationGraph::GetEdges for many vertices at once, on the device -------------------
+ * GetEdges (map/regularization_graph.cc:71-87) copies ALL connections of a vertex, sorts them with EdgeComparator
+ * (:61-69: status ascending, weight descending; ties broken by ascending neighbour like nrslam_b200_graph_get_edges)
+ * and keeps the prefix before the first weight < min_weight — the reference's O(N^2 log N) per frame,
+ * because CameraPoseAndDeformationOptimization calls it for every point (:251-336) but reads only the first
+ * ~regularizers_per_point entries that pass its filters. Here: one CTA per listed vertex ranks the row's entries by a
+ * 64-bit key (2 bits status | 32 bits inverted weight | 30 bits neighbour) — a segmented top-k without a full sort.
+ * out_entries[n * top_k]: the first min(count, top_k) CSR entry indices of the sorted list per vertex (-1 padded);
+ * out_count[n]: GetEdges(v).size(). Bit-exact with nrslam_b200_graph_get_edges. */
+int nrslam_b200_graph_get_edges_batch(nrslam_b200_ctx* ctx, const nrslam_b200_graph* g, int32_t n,
+                                      const int32_t* vertices, int32_t top_k, int32_t* out_entries,
+                                      int32_t* out_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,6 +202,17 @@ class Core:
         positions = _f32(positions)
         return self.L.nrslam_b200_graph_update_vertex(C.byref(g), int(vertex), ptr(positions, C.c_float))
 
+    def graph_get_edges_batch(self, graph, vertices, top_k=32):
+        """RegularizationGraph::GetEdges for many vertices in one launch: (entries [n, top_k] CSR entry indices, -1
+        padded; counts [n] = len(GetEdges(v)))."""
+        g = graph.struct()
+        v = np.ascontiguousarray(vertices, np.int32)
+        ent = np.full((len(v), int(top_k)), -1, np.int32)
+        cnt = np.zeros(len(v), np.int32)
+        self._check(self.L.nrslam_b200_graph_get_edges_batch(self._ctx, C.byref(g), len(v), ptr(v, C.c_int32),
+                                                             int(top_k), ptr(ent, C.c_int32), ptr(cnt, C.c_int32)))
+        return ent, cnt
+
     def graph_update_vertices(self, graph, vertices, positions):
         """The UpdateVertex loop of CameraPoseAndDeformationOptimization (g2o_optimization.cc:458-474) on the device:
         graph attribute arrays updated in place, returns UpdateVertex's good-connection count per vertex."""

@@ -4,6 +4,7 @@
 // modules/mapping/mapping.cc:88-113; modules/map/regularization_graph.cc:89-146 called per accepted point from
 // g2o_optimization.cc:458-474. The per-candidate routine lives in nrs_tri_core.cuh.
 #include <algorithm>
+#include <cmath>
 #include <string>
 
 #include "nrs_host.h"
@@ -62,6 +63,49 @@ __global__ void nrs_graph_update_kernel(int n_entries, const int* __restrict__ e
     out_max[e] = mx;
     if (bad) out_status[e] = NRSLAM_EDGE_BAD;
   }
+}
+
+// GetEdges as a segmented top-k (regularization_graph.cc:61-87). One CTA per listed vertex: every entry of the row gets
+// the number of entries that sort before it (keys are unique: the neighbour is part of the key); ranks below top_k are
+// written, and the list is cut at the smallest rank whose weight is < min_weight.
+__device__ __forceinline__ unsigned long long edge_key(unsigned status, float weight, int col) {
+  const unsigned wb = 0xFFFFFFFFu - __float_as_uint(weight);  // non-negative floats order like their bit patterns
+  return ((unsigned long long)(status & 3u) << 62) | ((unsigned long long)wb << 30) | (unsigned long long)(col & 0x3FFFFFFF);
+}
+__global__ void nrs_graph_keys_kernel(int nnz, const int* __restrict__ col, const int* __restrict__ eid,
+                                      const float* __restrict__ weight, const unsigned char* __restrict__ status,
+                                      unsigned long long* __restrict__ keys) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) keys[p] = edge_key(status[eid[p]], weight[eid[p]], col[p]);
+}
+__global__ void __launch_bounds__(128)
+nrs_graph_topk_kernel(const int* __restrict__ vertices, const int* __restrict__ rowptr, const int* __restrict__ eid,
+                      const float* __restrict__ weight, const unsigned long long* __restrict__ keys, float min_w,
+                      int top_k, int* __restrict__ out_entries, int* __restrict__ out_count) {
+  __shared__ int s_cut;
+  __shared__ unsigned long long s_keys[1024];
+  const int v = vertices[blockIdx.x];
+  const int p0 = rowptr[v], d = rowptr[v + 1] - p0;
+  if (threadIdx.x == 0) s_cut = d;
+  for (int k = threadIdx.x; k < top_k; k += blockDim.x) out_entries[(size_t)blockIdx.x * top_k + k] = -1;
+  const bool staged = d <= 1024;
+  if (staged)
+    for (int k = threadIdx.x; k < d; k += blockDim.x) s_keys[k] = keys[p0 + k];
+  __syncthreads();
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const unsigned long long mine = staged ? s_keys[k] : keys[p0 + k];
+    int rank = 0;
+    if (staged)
+      for (int q = 0; q < d; q++) rank += (s_keys[q] < mine) ? 1 : 0;
+    else
+      for (int q = 0; q < d; q++) rank += (keys[p0 + q] < mine) ? 1 : 0;
+    if (rank < top_k) out_entries[(size_t)blockIdx.x * top_k + rank] = p0 + k;
+    if (weight[eid[p0 + k]] < min_w) atomicMin(&s_cut, rank);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out_count[blockIdx.x] = s_cut;
+  // entries at or behind the cut are not part of the list
+  for (int k = s_cut + threadIdx.x; k < top_k; k += blockDim.x) out_entries[(size_t)blockIdx.x * top_k + k] = -1;
 }
 
 int tfail(nrslam_b200_ctx* ctx, int code, const std::string& msg) {
@@ -275,6 +319,55 @@ int nrslam_b200_graph_update_vertices(nrslam_b200_ctx* ctx, nrslam_b200_graph* g
   memcpy(g->max_distance, out.h<float>(q_max), E * sizeof(float));
   memcpy(g->status, out.h<unsigned char>(q_status), E);
   memcpy(good_out, out.h<int>(q_good), n * sizeof(int));
+  return 0;
+}
+
+int nrslam_b200_graph_get_edges_batch(nrslam_b200_ctx* ctx, const nrslam_b200_graph* g, int32_t n,
+                                      const int32_t* vertices, int32_t top_k, int32_t* out_entries,
+                                      int32_t* out_count) {
+  if (!ctx || !g || n < 0 || top_k < 1 || (n > 0 && (!vertices || !out_entries || !out_count)))
+    return tfail(ctx, NRSLAM_B200_ERR_ARG, "graph_get_edges_batch: bad argument");
+  if (n == 0) return 0;
+  const int V = g->n_vertices, E = g->n_edges;
+  for (int i = 0; i < n; i++)
+    if (vertices[i] < 0 || vertices[i] >= V) return tfail(ctx, NRSLAM_B200_ERR_ARG, "graph_get_edges_batch: bad vertex");
+  TRI_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  nrs::Arena& in = ctx->graph_in;
+  nrs::Arena& out = ctx->graph_out;
+  const size_t nnz = (size_t)g->rowptr[V];
+  const size_t need_in = ((size_t)n + V + 1 + 2 * nnz + E) * 4 + E + 8192;
+  const size_t need_out = ((size_t)n * top_k + n) * 4 + nnz * 8 + 8192;
+  if (!in.reserve(need_in, true) || !out.reserve(need_out, true))
+    return tfail(ctx, NRSLAM_B200_ERR_ALLOC, "graph_get_edges_batch: allocation failed");
+  const size_t o_vert = in.take<int>(n), o_row = in.take<int>(V + 1), o_col = in.take<int>(nnz), o_eid = in.take<int>(nnz),
+               o_w = in.take<float>(E), o_st = in.take<unsigned char>(E);
+  const size_t q_ent = out.take<int>((size_t)n * top_k), q_cnt = out.take<int>(n);
+  const size_t q_ret = out.used();  // only the part above travels back
+  const size_t q_keys = out.take<unsigned long long>(nnz);
+  memcpy(in.h<int>(o_vert), vertices, n * sizeof(int));
+  memcpy(in.h<int>(o_row), g->rowptr, (V + 1) * sizeof(int));
+  memcpy(in.h<int>(o_col), g->col, nnz * sizeof(int));
+  memcpy(in.h<int>(o_eid), g->eid, nnz * sizeof(int));
+  memcpy(in.h<float>(o_w), g->weight, E * sizeof(float));
+  memcpy(in.h<unsigned char>(o_st), g->status, E);
+  TRI_CUDA(ctx, cudaMemcpyAsync(in.dev(), in.host(), in.used(), cudaMemcpyHostToDevice, st));
+  // min_weight_ = InterpolationWeight(1.5 sigma, sigma) (regularization_graph.cc:28-31), evaluated on the host like the
+  // constructor does
+  const float s = g->weight_sigma, dm = (float)(s * 1.5);
+  const float min_w = std::exp(-(dm * dm) / (2 * s * s));
+  if (nnz > 0)
+    nrs_graph_keys_kernel<<<(int)((nnz + 255) / 256), 256, 0, st>>>((int)nnz, in.d<int>(o_col), in.d<int>(o_eid),
+                                                                   in.d<float>(o_w), in.d<unsigned char>(o_st),
+                                                                   out.d<unsigned long long>(q_keys));
+  nrs_graph_topk_kernel<<<n, 128, 0, st>>>(in.d<int>(o_vert), in.d<int>(o_row), in.d<int>(o_eid), in.d<float>(o_w),
+                                           out.d<unsigned long long>(q_keys), min_w, top_k, out.d<int>(q_ent),
+                                           out.d<int>(q_cnt));
+  TRI_CUDA(ctx, cudaGetLastError());
+  TRI_CUDA(ctx, cudaMemcpyAsync(out.host(), out.dev(), q_ret, cudaMemcpyDeviceToHost, st));
+  TRI_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(out_entries, out.h<int>(q_ent), (size_t)n * top_k * sizeof(int));
+  memcpy(out_count, out.h<int>(q_cnt), n * sizeof(int));
   return 0;
 }
 

@@ -124,3 +124,27 @@ def test_graph_update_vertices_bit_exact(core, n, frac):
     good_host = np.array([core.graph_update_vertex(g_host, int(v), Q) for v in verts], np.int32)
     assert (good_host == good_gpu).all() and (g_host.weight == g_ref.weight).all()
     assert (g_host.status == g_gpu.status).all()
+
+
+@pytest.mark.parametrize("n,k,top_k", [(600, 10, 32), (1500, 40, 16), (300, 299, 24)])
+def test_graph_get_edges_batch_bit_exact(core, n, k, top_k):
+    """Segmented top-k GetEdges vs the per-vertex host entry point (regularization_graph.cc:61-87), on a graph whose
+    edges carry all four statuses, equal weights (tie-break by neighbour) and weights below min_weight; k = n - 1 is the
+    reference's dense graph (every pair of landmarks in a frame is connected, mapping.cc:237-256)."""
+    rng = np.random.default_rng(n + k)
+    cam = synth.make_camera(synth.CONFIGS["c2"]["cam"])
+    P = synth.sheet_points(rng, cam, synth.CONFIGS["c2"]["size"], n)
+    g = synth.knn_graph(P, k, weight_sigma=0.12)
+    g.status[:] = rng.integers(0, 4, g.n_edges).astype(np.uint8)
+    dup = rng.choice(g.n_edges, g.n_edges // 5, replace=False)
+    g.weight[dup] = np.float32(0.75)                         # ties
+    verts = rng.permutation(n).astype(np.int32)[: max(1, n * 3 // 4)]
+    ent, cnt = core.graph_get_edges_batch(g, verts, top_k)
+    below = 0
+    for i, v in enumerate(verts):
+        ref = core.graph_get_edges(g, int(v))
+        assert cnt[i] == len(ref)
+        m = min(len(ref), top_k)
+        assert (ent[i, :m] == ref[:m]).all() and (ent[i, m:] == -1).all()
+        below += (g.rowptr[v + 1] - g.rowptr[v]) - len(ref)
+    assert below > 0   # the min_weight cut was exercised
