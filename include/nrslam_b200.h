@@ -347,7 +347,10 @@ enum {
   NRSLAM_B200_TRI_NEGATIVE_DEPTH = 6,   /* "Negative initial depth."                    .cc:659-661 */
   NRSLAM_B200_TRI_BAD_NEIGHBOURS = 7,   /* "Triangulation has to many bad neighbors."   .cc:781-783 */
   NRSLAM_B200_TRI_HIGH_ERROR = 8,       /* "Triangulation has to much error."           .cc:794-796 */
-  NRSLAM_B200_TRI_NAN = 9               /* result.hasNaN() (the caller's check, mapping.cc:98-99) */
+  NRSLAM_B200_TRI_NAN = 9,              /* result.hasNaN() (the caller's check, mapping.cc:98-99) */
+  NRSLAM_B200_TRI_SHORT_TRACK = 10,     /* "Short track" (TrackLenght < 5, mapping.cc:94,111-113)        tri_run_frame only */
+  NRSLAM_B200_TRI_NOT_RIGID = 11,       /* "Rigidity not detected" (mapping.cc:122-125)                  rigid branch */
+  NRSLAM_B200_TRI_RIGID_PARALLAX = 12   /* "Parallax error." (parallax window, depth, reprojection; mapping.cc:152-181) */
 };
 typedef struct nrslam_b200_tri nrslam_b200_tri;
 int nrslam_b200_tri_create(nrslam_b200_ctx* ctx, nrslam_b200_tri** out);
@@ -356,6 +359,19 @@ int nrslam_b200_tri_run(nrslam_b200_tri* tri, const nrslam_b200_camera* cam, int
                         const int32_t* track_ptr, const float* track_uv, const float* track_pose,
                         const int32_t* n_neighbours, const float* nb_pos, const uint8_t* nb_valid, float scale,
                         float* position_out, int32_t* status_out, int32_t* lm_iterations_out);
+/* The whole per-candidate compute of Mapping::LandmarkTriangulation (mapping/mapping.cc:65-212) in one launch: the
+ * deformable triangulation above for candidates with track length >= min_track (5 in the reference, :94; shorter ones
+ * get NRSLAM_B200_TRI_SHORT_TRACK), the RIGID mid-point triangulation of every candidate (:115-185; rigid_ok[c] =
+ * TemporalBuffer::CheckRigidity(first frame, last frame, 0.004) of its track, rad_per_pixel = Mapping::Options) and the
+ * reference's vote (:188-212): rigid results are used when n_rigid > 1.5 n_deformable, deformable ones when
+ * n_deformable >= 1.5 n_rigid, none otherwise; NaN positions are dropped. selected_out[c] = 1 when candidate c gets a
+ * map point at selected_pos_out[3c..]. All output arrays are required. */
+int nrslam_b200_tri_run_frame(nrslam_b200_tri* tri, const nrslam_b200_camera* cam, int32_t n_cand,
+                              const int32_t* track_ptr, const float* track_uv, const float* track_pose,
+                              const int32_t* n_neighbours, const float* nb_pos, const uint8_t* nb_valid,
+                              const uint8_t* rigid_ok, float rad_per_pixel, int32_t min_track, float scale,
+                              float* deform_pos_out, int32_t* deform_status_out, float* rigid_pos_out,
+                              int32_t* rigid_status_out, float* selected_pos_out, uint8_t* selected_out);
 /* Device time (CUDA events on the ctx stream) of the last run's kernel, and a re-run of it on the HBM-resident
  * staged batch (benchmark hook; results identical). */
 float nrslam_b200_tri_last_ms(const nrslam_b200_tri* tri);

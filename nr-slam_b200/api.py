@@ -568,6 +568,26 @@ class Triangulator:
                                                ptr(status, C.c_int32), ptr(iters, C.c_int32)))
         return dict(position=out, status=status, lm_iterations=iters, gpu_ms=self.L.nrslam_b200_tri_last_ms(self._h))
 
+    def run_frame(self, cam, track_ptr, track_uv, track_pose, n_neighbours, nb_pos, nb_valid, rigid_ok,
+                  rad_per_pixel, min_track=5, scale=1.0):
+        """Mapping::LandmarkTriangulation's per-candidate compute and vote (mapping/mapping.cc:65-212) in one launch."""
+        track_ptr = np.ascontiguousarray(track_ptr, np.int32)
+        n = len(track_ptr) - 1
+        uv, pose = _f32(track_uv), _f32(track_pose)
+        nnb = np.ascontiguousarray(n_neighbours, np.int32)
+        pos, val = _f32(nb_pos), np.ascontiguousarray(nb_valid, np.uint8)
+        rok = np.ascontiguousarray(rigid_ok, np.uint8)
+        dp, rp, sp = (np.zeros((n, 3), np.float32) for _ in range(3))
+        ds, rs = np.full(n, -1, np.int32), np.full(n, -1, np.int32)
+        sel = np.zeros(n, np.uint8)
+        self._check(self.L.nrslam_b200_tri_run_frame(
+            self._h, C.byref(cam), n, ptr(track_ptr, C.c_int32), ptr(uv, C.c_float), ptr(pose, C.c_float),
+            ptr(nnb, C.c_int32), ptr(pos, C.c_float), ptr(val, C.c_uint8), ptr(rok, C.c_uint8),
+            C.c_float(rad_per_pixel), int(min_track), C.c_float(scale), ptr(dp, C.c_float), ptr(ds, C.c_int32),
+            ptr(rp, C.c_float), ptr(rs, C.c_int32), ptr(sp, C.c_float), ptr(sel, C.c_uint8)))
+        return dict(deform_position=dp, deform_status=ds, rigid_position=rp, rigid_status=rs, selected_position=sp,
+                    selected=sel, gpu_ms=self.L.nrslam_b200_tri_last_ms(self._h))
+
     def run_batch(self, batch):
         """Convenience over a synth.triangulation_batch dict."""
         return self.run(batch["cam"], batch["track_ptr"], batch["track_uv"], batch["track_pose"],

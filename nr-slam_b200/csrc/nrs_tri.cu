@@ -18,14 +18,22 @@ nrs_tri_kernel(Cam cam, int n_cand, const int* __restrict__ track_ptr, const flo
                const float* __restrict__ track_pose, const int* __restrict__ n_neighbours,
                const float* __restrict__ nb_pos, const unsigned char* __restrict__ nb_valid,
                const int* __restrict__ order, float* __restrict__ position_out, int* __restrict__ status_out,
-               int* __restrict__ iters_out) {
+               int* __restrict__ iters_out, const unsigned char* __restrict__ rigid_ok, float rad_per_pixel,
+               int min_track, float* __restrict__ rigid_out, int* __restrict__ rigid_status) {
   extern __shared__ __align__(16) unsigned char tri_smem[];
   // longest tracks first (order[] sorts the candidates by descending track length) so the tail of the grid is cheap
   const int c = order[blockIdx.x];
   const int e0 = track_ptr[c], T = track_ptr[c + 1] - e0;
+  tri::RigidArgs rg;
+  rg.enabled = rigid_ok != nullptr;
+  rg.min_track = min_track;
+  rg.rad_per_pixel = rad_per_pixel;
+  rg.rigid_ok = rg.enabled ? rigid_ok[c] : 0;
+  rg.out = rg.enabled ? rigid_out + 3 * (size_t)c : nullptr;
+  rg.status = rg.enabled ? rigid_status + c : nullptr;
   tri::solve_candidate(cam, T, track_uv + 2 * (size_t)e0, track_pose + 7 * (size_t)e0, n_neighbours[c],
                        nb_pos + (size_t)e0 * tri::kNB * 3, nb_valid + (size_t)e0 * tri::kNB, tri_smem,
-                       position_out + 3 * (size_t)c, status_out + c, iters_out + c);
+                       position_out + 3 * (size_t)c, status_out + c, iters_out + c, rg);
 }
 
 // One thread per CSR entry of an updated vertex (regularization_graph.cc:107-128 UpdateConnection). Reads the edge
@@ -129,6 +137,11 @@ struct nrslam_b200_tri {
   nrs::Cam cam;
   size_t o_ptr = 0, o_uv = 0, o_pose = 0, o_nnb = 0, o_pos = 0, o_val = 0, o_order = 0;
   size_t o_out = 0, o_status = 0, o_iters = 0;
+  // frame mode (tri_run_frame): rigid branch inputs / outputs
+  bool frame = false;
+  size_t o_rok = 0, o_rout = 0, o_rstatus = 0;
+  float rad_per_pixel = 0.f;
+  int min_track = 1;
   float last_ms = 0.f;
   bool staged = false;
 };
@@ -142,7 +155,9 @@ int tri_launch(nrslam_b200_tri* t) {
   nrs_tri_kernel<<<t->n_cand, tri::kThreads, t->smem, st>>>(
       t->cam, t->n_cand, t->in.d<int>(t->o_ptr), t->in.d<float>(t->o_uv), t->in.d<float>(t->o_pose),
       t->in.d<int>(t->o_nnb), t->in.d<float>(t->o_pos), t->in.d<unsigned char>(t->o_val), t->in.d<int>(t->o_order),
-      t->out.d<float>(t->o_out), t->out.d<int>(t->o_status), t->out.d<int>(t->o_iters));
+      t->out.d<float>(t->o_out), t->out.d<int>(t->o_status), t->out.d<int>(t->o_iters),
+      t->frame ? t->in.d<unsigned char>(t->o_rok) : nullptr, t->rad_per_pixel, t->min_track,
+      t->frame ? t->out.d<float>(t->o_rout) : nullptr, t->frame ? t->out.d<int>(t->o_rstatus) : nullptr);
   TRI_CUDA(ctx, cudaGetLastError());
   TRI_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
   return 0;
@@ -167,16 +182,15 @@ void nrslam_b200_tri_destroy(nrslam_b200_tri* t) {
   delete t;
 }
 
-int nrslam_b200_tri_run(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32_t n_cand, const int32_t* track_ptr,
-                        const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
-                        const float* nb_pos, const uint8_t* nb_valid, float scale, float* position_out,
-                        int32_t* status_out, int32_t* lm_iterations_out) {
-  (void)scale;  // unused by the reference body as well (g2o_optimization.cc:559-814 never reads it)
+// Stage a batch, run the kernel, bring the results into the pinned output arena. rigid_ok == nullptr: deformable only.
+static int tri_stage_and_run(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32_t n_cand, const int32_t* track_ptr,
+                             const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
+                             const float* nb_pos, const uint8_t* nb_valid, const uint8_t* rigid_ok,
+                             float rad_per_pixel, int32_t min_track) {
   if (!t) return NRSLAM_B200_ERR_ARG;
   nrslam_b200_ctx* ctx = t->ctx;
-  if (!cam || n_cand < 0 || !track_ptr || !position_out || !status_out)
+  if (!cam || n_cand <= 0 || !track_ptr)
     return tfail(ctx, NRSLAM_B200_ERR_ARG, "tri_run: bad argument");
-  if (n_cand == 0) return 0;
   if (!track_uv || !track_pose || !n_neighbours || !nb_pos || !nb_valid)
     return tfail(ctx, NRSLAM_B200_ERR_ARG, "tri_run: bad argument");
   int t_max = 0;
@@ -191,7 +205,7 @@ int nrslam_b200_tri_run(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32
   TRI_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
 
-  const size_t need_in = (n_cand + 1 + 2 * (size_t)n_cand) * 4 + E * (2 + 7 + 3 * tri::kNB) * 4 + E * tri::kNB + 4096;
+  const size_t need_in = (n_cand + 1 + 2 * (size_t)n_cand) * 4 + E * (2 + 7 + 3 * tri::kNB) * 4 + E * tri::kNB + n_cand + 4096;
   if (!t->in.reserve(need_in, true)) return tfail(ctx, NRSLAM_B200_ERR_ALLOC, "tri_run: input arena allocation failed");
   t->o_ptr = t->in.take<int>(n_cand + 1);
   t->o_nnb = t->in.take<int>(n_cand);
@@ -206,16 +220,27 @@ int nrslam_b200_tri_run(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32
   memcpy(t->in.h<float>(t->o_pose), track_pose, 7 * E * sizeof(float));
   memcpy(t->in.h<float>(t->o_pos), nb_pos, 3 * tri::kNB * E * sizeof(float));
   memcpy(t->in.h<unsigned char>(t->o_val), nb_valid, tri::kNB * E);
+  t->frame = rigid_ok != nullptr;
+  t->rad_per_pixel = rad_per_pixel;
+  t->min_track = min_track;
+  if (t->frame) {
+    t->o_rok = t->in.take<unsigned char>(n_cand);
+    memcpy(t->in.h<unsigned char>(t->o_rok), rigid_ok, n_cand);
+  }
   int* order = t->in.h<int>(t->o_order);
   for (int c = 0; c < n_cand; c++) order[c] = c;
   std::stable_sort(order, order + n_cand, [&](int a, int b) {
     return track_ptr[a + 1] - track_ptr[a] > track_ptr[b + 1] - track_ptr[b];
   });
-  const size_t need_out = (size_t)n_cand * 5 * 4 + 4096;
+  const size_t need_out = (size_t)n_cand * 9 * 4 + 8192;
   if (!t->out.reserve(need_out, true)) return tfail(ctx, NRSLAM_B200_ERR_ALLOC, "tri_run: output arena allocation failed");
   t->o_out = t->out.take<float>(3 * (size_t)n_cand);
   t->o_status = t->out.take<int>(n_cand);
   t->o_iters = t->out.take<int>(n_cand);
+  if (t->frame) {
+    t->o_rout = t->out.take<float>(3 * (size_t)n_cand);
+    t->o_rstatus = t->out.take<int>(n_cand);
+  }
   t->n_cand = n_cand;
   t->t_max = t_max;
   t->smem = tri::work_bytes(t_max);
@@ -230,9 +255,66 @@ int nrslam_b200_tri_run(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32
   TRI_CUDA(ctx, cudaStreamSynchronize(st));
   TRI_CUDA(ctx, cudaEventElapsedTime(&t->last_ms, ctx->ev0, ctx->ev1));
   t->staged = true;
+  return 0;
+}
+
+int nrslam_b200_tri_run(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32_t n_cand, const int32_t* track_ptr,
+                        const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
+                        const float* nb_pos, const uint8_t* nb_valid, float scale, float* position_out,
+                        int32_t* status_out, int32_t* lm_iterations_out) {
+  (void)scale;  // unused by the reference body as well (g2o_optimization.cc:559-814 never reads it)
+  if (!t) return NRSLAM_B200_ERR_ARG;
+  if (n_cand < 0 || !position_out || !status_out) return tfail(t->ctx, NRSLAM_B200_ERR_ARG, "tri_run: bad argument");
+  if (n_cand == 0) return 0;
+  const int rc = tri_stage_and_run(t, cam, n_cand, track_ptr, track_uv, track_pose, n_neighbours, nb_pos, nb_valid,
+                                   nullptr, 0.f, 1);
+  if (rc) return rc;
   memcpy(position_out, t->out.h<float>(t->o_out), 3 * (size_t)n_cand * sizeof(float));
   memcpy(status_out, t->out.h<int>(t->o_status), n_cand * sizeof(int));
   if (lm_iterations_out) memcpy(lm_iterations_out, t->out.h<int>(t->o_iters), n_cand * sizeof(int));
+  return 0;
+}
+
+int nrslam_b200_tri_run_frame(nrslam_b200_tri* t, const nrslam_b200_camera* cam, int32_t n_cand,
+                              const int32_t* track_ptr, const float* track_uv, const float* track_pose,
+                              const int32_t* n_neighbours, const float* nb_pos, const uint8_t* nb_valid,
+                              const uint8_t* rigid_ok, float rad_per_pixel, int32_t min_track, float scale,
+                              float* deform_pos_out, int32_t* deform_status_out, float* rigid_pos_out,
+                              int32_t* rigid_status_out, float* selected_pos_out, uint8_t* selected_out) {
+  (void)scale;
+  if (!t) return NRSLAM_B200_ERR_ARG;
+  if (n_cand < 0 || !rigid_ok || !deform_pos_out || !deform_status_out || !rigid_pos_out || !rigid_status_out ||
+      !selected_pos_out || !selected_out)
+    return tfail(t->ctx, NRSLAM_B200_ERR_ARG, "tri_run_frame: bad argument");
+  if (n_cand == 0) return 0;
+  const int rc = tri_stage_and_run(t, cam, n_cand, track_ptr, track_uv, track_pose, n_neighbours, nb_pos, nb_valid,
+                                   rigid_ok, rad_per_pixel, min_track);
+  if (rc) return rc;
+  const float* dp = t->out.h<float>(t->o_out);
+  const int* ds = t->out.h<int>(t->o_status);
+  const float* rp = t->out.h<float>(t->o_rout);
+  const int* rs = t->out.h<int>(t->o_rstatus);
+  memcpy(deform_pos_out, dp, 3 * (size_t)n_cand * sizeof(float));
+  memcpy(deform_status_out, ds, n_cand * sizeof(int));
+  memcpy(rigid_pos_out, rp, 3 * (size_t)n_cand * sizeof(float));
+  memcpy(rigid_status_out, rs, n_cand * sizeof(int));
+  // the vote of mapping.cc:188-212 (host: two counts and a per-candidate pick)
+  int n_rigid = 0, n_def = 0;
+  for (int c = 0; c < n_cand; c++) {
+    n_rigid += rs[c] == NRSLAM_B200_TRI_OK;
+    n_def += ds[c] == NRSLAM_B200_TRI_OK;
+  }
+  for (int c = 0; c < n_cand; c++) {
+    const float* pick = nullptr;
+    if (n_rigid > 1.5 * n_def) {
+      if (rs[c] == NRSLAM_B200_TRI_OK) pick = rp + 3 * (size_t)c;
+    } else if (n_def >= 1.5 * n_rigid) {
+      if (ds[c] == NRSLAM_B200_TRI_OK) pick = dp + 3 * (size_t)c;
+    }
+    if (pick && (std::isnan(pick[0]) || std::isnan(pick[1]) || std::isnan(pick[2]))) pick = nullptr;
+    selected_out[c] = pick ? 1 : 0;
+    for (int i = 0; i < 3; i++) selected_pos_out[3 * (size_t)c + i] = pick ? pick[i] : 0.f;
+  }
   return 0;
 }
 

@@ -55,7 +55,19 @@ constexpr int kThreads = 128;
 
 enum {
   ST_OK = 0, ST_TOO_CLOSE = 1, ST_HIGH_REPROJ_FIRST = 2, ST_HIGH_REPROJ_SECOND = 3, ST_LOW_PARALLAX = 4,
-  ST_NO_NEIGHBOURS = 5, ST_NEGATIVE_DEPTH = 6, ST_BAD_NEIGHBOURS = 7, ST_HIGH_ERROR = 8, ST_NAN = 9
+  ST_NO_NEIGHBOURS = 5, ST_NEGATIVE_DEPTH = 6, ST_BAD_NEIGHBOURS = 7, ST_HIGH_ERROR = 8, ST_NAN = 9,
+  ST_SHORT_TRACK = 10, ST_NOT_RIGID = 11, ST_RIGID_PARALLAX = 12
+};
+
+// The rigid branch of Mapping::LandmarkTriangulation (mapping/mapping.cc:115-185) rides on the two-view quantities the
+// deformable pre-checks compute anyway. enabled == 0: DeformableTriangulation alone (nrslam_b200_tri_run).
+struct RigidArgs {
+  int enabled;
+  int min_track;         // TrackLenght(candidate) >= 5 gate of the deformable branch (mapping.cc:94)
+  float rad_per_pixel;   // Mapping::Options::rad_per_pixel
+  int rigid_ok;          // TemporalBuffer::CheckRigidity(first, last, 0.004) of this candidate's track (mapping.cc:123)
+  float* out;            // [3] rigid position
+  int* status;           // ST_OK / ST_TOO_CLOSE / ST_NOT_RIGID / ST_RIGID_PARALLAX
 };
 
 // ---- fp32 Sophus / Eigen restatements (no FMA contraction: NRS_F* are single-rounding intrinsics on the device) ----
@@ -435,7 +447,8 @@ TRI_DEV void solve3(const Work& w, int T) {
 
 // One candidate. uv [2T], pose [7T], nb_pos [3 kNB T], nb_valid [kNB T] are the candidate's slices (global memory).
 TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float* pose, int n_nb, const float* nb_pos,
-                             const unsigned char* nb_valid, void* smem, float* out, int* status_out, int* iters_out) {
+                             const unsigned char* nb_valid, void* smem, float* out, int* status_out, int* iters_out,
+                             const RigidArgs rg) {
   const int tid = TRI_TID, nt = TRI_NT;
   const int n = 3 * T;
   const Work w = carve(smem, T);
@@ -445,9 +458,11 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
   for (int i = tid; i < 3 * kNB * T; i += nt) w.nbp[i] = nb_pos[i];
   for (int i = tid; i < kNB * T; i += nt) w.nbv[i] = nb_valid[i];
   if (tid == 0) {
-    int st = ST_OK;
+    int st = ST_OK, rst = ST_OK;
+    float rX[3] = {0.f, 0.f, 0.f};
     if (n_nb <= 0) {
-      st = ST_TOO_CLOSE;
+      st = ST_TOO_CLOSE;   // g2o_optimization.cc:569-571 ; "Close features" for both branches, mapping.cc:90-94
+      rst = ST_TOO_CLOSE;
     } else {
       const float* cur_uv = uv;
       const float* prev_uv = uv + 2 * (T - 1);
@@ -457,25 +472,46 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
       normalized_f(cu, cur_ray);
       normalized_f(pu, prev_ray);
       const SE3f cur_T = load_pose(pose), prev_T = load_pose(pose + 7 * (T - 1));
-      float X[3], pc[3], pju, pjv;
+      float X[3], pc_cur[3], pc_prev[3], cu_u, cu_v, pr_u, pr_v;
       triangulate_mid_point(prev_ray, cur_ray, prev_T, cur_T, X);
-      map_f(cur_T, X, pc);
-      project_f(cam, pc[0], pc[1], pc[2], pju, pjv);
-      if ((double)sq_reproj(cur_uv, pju, pjv) > 5.991) st = ST_HIGH_REPROJ_FIRST;
-      if (st == ST_OK) {
-        map_f(prev_T, X, pc);
-        project_f(cam, pc[0], pc[1], pc[2], pju, pjv);
-        if ((double)sq_reproj(prev_uv, pju, pjv) > 5.991) st = ST_HIGH_REPROJ_SECOND;
+      map_f(cur_T, X, pc_cur);
+      project_f(cam, pc_cur[0], pc_cur[1], pc_cur[2], cu_u, cu_v);
+      map_f(prev_T, X, pc_prev);
+      project_f(cam, pc_prev[0], pc_prev[1], pc_prev[2], pr_u, pr_v);
+      const double e_cur = (double)sq_reproj(cur_uv, cu_u, cu_v), e_prev = (double)sq_reproj(prev_uv, pr_u, pr_v);
+      const SE3f ci = inverse_f(cur_T), pi = inverse_f(prev_T);
+      const float n1[3] = {NRS_FS(X[0], ci.t[0]), NRS_FS(X[1], ci.t[1]), NRS_FS(X[2], ci.t[2])};
+      const float n2[3] = {NRS_FS(X[0], pi.t[0]), NRS_FS(X[1], pi.t[1]), NRS_FS(X[2], pi.t[2])};
+      const float dot = NRS_FA(NRS_FA(NRS_FM(n1[0], n2[0]), NRS_FM(n1[1], n2[1])), NRS_FM(n1[2], n2[2]));
+      const float c = NRS_FD(dot, NRS_FM(norm_f(n1), norm_f(n2)));
+      const float parallax = acosf(fminf(c, 1.f));
+      // DeformableTriangulation's order (:618-635): first camera, second camera, parallax
+      if (e_cur > 5.991) st = ST_HIGH_REPROJ_FIRST;
+      else if (e_prev > 5.991) st = ST_HIGH_REPROJ_SECOND;
+      else if ((double)parallax < 0.0025 * 5.0) st = ST_LOW_PARALLAX;
+      if (rg.enabled) {
+        if (T < rg.min_track) st = ST_SHORT_TRACK;   // mapping.cc:94,111-113: DeformableTriangulation is not called
+        // rigid branch (mapping.cc:122-183): rigidity, parallax window, depth and reprojection in BOTH views;
+        // NaNs fall through every comparison exactly like in the reference
+        const float lo = NRS_FM(rg.rad_per_pixel, 10.f), hi = NRS_FM(rg.rad_per_pixel, 20.f);
+        if (!rg.rigid_ok) rst = ST_NOT_RIGID;
+        else if (parallax < lo || parallax > hi) rst = ST_RIGID_PARALLAX;
+        else if (pc_prev[2] < 0) rst = ST_RIGID_PARALLAX;
+        else if (e_prev > 5.991) rst = ST_RIGID_PARALLAX;
+        else if (pc_cur[2] < 0) rst = ST_RIGID_PARALLAX;
+        else if (e_cur > 5.991) rst = ST_RIGID_PARALLAX;
+        if (rst == ST_OK) {
+          rX[0] = X[0];
+          rX[1] = X[1];
+          rX[2] = X[2];
+        }
       }
-      if (st == ST_OK) {
-        const SE3f ci = inverse_f(cur_T), pi = inverse_f(prev_T);
-        const float n1[3] = {NRS_FS(X[0], ci.t[0]), NRS_FS(X[1], ci.t[1]), NRS_FS(X[2], ci.t[2])};
-        const float n2[3] = {NRS_FS(X[0], pi.t[0]), NRS_FS(X[1], pi.t[1]), NRS_FS(X[2], pi.t[2])};
-        const float dot = NRS_FA(NRS_FA(NRS_FM(n1[0], n2[0]), NRS_FM(n1[1], n2[1])), NRS_FM(n1[2], n2[2]));
-        const float c = NRS_FD(dot, NRS_FM(norm_f(n1), norm_f(n2)));
-        const float parallax = acosf(fminf(c, 1.f));
-        if ((double)parallax < 0.0025 * 5.0) st = ST_LOW_PARALLAX;
-      }
+    }
+    if (rg.enabled) {
+      rg.out[0] = rX[0];
+      rg.out[1] = rX[1];
+      rg.out[2] = rX[2];
+      *rg.status = rst;
     }
     w.ictl[0] = st;
   }

@@ -288,9 +288,94 @@ int triangulate_one(const Camera& cam, int T, const float* uv, const float* pose
   if (std::isnan(out[0]) || std::isnan(out[1]) || std::isnan(out[2])) return NRSLAM_B200_TRI_NAN;  // mapping.cc:98
   return NRSLAM_B200_TRI_OK;
 }
+// Rigid branch of Mapping::LandmarkTriangulation for one candidate (modules/mapping/mapping.cc:115-185).
+int rigid_one(const Camera& cam, int T, const float* uv, const float* pose, int n_nb, int rigid_ok, float rad_per_pixel,
+              float out[3]) {
+  out[0] = out[1] = out[2] = 0.f;
+  if (n_nb <= 0) return NRSLAM_B200_TRI_TOO_CLOSE;                      // :90-94 "Close features"
+  if (!rigid_ok) return NRSLAM_B200_TRI_NOT_RIGID;                       // :122-125
+  const float* cur_uv = uv;                                              // track.front()  (:118-119)
+  const float* prev_uv = uv + 2 * (T - 1);                               // track.back()
+  float cu[3], pu[3], cur_ray[3], prev_ray[3];
+  unproject_f(cam, cur_uv[0], cur_uv[1], cu);
+  unproject_f(cam, prev_uv[0], prev_uv[1], pu);
+  normalized_f(cu, cur_ray);
+  normalized_f(pu, prev_ray);
+  const SE3f cur_T = load_pose(pose), prev_T = load_pose(pose + 7 * (T - 1));
+  float X[3];
+  triangulate_mid_point(prev_ray, cur_ray, prev_T, cur_T, X);            // :137-139
+  const SE3f ci = inverse_f(cur_T), pi = inverse_f(prev_T);
+  const float n1[3] = {X[0] - ci.t[0], X[1] - ci.t[1], X[2] - ci.t[2]};
+  const float n2[3] = {X[0] - pi.t[0], X[1] - pi.t[1], X[2] - pi.t[2]};
+  const float parallax = rays_parallax(n1, n2);
+  if (parallax < rad_per_pixel * 10.f || parallax > rad_per_pixel * 20.f) return NRSLAM_B200_TRI_RIGID_PARALLAX;
+  float pc[3], proj[2];
+  map_f(prev_T, X, pc);                                                  // :158-168
+  if (pc[2] < 0) return NRSLAM_B200_TRI_RIGID_PARALLAX;
+  project_f(cam, pc, proj);
+  if (sq_reproj(prev_uv, proj) > 5.991) return NRSLAM_B200_TRI_RIGID_PARALLAX;
+  map_f(cur_T, X, pc);                                                   // :170-181
+  if (pc[2] < 0) return NRSLAM_B200_TRI_RIGID_PARALLAX;
+  project_f(cam, pc, proj);
+  if (sq_reproj(cur_uv, proj) > 5.991) return NRSLAM_B200_TRI_RIGID_PARALLAX;
+  out[0] = X[0];
+  out[1] = X[1];
+  out[2] = X[2];
+  return NRSLAM_B200_TRI_OK;
+}
 }  // namespace
 
 extern "C" {
+
+// Mapping::LandmarkTriangulation's per-candidate work and its vote (mapping/mapping.cc:65-205), sequential.
+int orc_landmark_triangulation_frame(const nrslam_b200_camera* cam_, int32_t n_cand, const int32_t* track_ptr,
+                                     const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
+                                     const float* nb_pos, const uint8_t* nb_valid, const uint8_t* rigid_ok,
+                                     float rad_per_pixel, int32_t min_track, float* deform_pos, int32_t* deform_status,
+                                     float* rigid_pos, int32_t* rigid_status, float* selected_pos, uint8_t* selected) {
+  Camera cam;
+  cam.model = cam_->model;
+  for (int i = 0; i < 8; i++) cam.p[i] = cam_->params[i];
+  const int NB = NRSLAM_B200_TRI_MAX_NB;
+  int n_rigid = 0, n_def = 0;
+  for (int c = 0; c < n_cand; c++) {
+    const int e0 = track_ptr[c], T = track_ptr[c + 1] - e0;
+    const float* uv = track_uv + 2 * (size_t)e0;
+    const float* pose = track_pose + 7 * (size_t)e0;
+    float d[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+    int ds;
+    if (n_neighbours[c] <= 0) {
+      ds = NRSLAM_B200_TRI_TOO_CLOSE;
+    } else if (T >= min_track) {                                         // :94
+      ds = triangulate_one(cam, T, uv, pose, n_neighbours[c], nb_pos + (size_t)e0 * NB * 3, nb_valid + (size_t)e0 * NB,
+                           0, d, nullptr);
+      if (ds != NRSLAM_B200_TRI_OK) d[0] = d[1] = d[2] = 0.f;
+    } else {
+      ds = NRSLAM_B200_TRI_SHORT_TRACK;                                  // :111-113
+    }
+    if (ds == NRSLAM_B200_TRI_OK) n_def++;                               // :100-103 (NaN results were mapped to an error)
+    const int rs = rigid_one(cam, T, uv, pose, n_neighbours[c], rigid_ok[c], rad_per_pixel, r);
+    if (rs == NRSLAM_B200_TRI_OK) n_rigid++;                             // :184-186
+    for (int i = 0; i < 3; i++) {
+      deform_pos[3 * (size_t)c + i] = d[i];
+      rigid_pos[3 * (size_t)c + i] = r[i];
+    }
+    deform_status[c] = ds;
+    rigid_status[c] = rs;
+  }
+  for (int c = 0; c < n_cand; c++) {                                     // :188-212
+    const float* pick = nullptr;
+    if (n_rigid > 1.5 * n_def) {
+      if (rigid_status[c] == NRSLAM_B200_TRI_OK) pick = rigid_pos + 3 * (size_t)c;
+    } else if (n_def >= 1.5 * n_rigid) {
+      if (deform_status[c] == NRSLAM_B200_TRI_OK) pick = deform_pos + 3 * (size_t)c;
+    }
+    if (pick && (std::isnan(pick[0]) || std::isnan(pick[1]) || std::isnan(pick[2]))) pick = nullptr;  // :210-213
+    selected[c] = pick ? 1 : 0;
+    for (int i = 0; i < 3; i++) selected_pos[3 * (size_t)c + i] = pick ? pick[i] : 0.f;
+  }
+  return 0;
+}
 
 int orc_deformable_triangulation(const nrslam_b200_camera* cam_, int32_t n_cand, const int32_t* track_ptr,
                                  const float* track_uv, const float* track_pose, const int32_t* n_neighbours,

@@ -12,10 +12,13 @@
 #include "../../include/nrslam_b200.h"
 #include "../../nr-slam_b200/csrc/nrs_tri_core.cuh"
 
-extern "C" int tri_emul_run(const nrslam_b200_camera* cam_, int32_t n_cand, const int32_t* track_ptr,
-                            const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
-                            const float* nb_pos, const uint8_t* nb_valid, float* position_out, int32_t* status_out,
-                            int32_t* lm_iterations_out) {
+// rigid_ok == nullptr: DeformableTriangulation only (nrslam_b200_tri_run); otherwise the frame mode of
+// nrslam_b200_tri_run_frame without the host-side vote.
+extern "C" int tri_emul_run_frame(const nrslam_b200_camera* cam_, int32_t n_cand, const int32_t* track_ptr,
+                                  const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
+                                  const float* nb_pos, const uint8_t* nb_valid, const uint8_t* rigid_ok,
+                                  float rad_per_pixel, int32_t min_track, float* position_out, int32_t* status_out,
+                                  int32_t* lm_iterations_out, float* rigid_out, int32_t* rigid_status) {
   nrs::Cam cam;
   cam.model = cam_->model;
   for (int i = 0; i < 8; i++) cam.p[i] = cam_->params[i];
@@ -25,11 +28,26 @@ extern "C" int tri_emul_run(const nrslam_b200_camera* cam_, int32_t n_cand, cons
     if (T < 1 || T > nrs::tri::kMaxTrack) return -3;
     smem.assign(nrs::tri::work_bytes(T) / 8 + 2, 0.0);
     int st = -1, it = 0;
+    nrs::tri::RigidArgs rg;
+    rg.enabled = rigid_ok != nullptr;
+    rg.min_track = min_track;
+    rg.rad_per_pixel = rad_per_pixel;
+    rg.rigid_ok = rg.enabled ? rigid_ok[c] : 0;
+    rg.out = rg.enabled ? rigid_out + 3 * (size_t)c : nullptr;
+    rg.status = rg.enabled ? rigid_status + c : nullptr;
     nrs::tri::solve_candidate(cam, T, track_uv + 2 * (size_t)e0, track_pose + 7 * (size_t)e0, n_neighbours[c],
                               nb_pos + (size_t)e0 * nrs::tri::kNB * 3, nb_valid + (size_t)e0 * nrs::tri::kNB,
-                              smem.data(), position_out + 3 * (size_t)c, &st, &it);
+                              smem.data(), position_out + 3 * (size_t)c, &st, &it, rg);
     status_out[c] = st;
     if (lm_iterations_out) lm_iterations_out[c] = it;
   }
   return 0;
+}
+
+extern "C" int tri_emul_run(const nrslam_b200_camera* cam_, int32_t n_cand, const int32_t* track_ptr,
+                            const float* track_uv, const float* track_pose, const int32_t* n_neighbours,
+                            const float* nb_pos, const uint8_t* nb_valid, float* position_out, int32_t* status_out,
+                            int32_t* lm_iterations_out) {
+  return tri_emul_run_frame(cam_, n_cand, track_ptr, track_uv, track_pose, n_neighbours, nb_pos, nb_valid, nullptr, 0.f,
+                            1, position_out, status_out, lm_iterations_out, nullptr, nullptr);
 }

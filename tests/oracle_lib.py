@@ -249,3 +249,25 @@ def graph_update_vertices(graph, vertices, positions):
                                      ptr(np.ascontiguousarray(positions, np.float32), C.c_float), ptr(good, C.c_int32))
     assert rc == 0
     return good
+
+
+def landmark_triangulation_frame(batch, rigid_ok, rad_per_pixel, min_track=5):
+    """orc_landmark_triangulation_frame: deformable + rigid branch + vote of Mapping::LandmarkTriangulation."""
+    L = lib()
+    n = int(batch["n_cand"])
+    dp, rp, sp = (np.zeros((n, 3), np.float32) for _ in range(3))
+    ds, rs = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    sel = np.zeros(n, np.uint8)
+    rc = L.orc_landmark_triangulation_frame(
+        C.byref(batch["cam"]), n, ptr(np.ascontiguousarray(batch["track_ptr"], np.int32), C.c_int32),
+        ptr(np.ascontiguousarray(batch["track_uv"], np.float32), C.c_float),
+        ptr(np.ascontiguousarray(batch["track_pose"], np.float32), C.c_float),
+        ptr(np.ascontiguousarray(batch["n_neighbours"], np.int32), C.c_int32),
+        ptr(np.ascontiguousarray(batch["nb_pos"], np.float32), C.c_float),
+        ptr(np.ascontiguousarray(batch["nb_valid"], np.uint8), C.c_uint8),
+        ptr(np.ascontiguousarray(rigid_ok, np.uint8), C.c_uint8), C.c_float(rad_per_pixel), int(min_track),
+        ptr(dp, C.c_float), ptr(ds, C.c_int32), ptr(rp, C.c_float), ptr(rs, C.c_int32), ptr(sp, C.c_float),
+        ptr(sel, C.c_uint8))
+    assert rc == 0
+    return dict(deform_position=dp, deform_status=ds, rigid_position=rp, rigid_status=rs, selected_position=sp,
+                selected=sel)

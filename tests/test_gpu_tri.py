@@ -148,3 +148,28 @@ def test_graph_get_edges_batch_bit_exact(core, n, k, top_k):
         assert (ent[i, :m] == ref[:m]).all() and (ent[i, m:] == -1).all()
         below += (g.rowptr[v + 1] - g.rowptr[v]) - len(ref)
     assert below > 0   # the min_weight cut was exercised
+
+
+@pytest.mark.parametrize("seed,min_track,all_rigid", [(13, 5, False), (14, 5, True), (15, 100, True)])
+def test_landmark_triangulation_frame_matches_oracle(core, seed, min_track, all_rigid):
+    """nrslam_b200_tri_run_frame = Mapping::LandmarkTriangulation's compute (mapping.cc:65-212): deformable branch for
+    tracks >= min_track, rigid branch for every candidate, and the vote. Statuses and the selection bit-exact; rigid
+    positions (pure fp32, same operation order) bit-exact; deformable positions as in the batched test."""
+    b = synth.triangulation_batch(seed=seed, n_cand=300, fail_frac=0.2, t_min=1, t_max=20)
+    rng = np.random.default_rng(seed)
+    rigid_ok = np.ones(300, np.uint8) if all_rigid else (rng.uniform(size=300) > 0.2).astype(np.uint8)
+    rpp = 0.004
+    tri = api.Triangulator(core)
+    r = tri.run_frame(b["cam"], b["track_ptr"], b["track_uv"], b["track_pose"], b["n_neighbours"], b["nb_pos"],
+                      b["nb_valid"], rigid_ok, rpp, min_track)
+    o = O.landmark_triangulation_frame(b, rigid_ok, rpp, min_track)
+    assert (r["deform_status"] == o["deform_status"]).all() and (r["rigid_status"] == o["rigid_status"]).all()
+    assert np.array_equal(r["rigid_position"], o["rigid_position"])
+    assert np.array_equal(r["selected"], o["selected"])
+    ok = o["deform_status"] == 0
+    if ok.any():
+        d = np.abs(r["deform_position"][ok] - o["deform_position"][ok]).max(axis=1)
+        assert (d <= 1e-5).mean() >= 0.99 and d.max() <= 2e-3
+    sel = o["selected"] == 1
+    assert np.abs(r["selected_position"][sel] - o["selected_position"][sel]).max(initial=0) <= 2e-3
+    tri.close()

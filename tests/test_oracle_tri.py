@@ -103,3 +103,63 @@ def test_kernel_routine_emulated_on_the_host_matches_the_oracle(seed, kw):
     ok = so == 0
     assert np.abs(po[ok] - pe[ok]).max() <= 2e-6 * 3.0
     assert (io == ie).mean() > 0.95   # noise-level trial decisions may differ (rho ~ 0 at convergence)
+
+
+def _frame_inputs(seed, n_cand):
+    """A frame the way Mapping::LandmarkTriangulation sees it: tracks of 1..20 frames (short ones skip the deformable
+    branch), a rigidity flag per candidate, rad_per_pixel of a 640x480 / 520 px focal camera scaled so that the
+    parallax window [10, 20] rad_per_pixel is hit by a good share of the candidates."""
+    b = synth.triangulation_batch(seed=seed, n_cand=n_cand, fail_frac=0.2, t_min=1, t_max=20)
+    rng = np.random.default_rng(seed)
+    rigid_ok = (rng.uniform(size=n_cand) > 0.2).astype(np.uint8)
+    return b, rigid_ok, 0.004
+
+
+def _emulate_frame(b, rigid_ok, rpp, min_track=5):
+    L = _emul_lib()
+    n = b["n_cand"]
+    dp, rp = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    ds, rs, it = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    rc = L.tri_emul_run_frame(C.byref(b["cam"]), n, ptr(b["track_ptr"], C.c_int32), ptr(b["track_uv"], C.c_float),
+                              ptr(b["track_pose"], C.c_float), ptr(b["n_neighbours"], C.c_int32),
+                              ptr(b["nb_pos"], C.c_float), ptr(b["nb_valid"], C.c_uint8), ptr(rigid_ok, C.c_uint8),
+                              C.c_float(rpp), int(min_track), ptr(dp, C.c_float), ptr(ds, C.c_int32),
+                              ptr(it, C.c_int32), ptr(rp, C.c_float), ptr(rs, C.c_int32))
+    assert rc == 0
+    return dp, ds, rp, rs
+
+
+def test_frame_mode_rigid_branch_and_vote():
+    b, rigid_ok, rpp = _frame_inputs(13, 200)
+    o = O.landmark_triangulation_frame(b, rigid_ok, rpp)
+    T = np.diff(b["track_ptr"])
+    close = b["n_neighbours"] == 0
+    assert (o["deform_status"][(T < 5) & ~close] == 10).all()          # "Short track"
+    assert (o["deform_status"][close] == 1).all() and (o["rigid_status"][close] == 1).all()
+    assert (o["rigid_status"][(rigid_ok == 0) & ~close] == 11).all()   # "Rigidity not detected"
+    assert {0, 12} <= set(o["rigid_status"].tolist())
+    n_r, n_d = (o["rigid_status"] == 0).sum(), (o["deform_status"] == 0).sum()
+    if n_r > 1.5 * n_d:
+        want = o["rigid_status"] == 0
+    elif n_d >= 1.5 * n_r:
+        want = o["deform_status"] == 0
+    else:
+        want = np.zeros(len(T), bool)
+    assert (o["selected"].astype(bool) == want).all()
+    # a rigid-dominated frame picks the rigid results
+    o2 = O.landmark_triangulation_frame(b, np.ones_like(rigid_ok), rpp, min_track=100)
+    assert (o2["deform_status"][~close] == 10).all()
+    assert (o2["selected"].astype(bool) == (o2["rigid_status"] == 0)).all() and o2["selected"].sum() > 0
+    assert np.array_equal(o2["selected_position"][o2["selected"] == 1], o2["rigid_position"][o2["selected"] == 1])
+
+
+def test_frame_mode_kernel_routine_emulated_on_the_host_matches_the_oracle():
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("CUDA headers not installed")
+    b, rigid_ok, rpp = _frame_inputs(13, 200)
+    o = O.landmark_triangulation_frame(b, rigid_ok, rpp)
+    dp, ds, rp, rs = _emulate_frame(b, rigid_ok, rpp)
+    assert (ds == o["deform_status"]).all() and (rs == o["rigid_status"]).all()
+    assert np.array_equal(rp, o["rigid_position"])                     # fp32 path, same operation order: bit-exact
+    ok = ds == 0
+    assert np.abs(dp[ok] - o["deform_position"][ok]).max() <= 6e-6
