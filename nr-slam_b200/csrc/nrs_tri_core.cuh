@@ -41,7 +41,9 @@
 #if defined(__CUDA_ARCH__)
 #define TRI_DMUL(a, b) __dmul_rn((a), (b))
 #define TRI_DADD(a, b) __dadd_rn((a), (b))
+#define TRI_FFS(m) __ffs((int)(m))
 #else
+#define TRI_FFS(m) __builtin_ffs((int)(m))
 #define TRI_DMUL(a, b) ((a) * (b))
 #define TRI_DADD(a, b) ((a) + (b))
 #endif
@@ -214,6 +216,7 @@ struct Work {
   double* dx;     // 3T last solution (stale after a failed factorisation, like g2o's _x)
   double* b;      // 3T
   double* r;      // 3T right-hand side scratch of the triangular solves
+  double* ld;     // 3T diagonal of L (kept apart so a column of the factorisation needs two barriers, not three)
   double* wpos;   // 3T world positions T_wc x
   double* err_r;  // 2T reprojection errors
   double* Jr;     // 6T numeric reprojection Jacobians (2x3 row-major)
@@ -227,15 +230,18 @@ struct Work {
   int* sfail;     // T seed failure codes
   unsigned char* cnt;  // T*T pair counts
   unsigned char* nbv;  // kNB T validity
+  unsigned short* vmask;  // T: bit j = neighbour j valid in this frame AND in the first one (edge test = one AND)
 };
 
 NRS_HD size_t work_bytes(int T) {
   const size_t n = 3 * (size_t)T;
-  size_t d = n * (n + 1) / 2 + 6 * n + 2 * T + 6 * T + 6 * T + 7 * T + 5 * kThreads + 8;
+  size_t d = n * (n + 1) / 2 + 7 * n + 2 * T + 6 * T + 6 * T + 7 * T + 5 * kThreads + 8;
   size_t bytes = d * sizeof(double);
   bytes += (size_t)3 * kNB * T * sizeof(float);
   bytes += (size_t)(8 + 2 * T) * sizeof(int);
   bytes += (size_t)T * T + (size_t)kNB * T;
+  bytes = (bytes + 1) & ~(size_t)1;
+  bytes += 2 * (size_t)T;
   return (bytes + 15) & ~(size_t)15;
 }
 TRI_DEV Work carve(void* smem, int T) {
@@ -248,6 +254,7 @@ TRI_DEV Work carve(void* smem, int T) {
   w.dx = d; d += n;
   w.b = d; d += n;
   w.r = d; d += n;
+  w.ld = d; d += n;
   w.wpos = d; d += n;
   w.err_r = d; d += 2 * T;
   w.Jr = d; d += 6 * T;
@@ -263,7 +270,9 @@ TRI_DEV Work carve(void* smem, int T) {
   w.sfail = ip; ip += T;
   unsigned char* c = reinterpret_cast<unsigned char*>(ip);
   w.cnt = c; c += (size_t)T * T;
-  w.nbv = c;
+  w.nbv = c; c += (size_t)kNB * T;
+  c = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(c) + 1) & ~(size_t)1);
+  w.vmask = reinterpret_cast<unsigned short*>(c);
   return w;
 }
 
@@ -298,8 +307,8 @@ TRI_DEV double evaluate(const Cam& cam, const Work& w, int T, int n_nb, const fl
       const double* wa = w.wpos + 3 * a;
       const double* wb = w.wpos + 3 * bb;
       const double D0 = wb[0] - wa[0], D1 = wb[1] - wa[1], D2 = wb[2] - wa[2];
-      for (int j = 0; j < n_nb; j++) {
-        if (!w.nbv[a * kNB + j] || !w.nbv[bb * kNB + j] || !w.nbv[j]) continue;
+      for (unsigned m = (unsigned)w.vmask[a] & (unsigned)w.vmask[bb]; m; m &= m - 1) {
+        const int j = TRI_FFS(m) - 1;  // ascending neighbour index, like the byte tests it replaces
         const float* pa = w.nbp + (a * kNB + j) * 3;
         const float* pb = w.nbp + (bb * kNB + j) * 3;
         const double e0 = (double)NRS_FS(pb[0], pa[0]) - D0;
@@ -361,12 +370,11 @@ TRI_DEV bool cholesky(const Work& w, int n) {
   const int KW = nt >= 16 ? 16 : nt, RW = nt / KW;
   const int tk = tid % KW, tr = tid / KW;
   for (int j = 0; j < n; j++) {
-    const double d = Wel(w, j, j);
-    if (d <= 0) return false;  // uniform: every thread reads the same value after the previous barrier
+    const double d = Wel(w, j, j);  // final since the barrier that closed the previous trailing update; never overwritten
+    if (d <= 0) return false;  // uniform: every thread reads the same value
     const double l = sqrt(d);
-    TRI_SYNC();  // everyone has read the pivot before it is overwritten
     for (int i = j + 1 + tid; i < n; i += nt) Wel(w, i, j) /= l;
-    if (tid == 0) Wel(w, j, j) = l;
+    if (tid == 0) w.ld[j] = l;
     TRI_SYNC();
     if (tr < RW)
       for (int i = j + 1 + tr; i < n; i += RW) {
@@ -379,22 +387,22 @@ TRI_DEV bool cholesky(const Work& w, int n) {
   return true;
 }
 
-// dx = (L L^T)^-1 b
+// dx = (L L^T)^-1 b. Forward substitution reads b-updates in r and writes y into dx; backward substitution updates dx
+// in place and writes the solution into r (a value is never overwritten in the step that reads it: one barrier per
+// column); the solution is copied to dx at the end.
 TRI_DEV void solve(const Work& w, int n) {
   const int tid = TRI_TID, nt = TRI_NT;
   for (int i = tid; i < n; i += nt) w.r[i] = w.b[i];
   TRI_SYNC();
   for (int j = 0; j < n; j++) {
-    const double yj = w.r[j] / Wel(w, j, j);
-    TRI_SYNC();
+    const double yj = w.r[j] / w.ld[j];
     for (int i = j + 1 + tid; i < n; i += nt) w.r[i] -= Wel(w, i, j) * yj;
-    if (tid == 0) w.r[j] = yj;
+    if (tid == 0) w.dx[j] = yj;
     TRI_SYNC();
   }
   for (int j = n - 1; j >= 0; j--) {
-    const double xj = w.r[j] / Wel(w, j, j);
-    TRI_SYNC();
-    for (int i = tid; i < j; i += nt) w.r[i] -= Wel(w, j, i) * xj;
+    const double xj = w.dx[j] / w.ld[j];
+    for (int i = tid; i < j; i += nt) w.dx[i] -= Wel(w, j, i) * xj;
     if (tid == 0) w.r[j] = xj;
     TRI_SYNC();
   }
@@ -412,27 +420,25 @@ TRI_DEV void solve3(const Work& w, int T) {
   for (int i = tid; i < n; i += nt) w.r[i] = w.b[i];
   TRI_SYNC();
   for (int j = 0; j < T; j++) {
-    const double l = Wel(w, j, j);
+    const double l = w.ld[j];
     const double y0 = w.r[3 * j] / l, y1 = w.r[3 * j + 1] / l, y2 = w.r[3 * j + 2] / l;
-    TRI_SYNC();
     for (int q = 3 * (j + 1) + tid; q < n; q += nt) {
       const int i = q / 3, c = q - 3 * i;
       w.r[q] -= Wel(w, i, j) * (c == 0 ? y0 : (c == 1 ? y1 : y2));
     }
     if (tid == 0) {
-      w.r[3 * j] = y0;
-      w.r[3 * j + 1] = y1;
-      w.r[3 * j + 2] = y2;
+      w.dx[3 * j] = y0;
+      w.dx[3 * j + 1] = y1;
+      w.dx[3 * j + 2] = y2;
     }
     TRI_SYNC();
   }
   for (int j = T - 1; j >= 0; j--) {
-    const double l = Wel(w, j, j);
-    const double x0 = w.r[3 * j] / l, x1 = w.r[3 * j + 1] / l, x2 = w.r[3 * j + 2] / l;
-    TRI_SYNC();
+    const double l = w.ld[j];
+    const double x0 = w.dx[3 * j] / l, x1 = w.dx[3 * j + 1] / l, x2 = w.dx[3 * j + 2] / l;
     for (int q = tid; q < 3 * j; q += nt) {
       const int i = q / 3, c = q - 3 * i;
-      w.r[q] -= Wel(w, j, i) * (c == 0 ? x0 : (c == 1 ? x1 : x2));
+      w.dx[q] -= Wel(w, j, i) * (c == 0 ? x0 : (c == 1 ? x1 : x2));
     }
     if (tid == 0) {
       w.r[3 * j] = x0;
@@ -556,6 +562,11 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
     for (int i = 0; i < 4; i++) Tw[i] = inv.q[i];
     for (int i = 0; i < 3; i++) Tw[4 + i] = inv.t[i];
     pose_normalize(Tw);  // g2o::SE3Quat ctor
+  }
+  for (int k = tid; k < T; k += nt) {
+    unsigned m = 0;
+    for (int j = 0; j < n_nb; j++) m |= (w.nbv[k * kNB + j] && w.nbv[j]) ? (1u << j) : 0u;
+    w.vmask[k] = (unsigned short)m;
   }
   for (int pr = tid; pr < T * T; pr += nt) {
     const int a = pr / T, bq = pr - a * T;
