@@ -228,6 +228,7 @@ struct Work {
   int* ictl;      // 8 control words: 0 status, 1 chol ok, 2 accept, 3 continue, 4 terminate, 5 qmax
   int* deg;       // T
   int* sfail;     // T seed failure codes
+  int* perm;      // 3T: coupled solves — permuted position -> dof (decoupled vertices component-major first, coupled last)
   unsigned char* cnt;  // T*T pair counts
   unsigned char* nbv;  // kNB T validity
   unsigned short* vmask;  // T: bit j = neighbour j valid in this frame AND in the first one (edge test = one AND)
@@ -238,7 +239,7 @@ NRS_HD size_t work_bytes(int T) {
   size_t d = n * (n + 1) / 2 + 7 * n + 2 * T + 6 * T + 6 * T + 7 * T + 5 * kThreads + 8;
   size_t bytes = d * sizeof(double);
   bytes += (size_t)3 * kNB * T * sizeof(float);
-  bytes += (size_t)(8 + 2 * T) * sizeof(int);
+  bytes += (size_t)(8 + 5 * T) * sizeof(int);
   bytes += (size_t)T * T + (size_t)kNB * T;
   bytes = (bytes + 1) & ~(size_t)1;
   bytes += 2 * (size_t)T;
@@ -268,6 +269,7 @@ TRI_DEV Work carve(void* smem, int T) {
   w.ictl = ip; ip += 8;
   w.deg = ip; ip += T;
   w.sfail = ip; ip += T;
+  w.perm = ip; ip += 3 * T;
   unsigned char* c = reinterpret_cast<unsigned char*>(ip);
   w.cnt = c; c += (size_t)T * T;
   w.nbv = c; c += (size_t)kNB * T;
@@ -387,12 +389,12 @@ TRI_DEV bool cholesky(const Work& w, int n) {
   return true;
 }
 
-// dx = (L L^T)^-1 b. Forward substitution reads b-updates in r and writes y into dx; backward substitution updates dx
+// dx = P^T (L L^T)^-1 P b for the factor of the PERMUTED matrix (perm[position] = dof). Forward substitution reads b-updates in r and writes y into dx; backward substitution updates dx
 // in place and writes the solution into r (a value is never overwritten in the step that reads it: one barrier per
 // column); the solution is copied to dx at the end.
-TRI_DEV void solve(const Work& w, int n) {
+TRI_DEV void solve(const Work& w, int n, const int* perm) {
   const int tid = TRI_TID, nt = TRI_NT;
-  for (int i = tid; i < n; i += nt) w.r[i] = w.b[i];
+  for (int i = tid; i < n; i += nt) w.r[i] = w.b[perm[i]];
   TRI_SYNC();
   for (int j = 0; j < n; j++) {
     const double yj = w.r[j] / w.ld[j];
@@ -406,7 +408,7 @@ TRI_DEV void solve(const Work& w, int n) {
     if (tid == 0) w.r[j] = xj;
     TRI_SYNC();
   }
-  for (int i = tid; i < n; i += nt) w.dx[i] = w.r[i];
+  for (int i = tid; i < n; i += nt) w.dx[perm[i]] = w.r[i];
   TRI_SYNC();
 }
 
@@ -637,6 +639,31 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
       for (int c = 0; c < 3; c++) w.b[3 * k + c] += J[c] * we0 + J[3 + c] * we1;
     }
     TRI_SYNC();
+    // Coupled linearisation: order the decoupled vertices first, component-major (three T' x T' diagonal blocks with
+    // nothing between them), and the vertices whose reprojection block is non-zero last. The dense factorisation of
+    // the permuted matrix then skips the structurally zero rows (L(i,j) == 0 test): its work is three T'^3 / 6
+    // blocks plus a thin dense border instead of (3T)^3 / 6.
+    if (w.ictl[1] != 0 && tid == 0) {
+      int Tp = 0;
+      for (int k = 0; k < T; k++) {
+        const double* H = w.Hr + 6 * k;
+        const bool nzk = H[0] != 0.0 || H[1] != 0.0 || H[2] != 0.0 || H[3] != 0.0 || H[4] != 0.0 || H[5] != 0.0;
+        Tp += nzk ? 0 : 1;
+      }
+      int r = 0, sdx = 0;
+      for (int k = 0; k < T; k++) {
+        const double* H = w.Hr + 6 * k;
+        const bool nzk = H[0] != 0.0 || H[1] != 0.0 || H[2] != 0.0 || H[3] != 0.0 || H[4] != 0.0 || H[5] != 0.0;
+        if (!nzk) {
+          for (int c = 0; c < 3; c++) w.perm[c * Tp + r] = 3 * k + c;
+          r++;
+        } else {
+          for (int c = 0; c < 3; c++) w.perm[3 * Tp + 3 * sdx + c] = 3 * k + c;
+          sdx++;
+        }
+      }
+    }
+    TRI_SYNC();
     if (it == 0) {  // computeLambdaInit :153-165 — every thread computes the same value
       double md = 0;
       for (int k = 0; k < T; k++) {
@@ -662,28 +689,30 @@ TRI_DEV void solve_candidate(const Cam& cam, int T, const float* uv, const float
           row[i] = TRI_DADD(TRI_DMUL(omega, (double)w.deg[i]), lambda);
         }
       } else
-      for (int i = tid; i < n; i += nt) {
+      for (int pi = tid; pi < n; pi += nt) {
+        const int i = w.perm[pi];
         const int a = i / 3, ci = i - 3 * a;
-        double* row = w.W + (size_t)i * (i + 1) / 2;
-        for (int j = 0; j <= i; j++) {
+        double* row = w.W + (size_t)pi * (pi + 1) / 2;
+        for (int pj = 0; pj <= pi; pj++) {
+          const int j = w.perm[pj];
           const int bq = j / 3, cj = j - 3 * bq;
           double v = 0;
           if (a == bq) {
-            const int lo = cj, hi = ci;  // cj <= ci inside the diagonal block
+            const int lo = cj < ci ? cj : ci, hi = cj < ci ? ci : cj;
             const int q = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
             v = w.Hr[6 * a + q];
             if (ci == cj) v += TRI_DADD(TRI_DMUL(omega, (double)w.deg[a]), lambda);  // same roundings as the decoupled path
           } else if (ci == cj) {
             v = -omega * (double)w.cnt[a * T + bq];
           }
-          row[j] = v;
+          row[pj] = v;
         }
       }
       TRI_SYNC();
       const bool ok2 = cholesky(w, coupled ? n : T);
       TRI_SYNC();
       if (ok2) {
-        if (coupled) solve(w, n); else solve3(w, T);
+        if (coupled) solve(w, n, w.perm); else solve3(w, T);
       }
       for (int i = tid; i < n; i += nt) w.x[i] += w.dx[i];
       TRI_SYNC();
