@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <numeric>
 #include <set>
+#include <thread>
 #include <vector>
 
 #include "nrs_host.h"
@@ -178,8 +179,12 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of) {
   if (hp.n_sort <= 1 || hp.points_fixed) return;
   std::vector<int> old_of_new(V);
   std::iota(old_of_new.begin(), old_of_new.end(), 0);
+  // keyframes are sorted independently: host threads take them round robin on large windows (same result)
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int n_threads = std::max(1, std::min(std::min(hp.F, hw > 0 ? hw : 1), V >= 4096 ? 16 : 1));
+  auto work = [&](int tix) {
   std::vector<std::pair<uint32_t, int>> keyed;
-  for (int k = 0; k < hp.F; k++) {
+  for (int k = tix; k < hp.F; k += n_threads) {
     const int b = hp.kf_begin[k], e = std::min(hp.kf_begin[k + 1], hp.n_sort);
     if (e - b < 2) continue;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -201,6 +206,15 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of) {
     }
     std::sort(keyed.begin(), keyed.end());
     for (int t = 0; t < e - b; t++) old_of_new[b + t] = keyed[t].second;
+  }
+  };
+  if (n_threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
   }
   for (int nw = 0; nw < V; nw++) row_of[old_of_new[nw]] = nw;
   auto permute = [&](std::vector<double>& v, int stride) {
@@ -1225,71 +1239,138 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
 
   // ---- springs inside a keyframe, dampers to the next newer keyframe (:982-1136)
   // sorted neighbour lists are cached per map point; (pair, keyframe) de-duplication is keyed by graph edge
-  std::vector<int> nb_ptr(M + 1, -1), nb_cnt(M, 0), nb_ent;
-  std::vector<int> cur(M, -1), nxt(M, -1);  // inserted_landmarks[k][mappoint] -> row
-  std::vector<int> spring_stamp(g->n_edges, -1), damper_stamp(g->n_edges, -1);
-  for (int o = hp.kf_begin[0]; o < hp.kf_begin[1]; o++) cur[obs_vertex[o]] = o;
-  for (int k = 0; k < F; k++) {
-    const bool has_next = k + 1 < F;
-    if (has_next)
-      for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) nxt[obs_vertex[o]] = o;
-    for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) {
+  // The sorted list of a map point is stored as (neighbour, edge) pairs, already cut at the first weight < min_weight
+  // (GetEdges) and at the first BAD edge (the loops' break; BAD sorts last), so the scans below read sequential memory.
+  std::vector<int> nb_ptr(M + 1, -1), nb_cnt(M, 0);
+  std::vector<int> nb_pair;  // 2 ints per entry: neighbour vertex, undirected edge id
+  {
+    std::vector<std::pair<unsigned long long, int>> keyed;
+    nb_pair.reserve(2 * (size_t)g->rowptr[M]);
+    std::vector<char> seen(M, 0);
+    for (int o = 0; o < O; o++) {
       const int mp = obs_vertex[o];
-      if (nb_ptr[mp] < 0) {
-        nb_ptr[mp] = (int)nb_ent.size();
-        nb_cnt[mp] = graph_sorted_entries(g, mp, min_w, nb_ent);
+      if (seen[mp]) continue;
+      seen[mp] = 1;
+      // GetEdges order (regularization_graph.cc:61-87): status asc, weight desc, neighbour asc — one 64-bit key
+      // (weights are non-negative floats: their bit patterns order like their values)
+      keyed.clear();
+      for (int p = g->rowptr[mp]; p < g->rowptr[mp + 1]; p++) {
+        const int ge = g->eid[p];
+        unsigned wb;
+        const float wgt = g->weight[ge];
+        memcpy(&wb, &wgt, 4);
+        const unsigned long long key = ((unsigned long long)(g->status[ge] & 3u) << 62) |
+                                       ((unsigned long long)(0xFFFFFFFFu - wb) << 30) |
+                                       (unsigned long long)(g->col[p] & 0x3FFFFFFF);
+        keyed.emplace_back(key, p);
       }
-      const int* ents = nb_ent.data() + nb_ptr[mp];
-      const int ne = nb_cnt[mp];
-      int n_regularizers = 0;
-      for (int t = 0; t < ne; t++) {
-        const int other = g->col[ents[t]], ge = g->eid[ents[t]];
-        if (n_regularizers > regularizers_per_point || g->status[ge] == NRSLAM_EDGE_BAD) break;  // :1035-1037
-        const int oidx = cur[other];
-        if (oidx < 0) continue;
-        if (spring_stamp[ge] == k) {  // :1049-1052 already inserted from the other endpoint
-          n_regularizers++;
-          continue;
-        }
-        spring_stamp[ge] = k;
-        hp.pair_i.push_back(o);
-        hp.pair_j.push_back(oidx);
-        hp.pair_w.push_back(-1.0);
-        hp.pair_d0.push_back((double)g->first_distance[ge]);
-        n_regularizers++;
+      std::sort(keyed.begin(), keyed.end());
+      nb_ptr[mp] = (int)nb_pair.size() / 2;
+      int cnt = 0;
+      for (const auto& kp : keyed) {
+        const int ge = g->eid[kp.second];
+        if (g->weight[ge] < min_w || g->status[ge] == NRSLAM_EDGE_BAD) break;  // GetEdges cut ; :1035-1037 break
+        nb_pair.push_back(g->col[kp.second]);
+        nb_pair.push_back(ge);
+        cnt++;
       }
-      if (has_next) {
-        const int nlidx = nxt[mp];
-        if (nlidx < 0) continue;
-        int n_reg2 = 0;
-        for (int t = 0; t < ne; t++) {
-          const int other = g->col[ents[t]], ge = g->eid[ents[t]];
-          if (n_reg2 > regularizers_per_point || g->status[ge] == NRSLAM_EDGE_BAD) break;
-          const int oidx = cur[other], noidx = nxt[other];
-          if (oidx < 0 || noidx < 0) continue;
-          if (damper_stamp[ge] == k) {
-            n_reg2++;
-            continue;
-          }
-          damper_stamp[ge] = k;
-          hp.dmp_v.push_back(o);
-          hp.dmp_v.push_back(oidx);
-          hp.dmp_v.push_back(nlidx);
-          hp.dmp_v.push_back(noidx);
-          hp.dmp_w.push_back((double)g->weight[ge]);
-          n_reg2++;
-        }
-      }
-    }
-    // slide: cur <- nxt
-    for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) cur[obs_vertex[o]] = -1;
-    if (has_next) {
-      for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) {
-        cur[obs_vertex[o]] = o;
-        nxt[obs_vertex[o]] = -1;
-      }
+      nb_cnt[mp] = cnt;
     }
   }
+  // Keyframes are independent here (a spring joins two points of ONE keyframe, a damper reads keyframes k and k + 1,
+  // the reference's de-duplication maps are per keyframe): host threads take keyframes round robin, every keyframe
+  // fills its own edge lists in the reference's order, and the lists are concatenated in keyframe order afterwards, so
+  // the result is identical to the sequential loop whatever the thread count.
+  struct KfEdges {
+    std::vector<int> pair_i, pair_j, dmp_v;
+    std::vector<double> pair_d0, dmp_w;
+  };
+  std::vector<KfEdges> per_kf(F);
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int n_threads = std::max(1, std::min(std::min(F, hw > 0 ? hw : 1), O >= 4096 ? 16 : 1));
+  auto work = [&](int tix) {
+    std::vector<int> cur(M, -1), nxt(M, -1);  // inserted_landmarks[k][mappoint] -> row
+    std::vector<int> spring_stamp(g->n_edges, -1), damper_stamp(g->n_edges, -1);
+    for (int k = tix; k < F; k += n_threads) {
+      KfEdges& out = per_kf[k];
+      const bool has_next = k + 1 < F;
+      const int nk = hp.kf_begin[k + 1] - hp.kf_begin[k];
+      out.pair_i.reserve(6 * (size_t)nk); out.pair_j.reserve(6 * (size_t)nk); out.pair_d0.reserve(6 * (size_t)nk);
+      out.dmp_v.reserve(20 * (size_t)nk); out.dmp_w.reserve(5 * (size_t)nk);
+      for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) cur[obs_vertex[o]] = o;
+      if (has_next)
+        for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) nxt[obs_vertex[o]] = o;
+      for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) {
+        const int mp = obs_vertex[o];
+        const int* ents = nb_pair.data() + 2 * (size_t)nb_ptr[mp];
+        const int ne = nb_cnt[mp];
+        int n_regularizers = 0;
+        for (int t = 0; t < ne; t++) {
+          const int other = ents[2 * t], ge = ents[2 * t + 1];
+          if (n_regularizers > regularizers_per_point) break;  // :1035-1037 (BAD edges are already cut off)
+          const int oidx = cur[other];
+          if (oidx < 0) continue;
+          if (spring_stamp[ge] == k) {  // :1049-1052 already inserted from the other endpoint
+            n_regularizers++;
+            continue;
+          }
+          spring_stamp[ge] = k;
+          out.pair_i.push_back(o);
+          out.pair_j.push_back(oidx);
+          out.pair_d0.push_back((double)g->first_distance[ge]);
+          n_regularizers++;
+        }
+        if (has_next) {
+          const int nlidx = nxt[mp];
+          if (nlidx < 0) continue;
+          int n_reg2 = 0;
+          for (int t = 0; t < ne; t++) {
+            const int other = ents[2 * t], ge = ents[2 * t + 1];
+            if (n_reg2 > regularizers_per_point) break;
+            const int oidx = cur[other], noidx = nxt[other];
+            if (oidx < 0 || noidx < 0) continue;
+            if (damper_stamp[ge] == k) {
+              n_reg2++;
+              continue;
+            }
+            damper_stamp[ge] = k;
+            out.dmp_v.push_back(o);
+            out.dmp_v.push_back(oidx);
+            out.dmp_v.push_back(nlidx);
+            out.dmp_v.push_back(noidx);
+            out.dmp_w.push_back((double)g->weight[ge]);
+            n_reg2++;
+          }
+        }
+      }
+      for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) cur[obs_vertex[o]] = -1;
+      if (has_next)
+        for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) nxt[obs_vertex[o]] = -1;
+    }
+  };
+  if (n_threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+  }
+  size_t np = 0, nd = 0;
+  for (const auto& e : per_kf) {
+    np += e.pair_i.size();
+    nd += e.dmp_w.size();
+  }
+  hp.pair_i.reserve(np); hp.pair_j.reserve(np); hp.pair_d0.reserve(np);
+  hp.dmp_v.reserve(4 * nd); hp.dmp_w.reserve(nd);
+  for (const auto& e : per_kf) {
+    hp.pair_i.insert(hp.pair_i.end(), e.pair_i.begin(), e.pair_i.end());
+    hp.pair_j.insert(hp.pair_j.end(), e.pair_j.begin(), e.pair_j.end());
+    hp.pair_d0.insert(hp.pair_d0.end(), e.pair_d0.begin(), e.pair_d0.end());
+    hp.dmp_v.insert(hp.dmp_v.end(), e.dmp_v.begin(), e.dmp_v.end());
+    hp.dmp_w.insert(hp.dmp_w.end(), e.dmp_w.begin(), e.dmp_w.end());
+  }
+  hp.pair_w.assign(np, -1.0);
   hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE};
   hp.op_args = {0, 0, iterations};
   hp.n_sort = O;
@@ -1660,19 +1741,24 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
   if (F < 3) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: fewer than 3 keyframes");  // :922-924
   if (O == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba: no observations");
   NRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  HostProf hprof;
   HostProblem hp;
   {
     const int brc = build_ba_problem(ctx, ctx->opt, cam, F, kf_pose_io, O, obs_kf, obs_vertex, uv, X_io, g, scale,
                                      iterations, hp);
     if (brc) return brc;
   }
+  hprof.mark("build_graph");
   Staged& st = ctx->staged[2];
   int rc = stage_problem(ctx, st, hp);
   if (rc) return rc;
+  hprof.mark("stage");
   const double t1 = wall_ms();
   if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes;
   rc = run_staged(ctx, st, stats);
   if (rc) return rc;
+  hprof.mark("run");
+  hprof.print("local_ba");
   const double* pose = st.out.h<double>(st.o_pose);
   const double* xd = st.out.h<double>(st.o_x);
   for (int i = 0; i < 7 * F; i++)
