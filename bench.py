@@ -69,14 +69,21 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """windows: [(t0, t1), ...] perf_counter intervals of the timed regions. Samples that arrived inside them are
+        used; a run too short to catch one (nvidia-smi needs ~0.3 s to start) falls back to every sample taken while
+        the sampler ran (warm-up and timed steps, the GPU is busy throughout) and says so in samples_in_timed_region."""
         if self.proc:
             self.proc.terminate()
+        lines = list(self.lines)
+        inside = [ln for (t, ln) in lines if windows and any(a <= t <= b for a, b in windows)]
+        n_inside = len(inside)
+        use = inside if inside else [ln for (_, ln) in lines]
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in use:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -90,7 +97,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_region": n_inside}
 
 
 def algorithmic_bytes(st, n_pose_edges=0):
@@ -237,6 +244,8 @@ def main():
         return r0, r1
 
     # ---- end-to-end through the C ABI (host buffers in, host results out)
+    sampler = ClockSampler(local_rank)   # started before the warm-up: nvidia-smi needs a few 100 ms to deliver its first line
+    sampler.start()
     for _ in range(args.warmup):
         frame_e2e()
     barrier()
@@ -245,6 +254,7 @@ def main():
         r0, r1 = frame_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_window = (t0, t0 + e2e_s)
     h2d = r0["stats"]["h2d_bytes"] + r1["stats"]["h2d_bytes"]
     d2h = r0["stats"]["d2h_bytes"] + r1["stats"]["d2h_bytes"]
     e2e_launches = r0["stats"]["kernel_launches"] + r1["stats"]["kernel_launches"]
@@ -254,8 +264,6 @@ def main():
         klt.retrack()
         core.resolve(0)
         core.resolve(1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     dev_ms = 0.0
     klt_ms = 0.0
@@ -270,7 +278,7 @@ def main():
         dev_ms += kms + s0["gpu_ms"] + s1["gpu_ms"]
     barrier()
     wall_s = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop([e2e_window, (wall0, wall0 + wall_s)])
     # the same frames without the KLT stage (optimisation only), end to end
     def frame_opt_only():
         r0 = core.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
