@@ -51,3 +51,28 @@ def test_partition_is_deterministic(window):
     a = api.shard_partition(4, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"], p["scale"])
     b = api.shard_partition(4, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"], p["scale"])
     assert np.array_equal(a["owner"], b["owner"]) and np.array_equal(a["n_halo"], b["n_halo"])
+
+
+@pytest.mark.parametrize("n,n_kf,threads_path", [(300, 6, False), (900, 8, True)])
+def test_graph_construction_matches_the_oracle_edge_for_edge_counts(n, n_kf, threads_path):
+    """The host graph build of the BA window (springs / dampers per keyframe, g2o_optimization.cc:982-1136) against the
+    oracle's, on a graph with mixed edge statuses, tied weights and weights below min_weight — the cases that exercise
+    the GetEdges order (status asc, weight desc, neighbour asc) and its cut. The larger window (>= 4096 observations)
+    takes the keyframe-parallel path; the counts must not depend on it."""
+    import oracle_lib
+    p = synth.ba_problem("c3", n=n, n_kf=n_kf, run=6)
+    g = p["graph"]
+    rng = np.random.default_rng(n)
+    g.status[:] = rng.choice([0, 1, 2, 2, 2, 3], g.n_edges).astype(np.uint8)
+    tie = rng.choice(g.n_edges, g.n_edges // 4, replace=False)
+    g.weight[tie] = np.float32(0.8)
+    low = rng.choice(g.n_edges, g.n_edges // 10, replace=False)
+    g.weight[low] = np.float32(1e-3)
+    assert (len(p["obs_kf"]) >= 4096) == threads_path
+    one = api.shard_partition(1, p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], g, p["scale"])
+    opt = oracle_lib.default_options()
+    opt.ba_iterations = 1
+    ref = oracle_lib.Oracle(opt).local_ba(p["cam"], p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], g,
+                                          p["scale"])
+    assert one["n_edges"][0, 0] == ref["stats"]["n_spring_edges"]
+    assert one["n_edges"][0, 1] == ref["stats"]["n_damper_edges"]
