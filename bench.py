@@ -201,6 +201,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # one process per GPU shares the host cores: cap the library's staging threads (BA graph build) per rank
+    os.environ.setdefault("NRSLAM_B200_HOST_THREADS", str(max(1, min(16, len(os.sched_getaffinity(0)) // world))))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dist = None

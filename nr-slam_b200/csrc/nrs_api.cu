@@ -49,6 +49,19 @@ struct HostProf {
   }
 };
 
+// Host threads for the keyframe-parallel staging of large BA windows: min(items, cores, 16), capped by
+// NRSLAM_B200_HOST_THREADS (one process per GPU shares the host: set it to cores / ranks there). 1 for small problems.
+int host_threads(int items, int problem_size) {
+  if (problem_size < 4096) return 1;
+  static const int cap = [] {
+    const char* e = getenv("NRSLAM_B200_HOST_THREADS");
+    const int v = e ? atoi(e) : 16;
+    return v < 1 ? 1 : v;
+  }();
+  const int hw = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(std::min(items, hw > 0 ? hw : 1), cap));
+}
+
 int fail(nrslam_b200_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
@@ -180,8 +193,7 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of) {
   std::vector<int> old_of_new(V);
   std::iota(old_of_new.begin(), old_of_new.end(), 0);
   // keyframes are sorted independently: host threads take them round robin on large windows (same result)
-  const int hw = (int)std::thread::hardware_concurrency();
-  const int n_threads = std::max(1, std::min(std::min(hp.F, hw > 0 ? hw : 1), V >= 4096 ? 16 : 1));
+  const int n_threads = host_threads(hp.F, V);
   auto work = [&](int tix) {
   std::vector<std::pair<uint32_t, int>> keyed;
   for (int k = tix; k < hp.F; k += n_threads) {
@@ -1286,8 +1298,7 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
     std::vector<double> pair_d0, dmp_w;
   };
   std::vector<KfEdges> per_kf(F);
-  const int hw = (int)std::thread::hardware_concurrency();
-  const int n_threads = std::max(1, std::min(std::min(F, hw > 0 ? hw : 1), O >= 4096 ? 16 : 1));
+  const int n_threads = host_threads(F, O);
   auto work = [&](int tix) {
     std::vector<int> cur(M, -1), nxt(M, -1);  // inserted_landmarks[k][mappoint] -> row
     std::vector<int> spring_stamp(g->n_edges, -1), damper_stamp(g->n_edges, -1);
