@@ -92,11 +92,13 @@ def _emulate(b):
 
 
 @pytest.mark.parametrize("seed,kw", [(7, {}), (8, dict(t_min=30, t_max=41)),
-                                     (9, dict(cam_spec=synth.CONFIGS["c4"]["cam"], size=synth.CONFIGS["c4"]["size"]))])
+                                     (9, dict(cam_spec=synth.CONFIGS["c4"]["cam"], size=synth.CONFIGS["c4"]["size"])),
+                                     (10, dict(t_min=44, t_max=48)),      # NRSLAM_B200_TRI_MAX_TRACK
+                                     (11, dict(t_min=1, t_max=3))])       # degenerate: one-frame tracks
 def test_kernel_routine_emulated_on_the_host_matches_the_oracle(seed, kw):
     if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
         pytest.skip("CUDA headers not installed")
-    b = synth.triangulation_batch(seed=seed, n_cand=100, fail_frac=0.3, **kw)
+    b = synth.triangulation_batch(seed=seed, n_cand=100 if kw.get("t_max", 20) < 44 else 40, fail_frac=0.3, **kw)
     po, so, io = O.deformable_triangulation(b)
     pe, se, ie = _emulate(b)
     assert (so == se).all()
