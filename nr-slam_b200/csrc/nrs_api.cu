@@ -21,6 +21,7 @@
 #include <thread>
 #include <vector>
 
+#include "nrs_direct_plan.h"
 #include "nrs_host.h"
 
 using namespace nrs;
@@ -153,6 +154,7 @@ struct HostProblem {
   std::vector<int> kf_begin;            // F+1: rows of pose slot k are [kf_begin[k], kf_begin[k+1]) (rows w/o pose: slot 0)
   int n_halo = 0;                       // landmark-sharded BA: trailing rows owned by other ranks (read-only copies)
   bool sharded = false;
+  bool direct = false;                  // tracking main rounds: exact multifrontal LL^T engine (nrs_direct.cu)
   std::vector<int> ops, op_args;
 };
 
@@ -185,13 +187,16 @@ inline uint32_t morton3(const double* p, const double* lo, const double* inv_ext
 
 // Re-order the first hp.n_sort rows of every pose-slot group along a Morton curve of their positions and rewrite
 // every row index of the problem. row_of[old] = new.
-void sort_rows(HostProblem& hp, std::vector<int>& row_of) {
+void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>* forced_old_of_new = nullptr) {
   const int V = hp.V;
   row_of.resize(V);
   std::iota(row_of.begin(), row_of.end(), 0);
-  if (hp.n_sort <= 1 || hp.points_fixed) return;
+  if (!forced_old_of_new && (hp.n_sort <= 1 || hp.points_fixed)) return;
   std::vector<int> old_of_new(V);
   std::iota(old_of_new.begin(), old_of_new.end(), 0);
+  if (forced_old_of_new) {
+    old_of_new = *forced_old_of_new;  // elimination order of the exact solve (nrs_direct_plan.h)
+  } else {
   // keyframes are sorted independently: host threads take them round robin on large windows (same result)
   const int n_threads = host_threads(hp.F, V);
   auto work = [&](int tix) {
@@ -227,6 +232,7 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of) {
     for (int t = 1; t < n_threads; t++) pool.emplace_back(work, t);
     work(0);
     for (auto& th : pool) th.join();
+  }
   }
   for (int nw = 0; nw < V; nw++) row_of[old_of_new[nw]] = nw;
   auto permute = [&](std::vector<double>& v, int stride) {
@@ -443,8 +449,28 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   const int F = hp.F, V = hp.V, P = (int)hp.pair_i.size(), D = (int)hp.dmp_w.size();
   const int U = (int)hp.un_w.size();
   st.valid = false;
+  st.use_direct = false;
   HostProf hprof;
-  sort_rows(hp, st.row_of);
+  // ---- exact-solve engine: symbolic analysis first, its elimination order becomes the row order
+  DirectPlanHost dplan;
+  bool direct = hp.direct && F == 1 && D == 0 && U == 0 && !hp.poses_fixed && !hp.points_fixed && !hp.sharded &&
+                hp.fixed0.empty() && hp.n_stage1 == 0 && V >= 1;
+  size_t dsmem = 0;
+  int dscratch = 0;
+  if (direct) {
+    const int depth = std::min(direct_depth(V, ctx->sm_count), env_int("NRSLAM_B200_DIRECT_DEPTH", 7));
+    build_direct_plan(V, hp.uv.data(), hp.pair_i, hp.pair_j, depth, dplan);
+    int max_ns = 0;
+    for (int t = 1; t <= dplan.n_nodes; t++) max_ns = std::max(max_ns, 3 * dplan.nv[t]);
+    dscratch = max_ns * (1 + direct_block_threads() / 32);
+    dsmem = direct_smem_bytes(dplan.max_path, dscratch, dplan.smem_doubles);
+    // the busiest team member's panel must fit one SM, the whole grid must be co-resident, one row group per thread
+    if (dsmem > 226 * 1024 || direct_max_grid(dsmem) < dplan.G ||
+        (V + dplan.G - 1) / dplan.G > direct_block_threads())
+      direct = false;
+  }
+  hprof.mark("direct_plan");
+  sort_rows(hp, st.row_of, direct ? &dplan.old_of_new : nullptr);
   hprof.mark("sort_rows");
 
   // incidence lists
@@ -497,6 +523,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     // the cluster-native CG loop (nrs_engine.cu: pcg_cluster) exchanges z through pushed halos
     if (pl->n_chunks == 0 || !pl->cluster_mode || !pl->resident || F != 1 || D != 0 || hp.points_fixed) continue;
     if (!env_int("NRSLAM_B200_HALO_PUSH", 1) || pl->n_chunks >= 65536) continue;
+    if (direct && pl == &planA) continue;  // the exact-solve engine runs this plan: no CG loop, no halos
     build_halo(*pl, inc_ptr, inc_other);
     // the coarse level needs the dense block preconditioner's layout and at most 16 aggregates
     int coarse = env_int("NRSLAM_B200_COARSE", 1) && pl->block_prec && pl->n_chunks <= 16 && pl->halo_rows < 255 * 256;
@@ -533,6 +560,13 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   sz((size_t)max_chunks * 4 * 3 * 2); sz(((size_t)F + 1) * 4 * 2);
   for (Plan* pl : {&planA, &planB}) {
     sz(pl->inc_halo.size() * 4); sz(pl->push_ptr.size() * 4); sz(pl->push_row.size() * 4); sz(pl->push_dst.size() * 4); sz(pl->xinc_ptr.size() * 4); sz(pl->xinc_idx.size() * 4);
+  }
+  std::vector<int> inc_pos;
+  if (direct) {
+    direct_inc_pos(dplan, inc_ptr, inc_other, inc_pos);
+    const size_t T1 = (size_t)dplan.n_nodes + 2;
+    sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 8); sz(T1 * 8);
+    sz(dplan.bnd.size() * 4); sz(dplan.bpath.size() * 4); sz(dplan.inv.size() * 4); sz(inc_pos.size() * 4);
   }
   need += 8192;
   if (!st.in.reserve(need, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "input arena allocation failed");
@@ -601,6 +635,22 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
       pl->d_xinc_idx = in.d<int>(put(in, pl->xinc_idx));
     }
   }
+  if (direct) {
+    direct::Plan& dp = st.dq.pl;
+    dp.V = V; dp.depth = dplan.depth; dp.G = dplan.G; dp.max_path = dplan.max_path;
+    dp.vb = in.d<int>(put(in, dplan.vb));
+    dp.nv = in.d<int>(put(in, dplan.nv));
+    dp.nbv = in.d<int>(put(in, dplan.nbv));
+    dp.bnd_ptr = in.d<int>(put(in, dplan.bnd_ptr));
+    dp.bnd = in.d<int>(put(in, dplan.bnd));
+    dp.bpath = in.d<int>(put(in, dplan.bpath));
+    dp.path_off = in.d<int>(put(in, dplan.path_off));
+    dp.inv_ptr = in.d<int>(put(in, dplan.inv_ptr));
+    dp.inv = in.d<int>(put(in, dplan.inv));
+    dp.p_off = in.d<long long>(put(in, dplan.p_off));
+    dp.u_off = in.d<long long>(put(in, dplan.u_off));
+    st.dq.inc_pos = in.d<int>(put(in, inc_pos));
+  }
   apply_plan(p, planA);
   st.h2d_bytes = in.used();
   st.block = planA.block;
@@ -635,6 +685,9 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   Arena& wk = st.work;
   size_t wneed = (size_t)V * 8 * (4 + 20 + 8 + 4 + 8 + 4 * 5) + (size_t)P * 40 + (size_t)D * 32 +
                  2 * (size_t)max_chunks * kChunkVals * 8 + 2 * (size_t)max_grid_used * kSlotVals * 8 + 32 * 256 + 4096;
+  if (direct)
+    wneed += ((size_t)dplan.p_total + (size_t)dplan.u_total + 18 * (size_t)V + (size_t)dplan.G * (28 + 4) + 64) * 8 +
+             16 * 256;
   if (!wk.reserve(wneed, false)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "work arena allocation failed");
   p.x_bak = wk.d<double>(wk.take<double>(4 * (size_t)V));
   p.jac = wk.d<double>(wk.take<double>(20 * (size_t)V));
@@ -652,6 +705,22 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   p.chunk_part = wk.d<double>(wk.take<double>(2 * (size_t)max_chunks * kChunkVals));
   p.slots = wk.d<double>(wk.take<double>(2 * (size_t)max_grid_used * kSlotVals));
   p.bar = ctx->bar;
+  if (direct) {
+    DirectParams& q = st.dq;
+    q.pl.panel = wk.d<double>(wk.take<double>((size_t)dplan.p_total + 1));
+    q.pl.upd = wk.d<double>(wk.take<double>((size_t)dplan.u_total + 1));
+    q.pl.fail = wk.d<int>(wk.take<int>(4));
+    q.cpl = wk.d<double>(wk.take<double>(18 * (size_t)V));
+    q.hpp_part = wk.d<double>(wk.take<double>(28 * (size_t)dplan.G));
+    q.hpp = wk.d<double>(wk.take<double>(28));
+    q.dslots = wk.d<double>(wk.take<double>(4 * (size_t)dplan.G));
+    q.dpose = wk.d<double>(wk.take<double>(8));
+    q.scratch_z = dscratch;
+    q.P = p;
+    st.use_direct = true;
+    st.dgrid = dplan.G;
+    st.dsmem = dsmem;
+  }
   if (st.has_plan2) {
     st.p2 = p;
     apply_plan(st.p2, planB);
@@ -674,8 +743,10 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
                const Params* override_params = nullptr, bool plan2 = false) {
   if (!st.valid) return fail(ctx, NRSLAM_B200_ERR_ARG, "no staged problem");
   NRS_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  const int rc = launch_engine(override_params ? *override_params : st.p, plan2 ? st.grid2 : st.grid,
-                               plan2 ? st.block2 : st.block, plan2 ? st.smem2 : st.smem, ctx->stream);
+  const bool direct = st.use_direct && !override_params && !plan2;
+  const int rc = direct ? launch_direct(st.dq, st.dgrid, st.dsmem, ctx->stream)
+                        : launch_engine(override_params ? *override_params : st.p, plan2 ? st.grid2 : st.grid,
+                                        plan2 ? st.block2 : st.block, plan2 ? st.smem2 : st.smem, ctx->stream);
   if (rc != 0)
     return fail(ctx, NRSLAM_B200_ERR_CUDA, std::string("engine launch: ") + cudaGetErrorString((cudaError_t)rc));
   NRS_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -697,15 +768,16 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
     stats->n_chi2_passes += es->n_chi2_passes;
     stats->kernel_launches += 1;
     if (!plan2) {
-      stats->grid_ctas = st.grid;
-      stats->block_threads = st.block;
+      stats->grid_ctas = direct ? st.dgrid : st.grid;
+      stats->block_threads = direct ? direct_block_threads() : st.block;
     }
     stats->d2h_bytes += copy_back ? (int64_t)st.out.used() : (int64_t)sizeof(EngineStats);
     for (int i = 0; i < es->n_trace && stats->n_trace < NRSLAM_B200_TRACE; i++)
       stats->chi2_trace[stats->n_trace++] = es->chi2_trace[i];
     stats->lambda_final = es->lambda_final;
     if (getenv("NRSLAM_B200_PROF")) {
-      fprintf(stderr, "[nrs prof] grid %d block %d barriers %d cycles:", st.grid, st.block, es->barriers);
+      fprintf(stderr, "[nrs prof] grid %d block %d barriers %d cycles:", direct ? st.dgrid : st.grid,
+              direct ? direct_block_threads() : st.block, es->barriers);
       for (int i = 0; i < 16; i++) fprintf(stderr, " %lld", es->prof[i]);
       fprintf(stderr, "\n");
     }
@@ -982,6 +1054,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   const std::vector<int> lost_list(lost_ordered.begin(), lost_ordered.end());
   const int n_lost = (int)lost_list.size();
   hp.n_sort = n;
+  hp.direct = env_int("NRSLAM_B200_DIRECT", 1) != 0;
   hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM,
             OP_FINAL_CHI2};
   hp.op_args = {0, 0, opt.pose_deform_iterations[0], 0, 0, opt.pose_deform_iterations[1], 0, 0};

@@ -1,0 +1,27 @@
+// nrs_direct.cuh — launch interface of the exact-solve tracking engine (nrs_direct.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "nrs_direct_core.cuh"
+#include "nrs_engine.cuh"
+
+namespace nrs {
+
+struct DirectParams {
+  Params P;            // the staged tracking problem (rows in elimination order)
+  direct::Plan pl;     // elimination tree + factor storage
+  const int* inc_pos;  // [2P] front position of the other endpoint of every incidence (nrs_direct_plan.h)
+  double* cpl;         // [18V] pose coupling blocks of the current linearisation
+  double* hpp_part;    // [G][28] per-CTA partial of H_pp / b_p
+  double* hpp;         // [28]   their sum (published by CTA 0 for the root front)
+  double* dslots;      // [2][G][2] grid-reduction slots
+  double* dpose;       // [8]    pose part of the last solution
+  int scratch_z;       // shared-memory doubles of the backward substitution scratch
+};
+
+size_t direct_smem_bytes(int max_path, int scratch_z, size_t panel_doubles);
+int direct_block_threads();
+int direct_max_grid(size_t smem);  // co-resident CTAs of the kernel with this much dynamic shared memory
+int launch_direct(const DirectParams& q, int grid, size_t smem, cudaStream_t stream);
+
+}  // namespace nrs

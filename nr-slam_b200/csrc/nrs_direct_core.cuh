@@ -1,0 +1,430 @@
+// nrs_direct_core.cuh — numeric half of the exact sparse LL^T used by the tracking solve (multifrontal, dense fronts).
+//
+// What it replaces: Eigen::SimplicialLLT::factorize / solve behind g2o's LinearSolverEigen
+//   third_party/g2o/g2o/solvers/eigen/linear_solver_eigen.h:92-136, called once per Levenberg trial from
+//   third_party/g2o/g2o/core/block_solver.hpp:329-341 via optimization_algorithm_levenberg.cpp:97-116.
+//
+// The elimination tree comes from nrs_direct_plan.h (geometric nested dissection, heap-numbered complete binary tree,
+// all index lists in 3x3-block units). 2^depth CTAs walk it leaf-to-root in lock-step; a node of level d is worked on
+// by a TEAM of 2^(depth-d) CTAs:
+//   stage AB  every team member assembles the node's pivot block F11 (original entries + the children's update
+//             matrices, pulled through inverse index maps — no atomics, fixed order) and ITS share of the boundary
+//             rows F21 (row k belongs to member k mod R), factorises the tall panel [F11 ; F21_mine] right-looking in
+//             shared memory (F11 redundantly: no intra-team sync), stores L11 (leader) / its L21 rows to global;
+//   -- grid barrier --
+//   stage C   member r computes the rows k = r (mod R) of the update matrix U = sum_children - L21 L21^T.
+//   -- grid barrier --
+// The right-hand side is the LAST boundary row of every front (augmented matrix), so the forward substitution is part
+// of the factorisation: the rhs row of a node's panel ends up holding y_own^T and the rhs row of U the reduced rhs.
+// The backward substitution needs no synchronisation at all: every CTA walks ITS root-to-leaf path and recomputes the
+// (bit-identical) solution of every front on it into a shared-memory path vector.
+// Diagonal 3x3 blocks of L are stored INVERTED, so scaling and substitution are multiplications.
+//
+// The file compiles for the device and — with NRS_DIRECT_HOST_EMULATION — for the host with one emulated thread per
+// CTA (the code between two syncs is race free), which is how the CPU test suite checks the arithmetic without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef NRS_DIRECT_HOST_EMULATION
+#define NRS_DD inline
+#define NRS_DSYNC() ((void)0)
+#define NRS_DLDCG(p) (*(p))
+#define NRS_DLDG(p) (*(p))
+#define NRS_DFAIL(p) (++*(p))
+#else
+#define NRS_DD __device__ __forceinline__
+#define NRS_DSYNC() __syncthreads()
+#define NRS_DLDCG(p) __ldcg(p)
+#define NRS_DLDG(p) __ldg(p)
+#define NRS_DFAIL(p) atomicAdd((p), 1)
+#endif
+
+namespace nrs {
+namespace direct {
+
+// Device view of the plan (nrs_direct_plan.h) plus the factor storage.
+struct Plan {
+  int V, depth, G, max_path;
+  const int *vb, *nv, *nbv, *bnd_ptr, *bnd, *bpath, *path_off, *inv_ptr, *inv;
+  const long long *p_off, *u_off;
+  double* panel;  // per node: (3 nv + 3 nbv) x 3 nv, row-major
+  double* upd;    // per node: 3 nbv x 3 nbv, row-major, lower block triangle valid
+  int* fail;      // bumped when a pivot is not positive (the reference's "Cholesky failure": solve() returns false)
+};
+
+// The linearised system H delta = b in global memory (written by the linearisation pass of nrs_direct.cu).
+struct Sys {
+  const double* dg;     // [8V]  symmetric 3x3 diagonal block: xx xy xz yy yz zz
+  const double* cpl;    // [18V] pose coupling H_{pose, v}: 6 x 3 row-major
+  const double* bvec;   // [4V]
+  const double* pc;     // [4P]  pair block: H_ij = -(s I + u u^T)
+  const double* hpp;    // [27]  H_pp upper packed (21) + b_p (6)
+  const int *inc_ptr, *inc_ent, *inc_pos;
+  double lambda;
+};
+
+struct Thr {
+  int tid, nthr;
+};
+
+NRS_DD int sym6i(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  // a <= c
+
+// Cholesky of a symmetric 3x3 (lower part read) and the inverse of its factor: W = L^-1 (lower).
+NRS_DD bool chol3_inv(const double a00, const double a10, const double a11, const double a20, const double a21,
+                      const double a22, double W[6]) {
+  bool ok = a00 > 0;
+  const double r0 = ok ? 1.0 / sqrt(a00) : 1.0;
+  const double l10 = a10 * r0, l20 = a20 * r0;
+  const double d1 = a11 - l10 * l10;
+  ok = ok && d1 > 0;
+  const double r1 = d1 > 0 ? 1.0 / sqrt(d1) : 1.0;
+  const double l21 = (a21 - l20 * l10) * r1;
+  const double d2 = a22 - l20 * l20 - l21 * l21;
+  ok = ok && d2 > 0;
+  const double r2 = d2 > 0 ? 1.0 / sqrt(d2) : 1.0;
+  W[0] = r0;                            // w00
+  W[1] = -l10 * r0 * r1;                // w10
+  W[2] = r1;                            // w11
+  W[4] = -l21 * r1 * r2;                // w21
+  W[3] = -(l20 * r0 + l21 * W[1]) * r2; // w20
+  W[5] = r2;                            // w22
+  return ok;
+}
+
+struct Front {
+  int t, d, r, R;
+  int nv, nbv, ns, ld;
+  int nmy;         // boundary rows of this team member
+  int rows_local;  // nv + nmy
+};
+
+NRS_DD Front front_of(const Plan& pl, int g, int d) {
+  Front f;
+  f.d = d;
+  f.t = (1 << d) + (g >> (pl.depth - d));
+  f.R = pl.G >> d;
+  f.r = g & (f.R - 1);
+  f.nv = NRS_DLDG(pl.nv + f.t);
+  f.nbv = NRS_DLDG(pl.nbv + f.t);
+  f.ns = 3 * f.nv;
+  f.ld = f.ns | 1;
+  f.nmy = (f.nbv > f.r) ? (f.nbv - f.r + f.R - 1) / f.R : 0;
+  f.rows_local = f.nv + f.nmy;
+  return f;
+}
+
+// local panel row of front position fp for this team member, -1 if the row belongs to another member
+NRS_DD int local_row(const Front& f, int fp) {
+  if (fp < f.nv) return fp;
+  const int k = fp - f.nv;
+  return ((k & (f.R - 1)) == f.r) ? f.nv + (k - f.r) / f.R : -1;
+}
+NRS_DD int front_pos(const Front& f, int li) { return li < f.nv ? li : f.nv + f.r + (li - f.nv) * f.R; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage AB: assemble + factorise + store. sp: rows_local*3 x ld doubles; s_w: 16 doubles.
+// A member without boundary rows that is not the leader has nothing to do.
+// ---------------------------------------------------------------------------------------------------------------
+NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, double* s_w, Thr th) {
+  const Front f = front_of(pl, g, d);
+  if (f.nmy == 0 && f.r != 0) return;
+  const int V = pl.V, ld = f.ld, nv = f.nv, rows = f.rows_local;
+  const int vb = NRS_DLDG(pl.vb + f.t);
+  const int T = (2 << pl.depth) - 1;
+  // (1) zero
+  for (int q = th.tid; q < 3 * rows * ld; q += th.nthr) sp[q] = 0.0;
+  NRS_DSYNC();
+  // (2) original entries of the pivot columns: one thread per own vertex
+  const int fp_rhs = nv + f.nbv - 1;
+  const int fp_pose = (f.t == 1) ? nv - 2 : nv + f.nbv - 3;
+  const int li_rhs = local_row(f, fp_rhs);
+  for (int j = th.tid; j < nv; j += th.nthr) {
+    const int v = vb + j;
+    double* col = sp + 3 * j;
+    if (v < V) {
+      const double* D = sys.dg + 8 * (size_t)v;
+      const double d0 = NRS_DLDCG(D), d1 = NRS_DLDCG(D + 1), d2 = NRS_DLDCG(D + 2), d3 = NRS_DLDCG(D + 3),
+                   d4 = NRS_DLDCG(D + 4), d5 = NRS_DLDCG(D + 5);
+      double* b = col + (size_t)(3 * j) * ld;
+      b[0] = d0 + sys.lambda; b[1] = d1; b[2] = d2;
+      b[ld] = d1; b[ld + 1] = d3 + sys.lambda; b[ld + 2] = d4;
+      b[2 * ld] = d2; b[2 * ld + 1] = d4; b[2 * ld + 2] = d5 + sys.lambda;
+      for (int a = 0; a < 2; a++) {
+        const int li = local_row(f, fp_pose + a);
+        if (li < 0) continue;
+        double* o = col + (size_t)(3 * li) * ld;
+        const double* c = sys.cpl + 18 * (size_t)v + 9 * a;
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) o[rr * ld + cc] = NRS_DLDCG(c + 3 * rr + cc);
+      }
+      if (li_rhs >= 0) {
+        double* o = col + (size_t)(3 * li_rhs) * ld;
+        const double* bb = sys.bvec + 4 * (size_t)v;
+        o[0] = NRS_DLDCG(bb);
+        o[1] = NRS_DLDCG(bb + 1);
+        o[2] = NRS_DLDCG(bb + 2);
+      }
+      const int a1 = NRS_DLDG(sys.inc_ptr + v + 1);
+      for (int a = NRS_DLDG(sys.inc_ptr + v); a < a1; a++) {
+        const int fp = NRS_DLDG(sys.inc_pos + a);
+        if (fp < 0) continue;
+        const int li = local_row(f, fp);
+        if (li < 0) continue;
+        const double* c = sys.pc + 4 * (size_t)(NRS_DLDG(sys.inc_ent + a) >> 1);
+        const double s = NRS_DLDCG(c), u0 = NRS_DLDCG(c + 1), u1 = NRS_DLDCG(c + 2), u2 = NRS_DLDCG(c + 3);
+        double* o = col + (size_t)(3 * li) * ld;
+        o[0] = -(s + u0 * u0); o[1] = -(u0 * u1); o[2] = -(u0 * u2);
+        o[ld] = -(u1 * u0); o[ld + 1] = -(s + u1 * u1); o[ld + 2] = -(u1 * u2);
+        o[2 * ld] = -(u2 * u0); o[2 * ld + 1] = -(u2 * u1); o[2 * ld + 2] = -(s + u2 * u2);
+      }
+    } else {  // pose pseudo-vertex (root only): a = 0 rotation, 1 translation
+      const int a = v - V;
+      double* b = col + (size_t)(3 * j) * ld;
+      for (int rr = 0; rr < 3; rr++)
+        for (int cc = 0; cc < 3; cc++) {
+          const int p = 3 * a + rr, q = 3 * a + cc;
+          b[rr * ld + cc] = NRS_DLDCG(sys.hpp + sym6i(p < q ? p : q, p < q ? q : p)) + (rr == cc ? sys.lambda : 0.0);
+        }
+      if (a == 0) {  // block (translation, rotation)
+        double* o = col + (size_t)(3 * (j + 1)) * ld;
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) o[rr * ld + cc] = NRS_DLDCG(sys.hpp + sym6i(cc, 3 + rr));
+      }
+      if (li_rhs >= 0) {
+        double* o = col + (size_t)(3 * li_rhs) * ld;
+        for (int cc = 0; cc < 3; cc++) o[cc] = NRS_DLDCG(sys.hpp + 21 + 3 * a + cc);
+      }
+    }
+  }
+  NRS_DSYNC();
+  // (3) children's update matrices (pull: every panel block gathers from both children)
+  if (2 * f.t <= T) {
+    for (int c = 2 * f.t; c <= 2 * f.t + 1; c++) {
+      const int* iv = pl.inv + NRS_DLDG(pl.inv_ptr + c);
+      const int ldc = 3 * NRS_DLDG(pl.nbv + c);
+      const double* U = pl.upd + NRS_DLDG(pl.u_off + c);
+      for (int q = th.tid; q < rows * nv; q += th.nthr) {
+        const int li = q / nv, j = q - li * nv;
+        if (li < j) continue;
+        const int cj = NRS_DLDG(iv + j);
+        if (cj < 0) continue;
+        const int ci = NRS_DLDG(iv + front_pos(f, li));
+        if (ci < 0) continue;
+        const double* u = U + (size_t)(3 * ci) * ldc + 3 * cj;
+        double* o = sp + (size_t)(3 * li) * ld + 3 * j;
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) o[rr * ld + cc] += NRS_DLDCG(u + (size_t)rr * ldc + cc);
+      }
+      NRS_DSYNC();
+    }
+  }
+  // (4) right-looking factorisation of the tall panel, one vertex column per step. s_w holds W_kk = L_kk^-1 of the
+  // current step; the thread that finishes block (k+1, k+1) computes the next one (look-ahead).
+  if (th.tid == 0 && nv > 0) {
+    double W[6];
+    if (!chol3_inv(sp[0], sp[ld], sp[ld + 1], sp[2 * ld], sp[2 * ld + 1], sp[2 * ld + 2], W)) NRS_DFAIL(pl.fail);
+    for (int i = 0; i < 6; i++) s_w[i] = W[i];
+  }
+  NRS_DSYNC();
+  for (int k = 0; k < nv; k++) {
+    const double w00 = s_w[0], w10 = s_w[1], w11 = s_w[2], w20 = s_w[3], w21 = s_w[4], w22 = s_w[5];
+    // scale the rows below: B <- B W^T
+    for (int li = k + 1 + th.tid; li < rows; li += th.nthr) {
+      double* o = sp + (size_t)(3 * li) * ld + 3 * k;
+      for (int rr = 0; rr < 3; rr++) {
+        const double b0 = o[rr * ld], b1 = o[rr * ld + 1], b2 = o[rr * ld + 2];
+        o[rr * ld] = b0 * w00;
+        o[rr * ld + 1] = b0 * w10 + b1 * w11;
+        o[rr * ld + 2] = b0 * w20 + b1 * w21 + b2 * w22;
+      }
+    }
+    NRS_DSYNC();
+    if (th.tid == th.nthr - 1) {  // the diagonal block of L is kept inverted
+      double* o = sp + (size_t)(3 * k) * ld + 3 * k;
+      o[0] = w00; o[1] = 0; o[2] = 0;
+      o[ld] = w10; o[ld + 1] = w11; o[ld + 2] = 0;
+      o[2 * ld] = w20; o[2 * ld + 1] = w21; o[2 * ld + 2] = w22;
+    }
+    // trailing update: block(li, j) -= block(li, k) block(j, k)^T for k < j < nv, li >= j
+    const int nj = nv - k - 1, w = rows - k - 1;
+    for (int q = th.tid; q < nj * w; q += th.nthr) {
+      const int jj = q / w, ii = q - jj * w;
+      if (ii < jj) continue;
+      const int j = k + 1 + jj, li = k + 1 + ii;
+      const double* A = sp + (size_t)(3 * li) * ld + 3 * k;
+      const double* B = sp + (size_t)(3 * j) * ld + 3 * k;
+      double* o = sp + (size_t)(3 * li) * ld + 3 * j;
+      double b[9];
+      for (int t = 0; t < 3; t++) {
+        b[3 * t] = B[t * ld];
+        b[3 * t + 1] = B[t * ld + 1];
+        b[3 * t + 2] = B[t * ld + 2];
+      }
+      double nb[9];
+      for (int rr = 0; rr < 3; rr++) {
+        const double a0 = A[rr * ld], a1 = A[rr * ld + 1], a2 = A[rr * ld + 2];
+        for (int cc = 0; cc < 3; cc++) {
+          nb[3 * rr + cc] = o[rr * ld + cc] - (a0 * b[3 * cc] + a1 * b[3 * cc + 1] + a2 * b[3 * cc + 2]);
+          o[rr * ld + cc] = nb[3 * rr + cc];
+        }
+      }
+      if (ii == 0 && jj == 0) {
+        double W[6];
+        if (!chol3_inv(nb[0], nb[3], nb[4], nb[6], nb[7], nb[8], W)) NRS_DFAIL(pl.fail);
+        for (int i = 0; i < 6; i++) s_w[i] = W[i];
+      }
+    }
+    NRS_DSYNC();
+  }
+  // (5) store: the leader writes L11, every member its boundary rows
+  double* Pg = pl.panel + NRS_DLDG(pl.p_off + f.t);
+  const int ns = f.ns;
+  const int first = (f.r == 0) ? 0 : 3 * nv;
+  for (int q = first * ns + th.tid; q < 3 * rows * ns; q += th.nthr) {
+    const int row = q / ns, c = q - row * ns;
+    const int li = row / 3, a = row - 3 * li;
+    Pg[(size_t)(3 * front_pos(f, li) + a) * ns + c] = sp[(size_t)row * ld + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage C: rows k = r (mod R) of U = sum_children U_c - L21 L21^T. sp: 3 (kmax + 1) x ld doubles.
+// ---------------------------------------------------------------------------------------------------------------
+NRS_DD void stage_c(const Plan& pl, int g, int d, double* sp, Thr th) {
+  const Front f = front_of(pl, g, d);
+  if (f.nmy == 0) return;
+  const int ld = f.ld, nv = f.nv, ns = f.ns, nbv = f.nbv;
+  const int T = (2 << pl.depth) - 1;
+  const int kmax = f.r + (f.nmy - 1) * f.R;
+  const double* Pg = pl.panel + NRS_DLDG(pl.p_off + f.t) + (size_t)(3 * nv) * ns;
+  for (int q = th.tid; q < 3 * (kmax + 1) * ns; q += th.nthr) {
+    const int row = q / ns, c = q - row * ns;
+    sp[(size_t)row * ld + c] = NRS_DLDCG(Pg + q);
+  }
+  NRS_DSYNC();
+  const bool kids = 2 * f.t <= T;
+  const int* iv0 = nullptr;
+  const int* iv1 = nullptr;
+  const double *U0 = nullptr, *U1 = nullptr;
+  int ld0 = 0, ld1 = 0;
+  if (kids) {
+    iv0 = pl.inv + NRS_DLDG(pl.inv_ptr + 2 * f.t) + nv;
+    iv1 = pl.inv + NRS_DLDG(pl.inv_ptr + 2 * f.t + 1) + nv;
+    U0 = pl.upd + NRS_DLDG(pl.u_off + 2 * f.t);
+    U1 = pl.upd + NRS_DLDG(pl.u_off + 2 * f.t + 1);
+    ld0 = 3 * NRS_DLDG(pl.nbv + 2 * f.t);
+    ld1 = 3 * NRS_DLDG(pl.nbv + 2 * f.t + 1);
+  }
+  double* Ug = pl.upd + NRS_DLDG(pl.u_off + f.t);
+  const int ldu = 3 * nbv;
+  for (int q = th.tid; q < f.nmy * nbv; q += th.nthr) {
+    const int m = q / nbv, j = q - m * nbv;
+    const int k = f.r + m * f.R;
+    if (j > k) continue;
+    double acc[9];
+    for (int i = 0; i < 9; i++) acc[i] = 0.0;
+    if (kids) {
+      const int c0k = NRS_DLDG(iv0 + k), c0j = NRS_DLDG(iv0 + j);
+      if (c0k >= 0 && c0j >= 0) {
+        const double* u = U0 + (size_t)(3 * c0k) * ld0 + 3 * c0j;
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) acc[3 * rr + cc] += NRS_DLDCG(u + (size_t)rr * ld0 + cc);
+      }
+      const int c1k = NRS_DLDG(iv1 + k), c1j = NRS_DLDG(iv1 + j);
+      if (c1k >= 0 && c1j >= 0) {
+        const double* u = U1 + (size_t)(3 * c1k) * ld1 + 3 * c1j;
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) acc[3 * rr + cc] += NRS_DLDCG(u + (size_t)rr * ld1 + cc);
+      }
+    }
+    const double* A = sp + (size_t)(3 * k) * ld;
+    const double* B = sp + (size_t)(3 * j) * ld;
+    double s[9];
+    for (int i = 0; i < 9; i++) s[i] = 0.0;
+    for (int c = 0; c < ns; c++) {
+      const double a0 = A[c], a1 = A[ld + c], a2 = A[2 * ld + c];
+      const double b0 = B[c], b1 = B[ld + c], b2 = B[2 * ld + c];
+      s[0] += a0 * b0; s[1] += a0 * b1; s[2] += a0 * b2;
+      s[3] += a1 * b0; s[4] += a1 * b1; s[5] += a1 * b2;
+      s[6] += a2 * b0; s[7] += a2 * b1; s[8] += a2 * b2;
+    }
+    double* o = Ug + (size_t)(3 * k) * ldu + 3 * j;
+    for (int rr = 0; rr < 3; rr++)
+      for (int cc = 0; cc < 3; cc++) o[(size_t)rr * ldu + cc] = acc[3 * rr + cc] - s[3 * rr + cc];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward substitution of the front of level d on CTA g's path. s_path: the solution of the ancestors' own
+// vertices (and, on return, of this front's). sp: 3 nv x ld (L11); s_z: ns + nparts * ns doubles.
+// The leader also writes the point rows of delta (4-double stride) and the pose delta.
+// ---------------------------------------------------------------------------------------------------------------
+NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double* sp, double* s_z, double* delta,
+                           double* dpose, Thr th) {
+  const Front f = front_of(pl, g, d);
+  const int ld = f.ld, nv = f.nv, ns = f.ns, nbv = f.nbv;
+  if (nv == 0) return;
+  const double* Pg = pl.panel + NRS_DLDG(pl.p_off + f.t);
+  // L11 -> shared memory
+  for (int q = th.tid; q < ns * ns; q += th.nthr) {
+    const int row = q / ns, c = q - row * ns;
+    sp[(size_t)row * ld + c] = NRS_DLDCG(Pg + q);
+  }
+  // z = y - L21^T x_boundary: groups of threads split the boundary rows, lanes the columns
+  const int nrows = 3 * (nbv - 1);
+  const int lanes = th.nthr >= 32 ? 32 : th.nthr;
+  const int ngrp = th.nthr / lanes, grp = th.tid / lanes, lane = th.tid - grp * lanes;
+  const double* L21 = Pg + (size_t)ns * ns;
+  const int* bp = pl.bpath + NRS_DLDG(pl.bnd_ptr + f.t);
+  double* part = s_z + ns;
+  for (int c = lane; c < ns; c += lanes) {
+    double s = 0;
+    for (int row = grp; row < nrows; row += ngrp) {
+      const int k = row / 3;
+      s += NRS_DLDCG(L21 + (size_t)row * ns + c) * s_path[NRS_DLDG(bp + k) + (row - 3 * k)];
+    }
+    part[grp * ns + c] = s;
+  }
+  NRS_DSYNC();
+  const double* y = L21 + (size_t)nrows * ns;  // first scalar row of the rhs block row
+  for (int c = th.tid; c < ns; c += th.nthr) {
+    double s = NRS_DLDCG(y + c);
+    for (int w = 0; w < ngrp; w++) s -= part[w * ns + c];
+    s_z[c] = s;
+  }
+  NRS_DSYNC();
+  // L11^T x = z, block row by block row from the bottom; diagonal blocks hold W = L_ii^-1, so x_i = W^T z_i
+  double* xo = s_path + NRS_DLDG(pl.path_off + f.t);
+  for (int i = nv - 1; i >= 0; i--) {
+    const double* Wd = sp + (size_t)(3 * i) * ld + 3 * i;
+    const double z0 = s_z[3 * i], z1 = s_z[3 * i + 1], z2 = s_z[3 * i + 2];
+    const double x2 = Wd[2 * ld + 2] * z2;
+    const double x1 = Wd[ld + 1] * z1 + Wd[2 * ld + 1] * z2;
+    const double x0 = Wd[0] * z0 + Wd[ld] * z1 + Wd[2 * ld] * z2;
+    const double* Li = sp + (size_t)(3 * i) * ld;
+    for (int c = th.tid; c < 3 * i; c += th.nthr) s_z[c] -= Li[c] * x0 + Li[ld + c] * x1 + Li[2 * ld + c] * x2;
+    if (th.tid == 0) {
+      xo[3 * i] = x0;
+      xo[3 * i + 1] = x1;
+      xo[3 * i + 2] = x2;
+    }
+    NRS_DSYNC();
+  }
+  if (f.r == 0) {
+    const int vb = NRS_DLDG(pl.vb + f.t);
+    for (int q = th.tid; q < ns; q += th.nthr) {
+      const int j = q / 3, a = q - 3 * j, v = vb + j;
+      if (v < pl.V)
+        delta[4 * (size_t)v + a] = xo[q];
+      else
+        dpose[3 * (v - pl.V) + a] = xo[q];
+    }
+  }
+}
+
+// Shared-memory doubles backward_front needs besides sp and s_path.
+NRS_DD int backward_scratch(int max_ns, int nthr) { return max_ns * (1 + (nthr >= 32 ? nthr / 32 : 1)); }
+
+}  // namespace direct
+}  // namespace nrs

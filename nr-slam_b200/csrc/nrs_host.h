@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/nrslam_b200.h"
+#include "nrs_direct.cuh"
 #include "nrs_engine.cuh"
 
 namespace nrs {
@@ -80,6 +81,11 @@ struct Staged {
   // dense block preconditioner): row_of[caller row] = engine row
   std::vector<int> row_of;
   Arena xin;  // landmark-sharded BA: push lists and edge-count flags of this rank
+  // exact-solve tracking engine (nrs_direct.cu): used for the first launch plan when the problem qualifies
+  bool use_direct = false;
+  DirectParams dq;
+  int dgrid = 0;
+  size_t dsmem = 0;
 };
 
 // Landmark-sharded BA: this rank's exchange buffer and the peer mappings of the other ranks' buffers.

@@ -1,0 +1,123 @@
+"""Exact sparse LL^T of the tracking solve (nr-slam_b200/csrc/nrs_direct_plan.h + nrs_direct_core.cuh), checked on the
+CPU: the symbolic analysis is plain C++, the numeric code is compiled for the host with one emulated thread per CTA
+(tests/emul/direct_emul.cc), and the result is compared with a dense numpy solve of the same system. This pins the
+solver that replaces Eigen::SimplicialLLT (third_party/g2o/g2o/solvers/eigen/linear_solver_eigen.h:92-188) without a GPU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    out = os.path.join(ROOT, "tests", "emul", "direct_emul.so")
+    src = os.path.join(ROOT, "tests", "emul", "direct_emul.cc")
+    deps = [src, os.path.join(ROOT, "nr-slam_b200", "csrc", "nrs_direct_core.cuh"),
+            os.path.join(ROOT, "nr-slam_b200", "csrc", "nrs_direct_plan.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", out, src])
+    return C.CDLL(out)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def random_system(n, k=10, seed=0, lam=1e-3):
+    rng = np.random.default_rng(seed)
+    uv = np.stack([rng.uniform(0, 640, n), rng.uniform(0, 480, n)], 1)
+    tree = cKDTree(uv)
+    kk = min(k + 1, n)
+    _, nb = tree.query(uv, k=kk)
+    nb = nb.reshape(n, kk)
+    a = np.repeat(np.arange(n), kk - 1)
+    b = nb[:, 1:].reshape(-1)
+    key = np.unique(np.minimum(a, b).astype(np.int64) * n + np.maximum(a, b))
+    key = key[(key // n) != (key % n)]
+    pi, pj = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    P = len(pi)
+    s = rng.uniform(0.5, 5.0, P)
+    u = rng.normal(size=(P, 3)) * 2.0
+    pc = np.concatenate([s[:, None], u], 1)
+    # per-vertex reprojection-like terms: omega A^T A, omega A^T B, omega B^T B
+    A = rng.normal(size=(n, 2, 6))
+    B = rng.normal(size=(n, 2, 3)) * 3.0
+    N = 3 * n + 6
+    H = np.zeros((N, N))
+    for i in range(n):
+        H[3 * i:3 * i + 3, 3 * i:3 * i + 3] += B[i].T @ B[i]
+        H[3 * n:, 3 * n:] += A[i].T @ A[i]
+        H[3 * n:, 3 * i:3 * i + 3] += A[i].T @ B[i]
+        H[3 * i:3 * i + 3, 3 * n:] += B[i].T @ A[i]
+    for e in range(P):
+        blk = s[e] * np.eye(3) + np.outer(u[e], u[e])
+        i, j = pi[e], pj[e]
+        H[3 * i:3 * i + 3, 3 * i:3 * i + 3] += blk
+        H[3 * j:3 * j + 3, 3 * j:3 * j + 3] += blk
+        H[3 * i:3 * i + 3, 3 * j:3 * j + 3] -= blk
+        H[3 * j:3 * j + 3, 3 * i:3 * i + 3] -= blk
+    rhs = rng.normal(size=N)
+    dg = np.zeros((n, 6))
+    cpl = np.zeros((n, 18))
+    for i in range(n):
+        D = H[3 * i:3 * i + 3, 3 * i:3 * i + 3]
+        dg[i] = [D[0, 0], D[0, 1], D[0, 2], D[1, 1], D[1, 2], D[2, 2]]
+        cpl[i] = H[3 * n:, 3 * i:3 * i + 3].reshape(-1)
+    hpp = np.zeros(27)
+    t = 0
+    for a_ in range(6):
+        for c_ in range(a_, 6):
+            hpp[t] = H[3 * n + a_, 3 * n + c_]
+            t += 1
+    hpp[21:] = rhs[3 * n:]
+    x = np.linalg.solve(H + lam * np.eye(N), rhs)
+    return dict(n=n, uv=uv, pi=pi, pj=pj, pc=pc, dg=dg, cpl=cpl, b=rhs[:3 * n].reshape(n, 3).copy(), hpp=hpp, lam=lam,
+                x=x)
+
+
+def solve_emulated(sy, depth=-1):
+    L = _lib()
+    n, P = sy["n"], len(sy["pi"])
+    delta = np.zeros((n, 3))
+    dpose = np.zeros(6)
+    stats = np.zeros(8, np.int64)
+    D = C.c_double
+    rc = L.direct_emul_solve(C.c_int32(n), _ptr(np.ascontiguousarray(sy["uv"]), D), C.c_int32(P),
+                             _ptr(sy["pi"], C.c_int32), _ptr(sy["pj"], C.c_int32),
+                             _ptr(np.ascontiguousarray(sy["dg"]), D), _ptr(np.ascontiguousarray(sy["cpl"]), D),
+                             _ptr(np.ascontiguousarray(sy["b"]), D), _ptr(np.ascontiguousarray(sy["pc"]), D),
+                             _ptr(sy["hpp"], D), C.c_double(sy["lam"]), C.c_int32(depth), _ptr(delta, D),
+                             _ptr(dpose, D), _ptr(stats, C.c_int64))
+    return rc, delta, dpose, stats
+
+
+@pytest.mark.parametrize("n,depth", [(5, -1), (12, 0), (40, 1), (40, 2), (150, -1), (300, 3), (300, 5), (700, -1)])
+def test_emulated_factorisation_matches_dense_solve(n, depth):
+    sy = random_system(n, seed=n + 7 * max(depth, 0))
+    rc, delta, dpose, stats = solve_emulated(sy, depth)
+    assert rc == 0 and stats[7] == 0
+    x = np.concatenate([delta.reshape(-1), dpose])
+    err = np.abs(x - sy["x"]).max() / np.abs(sy["x"]).max()
+    assert err < 1e-10, err
+
+
+def test_tracking_sized_problem_fits_shared_memory():
+    sy = random_system(2000, seed=3)
+    rc, delta, dpose, stats = solve_emulated(sy)
+    assert rc == 0
+    x = np.concatenate([delta.reshape(-1), dpose])
+    assert np.abs(x - sy["x"]).max() / np.abs(sy["x"]).max() < 1e-9
+    assert stats[0] == 7 and stats[1] == 128
+    assert stats[4] * 8 < 190 * 1024, "panel of the busiest team member must fit one SM's shared memory"
+
+
+def test_not_positive_definite_is_reported():
+    sy = random_system(60, seed=1)
+    sy["dg"][:, [0, 3, 5]] -= 1e4
+    rc, _, _, stats = solve_emulated(sy)
+    assert rc == 1 and stats[7] != 0
