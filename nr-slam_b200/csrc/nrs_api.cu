@@ -456,14 +456,15 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   bool direct = hp.direct && F == 1 && D == 0 && U == 0 && !hp.poses_fixed && !hp.points_fixed && !hp.sharded &&
                 hp.fixed0.empty() && hp.n_stage1 == 0 && V >= 1;
   size_t dsmem = 0;
-  int dscratch = 0;
+  int dscratch = 0, dmaxnv = 0;
   if (direct) {
     const int depth = std::min(direct_depth(V, ctx->sm_count), env_int("NRSLAM_B200_DIRECT_DEPTH", 7));
     build_direct_plan(V, hp.uv.data(), hp.pair_i, hp.pair_j, depth, dplan);
     int max_ns = 0;
     for (int t = 1; t <= dplan.n_nodes; t++) max_ns = std::max(max_ns, 3 * dplan.nv[t]);
     dscratch = max_ns * (1 + direct_block_threads() / 32);
-    dsmem = direct_smem_bytes(dplan.max_path, dscratch, dplan.smem_doubles);
+    dmaxnv = max_ns / 3;
+    dsmem = direct_smem_bytes(dplan.max_path, dscratch, dmaxnv, dplan.smem_doubles);
     // the busiest team member's panel must fit one SM, the whole grid must be co-resident, one row group per thread
     if (dsmem > 226 * 1024 || direct_max_grid(dsmem) < dplan.G ||
         (V + dplan.G - 1) / dplan.G > direct_block_threads())
@@ -686,7 +687,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   size_t wneed = (size_t)V * 8 * (4 + 20 + 8 + 4 + 8 + 4 * 5) + (size_t)P * 40 + (size_t)D * 32 +
                  2 * (size_t)max_chunks * kChunkVals * 8 + 2 * (size_t)max_grid_used * kSlotVals * 8 + 32 * 256 + 4096;
   if (direct)
-    wneed += ((size_t)dplan.p_total + (size_t)dplan.u_total + 18 * (size_t)V + (size_t)dplan.G * (28 + 4) + 64) * 8 +
+    wneed += ((size_t)dplan.p_total + (size_t)dplan.u_total + 18 * (size_t)V + (size_t)dplan.G * (28 + 4 + 32) + 64) * 8 +
              16 * 256;
   if (!wk.reserve(wneed, false)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "work arena allocation failed");
   p.x_bak = wk.d<double>(wk.take<double>(4 * (size_t)V));
@@ -716,6 +717,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     q.dslots = wk.d<double>(wk.take<double>(4 * (size_t)dplan.G));
     q.dpose = wk.d<double>(wk.take<double>(8));
     q.scratch_z = dscratch;
+    q.max_nv = dmaxnv;
+    q.plev = wk.d<long long>(wk.take<long long>(32 * (size_t)dplan.G));
     q.P = p;
     st.use_direct = true;
     st.dgrid = dplan.G;
@@ -780,6 +783,23 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
               direct ? direct_block_threads() : st.block, es->barriers);
       for (int i = 0; i < 16; i++) fprintf(stderr, " %lld", es->prof[i]);
       fprintf(stderr, "\n");
+      if (direct && st.dq.plev && getenv("NRSLAM_B200_PLEV")) {
+        std::vector<long long> lv(32 * (size_t)st.dgrid);
+        cudaMemcpy(lv.data(), st.dq.plev, lv.size() * 8, cudaMemcpyDeviceToHost);
+        const char* nm[3] = {"stageAB", "stageC", "backward"};
+        for (int ph = 0; ph < 3; ph++)
+          for (int d = 0; d <= st.dq.pl.depth; d++) {
+            long long mx = 0, sum = 0;
+            int arg = 0;
+            for (int g = 0; g < st.dgrid; g++) {
+              const long long v = lv[32 * (size_t)g + 8 * ph + d];
+              sum += v;
+              if (v > mx) { mx = v; arg = g; }
+            }
+            fprintf(stderr, "[nrs plev] %s level %d: max %lld (cta %d) mean %lld cta0 %lld\n", nm[ph], d, mx, arg,
+                    sum / st.dgrid, lv[8 * ph + d]);
+          }
+      }
     }
   }
   return 0;

@@ -68,6 +68,9 @@ struct DirectEngine {
   double lambda, ni;
   int lm_iters, lm_trials, n_sweeps, n_chi2, n_trace, n_fail, fail_seen;
   long long prof[16];
+#ifdef NRS_DIRECT_PLEV
+  long long plev[32];  // per tree level: cycles in stage AB [d], stage C [8 + d], backward [16 + d]
+#endif
 
   __device__ DirectEngine(const DirectParams& q, double* sm) : Q(q), P(q.P) {
     tid = threadIdx.x;
@@ -77,7 +80,7 @@ struct DirectEngine {
     s_pose = p; p += 8;
     s_pose_bak = p; p += 8;
     s_scal = p; p += 8;
-    s_w = p; p += 16;
+    s_w = p; p += 16 + 6 * ((Q.max_nv + 1) & ~1);
     s_hpp = p; p += 28;
     s_red = p; p += 27 * 8;
     s_rec = p; p += kRec * kDBlock;
@@ -95,6 +98,9 @@ struct DirectEngine {
     lm_iters = lm_trials = n_sweeps = n_chi2 = n_trace = n_fail = 0;
     fail_seen = 0;
     for (int i = 0; i < 16; i++) prof[i] = 0;
+#ifdef NRS_DIRECT_PLEV
+    for (int i = 0; i < 32; i++) plev[i] = 0;
+#endif
   }
 
   __device__ __forceinline__ void barrier() {
@@ -422,19 +428,27 @@ struct DirectEngine {
     sys.inc_ptr = P.inc_ptr;
     sys.inc_ent = P.inc_ent;
     sys.inc_pos = Q.inc_pos;
+    sys.inc_row = P.inc_row;
     sys.lambda = lambda;
     const direct::Thr th{tid, kDBlock};
     const int depth = Q.pl.depth;
     for (int d = depth; d >= 0; d--) {
       const long long t0 = clock64();
-      direct::stage_ab(Q.pl, sys, cta, d, sp, s_w, th);
+      direct::stage_ab(Q.pl, sys, cta, d, sp, s_w, th, prof);
       const long long t1 = clock64();
       prof[0] += t1 - t0;
+#ifdef NRS_DIRECT_PLEV
+      plev[d] += t1 - t0;
+#endif
       barrier();
       if (d > 0) {
         const long long t2 = clock64();
         direct::stage_c(Q.pl, cta, d, sp, th);
-        prof[1] += clock64() - t2;
+        const long long t2b = clock64();
+        prof[1] += t2b - t2;
+#ifdef NRS_DIRECT_PLEV
+        plev[8 + d] += t2b - t2;
+#endif
         barrier();
       }
     }
@@ -443,7 +457,15 @@ struct DirectEngine {
     fail_seen = f;
     if (failed) return false;
     const long long t3 = clock64();
-    for (int d = 0; d <= depth; d++) direct::backward_front(Q.pl, cta, d, s_path, sp, s_z, P.xcg, Q.dpose, th);
+    for (int d = 0; d <= depth; d++) {
+      const long long t4 = clock64();
+      direct::backward_front(Q.pl, cta, d, s_path, sp, s_z, P.xcg, Q.dpose, th, prof);
+#ifdef NRS_DIRECT_PLEV
+      plev[16 + d] += clock64() - t4;
+#else
+      (void)t4;
+#endif
+    }
     prof[2] += clock64() - t3;
     return true;
   }
@@ -591,6 +613,10 @@ struct DirectEngine {
       }
     }
     __syncthreads();
+#ifdef NRS_DIRECT_PLEV
+    if (Q.plev && tid == 0)
+      for (int i = 0; i < 32; i++) Q.plev[(size_t)cta * 32 + i] = plev[i];
+#endif
     if (cta == 0) {
       if (tid < 7) P.pose[tid] = s_pose[tid];
       if (tid == 0) {
@@ -621,8 +647,8 @@ __global__ void __launch_bounds__(kDBlock, 1) nrs_track_direct_kernel(const __gr
 
 }  // namespace
 
-size_t direct_smem_bytes(int max_path, int scratch_z, size_t panel_doubles) {
-  size_t d = 8 + 8 + 8 + 16 + 28 + 27 * 8 + (size_t)kRec * kDBlock + ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
+size_t direct_smem_bytes(int max_path, int scratch_z, int max_nv, size_t panel_doubles) {
+  size_t d = 8 + 8 + 8 + 16 + 6 * (size_t)((max_nv + 1) & ~1) + 28 + 27 * 8 + (size_t)kRec * kDBlock + ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
              panel_doubles + 2;
   return d * sizeof(double);
 }

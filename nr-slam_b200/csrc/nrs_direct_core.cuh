@@ -32,12 +32,16 @@
 #define NRS_DLDCG(p) (*(p))
 #define NRS_DLDG(p) (*(p))
 #define NRS_DFAIL(p) (++*(p))
+#define NRS_DCLOCK() 0LL
+#define NRS_DRSQRT(x) (1.0 / sqrt(x))
 #else
 #define NRS_DD __device__ __forceinline__
 #define NRS_DSYNC() __syncthreads()
 #define NRS_DLDCG(p) __ldcg(p)
 #define NRS_DLDG(p) __ldg(p)
 #define NRS_DFAIL(p) atomicAdd((p), 1)
+#define NRS_DCLOCK() clock64()
+#define NRS_DRSQRT(x) rsqrt(x)
 #endif
 
 namespace nrs {
@@ -60,7 +64,7 @@ struct Sys {
   const double* bvec;   // [4V]
   const double* pc;     // [4P]  pair block: H_ij = -(s I + u u^T)
   const double* hpp;    // [27]  H_pp upper packed (21) + b_p (6)
-  const int *inc_ptr, *inc_ent, *inc_pos;
+  const int *inc_ptr, *inc_ent, *inc_pos, *inc_row;
   double lambda;
 };
 
@@ -74,21 +78,39 @@ NRS_DD int sym6i(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  
 NRS_DD bool chol3_inv(const double a00, const double a10, const double a11, const double a20, const double a21,
                       const double a22, double W[6]) {
   bool ok = a00 > 0;
-  const double r0 = ok ? 1.0 / sqrt(a00) : 1.0;
+  const double r0 = ok ? NRS_DRSQRT(a00) : 1.0;
   const double l10 = a10 * r0, l20 = a20 * r0;
   const double d1 = a11 - l10 * l10;
   ok = ok && d1 > 0;
-  const double r1 = d1 > 0 ? 1.0 / sqrt(d1) : 1.0;
+  const double r1 = d1 > 0 ? NRS_DRSQRT(d1) : 1.0;
   const double l21 = (a21 - l20 * l10) * r1;
   const double d2 = a22 - l20 * l20 - l21 * l21;
   ok = ok && d2 > 0;
-  const double r2 = d2 > 0 ? 1.0 / sqrt(d2) : 1.0;
+  const double r2 = d2 > 0 ? NRS_DRSQRT(d2) : 1.0;
   W[0] = r0;                            // w00
   W[1] = -l10 * r0 * r1;                // w10
   W[2] = r1;                            // w11
   W[4] = -l21 * r1 * r2;                // w21
   W[3] = -(l20 * r0 + l21 * W[1]) * r2; // w20
   W[5] = r2;                            // w22
+  return ok;
+}
+
+// Inverse of a symmetric positive definite 3x3 (lower part read) by cofactors: M = A^-1, symmetric, packed like the
+// input (00 10 11 20 21 22). false when a leading principal minor is not positive.
+NRS_DD bool inv3_spd(const double a00, const double a10, const double a11, const double a20, const double a21,
+                     const double a22, double M[6]) {
+  const double c00 = a11 * a22 - a21 * a21, c10 = a21 * a20 - a10 * a22, c20 = a10 * a21 - a11 * a20;
+  const double c22 = a00 * a11 - a10 * a10;
+  const double det = a00 * c00 + a10 * c10 + a20 * c20;
+  const bool ok = a00 > 0 && c22 > 0 && det > 0;
+  const double r = ok ? 1.0 / det : 1.0;
+  M[0] = c00 * r;
+  M[1] = c10 * r;
+  M[2] = (a00 * a22 - a20 * a20) * r;
+  M[3] = c20 * r;
+  M[4] = (a10 * a20 - a00 * a21) * r;
+  M[5] = c22 * r;
   return ok;
 }
 
@@ -123,10 +145,12 @@ NRS_DD int local_row(const Front& f, int fp) {
 NRS_DD int front_pos(const Front& f, int li) { return li < f.nv ? li : f.nv + f.r + (li - f.nv) * f.R; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Stage AB: assemble + factorise + store. sp: rows_local*3 x ld doubles; s_w: 16 doubles.
+// Stage AB: assemble + factorise + store. sp: rows_local*3 x ld doubles; s_w: 16 + 6 nv doubles.
 // A member without boundary rows that is not the leader has nothing to do.
 // ---------------------------------------------------------------------------------------------------------------
-NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, double* s_w, Thr th) {
+NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, double* s_w, Thr th,
+                     long long* pf = nullptr) {
+  const long long c0 = NRS_DCLOCK();
   const Front f = front_of(pl, g, d);
   if (f.nmy == 0 && f.r != 0) return;
   const int V = pl.V, ld = f.ld, nv = f.nv, rows = f.rows_local;
@@ -165,19 +189,6 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
         o[1] = NRS_DLDCG(bb + 1);
         o[2] = NRS_DLDCG(bb + 2);
       }
-      const int a1 = NRS_DLDG(sys.inc_ptr + v + 1);
-      for (int a = NRS_DLDG(sys.inc_ptr + v); a < a1; a++) {
-        const int fp = NRS_DLDG(sys.inc_pos + a);
-        if (fp < 0) continue;
-        const int li = local_row(f, fp);
-        if (li < 0) continue;
-        const double* c = sys.pc + 4 * (size_t)(NRS_DLDG(sys.inc_ent + a) >> 1);
-        const double s = NRS_DLDCG(c), u0 = NRS_DLDCG(c + 1), u1 = NRS_DLDCG(c + 2), u2 = NRS_DLDCG(c + 3);
-        double* o = col + (size_t)(3 * li) * ld;
-        o[0] = -(s + u0 * u0); o[1] = -(u0 * u1); o[2] = -(u0 * u2);
-        o[ld] = -(u1 * u0); o[ld + 1] = -(s + u1 * u1); o[ld + 2] = -(u1 * u2);
-        o[2 * ld] = -(u2 * u0); o[2 * ld + 1] = -(u2 * u1); o[2 * ld + 2] = -(s + u2 * u2);
-      }
     } else {  // pose pseudo-vertex (root only): a = 0 rotation, 1 translation
       const int a = v - V;
       double* b = col + (size_t)(3 * j) * ld;
@@ -197,7 +208,25 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
       }
     }
   }
+  {  // pair blocks of the pivot columns: one thread per incidence of an own vertex (they are contiguous)
+    const int npts = (vb + nv <= V) ? nv : V - vb;
+    const int a0 = npts > 0 ? NRS_DLDG(sys.inc_ptr + vb) : 0, a1 = npts > 0 ? NRS_DLDG(sys.inc_ptr + vb + npts) : 0;
+    for (int a = a0 + th.tid; a < a1; a += th.nthr) {
+      const int fp = NRS_DLDG(sys.inc_pos + a);
+      if (fp < 0) continue;
+      const int li = local_row(f, fp);
+      if (li < 0) continue;
+      const int j = NRS_DLDG(sys.inc_row + a) - vb;
+      const double* c = sys.pc + 4 * (size_t)(NRS_DLDG(sys.inc_ent + a) >> 1);
+      const double s = NRS_DLDCG(c), u0 = NRS_DLDCG(c + 1), u1 = NRS_DLDCG(c + 2), u2 = NRS_DLDCG(c + 3);
+      double* o = sp + 3 * j + (size_t)(3 * li) * ld;
+      o[0] = -(s + u0 * u0); o[1] = -(u0 * u1); o[2] = -(u0 * u2);
+      o[ld] = -(u1 * u0); o[ld + 1] = -(s + u1 * u1); o[ld + 2] = -(u1 * u2);
+      o[2 * ld] = -(u2 * u0); o[2 * ld + 1] = -(u2 * u1); o[2 * ld + 2] = -(s + u2 * u2);
+    }
+  }
   NRS_DSYNC();
+  const long long c1 = NRS_DCLOCK();
   // (3) children's update matrices (pull: every panel block gathers from both children)
   if (2 * f.t <= T) {
     for (int c = 2 * f.t; c <= 2 * f.t + 1; c++) {
@@ -219,38 +248,29 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
       NRS_DSYNC();
     }
   }
-  // (4) right-looking factorisation of the tall panel, one vertex column per step. s_w holds W_kk = L_kk^-1 of the
-  // current step; the thread that finishes block (k+1, k+1) computes the next one (look-ahead).
+  const long long c2 = NRS_DCLOCK();
+  // (4) right-looking block LDL^T sweep of the tall panel, one vertex column (3x3 pivot) per step and ONE sync per step.
+  // Column k is left unscaled: with M_k = P_k^-1 (inverse of the 3x3 pivot block) the trailing update is
+  // block(li, j) -= B'(li, k) M_k B'(j, k)^T, so the only thing a step waits for is M_k — one symmetric 3x3 inverse
+  // (a single division) computed by the thread that finishes block (k+1, k+1) first. s_w is double-buffered by step
+  // parity. Afterwards every column is scaled to the Cholesky factor in one fully parallel pass (5).
   if (th.tid == 0 && nv > 0) {
-    double W[6];
-    if (!chol3_inv(sp[0], sp[ld], sp[ld + 1], sp[2 * ld], sp[2 * ld + 1], sp[2 * ld + 2], W)) NRS_DFAIL(pl.fail);
-    for (int i = 0; i < 6; i++) s_w[i] = W[i];
+    double M[6];
+    if (!inv3_spd(sp[0], sp[ld], sp[ld + 1], sp[2 * ld], sp[2 * ld + 1], sp[2 * ld + 2], M)) NRS_DFAIL(pl.fail);
+    for (int i = 0; i < 6; i++) s_w[i] = M[i];
   }
   NRS_DSYNC();
-  for (int k = 0; k < nv; k++) {
-    const double w00 = s_w[0], w10 = s_w[1], w11 = s_w[2], w20 = s_w[3], w21 = s_w[4], w22 = s_w[5];
-    // scale the rows below: B <- B W^T
-    for (int li = k + 1 + th.tid; li < rows; li += th.nthr) {
-      double* o = sp + (size_t)(3 * li) * ld + 3 * k;
-      for (int rr = 0; rr < 3; rr++) {
-        const double b0 = o[rr * ld], b1 = o[rr * ld + 1], b2 = o[rr * ld + 2];
-        o[rr * ld] = b0 * w00;
-        o[rr * ld + 1] = b0 * w10 + b1 * w11;
-        o[rr * ld + 2] = b0 * w20 + b1 * w21 + b2 * w22;
-      }
-    }
-    NRS_DSYNC();
-    if (th.tid == th.nthr - 1) {  // the diagonal block of L is kept inverted
-      double* o = sp + (size_t)(3 * k) * ld + 3 * k;
-      o[0] = w00; o[1] = 0; o[2] = 0;
-      o[ld] = w10; o[ld + 1] = w11; o[ld + 2] = 0;
-      o[2 * ld] = w20; o[2 * ld + 1] = w21; o[2 * ld + 2] = w22;
-    }
-    // trailing update: block(li, j) -= block(li, k) block(j, k)^T for k < j < nv, li >= j
+  for (int k = 0; k + 1 < nv; k++) {
+    const double* mw = s_w + 8 * (k & 1);
+    const double m00 = mw[0], m10 = mw[1], m11 = mw[2], m20 = mw[3], m21 = mw[4], m22 = mw[5];
     const int nj = nv - k - 1, w = rows - k - 1;
     for (int q = th.tid; q < nj * w; q += th.nthr) {
-      const int jj = q / w, ii = q - jj * w;
-      if (ii < jj) continue;
+      int jj = 0, ii = 0;
+      if (q > 0) {
+        jj = q / w;
+        ii = q - jj * w;
+        if (ii < jj) continue;
+      }
       const int j = k + 1 + jj, li = k + 1 + ii;
       const double* A = sp + (size_t)(3 * li) * ld + 3 * k;
       const double* B = sp + (size_t)(3 * j) * ld + 3 * k;
@@ -264,19 +284,51 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
       double nb[9];
       for (int rr = 0; rr < 3; rr++) {
         const double a0 = A[rr * ld], a1 = A[rr * ld + 1], a2 = A[rr * ld + 2];
+        const double t0 = a0 * m00 + a1 * m10 + a2 * m20;
+        const double t1 = a0 * m10 + a1 * m11 + a2 * m21;
+        const double t2 = a0 * m20 + a1 * m21 + a2 * m22;
         for (int cc = 0; cc < 3; cc++) {
-          nb[3 * rr + cc] = o[rr * ld + cc] - (a0 * b[3 * cc] + a1 * b[3 * cc + 1] + a2 * b[3 * cc + 2]);
+          nb[3 * rr + cc] = o[rr * ld + cc] - (t0 * b[3 * cc] + t1 * b[3 * cc + 1] + t2 * b[3 * cc + 2]);
           o[rr * ld + cc] = nb[3 * rr + cc];
         }
       }
-      if (ii == 0 && jj == 0) {
-        double W[6];
-        if (!chol3_inv(nb[0], nb[3], nb[4], nb[6], nb[7], nb[8], W)) NRS_DFAIL(pl.fail);
-        for (int i = 0; i < 6; i++) s_w[i] = W[i];
+      if (q == 0) {
+        double M[6];
+        if (!inv3_spd(nb[0], nb[3], nb[4], nb[6], nb[7], nb[8], M)) NRS_DFAIL(pl.fail);
+        double* mo = s_w + 8 * ((k + 1) & 1);
+        for (int i = 0; i < 6; i++) mo[i] = M[i];
       }
     }
     NRS_DSYNC();
   }
+  // (5) Cholesky scaling, fully parallel: W_k = chol(P_k)^-1 replaces the diagonal block (the diagonal of L is kept
+  // inverted), every block below it becomes B' W_k^T
+  double* s_wall = s_w + 16;
+  for (int k = th.tid; k < nv; k += th.nthr) {
+    double* o = sp + (size_t)(3 * k) * ld + 3 * k;
+    double W[6];
+    if (!chol3_inv(o[0], o[ld], o[ld + 1], o[2 * ld], o[2 * ld + 1], o[2 * ld + 2], W)) NRS_DFAIL(pl.fail);
+    for (int i = 0; i < 6; i++) s_wall[6 * k + i] = W[i];
+    o[0] = W[0]; o[1] = 0; o[2] = 0;
+    o[ld] = W[1]; o[ld + 1] = W[2]; o[ld + 2] = 0;
+    o[2 * ld] = W[3]; o[2 * ld + 1] = W[4]; o[2 * ld + 2] = W[5];
+  }
+  NRS_DSYNC();
+  for (int q = th.tid; q < nv * rows; q += th.nthr) {
+    const int k = q / rows, li = q - k * rows;
+    if (li <= k) continue;
+    const double* W = s_wall + 6 * k;
+    const double w00 = W[0], w10 = W[1], w11 = W[2], w20 = W[3], w21 = W[4], w22 = W[5];
+    double* o = sp + (size_t)(3 * li) * ld + 3 * k;
+    for (int rr = 0; rr < 3; rr++) {
+      const double b0 = o[rr * ld], b1 = o[rr * ld + 1], b2 = o[rr * ld + 2];
+      o[rr * ld] = b0 * w00;
+      o[rr * ld + 1] = b0 * w10 + b1 * w11;
+      o[rr * ld + 2] = b0 * w20 + b1 * w21 + b2 * w22;
+    }
+  }
+  NRS_DSYNC();
+  const long long c3 = NRS_DCLOCK();
   // (5) store: the leader writes L11, every member its boundary rows
   double* Pg = pl.panel + NRS_DLDG(pl.p_off + f.t);
   const int ns = f.ns;
@@ -285,6 +337,13 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
     const int row = q / ns, c = q - row * ns;
     const int li = row / 3, a = row - 3 * li;
     Pg[(size_t)(3 * front_pos(f, li) + a) * ns + c] = sp[(size_t)row * ld + c];
+  }
+  if (pf) {
+    const long long c4 = NRS_DCLOCK();
+    pf[3] += c1 - c0;
+    pf[4] += c2 - c1;
+    pf[8] += c3 - c2;
+    pf[9] += c4 - c3;
   }
 }
 
@@ -361,7 +420,8 @@ NRS_DD void stage_c(const Plan& pl, int g, int d, double* sp, Thr th) {
 // The leader also writes the point rows of delta (4-double stride) and the pose delta.
 // ---------------------------------------------------------------------------------------------------------------
 NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double* sp, double* s_z, double* delta,
-                           double* dpose, Thr th) {
+                           double* dpose, Thr th, long long* pf = nullptr) {
+  const long long c0 = NRS_DCLOCK();
   const Front f = front_of(pl, g, d);
   const int ld = f.ld, nv = f.nv, ns = f.ns, nbv = f.nbv;
   if (nv == 0) return;
@@ -387,6 +447,7 @@ NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double*
     part[grp * ns + c] = s;
   }
   NRS_DSYNC();
+  const long long c1 = NRS_DCLOCK();
   const double* y = L21 + (size_t)nrows * ns;  // first scalar row of the rhs block row
   for (int c = th.tid; c < ns; c += th.nthr) {
     double s = NRS_DLDCG(y + c);
@@ -410,6 +471,10 @@ NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double*
       xo[3 * i + 2] = x2;
     }
     NRS_DSYNC();
+  }
+  if (pf) {
+    pf[10] += c1 - c0;
+    pf[11] += NRS_DCLOCK() - c1;
   }
   if (f.r == 0) {
     const int vb = NRS_DLDG(pl.vb + f.t);

@@ -29,7 +29,7 @@ extern "C" int direct_emul_solve(int32_t V, const double* uv, int32_t P, const i
   for (auto& v : pi) v = new_of_old[v];
   for (auto& v : pj) v = new_of_old[v];
   // incidence lists exactly like stage_problem (nrs_api.cu)
-  std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P);
+  std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P), inc_row(2 * (size_t)P);
   for (int e = 0; e < P; e++) {
     inc_ptr[pi[e] + 1]++;
     inc_ptr[pj[e] + 1]++;
@@ -41,9 +41,11 @@ extern "C" int direct_emul_solve(int32_t V, const double* uv, int32_t P, const i
       int a = w[pi[e]]++;
       inc_other[a] = pj[e];
       inc_ent[a] = 2 * e;
+      inc_row[a] = pi[e];
       a = w[pj[e]]++;
       inc_other[a] = pi[e];
       inc_ent[a] = 2 * e + 1;
+      inc_row[a] = pj[e];
     }
   }
   std::vector<int> inc_pos;
@@ -65,10 +67,10 @@ extern "C" int direct_emul_solve(int32_t V, const double* uv, int32_t P, const i
   dp.panel = panel.data(); dp.upd = upd.data(); dp.fail = &fail;
   direct::Sys sys;
   sys.dg = dg8.data(); sys.cpl = cplp.data(); sys.bvec = b4.data(); sys.pc = pc; sys.hpp = hpp;
-  sys.inc_ptr = inc_ptr.data(); sys.inc_ent = inc_ent.data(); sys.inc_pos = inc_pos.data(); sys.lambda = lambda;
+  sys.inc_ptr = inc_ptr.data(); sys.inc_ent = inc_ent.data(); sys.inc_pos = inc_pos.data(); sys.inc_row = inc_row.data(); sys.lambda = lambda;
   int max_ns = 0;
   for (int t = 1; t <= pl.n_nodes; t++) max_ns = std::max(max_ns, 3 * pl.nv[t]);
-  std::vector<double> sp(pl.smem_doubles + 16), sw(16), spath(pl.max_path + 8), sz(2 * (size_t)max_ns + 8);
+  std::vector<double> sp(pl.smem_doubles + 16), sw(16 + 2 * (size_t)max_ns + 8), spath(pl.max_path + 8), sz(2 * (size_t)max_ns + 8);
   const direct::Thr th{0, 1};
   for (int d = pl.depth; d >= 0; d--) {
     for (int g = 0; g < pl.G; g++) direct::stage_ab(dp, sys, g, d, sp.data(), sw.data(), th);
