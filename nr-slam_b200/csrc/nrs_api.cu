@@ -464,7 +464,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     for (int t = 1; t <= dplan.n_nodes; t++) max_ns = std::max(max_ns, 3 * dplan.nv[t]);
     dscratch = max_ns * (1 + direct_block_threads() / 32);
     dmaxnv = max_ns / 3;
-    dsmem = direct_smem_bytes(dplan.max_path, dscratch, dmaxnv, dplan.smem_doubles);
+    dsmem = direct_smem_bytes(dplan.max_path, dscratch, dmaxnv, dplan.max_rows, dplan.smem_doubles);
     // the busiest team member's panel must fit one SM, the whole grid must be co-resident, one row group per thread
     if (dsmem > 226 * 1024 || direct_max_grid(dsmem) < dplan.G ||
         (V + dplan.G - 1) / dplan.G > direct_block_threads())
@@ -718,6 +718,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     q.dpose = wk.d<double>(wk.take<double>(8));
     q.scratch_z = dscratch;
     q.max_nv = dmaxnv;
+    q.max_rows = dplan.max_rows;
     q.plev = wk.d<long long>(wk.take<long long>(32 * (size_t)dplan.G));
     q.P = p;
     st.use_direct = true;

@@ -61,7 +61,7 @@ constexpr int kRec = 16;  // doubles per pose-block row record: A (12), omega, -
 struct DirectEngine {
   const DirectParams& Q;
   const Params& P;
-  double *s_pose, *s_pose_bak, *s_scal, *s_w, *s_hpp, *s_red, *s_rec, *s_path, *s_z, *sp;
+  double *s_pose, *s_pose_bak, *s_scal, *s_w, *s_v, *s_hpp, *s_red, *s_rec, *s_path, *s_z, *sp;
   int tid, G, cta;
   int rpc, lpr, slot, lane;  // rows per CTA, lanes per row, this thread's row slot / lane inside the row group
   unsigned long long gen;
@@ -80,13 +80,14 @@ struct DirectEngine {
     s_pose = p; p += 8;
     s_pose_bak = p; p += 8;
     s_scal = p; p += 8;
-    s_w = p; p += 16 + 6 * ((Q.max_nv + 1) & ~1);
+    s_w = p; p += 6 * ((Q.max_nv + 1) & ~1) + 8;
+    s_v = p; p += (size_t)Q.max_rows * 3 * (3 * direct::kPanel + 1) + 1;
     s_hpp = p; p += 28;
     s_red = p; p += 27 * 8;
-    s_rec = p; p += kRec * kDBlock;
     s_path = p; p += (Q.pl.max_path + 1) & ~1;
     s_z = p; p += (Q.scratch_z + 1) & ~1;
     sp = p;
+    s_rec = sp;  // the pose-block row records of the linearisation live in the (then idle) panel buffer
     rpc = (P.V + G - 1) / G;
     lpr = 16;
     while (lpr > 1 && lpr * rpc > kDBlock) lpr >>= 1;
@@ -434,7 +435,7 @@ struct DirectEngine {
     const int depth = Q.pl.depth;
     for (int d = depth; d >= 0; d--) {
       const long long t0 = clock64();
-      direct::stage_ab(Q.pl, sys, cta, d, sp, s_w, th, prof);
+      direct::stage_ab(Q.pl, sys, cta, d, sp, s_w, s_v, th, prof);
       const long long t1 = clock64();
       prof[0] += t1 - t0;
 #ifdef NRS_DIRECT_PLEV
@@ -647,9 +648,9 @@ __global__ void __launch_bounds__(kDBlock, 1) nrs_track_direct_kernel(const __gr
 
 }  // namespace
 
-size_t direct_smem_bytes(int max_path, int scratch_z, int max_nv, size_t panel_doubles) {
-  size_t d = 8 + 8 + 8 + 16 + 6 * (size_t)((max_nv + 1) & ~1) + 28 + 27 * 8 + (size_t)kRec * kDBlock + ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
-             panel_doubles + 2;
+size_t direct_smem_bytes(int max_path, int scratch_z, int max_nv, int max_rows, size_t panel_doubles) {
+  size_t d = 8 + 8 + 8 + 8 + 6 * (size_t)((max_nv + 1) & ~1) + (size_t)max_rows * 3 * (3 * direct::kPanel + 1) + 1 + 28 + 27 * 8 + ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
+             (panel_doubles > (size_t)kRec * kDBlock ? panel_doubles : (size_t)kRec * kDBlock) + 2;
   return d * sizeof(double);
 }
 

@@ -18,10 +18,11 @@ struct DirectParams {
   double* dpose;       // [8]    pose part of the last solution
   int scratch_z;       // shared-memory doubles of the backward substitution scratch
   int max_nv;          // most own vertices of any front
+  int max_rows;        // most panel rows of any team member
   long long* plev;     // [G][32] per-level cycle counters of every CTA (diagnostics, may be null)
 };
 
-size_t direct_smem_bytes(int max_path, int scratch_z, int max_nv, size_t panel_doubles);
+size_t direct_smem_bytes(int max_path, int scratch_z, int max_nv, int max_rows, size_t panel_doubles);
 int direct_block_threads();
 int direct_max_grid(size_t smem);  // co-resident CTAs of the kernel with this much dynamic shared memory
 int launch_direct(const DirectParams& q, int grid, size_t smem, cudaStream_t stream);

@@ -18,7 +18,8 @@
 // of the factorisation: the rhs row of a node's panel ends up holding y_own^T and the rhs row of U the reduced rhs.
 // The backward substitution needs no synchronisation at all: every CTA walks ITS root-to-leaf path and recomputes the
 // (bit-identical) solution of every front on it into a shared-memory path vector.
-// Diagonal 3x3 blocks of L are stored INVERTED, so scaling and substitution are multiplications.
+// The factorisation is a block L D L^T with 3x3 pivot blocks (no square roots: one reciprocal per pivot block): the
+// stored factor is the unit lower block-triangular L', the diagonal block positions hold the pivot blocks D_k.
 //
 // The file compiles for the device and — with NRS_DIRECT_HOST_EMULATION — for the host with one emulated thread per
 // CTA (the code between two syncs is race free), which is how the CPU test suite checks the arithmetic without a GPU.
@@ -29,19 +30,23 @@
 #ifdef NRS_DIRECT_HOST_EMULATION
 #define NRS_DD inline
 #define NRS_DSYNC() ((void)0)
+#define NRS_DSYNCWARP() ((void)0)
 #define NRS_DLDCG(p) (*(p))
 #define NRS_DLDG(p) (*(p))
 #define NRS_DFAIL(p) (++*(p))
 #define NRS_DCLOCK() 0LL
 #define NRS_DRSQRT(x) (1.0 / sqrt(x))
+#define NRS_DRCP(x) (1.0 / (x))
 #else
 #define NRS_DD __device__ __forceinline__
 #define NRS_DSYNC() __syncthreads()
+#define NRS_DSYNCWARP() __syncwarp()
 #define NRS_DLDCG(p) __ldcg(p)
 #define NRS_DLDG(p) __ldg(p)
 #define NRS_DFAIL(p) atomicAdd((p), 1)
 #define NRS_DCLOCK() clock64()
 #define NRS_DRSQRT(x) rsqrt(x)
+#define NRS_DRCP(x) nrs::direct::fast_rcp(x)
 #endif
 
 namespace nrs {
@@ -71,6 +76,23 @@ struct Sys {
 struct Thr {
   int tid, nthr;
 };
+
+#ifndef NRS_DIRECT_HOST_EMULATION
+// 1 / d to full double precision for normal positive d: hardware approximation + two Newton steps (the IEEE division
+// of CUDA costs several times more and sits on the pivot chain of the factorisation).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+#endif
+
+constexpr int kPanel = 4;  // vertex columns per panel of the blocked factorisation
 
 NRS_DD int sym6i(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  // a <= c
 
@@ -104,7 +126,7 @@ NRS_DD bool inv3_spd(const double a00, const double a10, const double a11, const
   const double c22 = a00 * a11 - a10 * a10;
   const double det = a00 * c00 + a10 * c10 + a20 * c20;
   const bool ok = a00 > 0 && c22 > 0 && det > 0;
-  const double r = ok ? 1.0 / det : 1.0;
+  const double r = ok ? NRS_DRCP(det) : 1.0;
   M[0] = c00 * r;
   M[1] = c10 * r;
   M[2] = (a00 * a22 - a20 * a20) * r;
@@ -144,11 +166,67 @@ NRS_DD int local_row(const Front& f, int fp) {
 }
 NRS_DD int front_pos(const Front& f, int li) { return li < f.nv ? li : f.nv + f.r + (li - f.nv) * f.R; }
 
+// Factorisation of the diagonal region [ka, kb) x [ka, kb) (at most kPanel vertex blocks a side) of the panel in sp by
+// ONE warp (nl lanes, warp-level syncs only): block L D L^T sweep with 3x3 pivots — per column M_k = D_k^-1 (cofactors,
+// one reciprocal; kept in s_m), then block(li, j) -= B'(li, k) M_k B'(j, k)^T on the unscaled blocks B' — and at the
+// end every block below the diagonal becomes L' = B' M_k. The diagonal blocks keep the pivots D_k.
+NRS_DD void diag_region(const Plan& pl, double* sp, int ld, int ka, int kb, double* s_m, int lane, int nl) {
+  const int nr = kb - ka;
+  const int nblk = nr * (nr + 1) / 2;  // lower block triangle, row-major: (0,0) (1,0) (1,1) (2,0) ...
+  for (int k = ka; k < kb; k++) {
+    const double* P = sp + (size_t)(3 * k) * ld + 3 * k;
+    double M[6];
+    if (!inv3_spd(P[0], P[ld], P[ld + 1], P[2 * ld], P[2 * ld + 1], P[2 * ld + 2], M) && lane == 0) NRS_DFAIL(pl.fail);
+    if (lane == 0)
+      for (int i = 0; i < 6; i++) s_m[6 * k + i] = M[i];
+    for (int q = lane; q < nblk; q += nl) {
+      int ii = 0;
+      while ((ii + 1) * (ii + 2) / 2 <= q) ii++;
+      const int jj = q - ii * (ii + 1) / 2;
+      const int li = ka + ii, j = ka + jj;
+      if (j <= k) continue;
+      const double* A = sp + (size_t)(3 * li) * ld + 3 * k;
+      const double* B = sp + (size_t)(3 * j) * ld + 3 * k;
+      double* o = sp + (size_t)(3 * li) * ld + 3 * j;
+      double b[9];
+      for (int t = 0; t < 3; t++) {
+        b[3 * t] = B[t * ld];
+        b[3 * t + 1] = B[t * ld + 1];
+        b[3 * t + 2] = B[t * ld + 2];
+      }
+      for (int rr = 0; rr < 3; rr++) {
+        const double a0 = A[rr * ld], a1 = A[rr * ld + 1], a2 = A[rr * ld + 2];
+        const double t0 = a0 * M[0] + a1 * M[1] + a2 * M[3];
+        const double t1 = a0 * M[1] + a1 * M[2] + a2 * M[4];
+        const double t2 = a0 * M[3] + a1 * M[4] + a2 * M[5];
+        for (int cc = 0; cc < 3; cc++) o[rr * ld + cc] -= t0 * b[3 * cc] + t1 * b[3 * cc + 1] + t2 * b[3 * cc + 2];
+      }
+    }
+    NRS_DSYNCWARP();
+  }
+  for (int q = lane; q < nblk; q += nl) {
+    int ii = 0;
+    while ((ii + 1) * (ii + 2) / 2 <= q) ii++;
+    const int kk = q - ii * (ii + 1) / 2;
+    if (kk >= ii) continue;
+    const double* M = s_m + 6 * (ka + kk);
+    double* o = sp + (size_t)(3 * (ka + ii)) * ld + 3 * (ka + kk);
+    for (int rr = 0; rr < 3; rr++) {
+      const double b0 = o[rr * ld], b1 = o[rr * ld + 1], b2 = o[rr * ld + 2];
+      o[rr * ld] = b0 * M[0] + b1 * M[1] + b2 * M[3];
+      o[rr * ld + 1] = b0 * M[1] + b1 * M[2] + b2 * M[4];
+      o[rr * ld + 2] = b0 * M[3] + b1 * M[4] + b2 * M[5];
+    }
+  }
+  NRS_DSYNCWARP();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// Stage AB: assemble + factorise + store. sp: rows_local*3 x ld doubles; s_w: 16 + 6 nv doubles.
+// Stage AB: assemble + factorise + store. sp: rows_local*3 x ld doubles; s_w: 6 nv doubles (M_k); s_v: rows_local x
+// (3 kPanel + 1) doubles per scalar row (the unscaled panel rows the trailing update multiplies with).
 // A member without boundary rows that is not the leader has nothing to do.
 // ---------------------------------------------------------------------------------------------------------------
-NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, double* s_w, Thr th,
+NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, double* s_w, double* s_v, Thr th,
                      long long* pf = nullptr) {
   const long long c0 = NRS_DCLOCK();
   const Front f = front_of(pl, g, d);
@@ -249,85 +327,135 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
     }
   }
   const long long c2 = NRS_DCLOCK();
-  // (4) right-looking block LDL^T sweep of the tall panel, one vertex column (3x3 pivot) per step and ONE sync per step.
-  // Column k is left unscaled: with M_k = P_k^-1 (inverse of the 3x3 pivot block) the trailing update is
-  // block(li, j) -= B'(li, k) M_k B'(j, k)^T, so the only thing a step waits for is M_k — one symmetric 3x3 inverse
-  // (a single division) computed by the thread that finishes block (k+1, k+1) first. s_w is double-buffered by step
-  // parity. Afterwards every column is scaled to the Cholesky factor in one fully parallel pass (5).
-  if (th.tid == 0 && nv > 0) {
-    double M[6];
-    if (!inv3_spd(sp[0], sp[ld], sp[ld + 1], sp[2 * ld], sp[2 * ld + 1], sp[2 * ld + 2], M)) NRS_DFAIL(pl.fail);
-    for (int i = 0; i < 6; i++) s_w[i] = M[i];
-  }
+  // (4) blocked right-looking block L D L^T of the tall panel, kPanel vertex columns (3 kPanel scalars) per step and
+  // TWO block syncs per step. With [k0, k1) the current panel and [k1, k2) the next one:
+  //   R  every row block below the panel's diagonal region solves against it (thread per row, registers):
+  //      B'_k = A_k - sum_{k' < k} B'_k' L'(k, k')^T, L'_k = B'_k M_k; the unscaled B' goes to the scratch s_v;
+  //   T  rank-(3 kPanel) update of everything right of the panel, block(li, j) -= B'(li, panel) L'(j, panel)^T, in 3x6
+  //      register tiles (18 accumulators, 9 shared-memory loads per 18 FMAs) — while warp 0 LOOKS AHEAD: it updates
+  //      the next panel's diagonal region first and factorises it (diag_region), so the pivot chain of panel p+1
+  //      overlaps the bulk update of panel p.
+  constexpr int kVS = 3 * kPanel + 1;                              // row stride of s_v (odd: conflict-free)
+  const int nl = th.nthr < 32 ? th.nthr : 32;                      // lanes of the look-ahead warp
+  const bool la_warp = th.tid < nl;                                // this thread belongs to it
+  const int gt = (th.nthr >= 64) ? th.tid - 32 : th.tid;           // bulk threads: everybody else (all, if one warp)
+  const int gn = (th.nthr >= 64) ? th.nthr - 32 : th.nthr;
+  if (la_warp && nv > 0) diag_region(pl, sp, ld, 0, nv < kPanel ? nv : kPanel, s_w, th.tid, nl);
   NRS_DSYNC();
-  for (int k = 0; k + 1 < nv; k++) {
-    const double* mw = s_w + 8 * (k & 1);
-    const double m00 = mw[0], m10 = mw[1], m11 = mw[2], m20 = mw[3], m21 = mw[4], m22 = mw[5];
-    const int nj = nv - k - 1, w = rows - k - 1;
-    for (int q = th.tid; q < nj * w; q += th.nthr) {
-      int jj = 0, ii = 0;
-      if (q > 0) {
-        jj = q / w;
-        ii = q - jj * w;
-        if (ii < jj) continue;
-      }
-      const int j = k + 1 + jj, li = k + 1 + ii;
-      const double* A = sp + (size_t)(3 * li) * ld + 3 * k;
-      const double* B = sp + (size_t)(3 * j) * ld + 3 * k;
-      double* o = sp + (size_t)(3 * li) * ld + 3 * j;
-      double b[9];
-      for (int t = 0; t < 3; t++) {
-        b[3 * t] = B[t * ld];
-        b[3 * t + 1] = B[t * ld + 1];
-        b[3 * t + 2] = B[t * ld + 2];
-      }
-      double nb[9];
-      for (int rr = 0; rr < 3; rr++) {
-        const double a0 = A[rr * ld], a1 = A[rr * ld + 1], a2 = A[rr * ld + 2];
-        const double t0 = a0 * m00 + a1 * m10 + a2 * m20;
-        const double t1 = a0 * m10 + a1 * m11 + a2 * m21;
-        const double t2 = a0 * m20 + a1 * m21 + a2 * m22;
-        for (int cc = 0; cc < 3; cc++) {
-          nb[3 * rr + cc] = o[rr * ld + cc] - (t0 * b[3 * cc] + t1 * b[3 * cc + 1] + t2 * b[3 * cc + 2]);
-          o[rr * ld + cc] = nb[3 * rr + cc];
+  for (int k0 = 0; k0 < nv; k0 += kPanel) {
+    const int k1 = (k0 + kPanel < nv) ? k0 + kPanel : nv;
+    const int k2 = (k1 + kPanel < nv) ? k1 + kPanel : nv;
+    const int nk = k1 - k0;
+    // ---- R
+    const long long r0 = NRS_DCLOCK();
+    for (int q = 3 * k1 + th.tid; q < 3 * rows; q += th.nthr) {  // one thread per scalar row of the panel
+      const int li = q / 3;
+      double* o = sp + (size_t)q * ld + 3 * k0;
+      double* vo = s_v + (size_t)q * kVS;
+      double X[kPanel][3];
+#pragma unroll
+      for (int kk = 0; kk < kPanel; kk++)
+        if (kk < nk) {
+          X[kk][0] = o[3 * kk];
+          X[kk][1] = o[3 * kk + 1];
+          X[kk][2] = o[3 * kk + 2];
+        }
+#pragma unroll
+      for (int kk = 0; kk < kPanel; kk++) {
+        if (kk < nk) {
+          const int k = k0 + kk;
+#pragma unroll
+          for (int kp = 0; kp < kPanel; kp++) {
+            if (kp < kk) {  // B'_kk -= B'_kp L'(k, k0 + kp)^T
+              const double* Lk = sp + (size_t)(3 * k) * ld + 3 * (k0 + kp);
+#pragma unroll
+              for (int cc = 0; cc < 3; cc++)
+                X[kk][cc] -= X[kp][0] * Lk[cc * ld] + X[kp][1] * Lk[cc * ld + 1] + X[kp][2] * Lk[cc * ld + 2];
+            }
+          }
         }
       }
-      if (q == 0) {
-        double M[6];
-        if (!inv3_spd(nb[0], nb[3], nb[4], nb[6], nb[7], nb[8], M)) NRS_DFAIL(pl.fail);
-        double* mo = s_w + 8 * ((k + 1) & 1);
-        for (int i = 0; i < 6; i++) mo[i] = M[i];
+#pragma unroll
+      for (int kk = 0; kk < kPanel; kk++)
+        if (kk < nk) {
+          const double* M = s_w + 6 * (k0 + kk);
+          const double b0 = X[kk][0], b1 = X[kk][1], b2 = X[kk][2];
+          vo[3 * kk] = b0;
+          vo[3 * kk + 1] = b1;
+          vo[3 * kk + 2] = b2;
+          o[3 * kk] = b0 * M[0] + b1 * M[1] + b2 * M[3];
+          o[3 * kk + 1] = b0 * M[1] + b1 * M[2] + b2 * M[4];
+          o[3 * kk + 2] = b0 * M[3] + b1 * M[4] + b2 * M[5];
+        }
+      (void)li;
+    }
+    NRS_DSYNC();
+    const long long r1 = NRS_DCLOCK();
+    if (pf) pf[13] += r1 - r0;
+    if (k1 >= nv) break;
+    const int nc = 3 * nk;
+    // ---- T, look-ahead part: blocks (li, j) of the next diagonal region, k1 <= j <= li < k2, then its factorisation
+    if (la_warp) {
+      const int nr = k2 - k1;
+      const int nblk = nr * (nr + 1) / 2;
+      for (int q = th.tid; q < nblk; q += nl) {
+        int ii = 0;
+        while ((ii + 1) * (ii + 2) / 2 <= q) ii++;
+        const int jj = q - ii * (ii + 1) / 2;
+        const int li = k1 + ii, j = k1 + jj;
+        const double* A = s_v + (size_t)li * (3 * kVS);
+        const double* B = sp + (size_t)(3 * j) * ld + 3 * k0;
+        double* o = sp + (size_t)(3 * li) * ld + 3 * j;
+        double acc[9];
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) acc[3 * rr + cc] = o[rr * ld + cc];
+        for (int c = 0; c < nc; c++) {
+          const double a0 = A[c], a1 = A[kVS + c], a2 = A[2 * kVS + c];
+          const double b0 = B[c], b1 = B[ld + c], b2 = B[2 * ld + c];
+          acc[0] -= a0 * b0; acc[1] -= a0 * b1; acc[2] -= a0 * b2;
+          acc[3] -= a1 * b0; acc[4] -= a1 * b1; acc[5] -= a1 * b2;
+          acc[6] -= a2 * b0; acc[7] -= a2 * b1; acc[8] -= a2 * b2;
+        }
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) o[rr * ld + cc] = acc[3 * rr + cc];
+      }
+      NRS_DSYNCWARP();
+      diag_region(pl, sp, ld, k1, k2, s_w, th.tid, nl);
+      if (pf) pf[14] += NRS_DCLOCK() - r1;
+    }
+    // ---- T, bulk: rows li >= k2, column pairs from k1
+    if (!la_warp || th.nthr < 64) {
+      const int ntj = (nv - k1 + 1) >> 1, w = rows - k2;
+      for (int q = gt; q < ntj * w; q += gn) {
+        const int jp = q / w, ii = q - jp * w;
+        const int j = k1 + 2 * jp, li = k2 + ii;
+        if (li < j) continue;
+        const bool two = (j + 1 < nv) && (li >= j + 1);
+        double* o = sp + (size_t)(3 * li) * ld + 3 * j;
+        double acc[18];
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 6; cc++) acc[6 * rr + cc] = (cc < 3 || two) ? o[rr * ld + cc] : 0.0;
+        const double* A = s_v + (size_t)li * (3 * kVS);
+        const double* B = sp + (size_t)(3 * j) * ld + 3 * k0;
+        for (int c = 0; c < nc; c++) {
+          const double a0 = A[c], a1 = A[kVS + c], a2 = A[2 * kVS + c];
+          const double b0 = B[c], b1 = B[ld + c], b2 = B[2 * ld + c];
+          acc[0] -= a0 * b0; acc[1] -= a0 * b1; acc[2] -= a0 * b2;
+          acc[6] -= a1 * b0; acc[7] -= a1 * b1; acc[8] -= a1 * b2;
+          acc[12] -= a2 * b0; acc[13] -= a2 * b1; acc[14] -= a2 * b2;
+          if (two) {
+            const double b3 = B[3 * ld + c], b4 = B[4 * ld + c], b5 = B[5 * ld + c];
+            acc[3] -= a0 * b3; acc[4] -= a0 * b4; acc[5] -= a0 * b5;
+            acc[9] -= a1 * b3; acc[10] -= a1 * b4; acc[11] -= a1 * b5;
+            acc[15] -= a2 * b3; acc[16] -= a2 * b4; acc[17] -= a2 * b5;
+          }
+        }
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < (two ? 6 : 3); cc++) o[rr * ld + cc] = acc[6 * rr + cc];
       }
     }
     NRS_DSYNC();
   }
-  // (5) Cholesky scaling, fully parallel: W_k = chol(P_k)^-1 replaces the diagonal block (the diagonal of L is kept
-  // inverted), every block below it becomes B' W_k^T
-  double* s_wall = s_w + 16;
-  for (int k = th.tid; k < nv; k += th.nthr) {
-    double* o = sp + (size_t)(3 * k) * ld + 3 * k;
-    double W[6];
-    if (!chol3_inv(o[0], o[ld], o[ld + 1], o[2 * ld], o[2 * ld + 1], o[2 * ld + 2], W)) NRS_DFAIL(pl.fail);
-    for (int i = 0; i < 6; i++) s_wall[6 * k + i] = W[i];
-    o[0] = W[0]; o[1] = 0; o[2] = 0;
-    o[ld] = W[1]; o[ld + 1] = W[2]; o[ld + 2] = 0;
-    o[2 * ld] = W[3]; o[2 * ld + 1] = W[4]; o[2 * ld + 2] = W[5];
-  }
-  NRS_DSYNC();
-  for (int q = th.tid; q < nv * rows; q += th.nthr) {
-    const int k = q / rows, li = q - k * rows;
-    if (li <= k) continue;
-    const double* W = s_wall + 6 * k;
-    const double w00 = W[0], w10 = W[1], w11 = W[2], w20 = W[3], w21 = W[4], w22 = W[5];
-    double* o = sp + (size_t)(3 * li) * ld + 3 * k;
-    for (int rr = 0; rr < 3; rr++) {
-      const double b0 = o[rr * ld], b1 = o[rr * ld + 1], b2 = o[rr * ld + 2];
-      o[rr * ld] = b0 * w00;
-      o[rr * ld + 1] = b0 * w10 + b1 * w11;
-      o[rr * ld + 2] = b0 * w20 + b1 * w21 + b2 * w22;
-    }
-  }
-  NRS_DSYNC();
   const long long c3 = NRS_DCLOCK();
   // (5) store: the leader writes L11, every member its boundary rows
   double* Pg = pl.panel + NRS_DLDG(pl.p_off + f.t);
@@ -348,7 +476,8 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Stage C: rows k = r (mod R) of U = sum_children U_c - L21 L21^T. sp: 3 (kmax + 1) x ld doubles.
+// Stage C: rows k = r (mod R) of U = sum_children U_c - (L21' D) L21'^T. sp: 3 (kmax + 1) x ld doubles (L21'), then
+// 3 nmy x ld doubles (this member's rows times D).
 // ---------------------------------------------------------------------------------------------------------------
 NRS_DD void stage_c(const Plan& pl, int g, int d, double* sp, Thr th) {
   const Front f = front_of(pl, g, d);
@@ -360,6 +489,28 @@ NRS_DD void stage_c(const Plan& pl, int g, int d, double* sp, Thr th) {
   for (int q = th.tid; q < 3 * (kmax + 1) * ns; q += th.nthr) {
     const int row = q / ns, c = q - row * ns;
     sp[(size_t)row * ld + c] = NRS_DLDCG(Pg + q);
+  }
+  NRS_DSYNC();
+  // V = L21'(my rows) D: one thread per (my row, pivot block); the pivots sit on the diagonal of L11
+  double* sv = sp + (size_t)(3 * (kmax + 1)) * ld;
+  {
+    const double* Pd = pl.panel + NRS_DLDG(pl.p_off + f.t);
+    for (int q = th.tid; q < f.nmy * nv; q += th.nthr) {
+      const int m = q / nv, kk = q - m * nv;
+      const int k = f.r + m * f.R;
+      const double* Dk = Pd + (size_t)(3 * kk) * ns + 3 * kk;
+      const double d00 = NRS_DLDCG(Dk), d10 = NRS_DLDCG(Dk + ns), d11 = NRS_DLDCG(Dk + ns + 1),
+                   d20 = NRS_DLDCG(Dk + 2 * (size_t)ns), d21 = NRS_DLDCG(Dk + 2 * (size_t)ns + 1),
+                   d22 = NRS_DLDCG(Dk + 2 * (size_t)ns + 2);
+      const double* Lr = sp + (size_t)(3 * k) * ld + 3 * kk;
+      double* o = sv + (size_t)(3 * m) * ld + 3 * kk;
+      for (int rr = 0; rr < 3; rr++) {
+        const double b0 = Lr[rr * ld], b1 = Lr[rr * ld + 1], b2 = Lr[rr * ld + 2];
+        o[rr * ld] = b0 * d00 + b1 * d10 + b2 * d20;
+        o[rr * ld + 1] = b0 * d10 + b1 * d11 + b2 * d21;
+        o[rr * ld + 2] = b0 * d20 + b1 * d21 + b2 * d22;
+      }
+    }
   }
   NRS_DSYNC();
   const bool kids = 2 * f.t <= T;
@@ -397,7 +548,7 @@ NRS_DD void stage_c(const Plan& pl, int g, int d, double* sp, Thr th) {
           for (int cc = 0; cc < 3; cc++) acc[3 * rr + cc] += NRS_DLDCG(u + (size_t)rr * ld1 + cc);
       }
     }
-    const double* A = sp + (size_t)(3 * k) * ld;
+    const double* A = sv + (size_t)(3 * m) * ld;
     const double* B = sp + (size_t)(3 * j) * ld;
     double s[9];
     for (int i = 0; i < 9; i++) s[i] = 0.0;
@@ -455,14 +606,11 @@ NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double*
     s_z[c] = s;
   }
   NRS_DSYNC();
-  // L11^T x = z, block row by block row from the bottom; diagonal blocks hold W = L_ii^-1, so x_i = W^T z_i
+  // L11'^T x = z with the unit lower block-triangular L11', block row by block row from the bottom (the rhs row of the
+  // panel already holds D^-1 L'^-1 b, see the header)
   double* xo = s_path + NRS_DLDG(pl.path_off + f.t);
   for (int i = nv - 1; i >= 0; i--) {
-    const double* Wd = sp + (size_t)(3 * i) * ld + 3 * i;
-    const double z0 = s_z[3 * i], z1 = s_z[3 * i + 1], z2 = s_z[3 * i + 2];
-    const double x2 = Wd[2 * ld + 2] * z2;
-    const double x1 = Wd[ld + 1] * z1 + Wd[2 * ld + 1] * z2;
-    const double x0 = Wd[0] * z0 + Wd[ld] * z1 + Wd[2 * ld] * z2;
+    const double x0 = s_z[3 * i], x1 = s_z[3 * i + 1], x2 = s_z[3 * i + 2];
     const double* Li = sp + (size_t)(3 * i) * ld;
     for (int c = th.tid; c < 3 * i; c += th.nthr) s_z[c] -= Li[c] * x0 + Li[ld + c] * x1 + Li[2 * ld + c] * x2;
     if (th.tid == 0) {

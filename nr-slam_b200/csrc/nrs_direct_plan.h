@@ -22,6 +22,7 @@
 // All index lists are in vertex (3x3 block) units.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include <algorithm>
 #include <numeric>
@@ -45,96 +46,9 @@ struct DirectPlanHost {
   long long p_total = 0, u_total = 0;
   int max_path = 0;           // scalars of the longest root-to-leaf path (own vertices)
   size_t smem_doubles = 0;    // shared-memory doubles the numeric kernel needs for this plan
+  int max_rows = 0;           // most panel rows (own + boundary share) of any team member
   std::vector<int> owner;     // [V] tree node owning a row
 };
-
-namespace direct_detail {
-
-struct Builder {
-  const double* uv;
-  const std::vector<std::vector<int>>* adj;  // by caller row
-  int depth;
-  std::vector<std::vector<int>> own;  // per node: caller rows
-  std::vector<int> side;              // scratch: 0 none, 1 left, 2 right (by caller row)
-
-  void split(int t, int d, std::vector<int>& ids) {
-    if (d == depth) {
-      own[t] = ids;
-      return;
-    }
-    std::vector<int> left, right;
-    if (ids.size() >= 2) {
-      double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
-      for (int i : ids)
-        for (int a = 0; a < 2; a++) {
-          lo[a] = std::min(lo[a], uv[2 * (size_t)i + a]);
-          hi[a] = std::max(hi[a], uv[2 * (size_t)i + a]);
-        }
-      const int ax = (hi[0] - lo[0] >= hi[1] - lo[1]) ? 0 : 1;
-      // median cut, ties by caller row: deterministic
-      std::vector<int> order(ids);
-      const size_t half = order.size() / 2;
-      std::nth_element(order.begin(), order.begin() + half, order.end(), [&](int a, int b) {
-        const double ua = uv[2 * (size_t)a + ax], ub = uv[2 * (size_t)b + ax];
-        return ua < ub || (ua == ub && a < b);
-      });
-      left.assign(order.begin(), order.begin() + half);
-      right.assign(order.begin() + half, order.end());
-      std::sort(left.begin(), left.end());
-      std::sort(right.begin(), right.end());
-      for (int i : left) side[i] = 1;
-      for (int i : right) side[i] = 2;
-      // cut vertices and their cut degree
-      std::vector<int> cutv;
-      std::vector<int> deg;
-      for (int i : ids) {
-        int dg = 0;
-        for (int o : (*adj)[i])
-          if (side[o] && side[o] != side[i]) dg++;
-        if (dg) {
-          cutv.push_back(i);
-          deg.push_back(dg);
-        }
-      }
-      // greedy vertex cover of the cut edges: highest remaining cut degree first (ties: lower row)
-      std::vector<int>& sep = own[t];
-      for (;;) {
-        int best = -1;
-        for (size_t k = 0; k < cutv.size(); k++)
-          if (deg[k] > 0 && (best < 0 || deg[k] > deg[best])) best = (int)k;
-        if (best < 0) break;
-        const int v = cutv[best];
-        sep.push_back(v);
-        for (int o : (*adj)[v]) {
-          if (!side[o] || side[o] == side[v]) continue;
-          // edge (v, o) is covered: o loses one cut degree
-          for (size_t k = 0; k < cutv.size(); k++)
-            if (cutv[k] == o) {
-              if (deg[k] > 0) deg[k]--;
-              break;
-            }
-        }
-        deg[best] = 0;
-        side[v] = 0;  // removed: its remaining edges no longer cross
-      }
-      std::sort(sep.begin(), sep.end());
-      std::vector<int> l2, r2;
-      for (int i : left)
-        if (side[i] == 1) l2.push_back(i);
-      for (int i : right)
-        if (side[i] == 2) r2.push_back(i);
-      for (int i : ids) side[i] = 0;
-      left.swap(l2);
-      right.swap(r2);
-    } else {
-      left = ids;  // 0 or 1 vertices: pushed down the left spine
-    }
-    split(2 * t, d + 1, left);
-    split(2 * t + 1, d + 1, right);
-  }
-};
-
-}  // namespace direct_detail
 
 // Depth of the dissection for V rows on at most max_ctas CTAs: leaves of >= ~8 vertices, at most 2^7 leaves.
 inline int direct_depth(int V, int max_ctas) {
@@ -152,20 +66,116 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
   pl.n_nodes = (2 << depth) - 1;
   pl.G = 1 << depth;
   const int T = pl.n_nodes;
-  std::vector<std::vector<int>> adj(V);
+  std::vector<int> adj_ptr(V + 1, 0), adj(2 * pair_i.size());
   for (size_t e = 0; e < pair_i.size(); e++) {
-    adj[pair_i[e]].push_back(pair_j[e]);
-    adj[pair_j[e]].push_back(pair_i[e]);
+    adj_ptr[pair_i[e] + 1]++;
+    adj_ptr[pair_j[e] + 1]++;
   }
-  direct_detail::Builder b;
-  b.uv = uv;
-  b.adj = &adj;
-  b.depth = depth;
-  b.own.assign(T + 1, {});
-  b.side.assign(V, 0);
-  std::vector<int> all(V);
-  std::iota(all.begin(), all.end(), 0);
-  b.split(1, 0, all);
+  for (int i = 0; i < V; i++) adj_ptr[i + 1] += adj_ptr[i];
+  {
+    std::vector<int> w(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (size_t e = 0; e < pair_i.size(); e++) {
+      adj[w[pair_i[e]]++] = pair_j[e];
+      adj[w[pair_j[e]]++] = pair_i[e];
+    }
+  }
+  // (1) k-d partition of the pixel coordinates: `depth` rounds of median cuts along the wider axis. Keys are
+  // (coordinate bits, caller row) packed into 64 bits: a total order, so the result is deterministic.
+  const int n_leaf = 1 << depth;
+  std::vector<int> ord(V), leaf(V, 0), lo_of(T + 2, 0), hi_of(T + 2, 0);
+  std::iota(ord.begin(), ord.end(), 0);
+  lo_of[1] = 0;
+  hi_of[1] = V;
+  {
+    std::vector<uint64_t> key(V);
+    auto fkey = [](double x) {  // order-preserving map of a float to uint32
+      const float f = (float)x;
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    };
+    for (int t = 1; t < n_leaf; t++) {
+      const int lo = lo_of[t], hi = hi_of[t], mid = lo + (hi - lo) / 2;
+      lo_of[2 * t] = lo;
+      hi_of[2 * t] = mid;
+      lo_of[2 * t + 1] = mid;
+      hi_of[2 * t + 1] = hi;
+      if (hi - lo < 2) {  // 0 or 1 vertices: pushed down the left spine
+        hi_of[2 * t] = hi;
+        lo_of[2 * t + 1] = hi;
+        continue;
+      }
+      double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+      for (int k = lo; k < hi; k++)
+        for (int a = 0; a < 2; a++) {
+          const double c = uv[2 * (size_t)ord[k] + a];
+          mn[a] = std::min(mn[a], c);
+          mx[a] = std::max(mx[a], c);
+        }
+      const int ax = (mx[0] - mn[0] >= mx[1] - mn[1]) ? 0 : 1;
+      for (int k = lo; k < hi; k++) key[k] = ((uint64_t)fkey(uv[2 * (size_t)ord[k] + ax]) << 32) | (uint32_t)ord[k];
+      std::nth_element(key.begin() + lo, key.begin() + mid, key.begin() + hi);
+      for (int k = lo; k < hi; k++) ord[k] = (int)(uint32_t)key[k];
+    }
+    for (int l = 0; l < n_leaf; l++)
+      for (int k = lo_of[n_leaf + l]; k < hi_of[n_leaf + l]; k++) leaf[ord[k]] = l;
+  }
+  // (2) every pair is cut at the lowest common ancestor of its endpoints' leaves
+  auto lca = [&](int a, int b) -> int {  // 0: same leaf
+    const unsigned x = (unsigned)(leaf[a] ^ leaf[b]);
+    if (!x) return 0;
+    const int hb = 31 - __builtin_clz(x);
+    return (1 << (depth - 1 - hb)) + (leaf[a] >> (hb + 1));
+  };
+  std::vector<int> cut_ptr(T + 2, 0), cut_e;
+  {
+    std::vector<int> node_of(pair_i.size());
+    for (size_t e = 0; e < pair_i.size(); e++) {
+      node_of[e] = lca(pair_i[e], pair_j[e]);
+      cut_ptr[node_of[e] + 1]++;
+    }
+    for (int t = 0; t <= T; t++) cut_ptr[t + 1] += cut_ptr[t];
+    cut_e.resize(pair_i.size());
+    std::vector<int> w(cut_ptr.begin(), cut_ptr.end() - 1);
+    for (size_t e = 0; e < pair_i.size(); e++) cut_e[w[node_of[e]]++] = (int)e;
+  }
+  // (3) separators, top down: greedy vertex cover (highest remaining cut degree first, ties: first touched) of the
+  // node's cut edges whose endpoints are not already in an ancestor's separator
+  std::vector<std::vector<int>> own(T + 1);
+  std::vector<char> insep(V, 0);
+  {
+    std::vector<int> deg(V, 0), touched;
+    for (int t = 1; t < n_leaf; t++) {
+      touched.clear();
+      for (int c = cut_ptr[t]; c < cut_ptr[t + 1]; c++) {
+        const int a = pair_i[cut_e[c]], b2 = pair_j[cut_e[c]];
+        if (insep[a] || insep[b2]) continue;
+        if (!deg[a]++) touched.push_back(a);
+        if (!deg[b2]++) touched.push_back(b2);
+      }
+      std::vector<int>& sep = own[t];
+      for (;;) {
+        int best = -1;
+        for (int v : touched)
+          if (deg[v] > 0 && (best < 0 || deg[v] > deg[best])) best = v;
+        if (best < 0) break;
+        sep.push_back(best);
+        insep[best] = 1;
+        deg[best] = 0;
+        for (int a = adj_ptr[best]; a < adj_ptr[best + 1]; a++) {
+          const int o = adj[a];
+          if (!insep[o] && deg[o] > 0 && lca(best, o) == t) deg[o]--;  // edge (best, o) is covered
+        }
+      }
+      for (int v : touched) deg[v] = 0;
+      std::sort(sep.begin(), sep.end());
+    }
+    for (int l = 0; l < n_leaf; l++) {
+      std::vector<int>& o = own[n_leaf + l];
+      for (int k = lo_of[n_leaf + l]; k < hi_of[n_leaf + l]; k++)
+        if (!insep[ord[k]]) o.push_back(ord[k]);
+    }
+  }
 
   // post-order row numbering
   pl.vb.assign(T + 1, 0);
@@ -189,8 +199,8 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
         st.push_back({2 * t + 1, 0});
       } else {
         pl.vb[t] = (int)pl.old_of_new.size();
-        pl.nv[t] = (int)b.own[t].size();
-        for (int o : b.own[t]) {
+        pl.nv[t] = (int)own[t].size();
+        for (int o : own[t]) {
           new_of_old[o] = (int)pl.old_of_new.size();
           pl.old_of_new.push_back(o);
         }
@@ -205,37 +215,48 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
     for (int k = 0; k < npts; k++) pl.owner[pl.vb[t] + k] = t;
   }
 
-  // boundaries, children before parents (descending heap index)
-  std::vector<std::vector<int>> bnd(T + 1);
-  std::vector<int> mark(V + 3, 0);
+  // boundaries, children before parents (descending heap index). A boundary vertex is owned by an ancestor, and the
+  // ancestors' own ranges ascend towards the root, so scanning them with a mark array emits the list sorted.
+  std::vector<int> tmp_ptr(T + 2, 0), tmp;  // lists in processing order (t descending)
+  std::vector<char> mark(V + 3, 0);
+  pl.nbv.assign(T + 1, 0);
+  tmp.reserve(32 * (size_t)T);
   for (int t = T; t >= 1; t--) {
-    std::vector<int>& bt = bnd[t];
     const int npts = (t == 1) ? pl.nv[t] - 2 : pl.nv[t];
     const int last_own = pl.vb[t] + pl.nv[t] - 1;  // root: V + 1
-    auto add = [&](int v) {
-      if (v > last_own && !mark[v]) {
-        mark[v] = 1;
-        bt.push_back(v);
-      }
-    };
     if (2 * t <= T)
       for (int c = 2 * t; c <= 2 * t + 1; c++)
-        for (int v : bnd[c]) add(v);
-    for (int k = 0; k < npts; k++)
-      for (int o : adj[pl.old_of_new[pl.vb[t] + k]]) add(new_of_old[o]);
-    add(V);
-    add(V + 1);
-    add(V + 2);
-    std::sort(bt.begin(), bt.end());
-    for (int v : bt) mark[v] = 0;
+        for (int k = tmp_ptr[c]; k < tmp_ptr[c] + pl.nbv[c]; k++)
+          if (tmp[k] > last_own) mark[tmp[k]] = 1;
+    for (int k = 0; k < npts; k++) {
+      const int o_row = pl.old_of_new[pl.vb[t] + k];
+      for (int a = adj_ptr[o_row]; a < adj_ptr[o_row + 1]; a++) {
+        const int v = new_of_old[adj[a]];
+        if (v > last_own) mark[v] = 1;
+      }
+    }
+    tmp_ptr[t] = (int)tmp.size();
+    for (int a = t / 2; a >= 1; a /= 2) {
+      const int e = pl.vb[a] + ((a == 1) ? pl.nv[a] - 2 : pl.nv[a]);
+      for (int v = pl.vb[a]; v < e; v++)
+        if (mark[v]) {
+          mark[v] = 0;
+          tmp.push_back(v);
+        }
+    }
+    if (t != 1) {
+      tmp.push_back(V);
+      tmp.push_back(V + 1);
+    }
+    tmp.push_back(V + 2);
+    pl.nbv[t] = (int)tmp.size() - tmp_ptr[t];
   }
-  pl.nbv.assign(T + 1, 0);
   pl.bnd_ptr.assign(T + 2, 0);
   pl.bnd.clear();
+  pl.bnd.reserve(tmp.size());
   for (int t = 1; t <= T; t++) {
     pl.bnd_ptr[t] = (int)pl.bnd.size();
-    pl.nbv[t] = (int)bnd[t].size();
-    pl.bnd.insert(pl.bnd.end(), bnd[t].begin(), bnd[t].end());
+    pl.bnd.insert(pl.bnd.end(), tmp.begin() + tmp_ptr[t], tmp.begin() + tmp_ptr[t] + pl.nbv[t]);
   }
   pl.bnd_ptr[T + 1] = (int)pl.bnd.size();
 
@@ -282,6 +303,7 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
   pl.u_off.assign(T + 1, 0);
   pl.p_total = pl.u_total = 0;
   size_t smem = 0;
+  pl.max_rows = 0;
   for (int t = 1; t <= T; t++) {
     const long long ns = 3LL * pl.nv[t], nb = 3LL * pl.nbv[t];
     pl.p_off[t] = pl.p_total;
@@ -295,7 +317,8 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
     const long long rows_ab = pl.nv[t] + (pl.nbv[t] + R - 1) / R;
     const long long ld = (ns | 1);
     const size_t ab = (size_t)(3 * rows_ab * ld);
-    const size_t c = (size_t)(nb * ld);            // stage C: every boundary row of the panel
+    const size_t c = (size_t)((nb + 3 * ((pl.nbv[t] + R - 1) / R)) * ld);  // stage C: all boundary rows + mine times D
+    pl.max_rows = std::max(pl.max_rows, (int)rows_ab);
     const size_t bw = (size_t)(ns * ld);           // backward: L11
     smem = std::max(smem, std::max(ab, std::max(c, bw)));
   }

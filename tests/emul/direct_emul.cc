@@ -70,10 +70,10 @@ extern "C" int direct_emul_solve(int32_t V, const double* uv, int32_t P, const i
   sys.inc_ptr = inc_ptr.data(); sys.inc_ent = inc_ent.data(); sys.inc_pos = inc_pos.data(); sys.inc_row = inc_row.data(); sys.lambda = lambda;
   int max_ns = 0;
   for (int t = 1; t <= pl.n_nodes; t++) max_ns = std::max(max_ns, 3 * pl.nv[t]);
-  std::vector<double> sp(pl.smem_doubles + 16), sw(16 + 2 * (size_t)max_ns + 8), spath(pl.max_path + 8), sz(2 * (size_t)max_ns + 8);
+  std::vector<double> sp(pl.smem_doubles + 16), sw(2 * (size_t)max_ns + 16), sv((size_t)pl.max_rows * 3 * (3 * direct::kPanel + 1) + 8), spath(pl.max_path + 8), sz(2 * (size_t)max_ns + 8);
   const direct::Thr th{0, 1};
   for (int d = pl.depth; d >= 0; d--) {
-    for (int g = 0; g < pl.G; g++) direct::stage_ab(dp, sys, g, d, sp.data(), sw.data(), th);
+    for (int g = 0; g < pl.G; g++) direct::stage_ab(dp, sys, g, d, sp.data(), sw.data(), sv.data(), th);
     if (d > 0)
       for (int g = 0; g < pl.G; g++) direct::stage_c(dp, g, d, sp.data(), th);
   }

@@ -10,7 +10,7 @@ import json
 d = json.load(open("gpurun_out/bench.json"))
 print({k: d[k] for k in ("value", "ms_per_step")}, "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "grid", d["config"].get("grid_ctas"))
 names = {0: "stage_ab", 1: "stage_c", 2: "backward", 3: "ab.zero+orig", 4: "ab.pull", 5: "linearise", 6: "solve", 7: "update+chi2",
-         8: "ab.factor", 9: "ab.store", 10: "bw.load+gemv", 11: "bw.subst", 12: "barriers", 15: "total"}
+         8: "ab.factor", 9: "ab.store", 10: "bw.load+gemv", 11: "bw.subst", 12: "barriers", 13: "ab.factor.R", 14: "ab.factor.T-lookahead(warp0)", 15: "total"}
 for line in open("gpurun_out/bench.err"):
     if "nrs prof] grid 128" in line or "nrs prof] grid 64" in line:
         v = [int(x) for x in line.split("cycles:")[1].split()]
