@@ -687,7 +687,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   size_t wneed = (size_t)V * 8 * (4 + 20 + 8 + 4 + 8 + 4 * 5) + (size_t)P * 40 + (size_t)D * 32 +
                  2 * (size_t)max_chunks * kChunkVals * 8 + 2 * (size_t)max_grid_used * kSlotVals * 8 + 32 * 256 + 4096;
   if (direct)
-    wneed += ((size_t)dplan.p_total + (size_t)dplan.u_total + 18 * (size_t)V + (size_t)dplan.G * (28 + 4 + 32) + 64) * 8 +
+    wneed += ((size_t)dplan.p_total + (size_t)dplan.u_total + 18 * (size_t)V + (size_t)dplan.G * (28 + 4 + 32) + 2 * (size_t)dplan.n_nodes + 72) * 8 +
              16 * 256;
   if (!wk.reserve(wneed, false)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "work arena allocation failed");
   p.x_bak = wk.d<double>(wk.take<double>(4 * (size_t)V));
@@ -719,6 +719,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     q.scratch_z = dscratch;
     q.max_nv = dmaxnv;
     q.max_rows = dplan.max_rows;
+    q.tbar = wk.d<unsigned long long>(wk.take<unsigned long long>(2 * (size_t)dplan.n_nodes + 8));
     q.plev = wk.d<long long>(wk.take<long long>(32 * (size_t)dplan.G));
     q.P = p;
     st.use_direct = true;

@@ -64,7 +64,7 @@ struct DirectEngine {
   double *s_pose, *s_pose_bak, *s_scal, *s_w, *s_v, *s_hpp, *s_red, *s_rec, *s_path, *s_z, *sp;
   int tid, G, cta;
   int rpc, lpr, slot, lane;  // rows per CTA, lanes per row, this thread's row slot / lane inside the row group
-  unsigned long long gen;
+  unsigned long long gen, nsolve;
   double lambda, ni;
   int lm_iters, lm_trials, n_sweeps, n_chi2, n_trace, n_fail, fail_seen;
   long long prof[16];
@@ -80,7 +80,7 @@ struct DirectEngine {
     s_pose = p; p += 8;
     s_pose_bak = p; p += 8;
     s_scal = p; p += 8;
-    s_w = p; p += 6 * ((Q.max_nv + 1) & ~1) + 8;
+    s_w = p; p += 6 * (((Q.max_nv + 1) & ~1) + 1) + 80 + 2;
     s_v = p; p += (size_t)Q.max_rows * 3 * (3 * direct::kPanel + 1) + 1;
     s_hpp = p; p += 28;
     s_red = p; p += 27 * 8;
@@ -94,6 +94,7 @@ struct DirectEngine {
     slot = tid / lpr;
     lane = tid - slot * lpr;
     gen = 0;
+    nsolve = 0;
     lambda = -1;
     ni = 2;
     lm_iters = lm_trials = n_sweeps = n_chi2 = n_trace = n_fail = 0;
@@ -112,6 +113,21 @@ struct DirectEngine {
       d_red_release_add_u64(P.bar, 1ULL);
       const unsigned long long target = gen * (unsigned long long)G;
       while (d_ld_acquire_u64(P.bar) < target) {
+      }
+    }
+    __syncthreads();
+    prof[12] += clock64() - t0;
+  }
+
+  // Barrier over the `count` CTAs that work on one tree node: arrivals are counted on the node's own counter, so
+  // independent subtrees never wait for each other (only the LM-level reductions are grid-wide).
+  __device__ __forceinline__ void team_barrier(unsigned long long* ctr, unsigned long long count) {
+    const long long t0 = clock64();
+    __syncthreads();
+    if (tid == 0) {
+      d_red_release_add_u64(ctr, 1ULL);
+      const unsigned long long target = nsolve * count;
+      while (d_ld_acquire_u64(ctr) < target) {
       }
     }
     __syncthreads();
@@ -433,7 +449,10 @@ struct DirectEngine {
     sys.lambda = lambda;
     const direct::Thr th{tid, kDBlock};
     const int depth = Q.pl.depth;
+    nsolve++;
     for (int d = depth; d >= 0; d--) {
+      const int t = (1 << d) + (cta >> (depth - d));
+      const unsigned long long R = (unsigned long long)(G >> d);
       const long long t0 = clock64();
       direct::stage_ab(Q.pl, sys, cta, d, sp, s_w, s_v, th, prof);
       const long long t1 = clock64();
@@ -441,7 +460,7 @@ struct DirectEngine {
 #ifdef NRS_DIRECT_PLEV
       plev[d] += t1 - t0;
 #endif
-      barrier();
+      team_barrier(Q.tbar + 2 * t, R);  // every member's L21 rows (and the leader's L11) are in global memory
       if (d > 0) {
         const long long t2 = clock64();
         direct::stage_c(Q.pl, cta, d, sp, th);
@@ -450,7 +469,7 @@ struct DirectEngine {
 #ifdef NRS_DIRECT_PLEV
         plev[8 + d] += t2b - t2;
 #endif
-        barrier();
+        team_barrier(Q.tbar + 2 * (t >> 1) + 1, 2 * R);  // both children's update matrices are complete
       }
     }
     const int f = __ldcg(Q.pl.fail);
@@ -649,7 +668,7 @@ __global__ void __launch_bounds__(kDBlock, 1) nrs_track_direct_kernel(const __gr
 }  // namespace
 
 size_t direct_smem_bytes(int max_path, int scratch_z, int max_nv, int max_rows, size_t panel_doubles) {
-  size_t d = 8 + 8 + 8 + 8 + 6 * (size_t)((max_nv + 1) & ~1) + (size_t)max_rows * 3 * (3 * direct::kPanel + 1) + 1 + 28 + 27 * 8 + ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
+  size_t d = 8 + 8 + 8 + 6 * (size_t)(((max_nv + 1) & ~1) + 1) + 82 + (size_t)max_rows * 3 * (3 * direct::kPanel + 1) + 1 + 28 + 27 * 8 + ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
              (panel_doubles > (size_t)kRec * kDBlock ? panel_doubles : (size_t)kRec * kDBlock) + 2;
   return d * sizeof(double);
 }
@@ -683,6 +702,8 @@ int launch_direct(const DirectParams& q, int grid, size_t smem, cudaStream_t str
   cudaError_t e = cudaMemsetAsync(q.P.bar, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(q.pl.fail, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(q.tbar, 0, sizeof(unsigned long long) * 2 * (size_t)((2 << q.pl.depth) + 1), stream);
   if (e != cudaSuccess) return (int)e;
   void* args[] = {const_cast<DirectParams*>(&q)};
   return (int)cudaLaunchCooperativeKernel((const void*)nrs_track_direct_kernel, dim3(grid), dim3(kDBlock), args, smem,

@@ -19,6 +19,7 @@ struct DirectParams {
   int scratch_z;       // shared-memory doubles of the backward substitution scratch
   int max_nv;          // most own vertices of any front
   int max_rows;        // most panel rows of any team member
+  unsigned long long* tbar;  // [2 (n_nodes + 2)] per-node barrier counters: 2t after stage AB, 2t + 1 children done
   long long* plev;     // [G][32] per-level cycle counters of every CTA (diagnostics, may be null)
 };
 

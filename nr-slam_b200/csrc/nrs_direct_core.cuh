@@ -221,6 +221,86 @@ NRS_DD void diag_region(const Plan& pl, double* sp, int ld, int ka, int kb, doub
   NRS_DSYNCWARP();
 }
 
+#ifndef NRS_DIRECT_HOST_EMULATION
+// Device version of [special update +] diag_region for the look-ahead warp: the critical latency chain of the whole
+// factorisation, so it is written for the fewest dependent instructions. Lane l < nblk owns ONE block (I, J) of the
+// region's lower block triangle in registers from the rank update through the pivot sweep to the final scaling;
+// per column the owners of column k publish their blocks to a small staging area (double-buffered by column parity),
+// everybody reads pivot / A / B from there. kPanel <= 4 (10 blocks <= 32 lanes).
+//   update: nc > 0 -> blk -= V(ka + I, 0:nc) L'(ka + J, k0cols)^T first (the rank-3 kPanel update of the previous panel)
+__device__ __forceinline__ void diag_region_dev(const Plan& pl, double* sp, int ld, int ka, int kb, double* s_m,
+                                                double* s_x, int lane, const double* s_v, int kvs, int k0, int nc) {
+  const int nr = kb - ka;
+  const int nblk = nr * (nr + 1) / 2;
+  const bool act = lane < nblk;
+  const int I = act ? (lane >= 1) + (lane >= 3) + (lane >= 6) : 0;
+  const int J = act ? lane - I * (I + 1) / 2 : 0;
+  double* o = sp + (size_t)(3 * (ka + I)) * ld + 3 * (ka + J);
+  double b[9];
+#pragma unroll
+  for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) b[3 * rr + cc] = act ? o[rr * ld + cc] : 0.0;
+  if (nc > 0 && act) {
+    const double* A = s_v + (size_t)(ka + I) * (3 * kvs);
+    const double* B = sp + (size_t)(3 * (ka + J)) * ld + 3 * k0;
+#pragma unroll 4
+    for (int c = 0; c < nc; c++) {
+      const double a0 = A[c], a1 = A[kvs + c], a2 = A[2 * kvs + c];
+      const double b0 = B[c], b1 = B[ld + c], b2 = B[2 * ld + c];
+      b[0] -= a0 * b0; b[1] -= a0 * b1; b[2] -= a0 * b2;
+      b[3] -= a1 * b0; b[4] -= a1 * b1; b[5] -= a1 * b2;
+      b[6] -= a2 * b0; b[7] -= a2 * b1; b[8] -= a2 * b2;
+    }
+  }
+  for (int k = 0; k < nr; k++) {
+    double* xs = s_x + 40 * (k & 1);  // [4][10]
+    if (act && J == k) {
+      double* x = xs + 10 * I;
+#pragma unroll
+      for (int i = 0; i < 9; i++) x[i] = b[i];
+    }
+    __syncwarp();
+    const double* P = xs + 10 * k;
+    double M[6];
+    const bool ok = inv3_spd(P[0], P[3], P[4], P[6], P[7], P[8], M);
+    if (lane == 0) {
+      if (!ok) NRS_DFAIL(pl.fail);
+#pragma unroll
+      for (int i = 0; i < 6; i++) s_m[6 * (ka + k) + i] = M[i];
+    }
+    if (act && J == k) {  // this block is final: pivot as is, below the diagonal L' = B' M
+      if (I > k) {
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+          const double b0 = b[3 * rr], b1 = b[3 * rr + 1], b2 = b[3 * rr + 2];
+          b[3 * rr] = b0 * M[0] + b1 * M[1] + b2 * M[3];
+          b[3 * rr + 1] = b0 * M[1] + b1 * M[2] + b2 * M[4];
+          b[3 * rr + 2] = b0 * M[3] + b1 * M[4] + b2 * M[5];
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) o[rr * ld + cc] = b[3 * rr + cc];
+    } else if (act && J > k) {
+      const double* A = xs + 10 * I;
+      const double* B = xs + 10 * J;
+#pragma unroll
+      for (int rr = 0; rr < 3; rr++) {
+        const double a0 = A[3 * rr], a1 = A[3 * rr + 1], a2 = A[3 * rr + 2];
+        const double t0 = a0 * M[0] + a1 * M[1] + a2 * M[3];
+        const double t1 = a0 * M[1] + a1 * M[2] + a2 * M[4];
+        const double t2 = a0 * M[3] + a1 * M[4] + a2 * M[5];
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) b[3 * rr + cc] -= t0 * B[3 * cc] + t1 * B[3 * cc + 1] + t2 * B[3 * cc + 2];
+      }
+    }
+  }
+  __syncwarp();
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // Stage AB: assemble + factorise + store. sp: rows_local*3 x ld doubles; s_w: 6 nv doubles (M_k); s_v: rows_local x
 // (3 kPanel + 1) doubles per scalar row (the unscaled panel rows the trailing update multiplies with).
@@ -340,7 +420,14 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
   const bool la_warp = th.tid < nl;                                // this thread belongs to it
   const int gt = (th.nthr >= 64) ? th.tid - 32 : th.tid;           // bulk threads: everybody else (all, if one warp)
   const int gn = (th.nthr >= 64) ? th.nthr - 32 : th.nthr;
+#ifndef NRS_DIRECT_HOST_EMULATION
+  static_assert(kPanel <= 4, "diag_region_dev keeps one block of the region per lane");
+  double* s_x = s_w + 6 * (((nv + 1) & ~1) + 1);  // staging area of the look-ahead warp: 2 x [4][10] doubles
+  if (la_warp && nv > 0)
+    diag_region_dev(pl, sp, ld, 0, nv < kPanel ? nv : kPanel, s_w, s_x, th.tid, s_v, kVS, 0, 0);
+#else
   if (la_warp && nv > 0) diag_region(pl, sp, ld, 0, nv < kPanel ? nv : kPanel, s_w, th.tid, nl);
+#endif
   NRS_DSYNC();
   for (int k0 = 0; k0 < nv; k0 += kPanel) {
     const int k1 = (k0 + kPanel < nv) ? k0 + kPanel : nv;
@@ -395,6 +482,12 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
     if (k1 >= nv) break;
     const int nc = 3 * nk;
     // ---- T, look-ahead part: blocks (li, j) of the next diagonal region, k1 <= j <= li < k2, then its factorisation
+#ifndef NRS_DIRECT_HOST_EMULATION
+    if (la_warp) {
+      diag_region_dev(pl, sp, ld, k1, k2, s_w, s_x, th.tid, s_v, kVS, k0, nc);
+      if (pf) pf[14] += NRS_DCLOCK() - r1;
+    }
+#else
     if (la_warp) {
       const int nr = k2 - k1;
       const int nblk = nr * (nr + 1) / 2;
@@ -421,8 +514,8 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
       }
       NRS_DSYNCWARP();
       diag_region(pl, sp, ld, k1, k2, s_w, th.tid, nl);
-      if (pf) pf[14] += NRS_DCLOCK() - r1;
     }
+#endif
     // ---- T, bulk: rows li >= k2, column pairs from k1
     if (!la_warp || th.nthr < 64) {
       const int ntj = (nv - k1 + 1) >> 1, w = rows - k2;
