@@ -154,7 +154,8 @@ struct HostProblem {
   std::vector<int> kf_begin;            // F+1: rows of pose slot k are [kf_begin[k], kf_begin[k+1]) (rows w/o pose: slot 0)
   int n_halo = 0;                       // landmark-sharded BA: trailing rows owned by other ranks (read-only copies)
   bool sharded = false;
-  bool direct = false;                  // tracking main rounds: exact multifrontal LL^T engine (nrs_direct.cu)
+  bool direct = false;                  // tracking: exact multifrontal L D L^T engine (nrs_direct.cu)
+  int n_unknown = 0;                    // direct engine: rows [n_unknown, V) are fixed vertices (0: every row is an unknown)
   std::vector<int> ops, op_args;
 };
 
@@ -195,7 +196,8 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
   std::vector<int> old_of_new(V);
   std::iota(old_of_new.begin(), old_of_new.end(), 0);
   if (forced_old_of_new) {
-    old_of_new = *forced_old_of_new;  // elimination order of the exact solve (nrs_direct_plan.h)
+    // elimination order of the exact solve (nrs_direct_plan.h); it may cover a prefix (the unknown rows) only
+    std::copy(forced_old_of_new->begin(), forced_old_of_new->end(), old_of_new.begin());
   } else {
   // keyframes are sorted independently: host threads take them round robin on large windows (same result)
   const int n_threads = host_threads(hp.F, V);
@@ -252,6 +254,33 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
   for (auto& v : hp.pair_i) v = row_of[v];
   for (auto& v : hp.pair_j) v = row_of[v];
   for (auto& v : hp.dmp_v) v = row_of[v];
+  if (forced_old_of_new) {  // per-row extras of the lost-point problem
+    auto permute_u8 = [&](std::vector<unsigned char>& v) {
+      if (v.empty()) return;
+      std::vector<unsigned char> o(V);
+      for (int nw = 0; nw < V; nw++) o[nw] = v[old_of_new[nw]];
+      v.swap(o);
+    };
+    permute_u8(hp.fixed0);
+    permute_u8(hp.rp_level0);
+    if (!hp.un_ptr.empty()) {
+      std::vector<int> np(V + 1, 0), nr;
+      std::vector<double> nwt;
+      nr.reserve(hp.un_ref.size());
+      nwt.reserve(hp.un_w.size());
+      for (int nw = 0; nw < V; nw++) {
+        const int o = old_of_new[nw];
+        for (int a = hp.un_ptr[o]; a < hp.un_ptr[o + 1]; a++) {
+          nr.push_back(row_of[hp.un_ref[a]]);
+          nwt.push_back(hp.un_w[a]);
+        }
+        np[nw + 1] = (int)nr.size();
+      }
+      hp.un_ptr.swap(np);
+      hp.un_ref.swap(nr);
+      hp.un_w.swap(nwt);
+    }
+  }
 }
 
 // Launch plan of one engine launch over the rows [0, kf_begin[F]).
@@ -453,13 +482,27 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   HostProf hprof;
   // ---- exact-solve engine: symbolic analysis first, its elimination order becomes the row order
   DirectPlanHost dplan;
-  bool direct = hp.direct && F == 1 && D == 0 && U == 0 && !hp.poses_fixed && !hp.points_fixed && !hp.sharded &&
-                hp.fixed0.empty() && hp.n_stage1 == 0 && V >= 1;
+  const int Vu = (hp.n_unknown > 0 && hp.n_unknown < V) ? hp.n_unknown : V;  // rows [Vu, V) are fixed vertices
+  bool direct = hp.direct && F == 1 && D == 0 && !hp.points_fixed && !hp.sharded && hp.n_stage1 == 0 && Vu >= 1 &&
+                (hp.poses_fixed || U == 0);
+  if (direct && !hp.fixed0.empty())
+    for (int r = 0; r < V && direct; r++) direct = (hp.fixed0[r] != 0) == (r >= Vu);
+  if (direct && hp.fixed0.empty() && Vu < V) direct = false;
   size_t dsmem = 0;
   int dscratch = 0, dmaxnv = 0;
   if (direct) {
-    const int depth = std::min(direct_depth(V, ctx->sm_count), env_int("NRSLAM_B200_DIRECT_DEPTH", 7));
-    build_direct_plan(V, hp.uv.data(), hp.pair_i, hp.pair_j, depth, dplan);
+    const int depth = std::min(direct_depth(Vu, ctx->sm_count), env_int("NRSLAM_B200_DIRECT_DEPTH", 7));
+    if (Vu == V) {
+      build_direct_plan(V, hp.uv.data(), hp.pair_i, hp.pair_j, depth, dplan, !hp.poses_fixed);
+    } else {  // only pairs between two unknowns couple unknowns
+      std::vector<int> pi, pj;
+      for (int e = 0; e < P; e++)
+        if (hp.pair_i[e] < Vu && hp.pair_j[e] < Vu) {
+          pi.push_back(hp.pair_i[e]);
+          pj.push_back(hp.pair_j[e]);
+        }
+      build_direct_plan(Vu, hp.uv.data(), pi, pj, depth, dplan, !hp.poses_fixed);
+    }
     int max_ns = 0;
     for (int t = 1; t <= dplan.n_nodes; t++) max_ns = std::max(max_ns, 3 * dplan.nv[t]);
     dscratch = max_ns * (1 + direct_block_threads() / 32);
@@ -467,7 +510,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     dsmem = direct_smem_bytes(dplan.max_path, dscratch, dmaxnv, dplan.max_rows, dplan.smem_doubles);
     // the busiest team member's panel must fit one SM, the whole grid must be co-resident, one row group per thread
     if (dsmem > 226 * 1024 || direct_max_grid(dsmem) < dplan.G ||
-        (V + dplan.G - 1) / dplan.G > direct_block_threads())
+        (Vu + dplan.G - 1) / dplan.G > direct_block_threads())
       direct = false;
   }
   hprof.mark("direct_plan");
@@ -638,7 +681,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   }
   if (direct) {
     direct::Plan& dp = st.dq.pl;
-    dp.V = V; dp.depth = dplan.depth; dp.G = dplan.G; dp.max_path = dplan.max_path;
+    dp.V = Vu; dp.np = dplan.np; dp.depth = dplan.depth; dp.G = dplan.G; dp.max_path = dplan.max_path;
     dp.vb = in.d<int>(put(in, dplan.vb));
     dp.nv = in.d<int>(put(in, dplan.nv));
     dp.nbv = in.d<int>(put(in, dplan.nbv));
@@ -1264,6 +1307,16 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
       for (int t = 0; t < n_un; t++) h2.un_ref[t] = cidx(un_ref_row[t]);
       h2.kf_begin = {0, Vc};
       h2.n_sort = 0;
+      // exact-solve engine: unknowns are the free deformation rows and the lost rows (a prefix of the rows); a lost
+      // point has no pixel of its own, so the dissection places it at its first reference vertex
+      h2.direct = env_int("NRSLAM_B200_DIRECT", 1) != 0 && env_int("NRSLAM_B200_DIRECT_LOST", 1) != 0;
+      h2.n_unknown = n_free + n_lost;
+      for (int v = 0; v < n_lost; v++)
+        if (un_ptr_l[v + 1] > un_ptr_l[v]) {
+          const int ref = h2.un_ref[un_ptr_l[v]];
+          h2.uv[2 * (size_t)(lost0 + v)] = h2.uv[2 * (size_t)ref];
+          h2.uv[2 * (size_t)(lost0 + v) + 1] = h2.uv[2 * (size_t)ref + 1];
+        }
       h2.ops = {OP_RESET, OP_OPTIMIZE};
       h2.op_args = {0, opt.lost_iterations};
       Staged& st2 = ctx->staged[3];
@@ -1278,7 +1331,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
       for (int v = 0; v < n_lost; v++)
         for (int k = 0; k < 3; k++)
           last_pos[3 * (size_t)lost_list[v] + k] =
-              (float)xl[4 * (size_t)(lost0 + v) + k] + last_pos[3 * (size_t)lost_list[v] + k];  // :544-552
+              (float)xl[4 * (size_t)st2.row_of[lost0 + v] + k] + last_pos[3 * (size_t)lost_list[v] + k];  // :544-552
     }
     for (int v = 0; v < n_lost; v++)
       if (lost_vertex_out) lost_vertex_out[v] = lost_list[v];

@@ -88,7 +88,7 @@ struct DirectEngine {
     s_z = p; p += (Q.scratch_z + 1) & ~1;
     sp = p;
     s_rec = sp;  // the pose-block row records of the linearisation live in the (then idle) panel buffer
-    rpc = (P.V + G - 1) / G;
+    rpc = (Q.pl.V + G - 1) / G;
     lpr = 16;
     while (lpr > 1 && lpr * rpc > kDBlock) lpr >>= 1;
     slot = tid / lpr;
@@ -138,7 +138,7 @@ struct DirectEngine {
   __device__ __forceinline__ int my_row() const {
     if (slot >= rpc) return -1;
     const int i = slot * G + cta;
-    return i < P.V ? i : -1;
+    return i < Q.pl.V ? i : -1;  // unknown rows only (fixed rows sit behind them)
   }
 
   // sum over the lanes of a row group (fixed tree)
@@ -266,7 +266,7 @@ struct DirectEngine {
     bool rec_written = false;
     if (i >= 0) {
       const D3 xi = dld3(P.x, i);
-      if (lane == 0 && P.rp_level[i] == 0) {
+      if (lane == 0 && __ldg(P.pt_kf + i) >= 0 && P.rp_level[i] == 0) {
         double pc[3], err[2];
         const double c2 = reproj_error(i, xi, pc, err);
         double rho, drho;
@@ -310,24 +310,48 @@ struct DirectEngine {
           b[0] = B[0] * we0 + B[3] * we1;
           b[1] = B[1] * we0 + B[4] * we1;
           b[2] = B[2] * we0 + B[5] * we1;
-          double* cp = Q.cpl + 18 * (size_t)i;
+          if (Q.pl.np) {
+            double* cp = Q.cpl + 18 * (size_t)i;
 #pragma unroll
-          for (int p = 0; p < 6; p++)
+            for (int p = 0; p < 6; p++)
 #pragma unroll
-            for (int cc = 0; cc < 3; cc++) cp[3 * p + cc] = omega * (A[p] * B[cc] + A[6 + p] * B[3 + cc]);
-          double* rec = s_rec + kRec * slot;
+              for (int cc = 0; cc < 3; cc++) cp[3 * p + cc] = omega * (A[p] * B[cc] + A[6 + p] * B[3 + cc]);
+            double* rec = s_rec + kRec * slot;
 #pragma unroll
-          for (int k = 0; k < 12; k++) rec[k] = A[k];
-          rec[12] = omega;
-          rec[14] = we0;
-          rec[15] = we1;
-          rec_written = true;
+            for (int k = 0; k < 12; k++) rec[k] = A[k];
+            rec[12] = omega;
+            rec[14] = we0;
+            rec[15] = we1;
+            rec_written = true;
+          }
         }
       }
-      if (LIN && lane == 0 && !rec_written) {
+      if (LIN && lane == 0 && !rec_written && Q.pl.np) {
         double* cp = Q.cpl + 18 * (size_t)i;
 #pragma unroll
         for (int k = 0; k < 18; k++) cp[k] = 0.0;
+      }
+      if (P.unary_on && lane == 0) {
+        // SpatialRegularizerFixed  optimization/spatial_regularizer_fixed.cc:32-43 — the reference value is read
+        // live from another (fixed) vertex and carries no Jacobian
+        for (int a = __ldg(P.un_ptr + i); a < __ldg(P.un_ptr + i + 1); a++) {
+          const double w = __ldg(P.un_w + a);
+          const D3 rf = dld3(P.x, __ldg(P.un_ref + a));
+          const double d0 = xi.x - rf.x, d1 = xi.y - rf.y, d2 = xi.z - rf.z;
+          const double c2 = w * w * (d0 * d0 + d1 * d1 + d2 * d2) * P.info_spatial;
+          double rho, drho;
+          huber(c2, P.delta_spatial, rho, drho);
+          chi += rho;
+          if (LIN) {
+            const double s = drho * P.info_spatial * w * w;
+            D[0] += s;
+            D[3] += s;
+            D[5] += s;
+            b[0] -= s * d0;
+            b[1] -= s * d1;
+            b[2] -= s * d2;
+          }
+        }
       }
       // regulariser incidences of the row, split over the lanes of the group
       const int a1 = __ldg(P.inc_ptr + i + 1);
@@ -335,11 +359,13 @@ struct DirectEngine {
         const int o = __ldg(P.inc_other + a), ent = __ldg(P.inc_ent + a);
         const int e = ent >> 1;
         const bool second = ent & 1;
-        if (!LIN && second) continue;  // chi2 only: the first endpoint counts the edge
+        // the first endpoint counts the edge's chi2 — unless it is a fixed row (then this row is the only unknown)
+        const bool counts = !second || o >= Q.pl.V;
+        if (!LIN && !counts) continue;
         const D3 xo = dld3(P.x, o);
         double s, u[3], c;
         const double ch = second ? pair_edge<LIN>(e, o, i, xo, xi, s, u, c) : pair_edge<LIN>(e, i, o, xi, xo, s, u, c);
-        if (!second) chi += ch;
+        if (counts) chi += ch;
         if (LIN) {
           D[0] += s + u[0] * u[0];
           D[1] += u[0] * u[1];
@@ -380,7 +406,7 @@ struct DirectEngine {
       }
       __syncthreads();
       // pose-block partial of this CTA: 21 entries of H_pp (upper) + 6 of b_p, rows added in slot order
-      if (tid < 27) {
+      if (tid < 27 && Q.pl.np) {
         const int v = tid;
         int a = 0, c = 0;
         if (v < 21) {
@@ -501,10 +527,11 @@ struct DirectEngine {
     grid_reduce2(chi, maxd, true);
     double currentChi = s_scal[0];
     double maxDiag = s_scal[1];
-    reduce_hpp();
+    if (Q.pl.np) reduce_hpp();
     n_sweeps++;
     if (iteration == 0) {  // computeLambdaInit, optimization_algorithm_levenberg.cpp:153-165
-      for (int a = 0; a < 6; a++) maxDiag = fmax(maxDiag, fabs(s_hpp[direct::sym6i(a, a)]));
+      if (Q.pl.np)
+        for (int a = 0; a < 6; a++) maxDiag = fmax(maxDiag, fabs(s_hpp[direct::sym6i(a, a)]));
       lambda = P.lm_tau * maxDiag;
       ni = 2;
     }
@@ -532,7 +559,7 @@ struct DirectEngine {
           scale += d.x * (lambda * d.x + bb.x) + d.y * (lambda * d.y + bb.y) + d.z * (lambda * d.z + bb.z);
         }
         const double* dp = s_path + 3 * (nv_root - 2);  // the root owns the pose: last 6 entries of its solution
-        if (tid == 0) {
+        if (tid == 0 && Q.pl.np) {
           for (int t = 0; t < 7; t++) s_pose_bak[t] = s_pose[t];
           double dl[6];
           for (int t = 0; t < 6; t++) dl[t] = dp[t];
@@ -564,7 +591,7 @@ struct DirectEngine {
           const int i = my_row();
           if (i >= 0 && lane == 0) dst3(P.x, i, dld3(P.x_bak, i));
           __syncthreads();
-          if (tid == 0)
+          if (tid == 0 && Q.pl.np)
             for (int t = 0; t < 7; t++) s_pose[t] = s_pose_bak[t];
           __syncthreads();
         }

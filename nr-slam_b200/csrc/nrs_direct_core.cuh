@@ -55,6 +55,7 @@ namespace direct {
 // Device view of the plan (nrs_direct_plan.h) plus the factor storage.
 struct Plan {
   int V, depth, G, max_path;
+  int np;  // pose pseudo-vertices owned by the root (2, or 0 when the pose is fixed)
   const int *vb, *nv, *nbv, *bnd_ptr, *bnd, *bpath, *path_off, *inv_ptr, *inv;
   const long long *p_off, *u_off;
   double* panel;  // per node: (3 nv + 3 nbv) x 3 nv, row-major
@@ -332,7 +333,7 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
       b[0] = d0 + sys.lambda; b[1] = d1; b[2] = d2;
       b[ld] = d1; b[ld + 1] = d3 + sys.lambda; b[ld + 2] = d4;
       b[2 * ld] = d2; b[2 * ld + 1] = d4; b[2 * ld + 2] = d5 + sys.lambda;
-      for (int a = 0; a < 2; a++) {
+      for (int a = 0; a < pl.np; a++) {
         const int li = local_row(f, fp_pose + a);
         if (li < 0) continue;
         double* o = col + (size_t)(3 * li) * ld;

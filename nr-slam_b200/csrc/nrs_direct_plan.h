@@ -35,6 +35,7 @@ struct DirectPlanHost {
   int depth = 0;    // leaves at this depth
   int n_nodes = 0;  // 2^(depth+1) - 1, nodes are 1..n_nodes
   int G = 1;        // CTAs = 2^depth
+  int np = 2;       // pose pseudo-vertices owned by the root: 2 (pose is an unknown) or 0 (pose fixed)
   std::vector<int> old_of_new;  // [V] elimination order: new row -> caller row
   // per node t (index 0 unused)
   std::vector<int> vb, nv, nbv;     // first own vertex, own count (root: + 2 pose), boundary count (incl. pose, rhs)
@@ -60,8 +61,10 @@ inline int direct_depth(int V, int max_ctas) {
 // Builds the plan. uv: [2V] pixel coordinates (caller rows); pair_i / pair_j: regulariser pairs (caller rows).
 // After the call the caller permutes its rows with plan.old_of_new and then calls direct_inc_pos with the new ids.
 inline void build_direct_plan(int V, const double* uv, const std::vector<int>& pair_i, const std::vector<int>& pair_j,
-                              int depth, DirectPlanHost& pl) {
+                              int depth, DirectPlanHost& pl, bool with_pose = true) {
   pl.V = V;
+  pl.np = with_pose ? 2 : 0;
+  const int np = pl.np;
   pl.depth = depth;
   pl.n_nodes = (2 << depth) - 1;
   pl.G = 1 << depth;
@@ -208,10 +211,10 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
       }
     }
   }
-  pl.nv[1] += 2;  // the pose pseudo-vertices V, V+1 follow the root's separator
+  pl.nv[1] += np;  // the pose pseudo-vertices V, V+1 follow the root's separator
   pl.owner.assign(V, 0);
   for (int t = 1; t <= T; t++) {
-    const int npts = (t == 1) ? pl.nv[t] - 2 : pl.nv[t];
+    const int npts = (t == 1) ? pl.nv[t] - np : pl.nv[t];
     for (int k = 0; k < npts; k++) pl.owner[pl.vb[t] + k] = t;
   }
 
@@ -222,7 +225,7 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
   pl.nbv.assign(T + 1, 0);
   tmp.reserve(32 * (size_t)T);
   for (int t = T; t >= 1; t--) {
-    const int npts = (t == 1) ? pl.nv[t] - 2 : pl.nv[t];
+    const int npts = (t == 1) ? pl.nv[t] - np : pl.nv[t];
     const int last_own = pl.vb[t] + pl.nv[t] - 1;  // root: V + 1
     if (2 * t <= T)
       for (int c = 2 * t; c <= 2 * t + 1; c++)
@@ -237,14 +240,14 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
     }
     tmp_ptr[t] = (int)tmp.size();
     for (int a = t / 2; a >= 1; a /= 2) {
-      const int e = pl.vb[a] + ((a == 1) ? pl.nv[a] - 2 : pl.nv[a]);
+      const int e = pl.vb[a] + ((a == 1) ? pl.nv[a] - np : pl.nv[a]);
       for (int v = pl.vb[a]; v < e; v++)
         if (mark[v]) {
           mark[v] = 0;
           tmp.push_back(v);
         }
     }
-    if (t != 1) {
+    if (t != 1 && np) {
       tmp.push_back(V);
       tmp.push_back(V + 1);
     }
@@ -335,7 +338,7 @@ inline void direct_inc_pos(const DirectPlanHost& pl, const std::vector<int>& inc
     const int* bb = pl.bnd.data() + pl.bnd_ptr[t];
     for (int a = inc_ptr[v]; a < inc_ptr[v + 1]; a++) {
       const int o = inc_other[a];
-      if (o <= v) continue;
+      if (o <= v || o >= pl.V) continue;  // earlier in the elimination order, or a fixed row (not an unknown)
       if (o < pl.vb[t] + pl.nv[t] && o < pl.V)
         inc_pos[a] = o - pl.vb[t];
       else

@@ -60,7 +60,7 @@ extern "C" int direct_emul_solve(int32_t V, const double* uv, int32_t P, const i
   std::vector<double> panel((size_t)pl.p_total + 1, 0.0), upd((size_t)pl.u_total + 1, 0.0);
   int fail = 0;
   direct::Plan dp;
-  dp.V = V; dp.depth = pl.depth; dp.G = pl.G; dp.max_path = pl.max_path;
+  dp.np = pl.np; dp.V = V; dp.depth = pl.depth; dp.G = pl.G; dp.max_path = pl.max_path;
   dp.vb = pl.vb.data(); dp.nv = pl.nv.data(); dp.nbv = pl.nbv.data(); dp.bnd_ptr = pl.bnd_ptr.data();
   dp.bnd = pl.bnd.data(); dp.bpath = pl.bpath.data(); dp.path_off = pl.path_off.data();
   dp.inv_ptr = pl.inv_ptr.data(); dp.inv = pl.inv.data(); dp.p_off = pl.p_off.data(); dp.u_off = pl.u_off.data();
