@@ -22,6 +22,8 @@
 #include <float.h>
 #include <stdio.h>
 
+#include <cuda/ptx>
+
 #include "nrs_direct.cuh"
 
 namespace nrs {
@@ -56,12 +58,19 @@ __device__ __forceinline__ void dst3(double* base, int i, const D3& v) {
 }
 
 constexpr int kDBlock = 256;
+// shared-memory doubles (even) of the pivot inverses + look-ahead staging / of the unscaled panel rows
+__host__ __device__ inline size_t direct_sw_doubles(int max_nv) { return 6 * (size_t)(((max_nv + 1) & ~1) + 1) + 82; }
+__host__ __device__ inline size_t direct_sv_doubles(int max_rows) {
+  return ((size_t)max_rows * 3 * (3 * direct::kPanel + 1) + 2) & ~(size_t)1;
+}
 constexpr int kRec = 16;  // doubles per pose-block row record: A (12), omega, -, we0, we1
 
 struct DirectEngine {
   const DirectParams& Q;
   const Params& P;
   double *s_pose, *s_pose_bak, *s_scal, *s_w, *s_v, *s_hpp, *s_red, *s_rec, *s_path, *s_z, *sp;
+  uint64_t* s_mbar;    // mbarrier of the bulk copies (TMA) of the backward substitution
+  unsigned mphase;
   int tid, G, cta;
   int rpc, lpr, slot, lane;  // rows per CTA, lanes per row, this thread's row slot / lane inside the row group
   unsigned long long gen, nsolve;
@@ -76,18 +85,25 @@ struct DirectEngine {
     tid = threadIdx.x;
     G = gridDim.x;
     cta = blockIdx.x;
-    double* p = sm;
+    double* p = sm;  // every piece has an even number of doubles: sp stays 16-byte aligned for the bulk copies
     s_pose = p; p += 8;
     s_pose_bak = p; p += 8;
     s_scal = p; p += 8;
-    s_w = p; p += 6 * (((Q.max_nv + 1) & ~1) + 1) + 80 + 2;
-    s_v = p; p += (size_t)Q.max_rows * 3 * (3 * direct::kPanel + 1) + 1;
+    s_mbar = reinterpret_cast<uint64_t*>(p); p += 2;
+    s_w = p; p += direct_sw_doubles(Q.max_nv);
+    s_v = p; p += direct_sv_doubles(Q.max_rows);
     s_hpp = p; p += 28;
     s_red = p; p += 27 * 8;
     s_path = p; p += (Q.pl.max_path + 1) & ~1;
     s_z = p; p += (Q.scratch_z + 1) & ~1;
     sp = p;
     s_rec = sp;  // the pose-block row records of the linearisation live in the (then idle) panel buffer
+    mphase = 0;
+    if (tid == 0) {
+      cuda::ptx::mbarrier_init(s_mbar, 1);
+      cuda::ptx::fence_proxy_async();
+    }
+    __syncthreads();
     rpc = (Q.pl.V + G - 1) / G;
     lpr = 16;
     while (lpr > 1 && lpr * rpc > kDBlock) lpr >>= 1;
@@ -505,7 +521,7 @@ struct DirectEngine {
     const long long t3 = clock64();
     for (int d = 0; d <= depth; d++) {
       const long long t4 = clock64();
-      direct::backward_front(Q.pl, cta, d, s_path, sp, s_z, P.xcg, Q.dpose, th, prof);
+      direct::backward_front(Q.pl, cta, d, s_path, sp, s_z, P.xcg, Q.dpose, th, prof, s_mbar, &mphase);
 #ifdef NRS_DIRECT_PLEV
       plev[16 + d] += clock64() - t4;
 #else
@@ -695,7 +711,8 @@ __global__ void __launch_bounds__(kDBlock, 1) nrs_track_direct_kernel(const __gr
 }  // namespace
 
 size_t direct_smem_bytes(int max_path, int scratch_z, int max_nv, int max_rows, size_t panel_doubles) {
-  size_t d = 8 + 8 + 8 + 6 * (size_t)(((max_nv + 1) & ~1) + 1) + 82 + (size_t)max_rows * 3 * (3 * direct::kPanel + 1) + 1 + 28 + 27 * 8 + ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
+  size_t d = 8 + 8 + 8 + 2 + direct_sw_doubles(max_nv) + direct_sv_doubles(max_rows) + 28 + 27 * 8 +
+             ((max_path + 1) & ~1) + ((scratch_z + 1) & ~1) +
              (panel_doubles > (size_t)kRec * kDBlock ? panel_doubles : (size_t)kRec * kDBlock) + 2;
   return d * sizeof(double);
 }

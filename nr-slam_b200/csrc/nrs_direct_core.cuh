@@ -26,6 +26,9 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#ifndef NRS_DIRECT_HOST_EMULATION
+#include <cuda/ptx>
+#endif
 
 #ifdef NRS_DIRECT_HOST_EMULATION
 #define NRS_DD inline
@@ -665,17 +668,29 @@ NRS_DD void stage_c(const Plan& pl, int g, int d, double* sp, Thr th) {
 // The leader also writes the point rows of delta (4-double stride) and the pose delta.
 // ---------------------------------------------------------------------------------------------------------------
 NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double* sp, double* s_z, double* delta,
-                           double* dpose, Thr th, long long* pf = nullptr) {
+                           double* dpose, Thr th, long long* pf = nullptr, uint64_t* mbar = nullptr,
+                           unsigned* mphase = nullptr) {
   const long long c0 = NRS_DCLOCK();
   const Front f = front_of(pl, g, d);
-  const int ld = f.ld, nv = f.nv, ns = f.ns, nbv = f.nbv;
+  const int nv = f.nv, ns = f.ns, nbv = f.nbv;
+  const int ld = ns;  // L11 is copied as it lies in global memory (rows are read along columns: no bank conflicts)
   if (nv == 0) return;
   const double* Pg = pl.panel + NRS_DLDG(pl.p_off + f.t);
-  // L11 -> shared memory
-  for (int q = th.tid; q < ns * ns; q += th.nthr) {
-    const int row = q / ns, c = q - row * ns;
-    sp[(size_t)row * ld + c] = NRS_DLDCG(Pg + q);
+  // L11 -> shared memory. Device: ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) issued by thread 0; it
+  // overlaps the L21^T x product below, which streams L21 from L2.
+#ifndef NRS_DIRECT_HOST_EMULATION
+  const unsigned bytes = ((unsigned)(ns * ns) * 8u + 15u) & ~15u;
+  if (th.tid == 0) {
+    cuda::ptx::fence_proxy_async();  // earlier generic-proxy accesses of sp / the panel are ordered before the copy
+    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, mbar,
+                                         bytes);
+    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, sp, Pg, bytes, mbar);
   }
+#else
+  for (int q = th.tid; q < ns * ns; q += th.nthr) sp[q] = Pg[q];
+  (void)mbar;
+  (void)mphase;
+#endif
   // z = y - L21^T x_boundary: groups of threads split the boundary rows, lanes the columns
   const int nrows = 3 * (nbv - 1);
   const int lanes = th.nthr >= 32 ? 32 : th.nthr;
@@ -685,9 +700,18 @@ NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double*
   double* part = s_z + ns;
   for (int c = lane; c < ns; c += lanes) {
     double s = 0;
-    for (int row = grp; row < nrows; row += ngrp) {
-      const int k = row / 3;
-      s += NRS_DLDCG(L21 + (size_t)row * ns + c) * s_path[NRS_DLDG(bp + k) + (row - 3 * k)];
+    for (int row = grp; row < nrows; row += 4 * ngrp) {  // four independent loads in flight per thread
+      double l[4], x[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int r = row + u * ngrp;
+        const int rc = r < nrows ? r : nrows - 1;
+        const int k = rc / 3;
+        l[u] = NRS_DLDCG(L21 + (size_t)rc * ns + c);
+        x[u] = (r < nrows) ? s_path[NRS_DLDG(bp + k) + (rc - 3 * k)] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) s += l[u] * x[u];
     }
     part[grp * ns + c] = s;
   }
@@ -699,11 +723,22 @@ NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double*
     for (int w = 0; w < ngrp; w++) s -= part[w * ns + c];
     s_z[c] = s;
   }
+#ifndef NRS_DIRECT_HOST_EMULATION
+  {  // the bulk copy has landed (bounded spin: a lost copy must not hang the grid)
+    const unsigned ph = *mphase;
+    for (int spin = 0; spin < (1 << 22); spin++)
+      if (cuda::ptx::mbarrier_try_wait_parity(mbar, ph)) break;
+    *mphase = ph ^ 1u;
+  }
+#endif
   NRS_DSYNC();
   // L11'^T x = z with the unit lower block-triangular L11', block row by block row from the bottom (the rhs row of the
-  // panel already holds D^-1 L'^-1 b, see the header)
+  // panel already holds D^-1 L'^-1 b, see the header). Rows whose update fits one warp's lanes are done by warp 0
+  // alone with warp-level syncs; the others wait at one block sync.
   double* xo = s_path + NRS_DLDG(pl.path_off + f.t);
-  for (int i = nv - 1; i >= 0; i--) {
+  const int wl = th.nthr >= 32 ? 32 : th.nthr;
+  int i = nv - 1;
+  for (; i >= 0 && 3 * i > 4 * wl; i--) {
     const double x0 = s_z[3 * i], x1 = s_z[3 * i + 1], x2 = s_z[3 * i + 2];
     const double* Li = sp + (size_t)(3 * i) * ld;
     for (int c = th.tid; c < 3 * i; c += th.nthr) s_z[c] -= Li[c] * x0 + Li[ld + c] * x1 + Li[2 * ld + c] * x2;
@@ -714,6 +749,20 @@ NRS_DD void backward_front(const Plan& pl, int g, int d, double* s_path, double*
     }
     NRS_DSYNC();
   }
+  if (th.tid < wl) {
+    for (; i >= 0; i--) {
+      const double x0 = s_z[3 * i], x1 = s_z[3 * i + 1], x2 = s_z[3 * i + 2];
+      const double* Li = sp + (size_t)(3 * i) * ld;
+      for (int c = th.tid; c < 3 * i; c += wl) s_z[c] -= Li[c] * x0 + Li[ld + c] * x1 + Li[2 * ld + c] * x2;
+      if (th.tid == 0) {
+        xo[3 * i] = x0;
+        xo[3 * i + 1] = x1;
+        xo[3 * i + 2] = x2;
+      }
+      NRS_DSYNCWARP();
+    }
+  }
+  NRS_DSYNC();
   if (pf) {
     pf[10] += c1 - c0;
     pf[11] += NRS_DCLOCK() - c1;

@@ -311,6 +311,7 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
     const long long ns = 3LL * pl.nv[t], nb = 3LL * pl.nbv[t];
     pl.p_off[t] = pl.p_total;
     pl.p_total += (ns + nb) * ns;
+    pl.p_total += pl.p_total & 1;  // panels start 16-byte aligned (bulk copies)
     pl.u_off[t] = pl.u_total;
     pl.u_total += nb * nb;
     // shared-memory need of the node's team member with the most rows (see nrs_direct_core.cuh):
@@ -322,7 +323,7 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
     const size_t ab = (size_t)(3 * rows_ab * ld);
     const size_t c = (size_t)((nb + 3 * ((pl.nbv[t] + R - 1) / R)) * ld);  // stage C: all boundary rows + mine times D
     pl.max_rows = std::max(pl.max_rows, (int)rows_ab);
-    const size_t bw = (size_t)(ns * ld);           // backward: L11
+    const size_t bw = (size_t)(ns * ns) + 2;       // backward: L11 as it lies in global memory
     smem = std::max(smem, std::max(ab, std::max(c, bw)));
   }
   pl.smem_doubles = smem;
