@@ -39,6 +39,15 @@ WORKLOAD = ("configs[1]: synthetic 640x480 pinhole, 2000 landmarks, REF mode (on
             "+ pose_deform(2x10 LM)")
 
 
+SEED = 1235
+
+
+def base_config():
+    """The workload description both arms print (the driver compares the two lines' `config`)."""
+    return {"workload": WORKLOAD, "seed": SEED, "landmarks": 2000, "frames_per_step": 1,
+            "l2_flush_between_steps": True}
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -147,7 +156,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp32 camera model)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD},
+            "config": base_config(),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "%d frames of configs[1], one stream on one thread like the reference; "
                                        "restatement of the reference algorithm (g2o LM + exact sparse Cholesky), "
@@ -165,7 +174,7 @@ def _ref_frame(i):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from nrslam_b200 import synth
-    p = synth.tracking_problem("c2", seed=1235 + (i % 4))
+    p = synth.tracking_problem("c2", seed=SEED)  # the frame the B200 arm tracks on rank 0
     o = oracle_lib.Oracle()
     if "k" not in _REF_KLT:  # the reference image is set once per keyframe, not per frame (tracking.cc:361-367)
         im = synth.klt_pair(seed=77, n_points=2000)
@@ -190,8 +199,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
-        args.steps = min(args.steps, 10)  # bounded sample (~0.5 s of CPU work per frame)
-        return run_reference(args)
+        return run_reference(args)  # one step = one frame = ~0.6 s of CPU work: K + W frames stay within minutes
     args.warmup = max(args.warmup, 3)
 
     import numpy as np
@@ -231,7 +239,7 @@ def main():
     core = api.Core(opt)
     # every rank tracks its own stream: a different seeded frame of the same shape (replicas, weak scaling)
     from nrslam_b200 import dist as nrs_dist
-    p = synth.tracking_problem("c2", seed=nrs_dist.stream_seed(1235, rank))
+    p = synth.tracking_problem("c2", seed=nrs_dist.stream_seed(SEED, rank))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     im = synth.klt_pair(seed=77 + rank, n_points=2000)
@@ -262,10 +270,13 @@ def main():
     e2e_launches = r0["stats"]["kernel_launches"] + r1["stats"]["kernel_launches"]
 
     # ---- device-resident: re-run the staged programs (pose_only, pose_deform main rounds) on HBM-resident inputs
+    has_lost = len(r1["lost"]) > 0
     for _ in range(args.warmup):
         klt.retrack()
         core.resolve(0)
         core.resolve(1)
+        if has_lost:
+            core.resolve(3)
     barrier()
     dev_ms = 0.0
     klt_ms = 0.0
@@ -276,8 +287,9 @@ def main():
         kms = klt.retrack()   # pyramid of the resident image + track kernel
         s0 = core.resolve(0)
         s1 = core.resolve(1)
+        s3 = core.resolve(3) if has_lost else {"gpu_ms": 0.0, "lm_iterations": 0, "pcg_iterations": 0}
         klt_ms += kms
-        dev_ms += kms + s0["gpu_ms"] + s1["gpu_ms"]
+        dev_ms += kms + s0["gpu_ms"] + s1["gpu_ms"] + s3["gpu_ms"]
     barrier()
     wall_s = time.perf_counter() - wall0
     clocks = sampler.stop([e2e_window, (wall0, wall0 + wall_s)])
@@ -304,37 +316,53 @@ def main():
     st.update(n_reproj_edges=r1["stats"]["n_reproj_edges"], n_points=r1["stats"]["n_points"], n_poses=1,
               n_pair_edges=r1["stats"]["n_pair_edges"], n_spring_edges=0, n_damper_edges=0)
     alg, b_sweep, b_mv = algorithmic_bytes(st)
+    direct = s1.get("direct_solves", 0) > 0
+    # exact-solve engine: a damped solve must read H once (one matvec's worth), write the factor once and read it in
+    # the forward and the backward substitution: B_solve = B_mv + 3 * 8 * nnz(L')
+    b_solve = b_mv + 3 * 8 * int(s1.get("factor_doubles", 0))
+    if direct:
+        alg += s1["direct_solves"] * b_solve
     ach = alg / (s1["gpu_ms"] * 1e-3) / 1e9
     traffic = None
+    prof = "r02_track_direct_ncu_summary.json" if direct else "r01_lm_track_ncu_summary.json"
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture (profiles/)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_lm_track_ncu_summary.json")))["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", prof)))["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "nrs_lm_kernel (pose+deformation launch)", "achieved": ach,
+    roofline = {"bound": "hbm", "kernel": ("nrs_track_direct_kernel" if direct else "nrs_lm_kernel") +
+                " (pose+deformation launch)", "achieved": ach,
                 "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_ms": s1["gpu_ms"],
-                "bytes_per_sweep": b_sweep, "bytes_per_matvec": b_mv, "sweeps": s1["n_sweeps"],
-                "matvecs": s1["pcg_iterations"], "chi2_passes": s1["n_chi2_passes"],
-                "note": "working set (<4 MB) lives in shared memory / L2 inside the launch; the kernel is bound by "
-                        "synchronisation and dependent-issue latency, not HBM (SURVEY.md 0.9, DESIGN.md 3)"}
+                "traffic": traffic, "traffic_source": "profiles/" + prof, "algorithmic_bytes_per_launch": alg,
+                "launch_ms": s1["gpu_ms"],
+                "bytes_per_sweep": b_sweep, "bytes_per_matvec": b_mv, "bytes_per_exact_solve": b_solve if direct else None,
+                "sweeps": s1["n_sweeps"], "matvecs": s1["pcg_iterations"], "exact_solves": s1.get("direct_solves", 0),
+                "factor_doubles": int(s1.get("factor_doubles", 0)), "chi2_passes": s1["n_chi2_passes"],
+                "note": "working set (factor 5.7 MB + update matrices, all L2-resident) never leaves the chip inside the "
+                        "launch; the kernel is bound by the sequential pivot chain of the factorisation and by "
+                        "synchronisation latency, not HBM (SURVEY.md 0.9, DESIGN.md 3b)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp32 camera model)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "seed": 1235, "landmarks": int(p["n"]),
-                       "pair_edges": int(r1["stats"]["n_pair_edges"]), "l2_flush_between_steps": True,
-                       "pcg_rel_tol": opt.pcg_rel_tol, "parallelism": "replicas x%d" % world,
-                       "grid_ctas": s1["grid_ctas"], "block_threads": s1["block_threads"]},
+            "config": base_config(),
+            "engine": {"pair_edges": int(r1["stats"]["n_pair_edges"]), "parallelism": "replicas x%d" % world,
+                       "solver": "exact block L D L^T (multifrontal, nested dissection)" if direct
+                       else "preconditioned CG, rel tol %g" % opt.pcg_rel_tol,
+                       "grid_ctas": s1["grid_ctas"], "block_threads": s1["block_threads"],
+                       "lost_points": int(len(r1["lost"]))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / args.steps, "launches_per_step": e2e_launches},
-            # per step: KLT pyramid (1 level-0 + 4 pyrDown + 5 Scharr) + 1 track kernel, 2 LM kernels
-            "gpu_launches": (11 + 2) * args.steps, "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            # per step: KLT pyramid (1 level-0 + 4 pyrDown + 5 Scharr) + 1 track kernel, 3 LM kernels (pose-only, main
+            # rounds, lost-point stage)
+            "gpu_launches": (11 + 2 + (1 if has_lost else 0)) * args.steps, "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "klt": {"device_ms_per_step": klt_ms / args.steps, "points": 2000, "image": "640x480",
                     "kernels_per_step": 11},
             "without_klt": {"value": world * args.steps / (dev_opt_ms_max * 1e-3),
                             "e2e_value": world * args.steps / (e2e_opt_ms_max * 1e-3), "unit": UNIT},
-            "lm_iterations_per_step": s0["lm_iterations"] + s1["lm_iterations"],
-            "pcg_iterations_per_step": s0["pcg_iterations"] + s1["pcg_iterations"],
+            "lm_iterations_per_step": s0["lm_iterations"] + s1["lm_iterations"] + s3["lm_iterations"],
+            "pcg_iterations_per_step": s0["pcg_iterations"] + s1["pcg_iterations"] + s3["pcg_iterations"],
+            "device_ms": {"klt": klt_ms / args.steps, "pose_only": s0["gpu_ms"], "pose_deform_main": s1["gpu_ms"],
+                          "lost_points": s3["gpu_ms"]},
             "roofline": roofline, "clocks": clocks}
 
     # ---- second quantity of the metric: deformable-BA LM iterations/s (one GPU)
@@ -378,35 +406,65 @@ def main():
         q3 = synth.ba_problem("c3")
         line["ba"] = ba_measure(q3, "c3", "configs[2]: 640x480 pinhole, 5000 landmarks / 30 "
                                 "keyframes / %d observations, %d springs, %d dampers, optimize(5)")
+        single3 = core.local_ba(q3["cam"], q3["kf_pose"], q3["obs_kf"], q3["obs_vertex"], q3["uv"], q3["X"],
+                                q3["graph"], q3["scale"]) if world > 1 else None
+        # the north-star target window: configs[3], Endomapper-shaped 1440x1080 fisheye, 20k landmarks / 100 keyframes
+        q4 = synth.ba_problem("c4")
+        line["ba_c4"] = ba_measure(q4, "c4", "configs[3]: 1440x1080 KannalaBrandt8, 20000 landmarks / 100 "
+                                   "keyframes / %d observations, %d springs, %d dampers, optimize(5)")
         if world > 1:
-            # ---- the path's one real exchange: ONE configs[2] window landmark-sharded over all ranks —
-            # halo rows and partial sums cross NVLink inside the persistent kernels (strong scaling of one problem,
-            # reported beside the replica numbers; results equal the single-GPU solve, tests/test_gpu_sharded_ba.py)
-            bargs = (q3["cam"], q3["kf_pose"], q3["obs_kf"], q3["obs_vertex"], q3["uv"], q3["X"], q3["graph"],
-                     q3["scale"])
-            part = api.shard_partition(world, *bargs[1:])
-            nrs_dist.attach_shards(core, dist, int((part["n_own"] + part["n_halo"]).max()), len(q3["kf_pose"]))
-            core.local_ba_sharded(*bargs)
-            ks = max(2, min(args.steps, 5))
-            sh_ms, sh_wall = 0.0, 0.0
-            for _ in range(ks):
-                barrier()
-                t0 = time.perf_counter()
-                rs = core.local_ba_sharded(*bargs)
-                sh_wall += 1e3 * (time.perf_counter() - t0)
-                sh_ms += rs["stats"]["gpu_ms"]
-            tt = torch.tensor([sh_ms, sh_wall], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            its = rs["stats"]["lm_iterations"]
-            line["ba_sharded"] = {
-                "metric": "deformable_ba_lm_iterations_per_sec", "unit": "iters/s", "scaling": "strong",
-                "value": ks * its / (float(tt[0]) * 1e-3), "e2e_value": ks * its / (float(tt[1]) * 1e-3),
-                "workload": "ONE configs[2] window (%d observations) landmark-sharded over %d GPUs: %s rows + %s halo "
-                            "rows per rank" % (len(q3["obs_kf"]), world, part["n_own"].tolist(),
-                                               part["n_halo"].tolist()),
-                "launch_ms": float(tt[0]) / ks, "e2e_ms": float(tt[1]) / ks, "lm_iterations": its,
-                "pcg_iterations": rs["stats"]["pcg_iterations"],
-                "single_gpu_launch_ms": line["ba"]["launch_ms"]}
+            # ---- the path's one real exchange: ONE window landmark-sharded over all ranks — halo rows and
+            # partial sums cross NVLink inside the persistent kernels (strong scaling of one problem, reported beside
+            # the replica numbers). The G-GPU == 1-GPU gate is evaluated HERE, in the driver-run bench: every rank also
+            # solves the window alone and the sharded result is compared with it.
+            single4 = core.local_ba(q4["cam"], q4["kf_pose"], q4["obs_kf"], q4["obs_vertex"], q4["uv"], q4["X"],
+                                    q4["graph"], q4["scale"])
+            parts = {}
+            for tag, q in (("c3", q3), ("c4", q4)):
+                parts[tag] = api.shard_partition(world, q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"],
+                                                 q["graph"], q["scale"])
+            max_rows = max(int((pt["n_own"] + pt["n_halo"]).max()) for pt in parts.values())
+            nrs_dist.attach_shards(core, dist, max_rows, max(len(q3["kf_pose"]), len(q4["kf_pose"])))
+
+            def sharded_measure(q, part, single, single_ms, label):
+                bargs = (q["cam"], q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
+                core.local_ba_sharded(*bargs)
+                ks = max(2, min(args.steps, 5))
+                sh_ms, sh_wall = 0.0, 0.0
+                for _ in range(ks):
+                    barrier()
+                    t0 = time.perf_counter()
+                    rs = core.local_ba_sharded(*bargs)
+                    sh_wall += 1e3 * (time.perf_counter() - t0)
+                    sh_ms += rs["stats"]["gpu_ms"]
+                tt = torch.tensor([sh_ms, sh_wall], dtype=torch.float64, device="cuda")
+                per_rank = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+                dist.all_gather(per_rank, tt)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                # equality gate: poses identical on every rank, sharded == single-GPU within fp32 output precision
+                X = nrs_dist.gather_sharded_ba(rs, dist)
+                poses = [None] * world
+                dist.all_gather_object(poses, rs["kf_pose"])
+                its = rs["stats"]["lm_iterations"]
+                ta, tb_ = np.array(single["stats"]["chi2_trace"]), np.array(rs["stats"]["chi2_trace"])
+                return {
+                    "metric": "deformable_ba_lm_iterations_per_sec", "unit": "iters/s", "scaling": "strong",
+                    "value": ks * its / (float(tt[0]) * 1e-3), "e2e_value": ks * its / (float(tt[1]) * 1e-3),
+                    "workload": "ONE %s window (%d observations, %d keyframes) landmark-sharded over %d GPUs: %s rows + "
+                                "%s halo rows per rank" % (label, len(q["obs_kf"]), len(q["kf_pose"]), world,
+                                                           part["n_own"].tolist(), part["n_halo"].tolist()),
+                    "launch_ms": float(tt[0]) / ks, "e2e_ms": float(tt[1]) / ks, "lm_iterations": its,
+                    "pcg_iterations": rs["stats"]["pcg_iterations"], "single_gpu_launch_ms": single_ms,
+                    "per_rank_launch_ms": [float(v[0]) / ks for v in per_rank],
+                    "per_rank_call_ms": [float(v[1]) / ks for v in per_rank],
+                    "poses_identical": bool(all(np.array_equal(poses[0], q_) for q_ in poses)),
+                    "max_pose_diff": float(np.abs(rs["kf_pose"] - single["kf_pose"]).max()),
+                    "max_point_diff": float(np.abs(X - single["X"]).max()),
+                    "chi2_trace_equal_1e-6": bool(len(ta) == len(tb_) and np.allclose(ta, tb_, rtol=1e-6)),
+                    "pcg_iterations_single": single["stats"]["pcg_iterations"]}
+
+            line["ba_sharded"] = sharded_measure(q4, parts["c4"], single4, line["ba_c4"]["launch_ms"], "configs[3]")
+            line["ba_sharded_c3"] = sharded_measure(q3, parts["c3"], single3, line["ba"]["launch_ms"], "configs[2]")
 
     # ---- one frame's batch of DeformableTriangulation candidates (Mapping::FrameMapping,
     # mapping.cc:60-113) and the RegularizationGraph update loop of the tracking frame (g2o_optimization.cc:458-474)

@@ -9,13 +9,16 @@
  *                                            modules/matching/lucas_kanade_tracker.h:55-70 (.cc:47-631)
  *   - RegularizationGraph::{GetEdges,UpdateVertex}   modules/map/regularization_graph.h:73,78 (.cc:71-146)
  * The reference has no FFI of its own; INTEGRATION.md shows the C++ shim that forwards the four
- * reference signatures to these entry points (nr-slam_b200/host/g2o_optimization_b200.cc).
+ * reference signatures to these entry points; the shim sources are shim/g2o_optimization_b200.cc and
+ * shim/lucas_kanade_tracker_b200.cc (compiled in the CPU test suite against stand-in headers, tests/test_shim.py).
  *
  * Conventions
  *   - extern "C", plain pointers and sizes, all pointers are HOST pointers unless a name ends in _dev.
  *   - geometry is fp32 at the boundary (the reference stores Eigen::Vector3f / Sophus::SE3f), indices int32.
  *   - a pose is 7 floats [qx qy qz qw tx ty tz] = Sophus::SE3f camera_transform_world (unit quaternion + t).
  *   - statuses use the reference enum values (utilities/landmark_status.h:23-30).
+ *   - object lifetime: trackers / extractors / triangulators / pre-processors created on a context hold a pointer
+ *     to it and must be destroyed BEFORE nrslam_b200_destroy(ctx) (destroying them afterwards is a use after free).
  *   - return value: 0 ok; < 0 CUDA / allocation / argument error; > 0 numerical condition
  *     (1 = fewer points than the reference needs, nothing done). Never throws, never aborts.
  *     nrslam_b200_last_error(ctx) returns a description of the last non-zero return.
@@ -32,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NRSLAM_B200_ABI_VERSION 1
+#define NRSLAM_B200_ABI_VERSION 2
 
 #define NRSLAM_B200_OK 0
 #define NRSLAM_B200_ERR_NO_DEVICE (-1)
@@ -123,6 +126,11 @@ typedef struct nrslam_b200_stats {
   int64_t h2d_bytes;          /* bytes copied host -> device by this call */
   int64_t d2h_bytes;          /* bytes copied device -> host by this call */
   int32_t grid_ctas, block_threads; /* launch geometry of the LM kernel */
+  /* ABI 2: exact-solve engine (block L D L^T, nrs_direct.cu) */
+  int32_t direct_solves;      /* damped systems factorised exactly (0: the CG engine ran) */
+  int32_t solve_failures;     /* factorisations that met a non-positive pivot / CG break-downs */
+  int64_t factor_doubles;     /* doubles of the stored factor L' (nnz incl. the dense-front padding), last launch */
+  int64_t update_doubles;     /* doubles of the update (Schur complement) matrices written per factorisation */
 } nrslam_b200_stats;
 
 typedef struct nrslam_b200_ctx nrslam_b200_ctx;
@@ -214,7 +222,8 @@ int nrslam_b200_shard_partition(const nrslam_b200_options* opt, int32_t world, i
                                 int32_t* n_edges_out);
 
 /* Re-run the device solve of the most recently staged problem on its HBM-resident inputs (no host<->device
- * copies, no host bookkeeping). which: 0 pose_only, 1 pose_deform (both robust rounds), 2 local_ba.
+ * copies, no host bookkeeping). which: 0 pose_only, 1 pose_deform (both robust rounds), 2 local_ba,
+ * 3 the lost-point stage of the last pose_deform call.
  * Benchmark / profiler hook: results are identical to the staged call's. */
 int nrslam_b200_resolve(nrslam_b200_ctx* ctx, int32_t which, nrslam_b200_stats* stats);
 

@@ -74,6 +74,12 @@ class Core:
         if rc != 0:
             raise NrslamError(rc, "nrslam_b200_create failed")
 
+    def _adopt(self, child):
+        """Registers a child object (KLT, ShiTomasi, Pre, Triangulator) that holds a pointer to this context; dead
+        references are dropped so the list does not grow over a sequence (point_reuse builds a tracker per frame)."""
+        self._children = [r for r in self._children if r() is not None]
+        self._children.append(weakref.ref(child))
+
     def close(self):
         if self._ctx:
             for ref in self._children:  # trackers hold a pointer to the context: destroy them first
@@ -186,7 +192,8 @@ class Core:
         return dict(rc=rc, kf_pose=kf_pose, X=X, owner=owner, stats=st.as_dict())
 
     def resolve(self, which):
-        """Re-run the device program of the last staged problem (0 pose_only, 1 pose_deform, 2 local_ba)."""
+        """Re-run the device program of the last staged problem (0 pose_only, 1 pose_deform, 2 local_ba, 3 the
+        lost-point stage of the last pose_deform call)."""
         st = Stats()
         self._check(self.L.nrslam_b200_resolve(self._ctx, int(which), C.byref(st)))
         return st.as_dict()
@@ -240,7 +247,7 @@ class KLT:
         if rc != 0:
             raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
         import weakref
-        core._children.append(weakref.ref(self))
+        core._adopt(self)
 
     def close(self):
         if self._h:
@@ -413,7 +420,7 @@ class ShiTomasi:
         if rc != 0:
             raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
         import weakref
-        core._children.append(weakref.ref(self))
+        core._adopt(self)
         self._shape = None
 
     def close(self):
@@ -460,7 +467,7 @@ class Pre:
         rc = self.L.nrslam_b200_pre_create(core._ctx, int(max_width), int(max_height), C.byref(self._h))
         if rc != 0:
             raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
-        core._children.append(weakref.ref(self))
+        core._adopt(self)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -533,7 +540,7 @@ class Triangulator:
         if rc != 0:
             raise NrslamError(rc, (self.L.nrslam_b200_last_error(core._ctx) or b"").decode())
         import weakref
-        core._children.append(weakref.ref(self))
+        core._adopt(self)
 
     def close(self):
         if self._h:

@@ -767,6 +767,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     q.P = p;
     st.use_direct = true;
     st.dgrid = dplan.G;
+    st.dfactor_doubles = dplan.p_total;
+    st.dupdate_doubles = dplan.u_total;
     st.dsmem = dsmem;
   }
   if (st.has_plan2) {
@@ -820,6 +822,12 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
       stats->block_threads = direct ? direct_block_threads() : st.block;
     }
     stats->d2h_bytes += copy_back ? (int64_t)st.out.used() : (int64_t)sizeof(EngineStats);
+    stats->solve_failures += es->pcg_fail;
+    if (direct) {
+      stats->direct_solves += es->lm_trials;
+      stats->factor_doubles = st.dfactor_doubles;
+      stats->update_doubles = st.dupdate_doubles;
+    }
     for (int i = 0; i < es->n_trace && stats->n_trace < NRSLAM_B200_TRACE; i++)
       stats->chi2_trace[stats->n_trace++] = es->chi2_trace[i];
     stats->lambda_final = es->lambda_final;
@@ -1814,8 +1822,14 @@ int nrslam_b200_local_ba_sharded(nrslam_b200_ctx* ctx, const nrslam_b200_camera*
   ShardPlan sp;
   shard_problem(G, obs_vertex, g->n_vertices, sh.rank, sh.world, hp, sp);
   const int n_own = sp.n_own[sh.rank];
-  if (hp.V > sh.max_rows) return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba_sharded: more rows than shard_init reserved");
-  if (n_own == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba_sharded: a rank owns no observation");
+  // The call is a collective: every rank derives the same partition, so the size checks run over ALL ranks and every
+  // rank leaves with the same code before anybody launches (a lone early exit would leave the peers spinning in the
+  // exchange until its timeout and mark their shard state broken).
+  for (int r = 0; r < sh.world; r++) {
+    if (sp.n_own[r] + (int)sp.halo[r].size() > sh.max_rows)
+      return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba_sharded: more rows than shard_init reserved (on some rank)");
+    if (sp.n_own[r] == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "local_ba_sharded: a rank owns no observation");
+  }
   Staged& st = ctx->staged[2];
   int rc = stage_problem(ctx, st, hp);
   if (rc) return rc;
@@ -1938,7 +1952,7 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
 }
 
 int nrslam_b200_resolve(nrslam_b200_ctx* ctx, int32_t which, nrslam_b200_stats* stats) {
-  if (!ctx || which < 0 || which > 2) return fail(ctx, NRSLAM_B200_ERR_ARG, "resolve: bad argument");
+  if (!ctx || which < 0 || which > 3) return fail(ctx, NRSLAM_B200_ERR_ARG, "resolve: bad argument");
   NRS_CUDA(ctx, cudaSetDevice(ctx->device));
   if (stats) memset(stats, 0, sizeof(*stats));
   const double t0 = wall_ms();

@@ -2531,14 +2531,15 @@ static const void* kernel_of(int wide) {
   return wide ? (const void*)nrs_lm_kernel_wide : (const void*)nrs_lm_kernel;
 }
 
+// The attribute belongs to the function in the CURRENT device's context, and several contexts on different devices
+// may live in one process (opt.device): it is set on every call instead of being cached process-wide (a cache made a
+// second device miss it; the call costs microseconds and is thread safe).
 static bool set_smem(size_t smem, int wide = 0) {
-  static size_t current[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > current[wide]) {
+  if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel_of(wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    current[wide] = smem;
   }
   return true;
 }

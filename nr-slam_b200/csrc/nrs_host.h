@@ -85,6 +85,7 @@ struct Staged {
   bool use_direct = false;
   DirectParams dq;
   int dgrid = 0;
+  long long dfactor_doubles = 0, dupdate_doubles = 0;
   size_t dsmem = 0;
 };
 

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_default_options(lib):
-    assert lib.nrslam_b200_abi_version() == 1
+    assert lib.nrslam_b200_abi_version() == 2
     o = api.default_options()
     assert abs(o.th_huber_2dof_sq - 5.99) < 1e-6 and abs(o.th_huber_3dof_sq - 0.584) < 1e-6
     assert list(o.pose_only_iterations) == [10, 10, 10] and list(o.pose_deform_iterations) == [10, 10]
