@@ -260,6 +260,27 @@ int nrslam_b200_klt_get_patch(nrslam_b200_klt* klt, int32_t idx, int16_t* gray_o
 int nrslam_b200_klt_insert_patch(nrslam_b200_klt* klt, float x, float y, const int16_t* gray,
                                  const int16_t* grad, const float* mean, const float* mean2,
                                  const uint8_t* valid);
+/* Batch form of InsertPhotometricInformation: n points (xy[2n], per point the arrays of insert_patch back to back). */
+int nrslam_b200_klt_insert_patches(nrslam_b200_klt* klt, int32_t n, const float* xy, const int16_t* gray,
+                                   const int16_t* grad, const float* mean, const float* mean2, const uint8_t* valid);
+/* ---- Tracking::PointReuse (modules/tracking/tracking.cc:394-506) ------------------------------------------------
+ * n map points: X_world[3n] = MapPoint::GetLastWorldPosition, in_frame[n] = 1 when Frame::LandmarkPosition(id) is ok
+ * (:398), forced[n] (optional) = 1 for the lost ids CameraPoseAndDeformationOptimization returned. Per point the
+ * PhotometricInformation of its two finest pyramid levels: gray[n][2][21*21] int16, grad[n][2][21*21][2] int16,
+ * mean[n][2], mean2[n][2], valid[n][2] (0 = empty Mat). pose = the frame's camera_transform_world. The function
+ * projects (fp32), keeps the points with depth >= 0 inside the image, tracks them with a fresh 2-level tracker
+ * (window 21, max_iters / epsilon / min_eig_threshold = Tracking::Options, initial flow = projection, SSIM 0.75)
+ * and gates by SquaredReprojectionError > 5.99.
+ * Outputs, one entry per candidate j < *n_cand_out in ascending point index: cand_out[j] (point index), seed_out
+ * (optional, the projection), uv_out[2j..] tracked keypoint, status_out (optional, LandmarkStatus after Track),
+ * accepted_out[j] = 1 when the reference inserts / refreshes the observation (:481-498). */
+int nrslam_b200_point_reuse(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, const float* pose, const uint8_t* image,
+                            int32_t width, int32_t height, int32_t pitch, const uint8_t* mask, int32_t mask_pitch,
+                            int32_t n, const float* X_world, const uint8_t* in_frame, const uint8_t* forced,
+                            int32_t max_iters, float epsilon, float min_eig_threshold, const int16_t* gray,
+                            const int16_t* grad, const float* mean, const float* mean2, const uint8_t* valid,
+                            int32_t* cand_out, float* seed_out, float* uv_out, uint8_t* status_out,
+                            uint8_t* accepted_out, int32_t* n_cand_out, int32_t* n_reused_out);
 int nrslam_b200_klt_clear(nrslam_b200_klt* klt);
 int32_t nrslam_b200_klt_num_points(const nrslam_b200_klt* klt);
 /* Re-run the last Track (pyramid of the device-resident current image + tracking kernel) on the device-resident

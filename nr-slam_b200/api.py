@@ -377,36 +377,63 @@ def project_points(cam, pose, X):
     return uv.astype(np.float32), Pc
 
 
-def point_reuse(make_klt, cam, pose, image, X_world, patches, in_frame, klt_max_iters=10, klt_eps=1e-4,
-                klt_min_eig=1e-4):
-    """Tracking::PointReuse (modules/tracking/tracking.cc:394-506) as a composition of the C-ABI pieces: project the
-    map points that are not in the frame, keep those inside the image with positive depth, track them with a fresh
-    2-level KLT fed from their stored patches (InsertPhotometricInformation, initial flow = projection, SSIM 0.75) and
-    gate by the squared reprojection error (> 5.99 rejected). `make_klt(max_level, max_iters, eps, min_eig)` builds the
-    tracker (api.KLT on the GPU, OracleKLT in the tests); `patches[i]` is the map point's PhotometricInformation
-    (levels 0..1 are used). Returns the candidate indices, their tracked keypoints and the accepted mask."""
-    from .abi import TRACKED_WITH_3D
+def pack_reuse_patches(patches, win=21):
+    """Two finest levels of every map point's PhotometricInformation as the flat arrays nrslam_b200_point_reuse takes."""
+    n, A = len(patches), win * win
+    gray = np.zeros((n, 2, A), np.int16)
+    grad = np.zeros((n, 2, A, 2), np.int16)
+    mean = np.zeros((n, 2), np.float32)
+    mean2 = np.zeros((n, 2), np.float32)
+    valid = np.zeros((n, 2), np.uint8)
+    for i, pt in enumerate(patches):
+        gray[i] = np.asarray(pt["gray"][:2]).reshape(2, A)
+        grad[i] = np.asarray(pt["grad"][:2]).reshape(2, A, 2)
+        mean[i] = pt["mean"][:2]
+        mean2[i] = pt["mean2"][:2]
+        valid[i] = pt["valid"][:2]
+    return gray, grad, mean, mean2, valid
+
+
+def _point_reuse_call(fn, ctx_args, cam, pose, image, X_world, patches, in_frame, forced, mask, klt_max_iters, klt_eps,
+                      klt_min_eig):
+    image = np.ascontiguousarray(image, np.uint8)
     h, w = image.shape
-    uv, Pc = project_points(cam, pose, X_world)
-    cand = [i for i in range(len(X_world))
-            if not in_frame[i] and Pc[i, 2] >= 0 and 0 <= uv[i, 0] < w and 0 <= uv[i, 1] < h]
-    if not cand:
-        return np.zeros(0, np.int64), np.zeros((0, 2), np.float32), np.zeros(0, bool)
-    klt = make_klt(1, klt_max_iters, klt_eps, klt_min_eig)
-    for i in cand:
-        pt = patches[i]
-        klt.insert_patch(uv[i, 0], uv[i, 1], dict(gray=np.ascontiguousarray(pt["gray"][:2]),
-                                                   grad=np.ascontiguousarray(pt["grad"][:2]),
-                                                   mean=np.ascontiguousarray(pt["mean"][:2]),
-                                                   mean2=np.ascontiguousarray(pt["mean2"][:2]),
-                                                   valid=np.ascontiguousarray(pt["valid"][:2])))
-    seeds = uv[cand]
-    r = klt.track(image, seeds, np.full(len(cand), TRACKED_WITH_3D, np.uint8), use_initial_flow=True, min_ssim=0.75)
-    klt.close()
-    d = r["pts"] - seeds                     # SquaredReprojectionError(projected_landmark, keypoint.pt)
-    err2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
-    accepted = (r["status"] == TRACKED_WITH_3D) & ~(err2 > np.float32(5.99))
-    return np.array(cand, np.int64), r["pts"], accepted
+    X = _f32(X_world).reshape(-1, 3)
+    n = len(X)
+    gray, grad, mean, mean2, valid = patches if isinstance(patches, tuple) else pack_reuse_patches(patches)
+    inf = np.ascontiguousarray(in_frame, np.uint8)
+    frc = None if forced is None else np.ascontiguousarray(forced, np.uint8)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    pose = _f32(pose)
+    cand = np.zeros(max(n, 1), np.int32)
+    seed = np.zeros((max(n, 1), 2), np.float32)
+    uv = np.zeros((max(n, 1), 2), np.float32)
+    st = np.zeros(max(n, 1), np.uint8)
+    acc = np.zeros(max(n, 1), np.uint8)
+    nc, nr = C.c_int32(0), C.c_int32(0)
+    rc = fn(*ctx_args, C.byref(cam), ptr(pose, C.c_float), ptr(image, C.c_uint8), w, h, image.strides[0],
+            ptr(m, C.c_uint8), 0 if m is None else m.strides[0], n, ptr(X, C.c_float), ptr(inf, C.c_uint8),
+            ptr(frc, C.c_uint8), int(klt_max_iters), C.c_float(klt_eps), C.c_float(klt_min_eig), ptr(gray, C.c_int16),
+            ptr(grad, C.c_int16), ptr(mean, C.c_float), ptr(mean2, C.c_float), ptr(valid, C.c_uint8),
+            ptr(cand, C.c_int32), ptr(seed, C.c_float), ptr(uv, C.c_float), ptr(st, C.c_uint8), ptr(acc, C.c_uint8),
+            C.byref(nc), C.byref(nr))
+    k = nc.value
+    return rc, dict(candidates=cand[:k].astype(np.int64), seeds=seed[:k].copy(), pts=uv[:k].copy(),
+                    status=st[:k].copy(), accepted=acc[:k].astype(bool), n_reused=nr.value)
+
+
+def point_reuse(core, cam, pose, image, X_world, patches, in_frame, forced=None, mask=None, klt_max_iters=10,
+                klt_eps=1e-4, klt_min_eig=1e-4):
+    """Tracking::PointReuse (modules/tracking/tracking.cc:394-506) through the C ABI (nrslam_b200_point_reuse):
+    project the map points that are not in the frame (or that were reported lost), keep those inside the image with
+    non-negative depth, track them with a fresh 2-level KLT fed from their stored patches (initial flow = projection,
+    SSIM 0.75) and gate by the squared reprojection error (> 5.99 rejected). `patches[i]` is the map point's
+    PhotometricInformation as returned by KLT.get_patch (or the tuple of pack_reuse_patches). Returns a dict:
+    candidates (point indices, ascending), seeds, pts (tracked keypoints), status, accepted, n_reused."""
+    rc, out = _point_reuse_call(core.L.nrslam_b200_point_reuse, (core._ctx,), cam, pose, image, X_world, patches,
+                                in_frame, forced, mask, klt_max_iters, klt_eps, klt_min_eig)
+    core._check(rc)
+    return out
 
 
 class ShiTomasi:

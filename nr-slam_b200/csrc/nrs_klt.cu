@@ -808,6 +808,121 @@ int nrslam_b200_klt_insert_patch(nrslam_b200_klt* k, float x, float y, const int
   return 0;
 }
 
+// Batch form of InsertPhotometricInformation (lucas_kanade_tracker.cc:610-620): n points in one set of copies.
+int nrslam_b200_klt_insert_patches(nrslam_b200_klt* k, int32_t n, const float* xy, const int16_t* gray,
+                                   const int16_t* grad, const float* mean, const float* mean2, const uint8_t* valid) {
+  if (!k || n < 0 || (n > 0 && (!xy || !gray || !grad || !mean || !mean2 || !valid)))
+    return kfail(k, NRSLAM_B200_ERR_ARG, "klt_insert_patches: bad argument");
+  if (n == 0) return 0;
+  KLT_CUDA(k, cudaSetDevice(k->ctx->device));
+  const int rc = ensure_points(k, k->n + n);
+  if (rc) return rc;
+  const int nl = k->n_levels();
+  const size_t slot = (size_t)k->n * nl, cnt = (size_t)n * nl;
+  cudaStream_t s = k->ctx->stream;
+  KLT_CUDA(k, cudaMemcpyAsync(k->ps.gray + slot * kArea, gray, cnt * kArea * sizeof(short), cudaMemcpyHostToDevice, s));
+  KLT_CUDA(k, cudaMemcpyAsync(k->ps.grad + slot * kArea, grad, cnt * kArea * sizeof(short2), cudaMemcpyHostToDevice, s));
+  KLT_CUDA(k, cudaMemcpyAsync(k->ps.mean + slot, mean, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
+  KLT_CUDA(k, cudaMemcpyAsync(k->ps.mean2 + slot, mean2, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
+  KLT_CUDA(k, cudaMemcpyAsync(k->ps.valid + slot, valid, cnt, cudaMemcpyHostToDevice, s));
+  KLT_CUDA(k, cudaMemcpyAsync(k->d_prev + 2 * (size_t)k->n, xy, 2 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
+  KLT_CUDA(k, cudaStreamSynchronize(s));
+  k->n += n;
+  k->have_track = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tracking::PointReuse — modules/tracking/tracking.cc:394-506
+// Candidates are the map points that are not in the frame with a 3-D position (in_frame[i] == 0) or that the optimiser
+// reported lost (forced[i] != 0), whose projection through the frame pose has non-negative depth and lies inside the
+// image (:397-414,431-440). They are tracked by a fresh 2-level tracker fed from their stored patches with the
+// projection as initial flow and SSIM 0.75 (:421-458), and accepted when still TRACKED_WITH_3D and within 5.99 px^2 of
+// the projection (:474-479). The reference walks an absl::flat_hash_set (unspecified order); candidates are taken in
+// ascending index here. fp32 throughout like Sophus::SE3f * Eigen::Vector3f and CameraModel::Project.
+// ---------------------------------------------------------------------------------------------------------------
+int nrslam_b200_point_reuse(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, const float* pose, const uint8_t* image,
+                            int32_t width, int32_t height, int32_t pitch, const uint8_t* mask, int32_t mask_pitch,
+                            int32_t n, const float* X_world, const uint8_t* in_frame, const uint8_t* forced,
+                            int32_t max_iters, float epsilon, float min_eig_threshold, const int16_t* gray,
+                            const int16_t* grad, const float* mean, const float* mean2, const uint8_t* valid,
+                            int32_t* cand_out, float* seed_out, float* uv_out, uint8_t* status_out,
+                            uint8_t* accepted_out, int32_t* n_cand_out, int32_t* n_reused_out) {
+  if (n_cand_out) *n_cand_out = 0;
+  if (n_reused_out) *n_reused_out = 0;
+  if (!ctx || !cam || !pose || !image || n < 0 || (n > 0 && (!X_world || !in_frame || !gray || !grad || !mean || !mean2 ||
+      !valid || !cand_out || !uv_out || !accepted_out)))
+    return NRSLAM_B200_ERR_ARG;
+  nrs::Cam c;
+  c.model = cam->model;
+  for (int i = 0; i < 8; i++) c.p[i] = cam->params[i];
+  // Eigen::Quaternion::_transformVector: v + w t + q x t with t = 2 q x v (the form Sophus::SE3f * point evaluates)
+  const float qx = pose[0], qy = pose[1], qz = pose[2], qw = pose[3];
+  std::vector<int32_t> cand;
+  std::vector<float> seeds;
+  for (int i = 0; i < n; i++) {
+    if (in_frame[i] && !(forced && forced[i])) continue;
+    const float x = X_world[3 * (size_t)i], y = X_world[3 * (size_t)i + 1], z = X_world[3 * (size_t)i + 2];
+    float tx = NRS_FS(NRS_FM(qy, z), NRS_FM(qz, y)), ty = NRS_FS(NRS_FM(qz, x), NRS_FM(qx, z)),
+          tz = NRS_FS(NRS_FM(qx, y), NRS_FM(qy, x));
+    tx = NRS_FA(tx, tx); ty = NRS_FA(ty, ty); tz = NRS_FA(tz, tz);
+    const float cx_ = NRS_FS(NRS_FM(qy, tz), NRS_FM(qz, ty)), cy_ = NRS_FS(NRS_FM(qz, tx), NRS_FM(qx, tz)),
+                cz_ = NRS_FS(NRS_FM(qx, ty), NRS_FM(qy, tx));
+    const float px = NRS_FA(NRS_FA(NRS_FA(x, NRS_FM(qw, tx)), cx_), pose[4]);
+    const float py = NRS_FA(NRS_FA(NRS_FA(y, NRS_FM(qw, ty)), cy_), pose[5]);
+    const float pz = NRS_FA(NRS_FA(NRS_FA(z, NRS_FM(qw, tz)), cz_), pose[6]);
+    if (pz < 0) continue;  // :403-405
+    float u, v;
+    nrs::project_f(c, px, py, pz, u, v);
+    if (!(u >= 0 && u < (float)width && v >= 0 && v < (float)height)) continue;  // :409-412
+    cand.push_back(i);
+    seeds.push_back(u);
+    seeds.push_back(v);
+  }
+  const int m = (int)cand.size();
+  if (n_cand_out) *n_cand_out = m;
+  if (m == 0) return 0;  // :416-418
+  nrslam_b200_klt* k = nullptr;
+  int rc = nrslam_b200_klt_create(ctx, kWin, 1, max_iters, epsilon, min_eig_threshold, &k);  // :424-426
+  if (rc) return rc;
+  // gather the candidates' two-level patches
+  const size_t A = kArea;
+  std::vector<int16_t> g2((size_t)m * 2 * A), d2((size_t)m * 2 * A * 2);
+  std::vector<float> m1((size_t)m * 2), m2((size_t)m * 2);
+  std::vector<uint8_t> va((size_t)m * 2);
+  for (int j = 0; j < m; j++) {
+    const size_t i = cand[j];
+    memcpy(&g2[(size_t)j * 2 * A], gray + i * 2 * A, 2 * A * sizeof(int16_t));
+    memcpy(&d2[(size_t)j * 4 * A], grad + i * 4 * A, 4 * A * sizeof(int16_t));
+    m1[2 * j] = mean[2 * i]; m1[2 * j + 1] = mean[2 * i + 1];
+    m2[2 * j] = mean2[2 * i]; m2[2 * j + 1] = mean2[2 * i + 1];
+    va[2 * j] = valid[2 * i]; va[2 * j + 1] = valid[2 * i + 1];
+  }
+  rc = nrslam_b200_klt_insert_patches(k, m, seeds.data(), g2.data(), d2.data(), m1.data(), m2.data(), va.data());
+  std::vector<float> pts(seeds);
+  std::vector<uint8_t> st(m, NRSLAM_TRACKED_WITH_3D);
+  int32_t n_tracked = 0;
+  if (!rc)
+    rc = nrslam_b200_klt_track(k, image, width, height, pitch, m, pts.data(), st.data(), 1, 0.75f, mask, mask_pitch,
+                               &n_tracked);  // :456-458
+  nrslam_b200_klt_destroy(k);
+  if (rc) return rc;
+  int reused = 0;
+  for (int j = 0; j < m; j++) {
+    cand_out[j] = cand[j];
+    if (seed_out) { seed_out[2 * j] = seeds[2 * j]; seed_out[2 * j + 1] = seeds[2 * j + 1]; }
+    uv_out[2 * j] = pts[2 * j];
+    uv_out[2 * j + 1] = pts[2 * j + 1];
+    if (status_out) status_out[j] = st[j];
+    const float dx = NRS_FS(seeds[2 * j], pts[2 * j]), dy = NRS_FS(seeds[2 * j + 1], pts[2 * j + 1]);
+    const float err2 = NRS_FA(NRS_FM(dx, dx), NRS_FM(dy, dy));  // SquaredReprojectionError, geometry_toolbox.cc
+    accepted_out[j] = (st[j] == NRSLAM_TRACKED_WITH_3D && !(err2 > 5.99f)) ? 1 : 0;  // :474-479
+    reused += accepted_out[j];
+  }
+  if (n_reused_out) *n_reused_out = reused;
+  return 0;
+}
+
 int nrslam_b200_klt_debug_level(nrslam_b200_klt* k, int32_t which, int32_t level, uint8_t* img_out, int16_t* deriv_out,
                                 int32_t* w_out, int32_t* h_out) {
   if (!k || level < 0 || level >= k->n_levels() || k->w == 0) return kfail(k, NRSLAM_B200_ERR_ARG, "klt_debug_level: bad argument");

@@ -271,3 +271,13 @@ def landmark_triangulation_frame(batch, rigid_ok, rad_per_pixel, min_track=5):
     assert rc == 0
     return dict(deform_position=dp, deform_status=ds, rigid_position=rp, rigid_status=rs, selected_position=sp,
                 selected=sel)
+
+
+def point_reuse(cam, pose, image, X_world, patches, in_frame, forced=None, mask=None, klt_max_iters=10, klt_eps=1e-4,
+                klt_min_eig=1e-4):
+    """Tracking::PointReuse restated in C++ (oracle/orc_reuse.cc, tracking.cc:394-506); same outputs as api.point_reuse."""
+    from nrslam_b200 import api
+    rc, out = api._point_reuse_call(lib().orc_point_reuse, (), cam, pose, image, X_world, patches, in_frame, forced, mask,
+                                    klt_max_iters, klt_eps, klt_min_eig)
+    assert rc == 0
+    return out

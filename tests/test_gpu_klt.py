@@ -140,31 +140,40 @@ def test_rejects_unsupported_window(core):
         api.KLT(core, win=15)
 
 
-def test_point_reuse_composition(core):
-    """Tracking::PointReuse (tracking.cc:394-506): projection -> 2-level KLT from stored patches with initial flow ->
-    5.99 gate; the GPU composition against the same composition on the oracle tracker."""
+def test_point_reuse_matches_the_cpp_oracle(core):
+    """Tracking::PointReuse (tracking.cc:394-506) through the C ABI (nrslam_b200_point_reuse: projection -> in-image
+    test -> 2-level KLT from stored patches with initial flow -> 5.99 gate) against the C++ restatement of the same
+    function (oracle/orc_reuse.cc). Candidate bookkeeping is exact; tracked positions within 0.05 px; <= 1 % flips."""
     im = synth.klt_pair(seed=51, n_points=400, shift=(1.2, -0.9))
     cam = abi.Camera.pinhole(520.0, 520.0, 320.0, 240.0)
-    pose = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
-    z = np.float32(3.0)
-    # map points whose projection is the true current position + a sub-pixel seed error; a few behind the camera
+    # a rotated, translated camera: exercises the fp32 quaternion rotation both sides restate
+    ang = np.deg2rad(7.0)
+    q = np.array([0.0, np.sin(ang / 2), 0.0, np.cos(ang / 2)], np.float32)
+    t = np.array([0.05, -0.02, 0.1], np.float32)
+    pose = np.concatenate([q, t]).astype(np.float32)
+    R = synth.quat_to_R(q.astype(np.float64))
+    z = 3.0
     rng = np.random.default_rng(3)
     target = im["pts_true"] + rng.normal(scale=0.6, size=im["pts_true"].shape).astype(np.float32)
-    X = np.stack([(target[:, 0] - 320) / 520 * z, (target[:, 1] - 240) / 520 * z, np.full(len(target), z)], 1).astype(np.float32)
-    X[::41, 2] = -1.0
+    Pc = np.stack([(target[:, 0] - 320) / 520 * z, (target[:, 1] - 240) / 520 * z, np.full(len(target), z)], 1)
+    Pc[::41, 2] = -1.0                        # behind the camera
+    X = ((Pc - t.astype(np.float64)) @ R).astype(np.float32)   # world points: Pc = R X + t
     donor = api.KLT(core)                     # the map's stored photometric information (5 levels)
     donor.set_reference(im["ref"], im["pts"])
-    patches = [donor.get_patch(i) for i in range(len(X))]
+    patches = api.pack_reuse_patches([donor.get_patch(i) for i in range(len(X))])
     in_frame = np.zeros(len(X), bool)
     in_frame[::7] = True
-    ga = api.point_reuse(lambda ml, mi, e, me: api.KLT(core, max_level=ml, max_iters=mi, eps=e, min_eig=me),
-                         cam, pose, im["cur"], X, patches, in_frame)
-    oa = api.point_reuse(lambda ml, mi, e, me: oracle_lib.OracleKLT(max_level=ml, max_iters=mi, eps=e, min_eig=me),
-                         cam, pose, im["cur"], X, patches, in_frame)
-    assert np.array_equal(ga[0], oa[0]) and len(ga[0]) > 250          # candidate bookkeeping: exact
-    assert not np.any(in_frame[ga[0]]) and np.all(X[ga[0], 2] > 0)
-    assert (ga[2] != oa[2]).mean() <= 0.01
-    both = ga[2] & oa[2]
-    assert both.mean() > 0.7 and np.abs(ga[1][both] - oa[1][both]).max() < 0.05
-    assert np.median(np.abs(ga[1][both] - im["pts_true"][ga[0]][both])) < 0.15
+    forced = np.zeros(len(X), bool)
+    forced[::14] = True                       # lost ids handed in by the optimiser are candidates although in the frame
+    ga = api.point_reuse(core, cam, pose, im["cur"], X, patches, in_frame, forced)
+    oa = oracle_lib.point_reuse(cam, pose, im["cur"], X, patches, in_frame, forced)
+    assert np.array_equal(ga["candidates"], oa["candidates"]) and len(ga["candidates"]) > 250   # bookkeeping: exact
+    c = ga["candidates"]
+    assert np.all(~in_frame[c] | forced[c]) and np.all(Pc[c, 2] > 0) and forced[::14][Pc[::14, 2] > 0].all()
+    assert np.abs(ga["seeds"] - oa["seeds"]).max() < 1e-4
+    assert (ga["accepted"] != oa["accepted"]).mean() <= 0.01 and (ga["status"] != oa["status"]).mean() <= 0.01
+    both = ga["accepted"] & oa["accepted"]
+    assert both.mean() > 0.7 and np.abs(ga["pts"][both] - oa["pts"][both]).max() < 0.05
+    assert ga["n_reused"] == int(ga["accepted"].sum())
+    assert np.median(np.abs(ga["pts"][both] - im["pts_true"][c][both])) < 0.15
     donor.close()

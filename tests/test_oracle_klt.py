@@ -83,3 +83,34 @@ def test_patch_get_insert_roundtrip():
     assert np.array_equal(ra["pts"], rb["pts"]) and np.array_equal(ra["status"], rb["status"])
     a.clear()
     assert a.num_points() == 0
+
+
+def test_point_reuse_oracle_bookkeeping_and_gate():
+    """oracle/orc_reuse.cc (Tracking::PointReuse, tracking.cc:394-506): points already in the frame are skipped unless
+    the optimiser reported them lost, points behind the camera or outside the image never become candidates, a seed
+    that the tracker moves by more than sqrt(5.99) px is rejected, the rest is re-found within a fraction of a pixel."""
+    from nrslam_b200 import abi, synth
+    im = synth.klt_pair(seed=51, n_points=80, shift=(1.2, -0.9))
+    k = oracle_lib.OracleKLT()
+    k.set_reference(im["ref"], im["pts"])
+    patches = [k.get_patch(i) for i in range(80)]
+    cam = abi.Camera.pinhole(520.0, 520.0, 320.0, 240.0)
+    pose = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    tg = im["pts_true"].copy()
+    tg[5] += np.array([6.0, 0.0], np.float32)          # seed 6 px off: KLT pulls it back -> reprojection gate rejects
+    z = 3.0
+    X = np.stack([(tg[:, 0] - 320) / 520 * z, (tg[:, 1] - 240) / 520 * z, np.full(len(tg), z)], 1).astype(np.float32)
+    X[7, 2] = -1.0                                      # behind the camera
+    X[9, 0] = 50.0                                      # projects outside the image
+    in_frame = np.zeros(80, bool)
+    in_frame[[2, 3]] = True
+    forced = np.zeros(80, bool)
+    forced[3] = True
+    o = oracle_lib.point_reuse(cam, pose, im["cur"], X, patches, in_frame, forced)
+    c = list(o["candidates"])
+    assert 2 not in c and 3 in c and 7 not in c and 9 not in c and c == sorted(c)
+    acc = dict(zip(c, o["accepted"]))
+    assert not acc[5]
+    ok = o["accepted"]
+    assert ok.mean() > 0.8 and o["n_reused"] == int(ok.sum())
+    assert np.abs(o["pts"][ok] - im["pts_true"][o["candidates"]][ok]).max() < 0.5
