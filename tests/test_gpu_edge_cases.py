@@ -79,17 +79,10 @@ def test_ragged_keyframes(core, oracle):
     assert np.abs(a["kf_pose"] - b["kf_pose"]).max() < 2e-6 and np.abs(a["X"] - b["X"]).max() < 2e-5
 
 
-def test_full_size_c4_ba_properties(core):
-    """BASELINE configs[3] at full size: KannalaBrandt8 1440x1080, 20k landmarks / 100 keyframes / 200k observations.
-    Size-independent properties: the accepted chi2 never increases, poses stay unit quaternions, the result is finite
-    and reproducible."""
-    q = synth.ba_problem("c4")
-    args = (q["cam"], q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
-    b = core.local_ba(*args)
-    tr = np.array(b["stats"]["chi2_trace"])
-    assert len(tr) == 5 and np.all(np.diff(tr) <= 0)
-    assert b["stats"]["n_reproj_edges"] == len(q["obs_kf"]) >= 190000
-    assert np.allclose(np.linalg.norm(b["kf_pose"][:, :4], axis=1), 1.0, atol=1e-6)
-    assert np.isfinite(b["X"]).all()
-    b2 = core.local_ba(*args)
-    assert np.array_equal(b["X"], b2["X"]) and np.array_equal(b["kf_pose"], b2["kf_pose"])
+def test_full_size_c4_matches_the_oracle(core):
+    """BASELINE configs[3] at FULL size (KannalaBrandt8 1440x1080, 20k landmarks / 100 keyframes / 200k observations)
+    against the oracle's result of the same window (tests/golden/ba_full_c4.npz): LM iteration and trial counts exact,
+    accepted chi2 trace 1e-5 relative, poses / points with the 10x looser KannalaBrandt8 bars (device atan2f / sinf /
+    cosf differ from glibc by ulps), plus monotone chi2, unit quaternions and run-to-run determinism."""
+    from test_gpu_parity import _compare_with_full_size_fixture
+    _compare_with_full_size_fixture(core, "c4", 5e-5, 5e-4)

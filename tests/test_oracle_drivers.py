@@ -101,3 +101,34 @@ def test_get_edges_order_and_cut(oracle):
         assert key == sorted(key)  # status asc, weight desc, neighbour asc
         assert np.all(g.weight[e] >= mw * (1 - 1e-6))
         assert np.all((ent >= g.rowptr[v]) & (ent < g.rowptr[v + 1]))
+
+
+def test_converged_cg_solver_path_equals_the_factorisation():
+    """The oracle's ORC_SOLVER=cg path (fp64 CG to a relative residual of 1e-14; used only to GENERATE the full-size BA
+    fixtures, tests/golden/make_ba_full.py) reproduces the sparse-Cholesky path on the reference's own 5-keyframe
+    window: same LM iteration / trial counts, identical fp32 outputs, chi2 trace to 1e-12."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, json, numpy as np\\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\\n"
+        "import oracle_lib\\n"
+        "from nrslam_b200 import synth\\n"
+        "q = synth.ba_problem('c1', n=200)\\n"
+        "r = oracle_lib.Oracle().local_ba(q['cam'], q['kf_pose'], q['obs_kf'], q['obs_vertex'], q['uv'], q['X'], q['graph'], q['scale'])\\n"
+        "print(json.dumps(dict(pose=r['kf_pose'].tolist(), X=r['X'].tolist(), trace=r['stats']['chi2_trace'],"
+        " it=r['stats']['lm_iterations'], tr=r['stats']['lm_trials'])))\\n") % (
+            os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("chol", "cg"):
+        env = dict(os.environ, ORC_SOLVER=mode)
+        r = subprocess.run([sys.executable, "-c", code.replace("\\n", "\n")], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = outs
+    assert a["it"] == b["it"] and a["tr"] == b["tr"]
+    assert np.abs(np.array(a["pose"]) - np.array(b["pose"])).max() < 1e-7
+    assert np.abs(np.array(a["X"]) - np.array(b["X"])).max() < 1e-6
+    assert np.abs(np.array(a["trace"]) / np.array(b["trace"]) - 1).max() < 1e-12
