@@ -59,7 +59,9 @@ __device__ __forceinline__ void dst3(double* base, int i, const D3& v) {
 
 constexpr int kDBlock = 256;
 // shared-memory doubles (even) of the pivot inverses + look-ahead staging / of the unscaled panel rows
-__host__ __device__ inline size_t direct_sw_doubles(int max_nv) { return 6 * (size_t)(((max_nv + 1) & ~1) + 1) + 82; }
+__host__ __device__ inline size_t direct_sw_doubles(int max_nv) {
+  return 6 * (size_t)(((max_nv + 1) & ~1) + 1) + 20 * direct::kPanel + 2;
+}
 __host__ __device__ inline size_t direct_sv_doubles(int max_rows) {
   return ((size_t)max_rows * 3 * (3 * direct::kPanel + 1) + 2) & ~(size_t)1;
 }

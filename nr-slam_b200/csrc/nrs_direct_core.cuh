@@ -96,7 +96,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 #endif
 
-constexpr int kPanel = 4;  // vertex columns per panel of the blocked factorisation
+constexpr int kPanel = 6;  // vertex columns per panel of the blocked factorisation
 
 NRS_DD int sym6i(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  // a <= c
 
@@ -230,14 +230,14 @@ NRS_DD void diag_region(const Plan& pl, double* sp, int ld, int ka, int kb, doub
 // factorisation, so it is written for the fewest dependent instructions. Lane l < nblk owns ONE block (I, J) of the
 // region's lower block triangle in registers from the rank update through the pivot sweep to the final scaling;
 // per column the owners of column k publish their blocks to a small staging area (double-buffered by column parity),
-// everybody reads pivot / A / B from there. kPanel <= 4 (10 blocks <= 32 lanes).
+// everybody reads pivot / A / B from there. kPanel <= 7 (28 blocks <= 32 lanes).
 //   update: nc > 0 -> blk -= V(ka + I, 0:nc) L'(ka + J, k0cols)^T first (the rank-3 kPanel update of the previous panel)
 __device__ __forceinline__ void diag_region_dev(const Plan& pl, double* sp, int ld, int ka, int kb, double* s_m,
                                                 double* s_x, int lane, const double* s_v, int kvs, int k0, int nc) {
   const int nr = kb - ka;
   const int nblk = nr * (nr + 1) / 2;
   const bool act = lane < nblk;
-  const int I = act ? (lane >= 1) + (lane >= 3) + (lane >= 6) : 0;
+  const int I = act ? (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15) + (lane >= 21) : 0;
   const int J = act ? lane - I * (I + 1) / 2 : 0;
   double* o = sp + (size_t)(3 * (ka + I)) * ld + 3 * (ka + J);
   double b[9];
@@ -258,7 +258,7 @@ __device__ __forceinline__ void diag_region_dev(const Plan& pl, double* sp, int 
     }
   }
   for (int k = 0; k < nr; k++) {
-    double* xs = s_x + 40 * (k & 1);  // [4][10]
+    double* xs = s_x + 10 * kPanel * (k & 1);  // [kPanel][10]
     if (act && J == k) {
       double* x = xs + 10 * I;
 #pragma unroll
@@ -425,8 +425,8 @@ NRS_DD void stage_ab(const Plan& pl, const Sys& sys, int g, int d, double* sp, d
   const int gt = (th.nthr >= 64) ? th.tid - 32 : th.tid;           // bulk threads: everybody else (all, if one warp)
   const int gn = (th.nthr >= 64) ? th.nthr - 32 : th.nthr;
 #ifndef NRS_DIRECT_HOST_EMULATION
-  static_assert(kPanel <= 4, "diag_region_dev keeps one block of the region per lane");
-  double* s_x = s_w + 6 * (((nv + 1) & ~1) + 1);  // staging area of the look-ahead warp: 2 x [4][10] doubles
+  static_assert(kPanel <= 7, "diag_region_dev keeps one block of the region per lane (28 blocks <= 32 lanes)");
+  double* s_x = s_w + 6 * (((nv + 1) & ~1) + 1);  // staging area of the look-ahead warp: 2 x [kPanel][10] doubles
   if (la_warp && nv > 0)
     diag_region_dev(pl, sp, ld, 0, nv < kPanel ? nv : kPanel, s_w, s_x, th.tid, s_v, kVS, 0, 0);
 #else
