@@ -63,6 +63,33 @@ int host_threads(int items, int problem_size) {
   return std::max(1, std::min(std::min(items, hw > 0 ? hw : 1), cap));
 }
 
+// Host threads for the per-frame staging loops of the tracking path (a few thousand independent items of ~0.3 us):
+// at most 4, none below 512 items; NRSLAM_B200_HOST_THREADS caps it like the BA staging.
+int frame_threads(int items) {
+  if (items < 512) return 1;
+  static const int cap = [] {
+    const char* e = getenv("NRSLAM_B200_HOST_THREADS");
+    const int v = e ? atoi(e) : 4;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+  }();
+  const int hw = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(cap, hw > 1 ? hw - 1 : 1));
+}
+
+// fn(t, n_threads) on n_threads threads (the caller is thread 0); returns when all are done.
+template <typename Fn>
+void run_threads(int n_threads, Fn fn) {
+  if (n_threads <= 1) {
+    fn(0, 1);
+    return;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(n_threads - 1);
+  for (int t = 1; t < n_threads; t++) pool.emplace_back(fn, t, n_threads);
+  fn(0, n_threads);
+  for (auto& th : pool) th.join();
+}
+
 int fail(nrslam_b200_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
@@ -491,7 +518,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   size_t dsmem = 0;
   int dscratch = 0, dmaxnv = 0;
   if (direct) {
-    const int depth = std::min(direct_depth(Vu, ctx->sm_count), env_int("NRSLAM_B200_DIRECT_DEPTH", 7));
+    const int depth = std::min(direct_depth(Vu, ctx->sm_count, hp.poses_fixed ? env_int("NRSLAM_B200_LOST_LEAF", 8) : 8),
+                               env_int("NRSLAM_B200_DIRECT_DEPTH", 7));
     if (Vu == V) {
       build_direct_plan(V, hp.uv.data(), hp.pair_i, hp.pair_j, depth, dplan, !hp.poses_fixed);
     } else {  // only pairs between two unknowns couple unknowns
@@ -1097,11 +1125,25 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   std::vector<int> pair_stamp(g->n_edges, 0);  // spatial_connections_ids de-duplication, keyed by graph edge
   std::set<int> lost_ordered;                  // absl::btree_set<ID> (:222)
   std::vector<int> ent;
+  // GetEdges of every point (sort of its connections, regularization_graph.cc:71-87) is independent of the other
+  // points: host threads fill the sorted lists, the order-dependent selection below walks them sequentially
+  std::vector<int> ent_ptr(n + 1, 0), ent_cnt(n, 0);
+  for (int idx = 0; idx < n; idx++)
+    ent_ptr[idx + 1] = ent_ptr[idx] + (g->rowptr[point_vertex[idx] + 1] - g->rowptr[point_vertex[idx]]);
+  std::vector<int> ent_flat(ent_ptr[n]);
+  run_threads(frame_threads(n), [&](int t, int nt) {
+    std::vector<int> loc;
+    const int b = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt);
+    for (int idx = b; idx < e; idx++) {
+      loc.clear();
+      ent_cnt[idx] = graph_sorted_entries(g, point_vertex[idx], min_w, loc);
+      std::copy(loc.begin(), loc.end(), ent_flat.begin() + ent_ptr[idx]);
+    }
+  });
   for (int idx = 0; idx < n; idx++) {
-    ent.clear();
-    graph_sorted_entries(g, point_vertex[idx], min_w, ent);
     int n_regularizers = 0;
-    for (int pe : ent) {
+    for (int q = 0; q < ent_cnt[idx]; q++) {
+      const int pe = ent_flat[ent_ptr[idx] + q];
       const int other = g->col[pe], ge = g->eid[pe];
       if (n_regularizers > regularizers_per_point || g->status[ge] == NRSLAM_EDGE_BAD) break;  // :258-261
       if (vfs[other] < 0 || vfs[other] != NRSLAM_TRACKED_WITH_3D) {                             // :264-273
@@ -1195,11 +1237,18 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   }
   hprof.mark("gate");
   // ---- regularisation-graph refresh (:458-474)
-  for (int idx = 0; idx < n; idx++) {
-    if (!inliers[idx]) continue;
-    const int good = graph_update_vertex(g, point_vertex[idx], last_pos);
-    if (good < regularizers_per_point * 0.5) status[idx] = NRSLAM_BAD;
-  }
+  // Positions are fixed during the loop and UpdateConnection is idempotent (max / min / weight / "set BAD" from the
+  // two endpoint positions only, regularization_graph.cc:89-128), so the loop is order independent: host threads take
+  // ranges of points. An edge with two accepted endpoints is written twice with identical values — through relaxed
+  // atomics-free stores of the same bits, which is benign on every platform this library targets.
+  run_threads(frame_threads(n), [&](int t, int nt) {
+    const int b = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt);
+    for (int idx = b; idx < e; idx++) {
+      if (!inliers[idx]) continue;
+      const int good = graph_update_vertex(g, point_vertex[idx], last_pos);
+      if (good < regularizers_per_point * 0.5) status[idx] = NRSLAM_BAD;
+    }
+  });
   hprof.mark("update_vertex");
   if (status_out) memcpy(status_out, status.data(), n);
   if (stats) {

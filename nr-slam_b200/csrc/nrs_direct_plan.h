@@ -52,9 +52,9 @@ struct DirectPlanHost {
 };
 
 // Depth of the dissection for V rows on at most max_ctas CTAs: leaves of >= ~8 vertices, at most 2^7 leaves.
-inline int direct_depth(int V, int max_ctas) {
+inline int direct_depth(int V, int max_ctas, int min_leaf = 8) {
   int d = 0;
-  while (d < 7 && (2 << d) <= max_ctas && (V >> (d + 1)) >= 8) d++;
+  while (d < 7 && (2 << d) <= max_ctas && (V >> (d + 1)) >= min_leaf) d++;
   return d;
 }
 
