@@ -189,6 +189,77 @@ def _ref_frame(i):
     return 0
 
 
+SWEEP = [  # observations -> (camera config, landmarks, keyframes, visibility run)
+    (1000, "c3", 200, 5, 5), (2000, "c3", 400, 5, 5), (5000, "c3", 1000, 10, 5), (10000, "c3", 1000, 20, 10),
+    (20000, "c3", 2000, 30, 10), (50000, "c3", 5000, 30, 10), (100000, "c3", 10000, 60, 10),
+    (200000, "c4", 20000, 100, 10)]
+
+
+def run_sweep(args):
+    """BASELINE configs[4] in REF mode (the parity-graded mode; EDG 'nodes' have no reference counterpart):
+    deformable BA over 1k ... 200k observations on ONE GPU. Per size: device time of one optimize(5) launch on the
+    HBM-resident staged window with the L2 flushed before every launch (256 MB write), LM iterations/s, CG iterations,
+    the algorithmic bytes of SURVEY 8(d) and the fraction of the measured HBM peak; the oracle (one host core) is timed
+    beside it where it finishes in seconds. Inside a launch the window is re-read hundreds of times and stays
+    L2-resident up to ~100k observations — the fraction is a latency-bound figure, not a bandwidth claim."""
+    import numpy as np
+    import torch
+    import nrslam_b200  # noqa: F401
+    from nrslam_b200 import api, synth
+    torch.cuda.set_device(0)
+    core = api.Core()
+    pk, pk_kind = peaks()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    rows = []
+    for n_obs, cfg, n, n_kf, run in SWEEP:
+        q = synth.ba_problem(cfg, n=n, n_kf=n_kf, run=run)
+        bargs = (q["cam"], q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
+        t0 = time.perf_counter()
+        b = core.local_ba(*bargs)
+        e2e_first = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        b = core.local_ba(*bargs)
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+        ms = []
+        for _ in range(max(3, min(args.steps, 5))):
+            flush.zero_()
+            torch.cuda.synchronize()
+            sb = core.resolve(2)
+            ms.append(sb["gpu_ms"])
+        stb = dict(sb)
+        stb.update({k: b["stats"][k] for k in ("n_reproj_edges", "n_points", "n_poses", "n_pair_edges",
+                                                "n_spring_edges", "n_damper_edges")})
+        alg, bsw, bmv = algorithmic_bytes(stb)
+        launch = float(np.median(ms))
+        row = {"observations": int(len(q["obs_kf"])), "landmarks": n, "keyframes": n_kf, "camera": cfg,
+               "springs": b["stats"]["n_spring_edges"], "dampers": b["stats"]["n_damper_edges"],
+               "launch_ms": launch, "e2e_ms": e2e_ms, "lm_iterations": sb["lm_iterations"],
+               "lm_iterations_per_sec": sb["lm_iterations"] / (launch * 1e-3),
+               "e2e_lm_iterations_per_sec": b["stats"]["lm_iterations"] / (e2e_ms * 1e-3),
+               "pcg_iterations": sb["pcg_iterations"], "grid_ctas": sb["grid_ctas"],
+               "bytes_per_sweep": bsw, "bytes_per_matvec": bmv, "algorithmic_bytes_per_launch": alg,
+               "achieved_gbs": alg / (launch * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (launch * 1e-3) / 1e9 / pk["hbm_gbs"],
+               "us_per_cg_iteration": 1e3 * launch / max(sb["pcg_iterations"], 1),
+               "matvec_us_at_hbm_peak": bmv / (pk["hbm_gbs"] * 1e9) * 1e6}
+        if n_obs <= 2000 and not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib
+            t0 = time.perf_counter()
+            ab = oracle_lib.Oracle().local_ba(*bargs)
+            dt = time.perf_counter() - t0
+            row["cpu_baseline"] = {"value": ab["stats"]["lm_iterations"] / dt, "unit": "iters/s", "cores": 1,
+                                   "kind": "port", "sample": "one call, %.1f s" % dt}
+        rows.append(row)
+        print("sweep %7d obs: %8.2f ms  %7.1f LM it/s  %5d CG  %6.2f us/CG  frac %.4f" % (
+            row["observations"], launch, row["lm_iterations_per_sec"], row["pcg_iterations"],
+            row["us_per_cg_iteration"], row["frac_of_hbm_peak"]), file=sys.stderr, flush=True)
+    print(json.dumps({"metric": "deformable_ba_lm_iterations_per_sec", "unit": "iters/s", "n_gpus": 1,
+                      "config": {"workload": "configs[4]: BA sweep over observations, REF mode, optimize(5), one GPU",
+                                 "l2_flush_between_launches": True},
+                      "peak_gbs": pk["hbm_gbs"], "peak_kind": pk_kind, "sweep": rows}), flush=True)
+    core.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,10 +268,13 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-ba", action="store_true", help="skip the secondary BA measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sweep", action="store_true", help="configs[4]: BA sweep over 1k..200k observations (REF mode), one JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)  # one step = one frame = ~0.6 s of CPU work: K + W frames stay within minutes
     args.warmup = max(args.warmup, 3)
+    if args.sweep:
+        return run_sweep(args)
 
     import numpy as np
     import torch
