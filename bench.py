@@ -321,11 +321,11 @@ def main():
     klt.set_reference(im["ref"], im["pts"])
 
     def frame_e2e():
+        # Tracking::TrackCameraAndDeformation (tracking.cc:291-301): data association, then pose-only and
+        # pose+deformation as ONE C-ABI call (same results as the two calls; tests/test_gpu_parity.py)
         klt.track(im["cur"], im["pts"], im["status"])
-        r0 = core.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
-        r1 = core.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
-                              p["graph"].copy(), p["scale"], r0["pose"], p["last_world_position"])
-        return r0, r1
+        return core.track_pose_and_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
+                                          p["graph"].copy(), p["scale"], p["seed_pose"], p["last_world_position"])
 
     # ---- end-to-end through the C ABI (host buffers in, host results out)
     sampler = ClockSampler(local_rank)   # started before the warm-up: nvidia-smi needs a few 100 ms to deliver its first line
@@ -369,9 +369,8 @@ def main():
     clocks = sampler.stop([e2e_window, (wall0, wall0 + wall_s)])
     # the same frames without the KLT stage (optimisation only), end to end
     def frame_opt_only():
-        r0 = core.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
-        core.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
-                         p["graph"].copy(), p["scale"], r0["pose"], p["last_world_position"])
+        core.track_pose_and_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
+                                   p["graph"].copy(), p["scale"], p["seed_pose"], p["last_world_position"])
     t0 = time.perf_counter()
     for _ in range(args.steps):
         frame_opt_only()

@@ -173,6 +173,21 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
                             float* median_deformation_out, int32_t* lost_vertex_out, int32_t* n_lost_out,
                             nrslam_b200_stats* stats);
 
+/* ---- Tracking::TrackCameraAndDeformation after the data association (tracking/tracking.cc:291-330) -------------
+ * CameraPoseOptimization followed by CameraPoseAndDeformationOptimization on the same TRACKED_WITH_3D points, the
+ * second seeded with the first one's pose. Arguments as nrslam_b200_pose_deform (pose_io: the motion-model seed in,
+ * the final pose out); pose_only_out[7] / pose_only_inlier_out[n] (optional) return what CameraPoseOptimization alone
+ * would have returned. Results equal the two calls in sequence bit for bit; the host staging of the second problem
+ * overlaps the first kernel and the seed pose never leaves HBM. */
+int nrslam_b200_track_pose_and_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                                      const float* X_rest, const int32_t* point_vertex,
+                                      const int8_t* vertex_frame_status, nrslam_b200_graph* g, float scale,
+                                      float* pose_io, float* last_world_position_io, float* deformation_out,
+                                      float* X_out, float* chi2_out, uint8_t* status_out,
+                                      float* median_deformation_out, int32_t* lost_vertex_out, int32_t* n_lost_out,
+                                      float* pose_only_out, uint8_t* pose_only_inlier_out,
+                                      nrslam_b200_stats* stats_pose_only, nrslam_b200_stats* stats);
+
 /* ---- LocalDeformableBundleAdjustment (g2o_optimization.cc:880-1161) ---------------------------
  * n_kf keyframes of the window, OLDEST FIRST (the reference walks keyframes_in_optimization.rbegin(),
  * :930,982). n_obs observations grouped by keyframe in that order, inside a keyframe in

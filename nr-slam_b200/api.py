@@ -143,6 +143,38 @@ class Core:
         return dict(rc=rc, pose=pose, deformation=d, X=Xo, chi2=chi2, status=status, median=med.value,
                     lost=lost[: nl.value].copy(), last_pos=last_pos, stats=st.as_dict())
 
+    def track_pose_and_deform(self, cam, uv, X_rest, point_vertex, vfs, graph, scale, pose, last_pos):
+        """Tracking::TrackCameraAndDeformation after the data association (tracking.cc:291-330): CameraPoseOptimization
+        then CameraPoseAndDeformationOptimization seeded with its pose, as ONE call (nrslam_b200_track_pose_and_deform).
+        Returns (pose_only result, pose_deform result) with the same keys as the two separate calls."""
+        n = len(uv)
+        M = graph.n_vertices
+        uv, X_rest = _f32(uv), _f32(X_rest)
+        pv = np.ascontiguousarray(point_vertex, np.int32)
+        vfs = np.ascontiguousarray(vfs, np.int8)
+        pose = np.array(pose, np.float32)
+        last_pos = np.array(last_pos, np.float32)
+        d = np.zeros((n, 3), np.float32)
+        Xo = np.zeros((n, 3), np.float32)
+        chi2 = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        med = C.c_float(0)
+        lost = np.zeros(max(M, 1), np.int32)
+        nl = C.c_int32(0)
+        pose0 = np.zeros(7, np.float32)
+        inl0 = np.zeros(n, np.uint8)
+        st0, st = Stats(), Stats()
+        g = graph.struct()
+        rc = self._check(self.L.nrslam_b200_track_pose_and_deform(
+            self._ctx, C.byref(cam), n, ptr(uv, C.c_float), ptr(X_rest, C.c_float), ptr(pv, C.c_int32),
+            ptr(vfs, C.c_int8), C.byref(g), C.c_float(scale), ptr(pose, C.c_float), ptr(last_pos, C.c_float),
+            ptr(d, C.c_float), ptr(Xo, C.c_float), ptr(chi2, C.c_float), ptr(status, C.c_uint8), C.byref(med),
+            ptr(lost, C.c_int32), C.byref(nl), ptr(pose0, C.c_float), ptr(inl0, C.c_uint8), C.byref(st0), C.byref(st)))
+        r0 = dict(rc=rc, pose=pose0, inliers=inl0.astype(bool), stats=st0.as_dict())
+        r1 = dict(rc=rc, pose=pose, deformation=d, X=Xo, chi2=chi2, status=status, median=med.value,
+                  lost=lost[: nl.value].copy(), last_pos=last_pos, stats=st.as_dict())
+        return r0, r1
+
     def local_ba(self, cam, kf_pose, obs_kf, obs_vertex, uv, X, graph, scale, iterations=0):
         F = len(kf_pose)
         O = len(obs_kf)

@@ -182,6 +182,7 @@ struct HostProblem {
   int n_halo = 0;                       // landmark-sharded BA: trailing rows owned by other ranks (read-only copies)
   bool sharded = false;
   bool direct = false;                  // tracking: exact multifrontal L D L^T engine (nrs_direct.cu)
+  const double* pose_seed_dev = nullptr;  // seed poses already on the device (result of an earlier launch on the ctx stream)
   int n_unknown = 0;                    // direct engine: rows [n_unknown, V) are fixed vertices (0: every row is an unknown)
   std::vector<int> ops, op_args;
 };
@@ -662,6 +663,10 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     p.op_arg[i] = hp.op_args[i];
   }
   p.pose_seed = in.d<double>(put(in, hp.pose_seed));
+  if (hp.pose_seed_dev) {
+    p.pose_seed = hp.pose_seed_dev;
+    p.seed_via_f32 = 1;
+  }
   p.x_seed = in.d<double>(put(in, hp.x_seed));
   p.rest = in.d<double>(put(in, hp.rest));
   p.uv = in.d<double>(put(in, hp.uv));
@@ -816,6 +821,40 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   return 0;
 }
 
+// Launch the staged program WITHOUT waiting: the kernel and the copy of its (small) statistics are queued on the ctx
+// stream between the second pair of events; finish_async() collects them after a later synchronisation.
+int launch_async(nrslam_b200_ctx* ctx, Staged& st) {
+  if (!st.valid) return fail(ctx, NRSLAM_B200_ERR_ARG, "no staged problem");
+  NRS_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+  const int rc = st.use_direct ? launch_direct(st.dq, st.dgrid, st.dsmem, ctx->stream)
+                               : launch_engine(st.p, st.grid, st.block, st.smem, ctx->stream);
+  if (rc != 0)
+    return fail(ctx, NRSLAM_B200_ERR_CUDA, std::string("engine launch: ") + cudaGetErrorString((cudaError_t)rc));
+  NRS_CUDA(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+  NRS_CUDA(ctx, cudaMemcpyAsync(st.out.host(), st.out.dev(), st.out.used(), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+void finish_async(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats) {
+  if (!stats) return;
+  const EngineStats* es = st.out.h<EngineStats>(st.o_stats);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+  stats->gpu_ms += ms;
+  stats->lm_iterations += es->lm_iterations;
+  stats->lm_trials += es->lm_trials;
+  stats->pcg_iterations += es->pcg_iterations;
+  stats->n_sweeps += es->n_sweeps;
+  stats->n_chi2_passes += es->n_chi2_passes;
+  stats->kernel_launches += 1;
+  stats->grid_ctas = st.use_direct ? st.dgrid : st.grid;
+  stats->block_threads = st.use_direct ? direct_block_threads() : st.block;
+  stats->d2h_bytes += (int64_t)st.out.used();
+  for (int i = 0; i < es->n_trace && stats->n_trace < NRSLAM_B200_TRACE; i++)
+    stats->chi2_trace[stats->n_trace++] = es->chi2_trace[i];
+  stats->lambda_final = es->lambda_final;
+}
+
 // Launch the staged program, bring the results back, fill stats. Blocks until done.
 int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool copy_back = true,
                const Params* override_params = nullptr, bool plan2 = false) {
@@ -943,6 +982,7 @@ int nrslam_b200_create(const nrslam_b200_options* opt, nrslam_b200_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess ||
       cudaMalloc(&ctx->bar, 256) != cudaSuccess) {
     delete ctx;
     return NRSLAM_B200_ERR_CUDA;
@@ -967,6 +1007,8 @@ void nrslam_b200_destroy(nrslam_b200_ctx* ctx) {
   if (ctx->bar) cudaFree(ctx->bar);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -997,8 +1039,18 @@ int32_t nrslam_b200_graph_update_vertex(nrslam_b200_graph* g, int32_t vertex, co
 // =====================================================================================================
 // CameraPoseOptimization — g2o_optimization.cc:50-146
 // =====================================================================================================
-int nrslam_b200_pose_only(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
-                          const float* X, float* pose_io, uint8_t* inlier_out, nrslam_b200_stats* stats) {
+}  // extern "C"
+
+namespace {
+int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                     const float* X_rest, const int32_t* point_vertex, const int8_t* vfs, nrslam_b200_graph* g,
+                     float scale, float* pose_io, float* last_pos, float* deformation_out, float* X_out,
+                     float* chi2_out, uint8_t* status_out, float* median_deformation_out, int32_t* lost_vertex_out,
+                     int32_t* n_lost_out, nrslam_b200_stats* stats, const double* pose_seed_dev);
+
+// async: stage + launch only (results are collected by the caller after a later synchronisation of the ctx stream)
+int pose_only_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv, const float* X,
+                   float* pose_io, uint8_t* inlier_out, nrslam_b200_stats* stats, bool async) {
   if (!ctx || !cam || !uv || !X || !pose_io || n < 0) return fail(ctx, NRSLAM_B200_ERR_ARG, "pose_only: bad argument");
   const double t0 = wall_ms();
   if (stats) memset(stats, 0, sizeof(*stats));
@@ -1041,6 +1093,14 @@ int nrslam_b200_pose_only(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, i
   if (rc) return rc;
   const double t1 = wall_ms();
   if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes;
+  if (async) {
+    if (stats) {
+      stats->n_reproj_edges = n;
+      stats->n_poses = 1;
+      stats->stage_ms = (float)(t1 - t0);
+    }
+    return launch_async(ctx, st);
+  }
   rc = run_staged(ctx, st, stats);
   if (rc) return rc;
   const double* pose = st.out.h<double>(st.o_pose);
@@ -1059,16 +1119,69 @@ int nrslam_b200_pose_only(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, i
   }
   return 0;
 }
+}  // namespace
 
-// =====================================================================================================
-// CameraPoseAndDeformationOptimization — g2o_optimization.cc:148-557
-// =====================================================================================================
+extern "C" {
+int nrslam_b200_pose_only(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                          const float* X, float* pose_io, uint8_t* inlier_out, nrslam_b200_stats* stats) {
+  return pose_only_impl(ctx, cam, n, uv, X, pose_io, inlier_out, stats, false);
+}
+
 int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
                             const float* X_rest, const int32_t* point_vertex,
                             const int8_t* vfs, nrslam_b200_graph* g, float scale, float* pose_io,
                             float* last_pos, float* deformation_out, float* X_out, float* chi2_out,
                             uint8_t* status_out, float* median_deformation_out, int32_t* lost_vertex_out,
                             int32_t* n_lost_out, nrslam_b200_stats* stats) {
+  return pose_deform_impl(ctx, cam, n, uv, X_rest, point_vertex, vfs, g, scale, pose_io, last_pos, deformation_out,
+                          X_out, chi2_out, status_out, median_deformation_out, lost_vertex_out, n_lost_out, stats,
+                          nullptr);
+}
+
+// Tracking::TrackCameraAndDeformation after the data association (tracking.cc:291-330): CameraPoseOptimization, then
+// CameraPoseAndDeformationOptimization seeded with its result, on the same TRACKED_WITH_3D points. Same results as the
+// two calls in sequence (bit for bit: the pose+deformation kernel reads the seed pose straight from the pose-only
+// kernel's output in HBM), but the host staging of the second problem overlaps the first kernel.
+int nrslam_b200_track_pose_and_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                                      const float* X_rest, const int32_t* point_vertex, const int8_t* vfs,
+                                      nrslam_b200_graph* g, float scale, float* pose_io, float* last_pos,
+                                      float* deformation_out, float* X_out, float* chi2_out, uint8_t* status_out,
+                                      float* median_deformation_out, int32_t* lost_vertex_out, int32_t* n_lost_out,
+                                      float* pose_only_out, uint8_t* pose_only_inlier_out,
+                                      nrslam_b200_stats* stats_pose_only, nrslam_b200_stats* stats) {
+  if (!ctx || !pose_io) return fail(ctx, NRSLAM_B200_ERR_ARG, "track_pose_and_deform: bad argument");
+  float seed[7];
+  memcpy(seed, pose_io, sizeof(seed));
+  int rc = pose_only_impl(ctx, cam, n, uv, X_rest, seed, nullptr, stats_pose_only, true);
+  if (rc) return rc;
+  nrs::Staged& st0 = ctx->staged[0];
+  rc = pose_deform_impl(ctx, cam, n, uv, X_rest, point_vertex, vfs, g, scale, pose_io, last_pos, deformation_out, X_out,
+                        chi2_out, status_out, median_deformation_out, lost_vertex_out, n_lost_out, stats,
+                        st0.out.d<double>(st0.o_pose));
+  // the stream has been synchronised by the second stage: the pose-only results are on the host
+  finish_async(ctx, st0, stats_pose_only);
+  const double* pose0 = st0.out.h<double>(st0.o_pose);
+  if (pose_only_out) pose_to_f7(pose0, pose_only_out);
+  if (pose_only_inlier_out) {
+    const unsigned char* lvl = st0.out.h<unsigned char>(st0.o_rp_level);
+    for (int i = 0; i < n; i++) pose_only_inlier_out[i] = lvl[i] == 0;
+  }
+  if (rc) return rc;
+  for (int i = 0; i < 7; i++)
+    if (!std::isfinite(pose0[i])) return fail(ctx, NRSLAM_B200_NUM_NONFINITE, "pose_only: non-finite pose");
+  return 0;
+}
+}  // extern "C"
+
+namespace {
+// =====================================================================================================
+// CameraPoseAndDeformationOptimization — g2o_optimization.cc:148-557
+// =====================================================================================================
+int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_t n, const float* uv,
+                     const float* X_rest, const int32_t* point_vertex, const int8_t* vfs, nrslam_b200_graph* g,
+                     float scale, float* pose_io, float* last_pos, float* deformation_out, float* X_out,
+                     float* chi2_out, uint8_t* status_out, float* median_deformation_out, int32_t* lost_vertex_out,
+                     int32_t* n_lost_out, nrslam_b200_stats* stats, const double* pose_seed_dev) {
   if (!ctx || !cam || !uv || !X_rest || !point_vertex || !vfs || !g || !pose_io || !last_pos || n < 0)
     return fail(ctx, NRSLAM_B200_ERR_ARG, "pose_deform: bad argument");
   const double t0 = wall_ms();
@@ -1106,6 +1219,7 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   hp.th3f = th3;
   hp.pose_seed.resize(7);
   pose_from_f7(pose_io, hp.pose_seed.data());
+  hp.pose_seed_dev = pose_seed_dev;
   hp.x_seed.assign(4 * (size_t)n, 0.0);  // deformation vertices start at the origin (:188,345-348)
   hp.rest.resize(4 * (size_t)n);
   hp.uv.resize(2 * (size_t)n);
@@ -1399,11 +1513,11 @@ int nrslam_b200_pose_deform(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam,
   if (stats) stats->host_ms = (float)(wall_ms() - t0);
   return 0;
 }
+}  // namespace
 
 // =====================================================================================================
 // LocalDeformableBundleAdjustment — g2o_optimization.cc:880-1161
 // =====================================================================================================
-}  // extern "C"
 
 namespace {
 // Graph construction of the BA window (vertices, reprojection edges, springs, dampers) in the reference's order.

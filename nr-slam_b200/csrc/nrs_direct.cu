@@ -636,7 +636,17 @@ struct DirectEngine {
           barrier();
           for (int i = gt; i < P.V; i += gsz) dst3(P.x, i, dld3c(P.x_seed, i));
           __syncthreads();
-          if (tid < 7) s_pose[tid] = P.pose_seed[tid];
+          if (P.seed_via_f32) {
+            if (tid == 0) {  // g2o_optimization.cc:144-145 then :69-71 — the pose crosses the Frame as Sophus::SE3f
+              double sd[7];
+              float sf[7];
+              for (int t = 0; t < 7; t++) sd[t] = __ldcg(P.pose_seed + t);
+              pose_to_f7(sd, sf);
+              pose_from_f7(sf, s_pose);
+            }
+          } else if (tid < 7) {
+            s_pose[tid] = P.pose_seed[tid];
+          }
           __syncthreads();
         } break;
         case OP_CLEAR_LEVELS: {

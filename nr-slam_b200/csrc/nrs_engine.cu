@@ -2401,7 +2401,19 @@ struct Engine {
           barrier();
           for_rows([&](int i) { st3(P.x, i, ld3c(P.x_seed, i)); });
           __syncthreads();
-          for (int t = tid; t < 7 * F; t += nthr) s_pose[t] = P.pose_seed[t];
+          if (P.seed_via_f32) {
+            if (tid == 0) {  // the seed is an earlier launch's fp64 result crossing the Frame as Sophus::SE3f
+              for (int k = 0; k < F; k++) {
+                double sd[7];
+                float sf[7];
+                for (int t = 0; t < 7; t++) sd[t] = __ldcg(P.pose_seed + 7 * k + t);
+                pose_to_f7(sd, sf);
+                pose_from_f7(sf, s_pose + 7 * k);
+              }
+            }
+          } else {
+            for (int t = tid; t < 7 * F; t += nthr) s_pose[t] = P.pose_seed[t];
+          }
           __syncthreads();
         } break;
         case OP_CLEAR_LEVELS: {

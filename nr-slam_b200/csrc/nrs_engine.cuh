@@ -94,6 +94,8 @@ struct Params {
   // poses: 7 doubles each (q xyzw, t)
   double* pose;
   const double* pose_seed;
+  int seed_via_f32;         // 1: the seed is the fp64 result of an earlier launch and passes through Sophus::SE3f (fp32)
+                            //    like the reference's Frame does between the two tracking drivers
   // point vertices, 4-double stride
   double* x;
   const double* x_seed;

@@ -109,6 +109,7 @@ struct nrslam_b200_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // asynchronous launches (nrslam_b200_track_pose_and_deform)
   std::string err;
   nrs::Staged staged[4];  // 0 pose_only, 1 pose_deform, 2 local_ba, 3 lost-point stage
   unsigned long long* bar = nullptr;

@@ -198,12 +198,12 @@ NRS_HD void huber(double e, double delta, double& rho, double& drho) {
 }
 
 // Sophus::SE3f (7 floats) -> fp64 pose (g2o_optimization.cc:69-71: cast<double>() + SE3Quat ctor normalises)
-inline void pose_from_f7(const float* p, double* T) {
+NRS_HD void pose_from_f7(const float* p, double* T) {
   for (int i = 0; i < 7; i++) T[i] = p[i];
   pose_normalize(T);
 }
 // fp64 pose -> Sophus::SE3f through a 4x4 fp32 matrix (g2o_optimization.cc:144-145)
-inline void pose_to_f7(const double* T, float* p) {
+NRS_HD void pose_to_f7(const double* T, float* p) {
   double R[9];
   quat_to_R(T, R);
   float Rf[9], qf[4];

@@ -149,6 +149,26 @@ def test_resolve_is_idempotent(core):
     assert np.allclose(s1["chi2_trace"], main, rtol=1e-12)
 
 
+def test_fused_frame_call_equals_the_two_calls(core):
+    """nrslam_b200_track_pose_and_deform (tracking.cc:291-330 as one call: the host staging of the second problem
+    overlaps the pose-only kernel, the seed pose stays in HBM) returns bit for bit what CameraPoseOptimization followed by
+    CameraPoseAndDeformationOptimization return."""
+    p = synth.tracking_problem("c2", n=600)
+    a0 = core.pose_only(p["cam"], p["uv"], p["X_rest"], p["seed_pose"])
+    ga = p["graph"].copy()
+    a1 = core.pose_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"], ga, p["scale"],
+                          a0["pose"], p["last_world_position"])
+    gb = p["graph"].copy()
+    b0, b1 = core.track_pose_and_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
+                                        gb, p["scale"], p["seed_pose"], p["last_world_position"])
+    assert np.array_equal(a0["pose"], b0["pose"]) and np.array_equal(a0["inliers"], b0["inliers"])
+    for k in ("pose", "deformation", "X", "chi2", "status", "lost", "last_pos"):
+        assert np.array_equal(a1[k], b1[k]), k
+    assert a1["median"] == b1["median"]
+    assert np.array_equal(ga.weight, gb.weight) and np.array_equal(ga.status, gb.status)
+    assert a0["stats"]["chi2_trace"] == b0["stats"]["chi2_trace"] and a1["stats"]["chi2_trace"] == b1["stats"]["chi2_trace"]
+
+
 def _compare_with_full_size_fixture(core, cfg, pose_tol, pt_tol):
     """CUDA BA on a full-size BASELINE window against the ORACLE's result of the same seeded window
     (tests/golden/ba_full_<cfg>.npz, generated by tests/golden/make_ba_full.py with the oracle's converged-CG solver)."""
