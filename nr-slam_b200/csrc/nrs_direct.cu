@@ -349,10 +349,10 @@ struct DirectEngine {
 #pragma unroll
         for (int k = 0; k < 18; k++) cp[k] = 0.0;
       }
-      if (P.unary_on && lane == 0) {
+      if (P.unary_on) {
         // SpatialRegularizerFixed  optimization/spatial_regularizer_fixed.cc:32-43 — the reference value is read
-        // live from another (fixed) vertex and carries no Jacobian
-        for (int a = __ldg(P.un_ptr + i); a < __ldg(P.un_ptr + i + 1); a++) {
+        // live from another (fixed) vertex and carries no Jacobian; the lanes of the row group split the edges
+        for (int a = __ldg(P.un_ptr + i) + lane; a < __ldg(P.un_ptr + i + 1); a += lpr) {
           const double w = __ldg(P.un_w + a);
           const D3 rf = dld3(P.x, __ldg(P.un_ref + a));
           const double d0 = xi.x - rf.x, d1 = xi.y - rf.y, d2 = xi.z - rf.z;

@@ -885,6 +885,7 @@ int Optimizer::lm_solve(int iteration) {
     }
     qmax++;
   } while (rho < 0 && qmax < 10);
+  if (getenv("ORC_TRACE_TRIALS")) fprintf(stderr, "[orc] lm iteration %d: %d trials, lambda %.3g\n", iteration, qmax, lambda_);
   stats.lambda = lambda_;
   stats.chi2_final = currentChi;
   stats.chi2_trace.push_back(currentChi);
