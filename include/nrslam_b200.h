@@ -131,6 +131,8 @@ typedef struct nrslam_b200_stats {
   int32_t solve_failures;     /* factorisations that met a non-positive pivot / CG break-downs */
   int64_t factor_doubles;     /* doubles of the stored factor L' (nnz incl. the dense-front padding), last launch */
   int64_t update_doubles;     /* doubles of the update (Schur complement) matrices written per factorisation */
+  int32_t plan_reused;        /* 1: the symbolic analysis of the previous frame was re-used (same points, pairs inside its adjacency) */
+  int32_t reserved0;
 } nrslam_b200_stats;
 
 typedef struct nrslam_b200_ctx nrslam_b200_ctx;

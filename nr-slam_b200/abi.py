@@ -59,7 +59,7 @@ class Stats(C.Structure):
         ("lambda_final", C.c_double), ("gpu_ms", C.c_float), ("host_ms", C.c_float), ("stage_ms", C.c_float),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("grid_ctas", C.c_int32), ("block_threads", C.c_int32),
         ("direct_solves", C.c_int32), ("solve_failures", C.c_int32), ("factor_doubles", C.c_int64),
-        ("update_doubles", C.c_int64),
+        ("update_doubles", C.c_int64), ("plan_reused", C.c_int32), ("reserved0", C.c_int32),
     ]
 
     def as_dict(self):

@@ -21,7 +21,6 @@
 #include <thread>
 #include <vector>
 
-#include "nrs_direct_plan.h"
 #include "nrs_host.h"
 
 using namespace nrs;
@@ -182,6 +181,7 @@ struct HostProblem {
   int n_halo = 0;                       // landmark-sharded BA: trailing rows owned by other ranks (read-only copies)
   bool sharded = false;
   bool direct = false;                  // tracking: exact multifrontal L D L^T engine (nrs_direct.cu)
+  const std::vector<int32_t>* plan_key = nullptr;  // identity of the rows (map points in frame order): enables plan re-use
   const double* pose_seed_dev = nullptr;  // seed poses already on the device (result of an earlier launch on the ctx stream)
   int n_unknown = 0;                    // direct engine: rows [n_unknown, V) are fixed vertices (0: every row is an unknown)
   std::vector<int> ops, op_args;
@@ -509,7 +509,10 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   st.use_direct = false;
   HostProf hprof;
   // ---- exact-solve engine: symbolic analysis first, its elimination order becomes the row order
-  DirectPlanHost dplan;
+  DirectPlanHost dplan_local;
+  const bool cacheable = hp.plan_key != nullptr && env_int("NRSLAM_B200_PLAN_CACHE", 1) != 0;
+  DirectPlanHost& dplan = cacheable ? ctx->plan_cache.plan : dplan_local;
+  st.plan_reused = false;
   const int Vu = (hp.n_unknown > 0 && hp.n_unknown < V) ? hp.n_unknown : V;  // rows [Vu, V) are fixed vertices
   bool direct = hp.direct && F == 1 && D == 0 && !hp.points_fixed && !hp.sharded && hp.n_stage1 == 0 && Vu >= 1 &&
                 (hp.poses_fixed || U == 0);
@@ -521,7 +524,40 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   if (direct) {
     const int depth = std::min(direct_depth(Vu, ctx->sm_count, hp.poses_fixed ? env_int("NRSLAM_B200_LOST_LEAF", 8) : 8),
                                env_int("NRSLAM_B200_DIRECT_DEPTH", 7));
-    if (Vu == V) {
+    bool reuse = false;
+    if (cacheable && Vu == V) {
+      PlanCache& pc = ctx->plan_cache;
+      if (pc.valid && pc.plan.V == V && pc.depth == depth && pc.np == (hp.poses_fixed ? 0 : 2) && pc.key == *hp.plan_key) {
+        if (pc.pair_i == hp.pair_i && pc.pair_j == hp.pair_j) {
+          reuse = true;  // the very same structure
+        } else {         // every pair inside the adjacency the plan was built from?
+          reuse = true;
+          for (int e = 0; e < P && reuse; e++) {
+            const uint64_t a = (uint64_t)std::min(hp.pair_i[e], hp.pair_j[e]), b = (uint64_t)std::max(hp.pair_i[e], hp.pair_j[e]);
+            reuse = std::binary_search(pc.pairs.begin(), pc.pairs.end(), (a << 32) | b);
+          }
+        }
+      }
+      if (reuse) {
+        pc.reuses++;
+      } else {
+        build_direct_plan(V, hp.uv.data(), hp.pair_i, hp.pair_j, depth, dplan, !hp.poses_fixed);
+        pc.valid = true;
+        pc.depth = depth;
+        pc.np = hp.poses_fixed ? 0 : 2;
+        pc.key = *hp.plan_key;
+        pc.pair_i = hp.pair_i;
+        pc.pair_j = hp.pair_j;
+        pc.pairs.resize(P);
+        for (int e = 0; e < P; e++) {
+          const uint64_t a = (uint64_t)std::min(hp.pair_i[e], hp.pair_j[e]), b = (uint64_t)std::max(hp.pair_i[e], hp.pair_j[e]);
+          pc.pairs[e] = (a << 32) | b;
+        }
+        std::sort(pc.pairs.begin(), pc.pairs.end());
+        pc.builds++;
+      }
+      st.plan_reused = reuse;
+    } else if (Vu == V) {
       build_direct_plan(V, hp.uv.data(), hp.pair_i, hp.pair_j, depth, dplan, !hp.poses_fixed);
     } else {  // only pairs between two unknowns couple unknowns
       std::vector<int> pi, pj;
@@ -894,6 +930,7 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
       stats->direct_solves += es->lm_trials;
       stats->factor_doubles = st.dfactor_doubles;
       stats->update_doubles = st.dupdate_doubles;
+      stats->plan_reused += st.plan_reused ? 1 : 0;
     }
     for (int i = 0; i < es->n_trace && stats->n_trace < NRSLAM_B200_TRACE; i++)
       stats->chi2_trace[stats->n_trace++] = es->chi2_trace[i];
@@ -1284,6 +1321,8 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
   const int n_lost = (int)lost_list.size();
   hp.n_sort = n;
   hp.direct = env_int("NRSLAM_B200_DIRECT", 1) != 0;
+  const std::vector<int32_t> plan_key(point_vertex, point_vertex + n);
+  hp.plan_key = &plan_key;
   hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM, OP_RESET, OP_OPTIMIZE, OP_RELEVEL_DEFORM,
             OP_FINAL_CHI2};
   hp.op_args = {0, 0, opt.pose_deform_iterations[0], 0, 0, opt.pose_deform_iterations[1], 0, 0};

@@ -10,6 +10,7 @@
 
 #include "../../include/nrslam_b200.h"
 #include "nrs_direct.cuh"
+#include "nrs_direct_plan.h"
 #include "nrs_engine.cuh"
 
 namespace nrs {
@@ -86,6 +87,7 @@ struct Staged {
   DirectParams dq;
   int dgrid = 0;
   long long dfactor_doubles = 0, dupdate_doubles = 0;
+  bool plan_reused = false;  // the symbolic analysis of the previous frame was re-used
   size_t dsmem = 0;
 };
 
@@ -103,6 +105,21 @@ struct Shard {
 
 }  // namespace nrs
 
+namespace nrs {
+// Symbolic analysis of the exact solve kept across frames: a tracking frame whose optimised points are
+// the same map points in the same order as the previous frame's, and whose regulariser pairs all lie inside the
+// adjacency the plan was built from, re-uses the plan (a missing pair is a zero block of the same front).
+struct PlanCache {
+  DirectPlanHost plan;
+  bool valid = false;
+  int depth = -1, np = -1;
+  std::vector<int32_t> key;          // point_vertex of the frame the plan was built for
+  std::vector<uint64_t> pairs;       // sorted (min << 32 | max) of the pairs it was built from (caller rows)
+  std::vector<int> pair_i, pair_j;   // the same pairs in their original order (exact-match fast path)
+  long long builds = 0, reuses = 0;
+};
+}  // namespace nrs
+
 struct nrslam_b200_ctx {
   nrslam_b200_options opt;
   int device = 0;
@@ -115,5 +132,6 @@ struct nrslam_b200_ctx {
   unsigned long long* bar = nullptr;
   int max_cluster = -1;   // largest schedulable thread-block cluster of the LM kernel (queried lazily)
   nrs::Shard shard;
+  nrs::PlanCache plan_cache;       // main rounds of pose_deform
   nrs::Arena graph_in, graph_out;  // nrslam_b200_graph_update_vertices staging (nrs_tri.cu)
 };

@@ -114,3 +114,41 @@ def test_exact_solve_engine_agrees_with_the_cg_engine_at_every_size(core, n):
     assert np.abs(a["deformation"] - b["deformation"]).max() < 5e-5
     ta, tb = np.array(a["stats"]["chi2_trace"]), np.array(b["stats"]["chi2_trace"])
     assert len(ta) == len(tb) and np.abs(ta / tb - 1).max() < 1e-5
+
+
+def test_symbolic_plan_is_reused_across_frames(core):
+    """The nested-dissection plan of the exact solve is kept across frames: a frame with the same
+    points and the same regulariser pairs re-uses it (bit-identical result), a frame whose pairs are a SUBSET of the
+    plan's adjacency re-uses it too (missing pairs are zero blocks) and agrees with a freshly analysed solve; a frame
+    with other points rebuilds."""
+    import os
+    p = synth.tracking_problem("c2", n=900, seed=77)
+    args = (p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"])
+
+    def run(graph, cache=True, a=args):
+        os.environ["NRSLAM_B200_PLAN_CACHE"] = "1" if cache else "0"
+        try:
+            return core.pose_deform(*a, graph, p["scale"], p["seed_pose"], p["last_world_position"])
+        finally:
+            os.environ.pop("NRSLAM_B200_PLAN_CACHE", None)
+
+    r1 = run(p["graph"].copy())
+    r2 = run(p["graph"].copy())
+    assert r2["stats"]["plan_reused"] == 1
+    for k in ("pose", "deformation", "status", "lost"):
+        assert np.array_equal(r1[k], r2[k]), k
+    # some edges go BAD: the selection of the affected points stops earlier -> a subset of the cached adjacency
+    g = p["graph"].copy()
+    g.status[::37] = abi.EDGE_BAD
+    r3 = run(g.copy())
+    r4 = run(g.copy(), cache=False)
+    assert r3["stats"]["plan_reused"] == 1 and r4["stats"]["plan_reused"] == 0
+    assert r3["stats"]["n_pair_edges"] < r1["stats"]["n_pair_edges"]
+    assert np.array_equal(r3["status"], r4["status"]) and np.array_equal(r3["lost"], r4["lost"])
+    assert r3["stats"]["lm_trials"] == r4["stats"]["lm_trials"]
+    assert np.abs(r3["pose"] - r4["pose"]).max() < 2e-6 and np.abs(r3["deformation"] - r4["deformation"]).max() < 2e-5
+    # other points: rebuild
+    q = synth.tracking_problem("c2", n=900, seed=78)
+    r5 = core.pose_deform(q["cam"], q["uv"], q["X_rest"], q["point_vertex"], q["vertex_frame_status"], q["graph"].copy(),
+                          q["scale"], q["seed_pose"], q["last_world_position"])
+    assert r5["stats"]["plan_reused"] == 0 and r5["stats"]["direct_solves"] > 0
