@@ -1189,8 +1189,15 @@ int nrslam_b200_track_pose_and_deform(nrslam_b200_ctx* ctx, const nrslam_b200_ca
   if (!ctx || !pose_io) return fail(ctx, NRSLAM_B200_ERR_ARG, "track_pose_and_deform: bad argument");
   float seed[7];
   memcpy(seed, pose_io, sizeof(seed));
+  if (n > 0 && frame_threads(n) > 1) {  // the staging threads wake up while the pose-only problem is staged
+    ctx->pool.start(frame_threads(n) - 1);
+    ctx->pool.begin();
+  }
   int rc = pose_only_impl(ctx, cam, n, uv, X_rest, seed, nullptr, stats_pose_only, true);
-  if (rc) return rc;
+  if (rc) {
+    ctx->pool.end();
+    return rc;
+  }
   nrs::Staged& st0 = ctx->staged[0];
   rc = pose_deform_impl(ctx, cam, n, uv, X_rest, point_vertex, vfs, g, scale, pose_io, last_pos, deformation_out, X_out,
                         chi2_out, status_out, median_deformation_out, lost_vertex_out, n_lost_out, stats,
@@ -1225,6 +1232,14 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n_lost_out) *n_lost_out = 0;
   if (n == 0) return fail(ctx, NRSLAM_B200_NUM_TOO_FEW, "pose_deform: no observations");
+  if (frame_threads(n) > 1) {  // wake the staging threads now: they spin until the regulariser selection is done
+    ctx->pool.start(frame_threads(n) - 1);
+    ctx->pool.begin();
+  }
+  struct SpinWindow {  // whatever path leaves this function, the workers go back to sleep
+    HostPool& p;
+    ~SpinWindow() { p.end(); }
+  } spin_window{ctx->pool};
   NRS_CUDA(ctx, cudaSetDevice(ctx->device));
   const nrslam_b200_options& opt = ctx->opt;
   const int M = g->n_vertices;
@@ -1282,7 +1297,7 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
   for (int idx = 0; idx < n; idx++)
     ent_ptr[idx + 1] = ent_ptr[idx] + (g->rowptr[point_vertex[idx] + 1] - g->rowptr[point_vertex[idx]]);
   std::vector<int> ent_flat(ent_ptr[n]);
-  run_threads(frame_threads(n), [&](int t, int nt) {
+  ctx->pool.run([&](int t, int nt) {
     std::vector<int> loc;
     const int b = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt);
     for (int idx = b; idx < e; idx++) {
@@ -1291,6 +1306,7 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
       std::copy(loc.begin(), loc.end(), ent_flat.begin() + ent_ptr[idx]);
     }
   });
+  ctx->pool.end();
   for (int idx = 0; idx < n; idx++) {
     int n_regularizers = 0;
     for (int q = 0; q < ent_cnt[idx]; q++) {
@@ -1394,7 +1410,7 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
   // two endpoint positions only, regularization_graph.cc:89-128), so the loop is order independent: host threads take
   // ranges of points. An edge with two accepted endpoints is written twice with identical values — through relaxed
   // atomics-free stores of the same bits, which is benign on every platform this library targets.
-  run_threads(frame_threads(n), [&](int t, int nt) {
+  ctx->pool.run([&](int t, int nt) {
     const int b = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt);
     for (int idx = b; idx < e; idx++) {
       if (!inliers[idx]) continue;

