@@ -16,6 +16,12 @@ pytestmark = pytest.mark.gpu
 
 POSE_TOL = 2e-6
 PT_TOL = 2e-5
+# pose+deformation tracking runs on the exact-solve engine (block L D L^T like the reference's Cholesky): measured against
+# the oracle on these problems (tools/paritycheck.py): poses <= 4e-9, deformations <= 3e-7, accepted chi2 trace <= 9e-8
+# relative — the bars are 10x tighter than the CG engine's (round 1) and still leave > 5x headroom
+TRACK_POSE_TOL = 2e-7
+TRACK_PT_TOL = 2e-6
+TRACK_TRACE_RTOL = 1e-6
 
 
 def check_trace(a, b, rtol=1e-5):
@@ -60,17 +66,17 @@ def test_pose_deform(core, oracle, cfg, n, kw):
     a, ga = run_pd(oracle, p)
     b, gb = run_pd(core, p)
     kb8 = cfg == "c4"
-    assert np.abs(a["pose"] - b["pose"]).max() < (POSE_TOL if not kb8 else 2e-5)
-    assert np.abs(a["deformation"] - b["deformation"]).max() < (PT_TOL if not kb8 else 2e-4)
-    assert np.abs(a["X"] - b["X"]).max() < (PT_TOL if not kb8 else 2e-4)
-    assert np.abs(a["last_pos"] - b["last_pos"]).max() < (PT_TOL if not kb8 else 2e-4)
+    assert np.abs(a["pose"] - b["pose"]).max() < (TRACK_POSE_TOL if not kb8 else 2e-5)
+    assert np.abs(a["deformation"] - b["deformation"]).max() < (TRACK_PT_TOL if not kb8 else 2e-4)
+    assert np.abs(a["X"] - b["X"]).max() < (TRACK_PT_TOL if not kb8 else 2e-4)
+    assert np.abs(a["last_pos"] - b["last_pos"]).max() < (TRACK_PT_TOL if not kb8 else 2e-4)
     assert np.allclose(a["chi2"], b["chi2"], rtol=1e-4 if not kb8 else 1e-2, atol=1e-3 if not kb8 else 5e-2)
-    assert abs(a["median"] - b["median"]) < PT_TOL * (10 if kb8 else 1)
+    assert abs(a["median"] - b["median"]) < (TRACK_PT_TOL if not kb8 else 2e-4)
     # bookkeeping: bit-exact
     if not kb8:
         assert np.array_equal(a["status"], b["status"])
         assert np.array_equal(ga.status, gb.status)
-        check_trace(a, b)
+        check_trace(a, b, rtol=TRACK_TRACE_RTOL)
     else:  # fp32 transcendental ulps can flip a threshold tie; report-level check
         assert (a["status"] != b["status"]).mean() < 0.01
     assert np.array_equal(a["lost"], b["lost"])
@@ -79,7 +85,7 @@ def test_pose_deform(core, oracle, cfg, n, kw):
         assert a["stats"]["n_fixed_edges"] == b["stats"]["n_fixed_edges"]
     # graph attributes are fp32 functions of positions that agree to PT_TOL each: distances to 2 PT_TOL absolute,
     # weights exp(-d^2 / 2 sigma^2) to |dw| <= d / sigma^2 * 2 PT_TOL
-    dtol = 2 * (PT_TOL if not kb8 else 2e-4)
+    dtol = 2 * (TRACK_PT_TOL if not kb8 else 2e-4)
     assert np.allclose(ga.weight, gb.weight, rtol=1e-4, atol=dtol)
     assert np.allclose(ga.max_distance, gb.max_distance, rtol=0, atol=dtol)
     assert np.allclose(ga.min_distance, gb.min_distance, rtol=0, atol=dtol)
@@ -92,8 +98,8 @@ def test_pose_deform_with_bad_graph_edges(core, oracle):
     a, ga = run_pd(oracle, p)
     b, gb = run_pd(core, p)
     assert a["stats"]["n_pair_edges"] == b["stats"]["n_pair_edges"]
-    assert np.abs(a["pose"] - b["pose"]).max() < POSE_TOL
-    assert np.abs(a["deformation"] - b["deformation"]).max() < PT_TOL
+    assert np.abs(a["pose"] - b["pose"]).max() < TRACK_POSE_TOL
+    assert np.abs(a["deformation"] - b["deformation"]).max() < TRACK_PT_TOL
     assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["lost"], b["lost"])
     assert np.array_equal(ga.status, gb.status)
 
