@@ -318,6 +318,9 @@ struct Plan {
   size_t smem = 0;
   std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr;
   const int *d_chunk_kf = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_kf_chunk_ptr = nullptr;
+  // wide CG loop: one contiguous row range per CTA, cut into segments at the pose-slot boundaries
+  std::vector<int> wseg_ptr, wseg_begin, wseg_end, kf_wseg_ptr;
+  const int *d_wseg_ptr = nullptr, *d_wseg_begin = nullptr, *d_wseg_end = nullptr, *d_kf_wseg_ptr = nullptr;
   // halo push lists of the cluster-native CG loop (built when the plan qualifies for it)
   int halo_rows = 0, coarse = 0;
   std::vector<int> inc_halo, push_ptr, push_row, push_dst, xinc_ptr, xinc_idx;
@@ -372,7 +375,7 @@ void build_halo(Plan& pl, const std::vector<int>& inc_ptr, const std::vector<int
 // The path is bound by synchronisation latency: prefer ONE thread-block cluster (hardware barrier) whenever the
 // rows fit a cluster's threads; otherwise a cooperative grid with the atomics barrier.
 int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int>& kf_begin,
-              const std::vector<int>& inc_ptr, Plan& pl) {
+              const std::vector<int>& inc_ptr, Plan& pl, const std::vector<int>* dinc_ptr = nullptr) {
   const int F = hp.F;
   pl.V = kf_begin[F];
   if (ctx->max_cluster < 0) ctx->max_cluster = engine_max_cluster(kMaxBlock, 200 * 1024);
@@ -464,10 +467,12 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
       if (max_grid <= 0) return fail(ctx, NRSLAM_B200_ERR_CUDA, "kernel cannot be made resident");
       // more chunks than one CTA per SM can take in one pass: the two-CTAs-per-SM variant hides the gather latency
       if (!hp.points_fixed && n_chunks > max_grid && env_int("NRSLAM_B200_WIDE", 1)) {
-        const int mg2 = engine_max_grid(block, smem, 1);
+        const size_t smem_w = engine_smem_bytes_wide(F);
+        const int mg2 = engine_max_grid(block, smem_w, 1);
         if (mg2 > max_grid) {
           wide = 1;
           max_grid = mg2;
+          smem = smem_w;
         }
       }
       grid = std::max(1, std::min(n_chunks, max_grid));
@@ -487,6 +492,37 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
   }
   pl.n_chunks = n_chunks; pl.grid = grid; pl.block = block; pl.cluster_mode = cluster_mode; pl.resident = resident;
   pl.res_rows = res_rows; pl.res_inc = res_inc; pl.block_prec = block_prec; pl.smem = smem; pl.wide = wide;
+  if (wide && !cluster_mode) {
+    // CTA b owns rows [V b / G, V (b + 1) / G); a segment = the part of that range inside one pose slot. Rows are
+    // slot-major, so the segments of a slot are contiguous in this numbering.
+    // Ranges are balanced by gather work (1 per row + 1 per pair incidence + 2 per damper incidence), not by rows.
+    const int Vr = pl.V;
+    std::vector<long long> wsum(Vr + 1, 0);
+    for (int i = 0; i < Vr; i++)
+      wsum[i + 1] = wsum[i] + 2 + (inc_ptr[i + 1] - inc_ptr[i]) + 2LL * (dinc_ptr ? (*dinc_ptr)[i + 1] - (*dinc_ptr)[i] : 0);
+    std::vector<int> cut(grid + 1, 0);
+    for (int b = 1; b < grid; b++)
+      cut[b] = (int)(std::lower_bound(wsum.begin(), wsum.end(), wsum[Vr] * b / grid) - wsum.begin());
+    cut[grid] = Vr;
+    for (int b = 1; b <= grid; b++) cut[b] = std::max(cut[b], cut[b - 1]);
+    pl.wseg_ptr.assign(grid + 1, 0);
+    pl.kf_wseg_ptr.assign(F + 1, 0);
+    int k = 0;
+    for (int b = 0; b < grid; b++) {
+      int r = cut[b];
+      const int r1 = cut[b + 1];
+      while (r < r1) {
+        while (k < F && kf_begin[k + 1] <= r) k++;
+        const int e = std::min(r1, kf_begin[std::min(k, F - 1) + 1]);
+        pl.wseg_begin.push_back(r);
+        pl.wseg_end.push_back(e);
+        pl.kf_wseg_ptr[std::min(k, F - 1) + 1]++;
+        r = e;
+      }
+      pl.wseg_ptr[b + 1] = (int)pl.wseg_begin.size();
+    }
+    for (int q = 0; q < F; q++) pl.kf_wseg_ptr[q + 1] += pl.kf_wseg_ptr[q];
+  }
   return 0;
 }
 
@@ -496,6 +532,8 @@ void apply_plan(Params& p, const Plan& pl) {
   p.block_prec = pl.block_prec; p.wide = pl.wide;
   p.chunk_kf = pl.d_chunk_kf; p.chunk_begin = pl.d_chunk_begin; p.chunk_end = pl.d_chunk_end;
   p.kf_chunk_ptr = pl.d_kf_chunk_ptr;
+  p.n_wseg = (int)pl.wseg_begin.size();
+  p.wseg_ptr = pl.d_wseg_ptr; p.wseg_begin = pl.d_wseg_begin; p.wseg_end = pl.d_wseg_end; p.kf_wseg_ptr = pl.d_kf_wseg_ptr;
   p.coarse = pl.coarse;
   p.halo_rows = pl.halo_rows; p.inc_halo = pl.d_inc_halo; p.push_ptr = pl.d_push_ptr; p.push_row = pl.d_push_row;
   p.push_dst = pl.d_push_dst;
@@ -618,10 +656,10 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   {
     std::vector<int> kfb(hp.kf_begin);
     kfb[F] = V1;
-    const int rc = make_plan(ctx, hp, kfb, inc_ptr, planA);
+    const int rc = make_plan(ctx, hp, kfb, inc_ptr, planA, &dinc_ptr);
     if (rc) return rc;
     if (V1 < V && !hp.sharded) {
-      const int rc2 = make_plan(ctx, hp, hp.kf_begin, inc_ptr, planB);
+      const int rc2 = make_plan(ctx, hp, hp.kf_begin, inc_ptr, planB, &dinc_ptr);
       if (rc2) return rc2;
     }
   }
@@ -668,6 +706,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   sz((size_t)V); sz((size_t)V); sz((size_t)P);
   sz((size_t)max_chunks * 4 * 3 * 2); sz(((size_t)F + 1) * 4 * 2);
   for (Plan* pl : {&planA, &planB}) {
+    sz(pl->wseg_ptr.size() * 4); sz(pl->wseg_begin.size() * 4); sz(pl->wseg_end.size() * 4); sz(pl->kf_wseg_ptr.size() * 4);
     sz(pl->inc_halo.size() * 4); sz(pl->push_ptr.size() * 4); sz(pl->push_row.size() * 4); sz(pl->push_dst.size() * 4); sz(pl->xinc_ptr.size() * 4); sz(pl->xinc_idx.size() * 4);
   }
   std::vector<int> inc_pos;
@@ -739,6 +778,12 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     pl->d_chunk_begin = in.d<int>(put(in, pl->chunk_begin));
     pl->d_chunk_end = in.d<int>(put(in, pl->chunk_end));
     pl->d_kf_chunk_ptr = in.d<int>(put(in, pl->kf_chunk_ptr));
+    if (!pl->wseg_ptr.empty()) {
+      pl->d_wseg_ptr = in.d<int>(put(in, pl->wseg_ptr));
+      pl->d_wseg_begin = in.d<int>(put(in, pl->wseg_begin));
+      pl->d_wseg_end = in.d<int>(put(in, pl->wseg_end));
+      pl->d_kf_wseg_ptr = in.d<int>(put(in, pl->kf_wseg_ptr));
+    }
     if (!pl->push_ptr.empty()) {
       pl->d_inc_halo = in.d<int>(put(in, pl->inc_halo));
       pl->d_push_ptr = in.d<int>(put(in, pl->push_ptr));
@@ -798,6 +843,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   Arena& wk = st.work;
   size_t wneed = (size_t)V * 8 * (4 + 20 + 8 + 4 + 8 + 4 * 5) + (size_t)P * 40 + (size_t)D * 32 +
                  2 * (size_t)max_chunks * kChunkVals * 8 + 2 * (size_t)max_grid_used * kSlotVals * 8 + 32 * 256 + 4096;
+  const size_t max_wseg = std::max(planA.wseg_begin.size(), planB.wseg_begin.size());
+  if (max_wseg > 0) wneed += 2 * max_wseg * 8 * 8 + 2 * (size_t)P * 32 + 4 * (size_t)D * 32 + 4 * (size_t)V * 8 + 8 * 256;
   if (direct)
     wneed += ((size_t)dplan.p_total + (size_t)dplan.u_total + 18 * (size_t)V + (size_t)dplan.G * (28 + 4 + 32) + 2 * (size_t)dplan.n_nodes + 72) * 8 +
              16 * 256;
@@ -817,6 +864,12 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   p.dc = wk.d<double>(wk.take<double>(4 * (size_t)std::max(D, 1)));
   p.chunk_part = wk.d<double>(wk.take<double>(2 * (size_t)max_chunks * kChunkVals));
   p.slots = wk.d<double>(wk.take<double>(2 * (size_t)max_grid_used * kSlotVals));
+  if (max_wseg > 0) {
+    p.wseg_part = wk.d<double>(wk.take<double>(2 * max_wseg * 8));
+    p.wvec = wk.d<double>(wk.take<double>(4 * (size_t)V));
+    p.wrec = wk.d<double>(wk.take<double>(8 * (size_t)std::max(P, 1)));
+    p.wdrec = wk.d<double>(wk.take<double>(16 * (size_t)std::max(D, 1)));
+  }
   p.bar = ctx->bar;
   if (direct) {
     DirectParams& q = st.dq;

@@ -83,6 +83,24 @@ __device__ __forceinline__ V3 ld3p(const double* base, int i) {
   return V3{a.x, a.y, base[4 * (size_t)i + 2]};
 }
 
+// One 4-double record (32 bytes, 32-byte aligned) with ONE 256-bit access (sm_100: LDG.256 / STG.256). The wide CG
+// loop is bound by L1TEX wavefronts (distinct 128-byte lines per load instruction): half the instructions of the
+// double2 + double pair per gathered row.
+struct __align__(32) D4 {
+  double x, y, z, w;
+};
+__device__ __forceinline__ D4 ld4(const double* base, size_t i) {
+  D4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(base + 4 * i)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st4(double* base, size_t i, double x, double y, double z, double w = 0.0) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(base + 4 * i), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
+}
+
 // 3-double packed rows (shared-memory copies of z): a 32-byte row stride touches only half of the banks when lanes
 // gather random rows; 24-byte rows spread over all of them
 __device__ __forceinline__ V3 ld3s(const double* base, int i) {
@@ -176,6 +194,24 @@ __device__ __forceinline__ double sum_chunk_partials_of(const Params& P, int k, 
   return s;
 }
 
+// The same over the segment partials of the wide CG loop (Engine<true>::pcg_wide).
+__device__ __forceinline__ double sum_wseg_partials_of(const Params& P, int k, int v, int par) {
+  const int c1 = P.kf_wseg_ptr[k + 1];
+  double s = 0;
+  for (int c0 = P.kf_wseg_ptr[k]; c0 < c1; c0 += 8) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int c = min(c0 + u, c1 - 1);
+      t[u] = __ldcg(P.wseg_part + ((size_t)par * P.n_wseg + c) * 8 + v);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (c0 + u < c1) s += t[u];
+  }
+  return s;
+}
+
 // ---- multi-GPU exchange of the landmark-sharded BA (cooperative-grid mode only). Called by every CTA with this
 // GPU's totals in s_scal[0..n): CTA 0 pushes them (and, kind 1 / 2, this rank's 6 F CG pose partials / 27 F
 // linearisation pose blocks summed over its chunks) into the record [parity][rank] of EVERY rank's reduction buffer,
@@ -202,7 +238,8 @@ __device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int
     const int per = (kind == 1) ? 6 : 27;
     const int nx = (kind == 0) ? 0 : per * P.F;
     for (int t = tid; t < nx; t += nthr) {
-      const double s = sum_chunk_partials_of(P, t / per, t % per, par);
+      const double s = (kind == 1 && P.wide) ? sum_wseg_partials_of(P, t / per, t % per, par)
+                                             : sum_chunk_partials_of(P, t / per, t % per, par);
       for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
     }
     __syncthreads();
@@ -284,7 +321,7 @@ struct Engine {
     const int F = p.F;
     s_pose = sm;            sm += 7 * F;
     s_pose_bak = sm;        sm += 7 * F;
-    s_H = sm;               sm += 21 * F;
+    s_H = sm;               if (!WIDE) sm += 21 * F;
     s_M = sm;               sm += 36 * F;
     s_bp = sm;              sm += 6 * F;
     s_xp = sm;              sm += 6 * F;
@@ -294,13 +331,18 @@ struct Engine {
     s_qp = sm;              sm += 6 * F;
     s_red = sm;             sm += 32 * kChunkVals;
     s_scal = sm;            sm += 32;
-    s_pr = sm;              sm += 6 * kMaxRows;
-    s_gather = sm;          sm += 2 * 16 * kGatherVals;
+    s_pr = sm;              if (!WIDE) sm += 6 * kMaxRows;
+    s_gather = sm;          if (!WIDE) sm += 2 * 16 * kGatherVals;
     s_flag = reinterpret_cast<int*>(sm);  sm += 2;
     sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~uintptr_t(15));  // double2 accesses below
     // the pose-block records of the linearisation and the Jacobian cache of the CG loop are never live together
     s_rowA = sm;
-    if (!p.resident) sm += 16 * kMaxRows;
+    // wide variant (engine_smem_bytes_wide): the CG loop keeps its pose partials in registers (no s_pr), there is no
+    // cluster (no s_gather) and H_pp — filled after the linearisation's row records were reduced, read until the
+    // next linearisation — lives on top of those records: two CTAs per SM fit up to ~110 poses
+    if (WIDE) s_H = sm;
+    if (WIDE) sm += (21 * F > 16 * kMaxRows) ? 21 * F : 16 * kMaxRows;
+    else if (!p.resident) sm += 16 * kMaxRows;
     if (p.resident) {
       const int R = p.res_rows, CI = p.res_inc;
       s_jac = sm;           sm += (kJS * (size_t)R > 16 * (size_t)kMaxRows) ? kJS * (size_t)R : 16 * (size_t)kMaxRows;
@@ -418,7 +460,7 @@ struct Engine {
   // ---- grid reduction of n (<= 4) values: v[k] are per-thread partials. maxmask bit k: max instead of sum.
   // Result (identical in every CTA) lands in s_scal[0..n). Includes one grid barrier.
   template <int N>
-  __device__ __forceinline__ void grid_reduce(double (&v)[N], unsigned maxmask, int xkind = 0) {
+  __device__ __forceinline__ void grid_reduce(double (&v)[N], unsigned maxmask, int xkind = 0, int xpar = -1) {
     const int par = gen & 1;
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -465,7 +507,7 @@ struct Engine {
       if (lane == 0) s_scal[k] = s;
     }
     __syncthreads();
-    if (P.world > 1) xexchange(N, maxmask, xkind, par);
+    if (P.world > 1) xexchange(N, maxmask, xkind, xpar >= 0 ? xpar : par);
   }
 
   // ---- multi-GPU (landmark-sharded BA): see xexchange_impl. The exchange is a free function that gets the engine
@@ -721,11 +763,22 @@ struct Engine {
 #pragma unroll
             for (int k = 0; k < 6; k++) B[k] = 0;
           }
+          if constexpr (WIDE) {
+            // component-major (10 double2 planes of V rows): the wide CG loop reads it one thread per row, coalesced
+            double2* jt = reinterpret_cast<double2*>(P.jac) + i;
+            const size_t V = (size_t)P.V;
+#pragma unroll
+            for (int k = 0; k < 6; k++) jt[k * V] = make_double2(A[2 * k], A[2 * k + 1]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) jt[(6 + k) * V] = make_double2(B[2 * k], B[2 * k + 1]);
+            jt[9 * V] = make_double2(omega, 0.0);
+          } else {
 #pragma unroll
           for (int k = 0; k < 6; k++) reinterpret_cast<double2*>(jo)[k] = make_double2(A[2 * k], A[2 * k + 1]);
 #pragma unroll
           for (int k = 0; k < 3; k++) reinterpret_cast<double2*>(jo)[6 + k] = make_double2(B[2 * k], B[2 * k + 1]);
           reinterpret_cast<double2*>(jo)[9] = make_double2(omega, 0.0);
+          }
         }
         if (!var && !P.points_fixed && LIN) {
           double2* d = reinterpret_cast<double2*>(P.dg + 8 * (size_t)i);
@@ -1526,6 +1579,434 @@ struct Engine {
   }
 
   // ================================================================================================
+  // CG loop of the WIDE variant (large BA windows, cooperative grid, vectors in L2 / HBM). Same recurrences and the
+  // same 3x3 block-Jacobi preconditioner as pcg(), organised for throughput instead of lock-step chunk passes:
+  //  * every CTA owns ONE contiguous row range of equal length (host: wseg_*), cut into segments at the pose-slot
+  //    boundaries — no chunk-count quantisation between CTAs;
+  //  * a row group (kTPR lanes) keeps the pose partial of its rows in REGISTERS for a whole segment: one block
+  //    reduction per segment (usually one or two per CTA and iteration) instead of three block syncs per 128-row
+  //    chunk pass, so the warps of a CTA run through their rows independently and hide each other's gather chains;
+  //  * the pair coefficients are expanded into incidence order once per solve (wrec) and a damper incidence is one
+  //    record (the three other vertices ordered (+, -, -) and the coefficient): c (z_i + z_+ - z_- - z_-), one
+  //    dependent level and one gathered row less than id -> vertices -> four rows;
+  //  * the update pass runs one thread per row.
+  // All sums keep a fixed order: results are reproducible run to run.
+  // ================================================================================================
+  __device__ __forceinline__ double block_sum(double v, int buf) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+    double* b = s_scal + 8 + 8 * buf;  // two buffers: the next call may start before every thread has read this one
+    if (lane == 0) b[warp] = v;
+    __syncthreads();
+    double s = 0;
+    for (int w = 0; w < nw; w++) s += b[w];
+    return s;
+  }
+
+  // Row-local part of the NEXT matvec, evaluated where z_i is produced (initial residual, update pass):
+  // wl_i = (lambda + s_unary) z_i + B_i^T t_i with t_i = omega_i (A_i z_p + B_i z_i), and the row's pose partial
+  // A_i^T t_i added to red. A fixed row (z_i = 0) still feeds the pose rows. The Jacobian is component-major here.
+  __device__ __forceinline__ void wide_row_local(int i, bool fixed, double su, const V3& z, bool pos, double (&red)[6]) {
+    const int kf = P.pt_kf[i];
+    const double2* jt = reinterpret_cast<const double2*>(P.jac) + i;
+    const size_t V = (size_t)P.V;
+    V3 wl{(lambda + su) * z.x, (lambda + su) * z.y, (lambda + su) * z.z};
+    if (kf >= 0) {
+      double2 j[10];
+#pragma unroll
+      for (int k = 0; k < 10; k++) j[k] = jt[k * V];
+      const double omega = j[9].x;
+      if (omega != 0) {
+        double A[12], B[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          A[2 * k] = j[k].x;
+          A[2 * k + 1] = j[k].y;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          B[2 * k] = j[6 + k].x;
+          B[2 * k + 1] = j[6 + k].y;
+        }
+        double jp0 = 0, jp1 = 0;
+        if (pos) {
+          const double* pk = s_zp + 6 * kf;
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            jp0 += A[a] * pk[a];
+            jp1 += A[6 + a] * pk[a];
+          }
+        }
+        const double t0 = omega * (jp0 + B[0] * z.x + B[1] * z.y + B[2] * z.z);
+        const double t1 = omega * (jp1 + B[3] * z.x + B[4] * z.y + B[5] * z.z);
+        wl.x += B[0] * t0 + B[3] * t1;
+        wl.y += B[1] * t0 + B[4] * t1;
+        wl.z += B[2] * t0 + B[5] * t1;
+        if (pos) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) red[a] += A[a] * t0 + A[6 + a] * t1;
+        }
+      }
+    }
+    if (!fixed) st4(P.wvec, i, wl.x, wl.y, wl.z);
+  }
+
+  // One thread per row over this CTA's segments; fn(i, red) adds the row's pose partial to red. The partials of a
+  // segment are summed in a fixed order (lanes, warps) and stored to wseg_part[buf][segment].
+  template <typename Fn>
+  __device__ __forceinline__ void wide_segments(int sg0, int sg1, bool pos, int buf, Fn fn) {
+    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+    int slot = 0;
+    for (int sg = sg0; sg < sg1; sg++) {
+      const int se = P.wseg_end[sg];
+      double red[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = P.wseg_begin[sg] + tid; i < se; i += nthr) fn(i, red);
+      if (pos) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) red[a] += __shfl_xor_sync(0xffffffffu, red[a], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) s_red[(slot * nw + warp) * 6 + a] = red[a];
+        }
+        slot++;
+        if (slot == 8 || sg == sg1 - 1) {  // the warps of up to 8 segments are combined per flush
+          __syncthreads();
+          for (int tt = tid; tt < slot * 6; tt += nthr) {
+            const int sl = tt / 6, a = tt % 6;
+            double sum = 0;
+            for (int w = 0; w < nw; w++) sum += s_red[(sl * nw + w) * 6 + a];
+            P.wseg_part[((size_t)buf * P.n_wseg + (sg - slot + 1 + sl)) * 8 + a] = sum;
+          }
+          __syncthreads();
+          slot = 0;
+        }
+      }
+    }
+  }
+
+  __device__ bool pcg_wide() {
+    const int F = P.F;
+    const bool pos = !P.poses_fixed;
+    if (tid == 0) *s_flag = 0;
+    __syncthreads();
+    if (pos) {
+      for (int k = tid; k < F; k += nthr)
+        if (!invert6(s_H + 21 * k, lambda, s_M + 36 * k)) *s_flag = 1;
+    }
+    __syncthreads();
+    if (*s_flag) return false;  // uniform: every CTA inverts the same blocks
+    const int sg0 = P.wseg_ptr[blockIdx.x], sg1 = P.wseg_ptr[blockIdx.x + 1];
+    const int r0 = sg0 < sg1 ? P.wseg_begin[sg0] : 0, r1 = sg0 < sg1 ? P.wseg_end[sg1 - 1] : 0;  // this CTA's rows
+    double* const minvA = P.minv;                      // m00 m01 m02 m11
+    double* const minvB = P.minv + 4 * (size_t)P.V;    // m12 m22 s_unary -
+    // ---- incidence records of this CTA's rows
+    {
+      const int ab = P.inc_ptr[r0], ae = P.inc_ptr[r1];
+      for (int a = ab + tid; a < ae; a += nthr) {
+        const double2* cf = reinterpret_cast<const double2*>(P.pc + 4 * (size_t)(P.inc_ent[a] >> 1));
+        const double2 c0 = __ldcg(cf), c1 = __ldcg(cf + 1);
+        st4(P.wrec, a, c0.x, c0.y, c1.x, c1.y);
+      }
+      if (P.D > 0) {
+        const int db = P.dinc_ptr[r0], de = P.dinc_ptr[r1];
+        for (int a = db + tid; a < de; a += nthr) {
+          const int ent = P.dinc_ent[a], role = ent & 3;
+          const int4 v = __ldg(reinterpret_cast<const int4*>(P.dmp_v) + (ent >> 2));
+          // J = (-w, +w, +w, -w) I over (x, y, z, w): H_rk = c sigma_r sigma_k; seen from role r exactly one of the
+          // three other vertices enters with +c
+          int o0, o1, o2;
+          if (role == 0) { o0 = v.w; o1 = v.y; o2 = v.z; }
+          else if (role == 1) { o0 = v.z; o1 = v.x; o2 = v.w; }
+          else if (role == 2) { o0 = v.y; o1 = v.x; o2 = v.w; }
+          else { o0 = v.x; o1 = v.y; o2 = v.z; }
+          st4(P.wdrec, a, __hiloint2double(o1, o0), __hiloint2double(0, o2), __ldcg(P.dc + 4 * (size_t)(ent >> 2)), 0.0);
+        }
+      }
+    }
+    // ---- pose part of the initial residual (replicated per CTA): z_p is read by the rows below
+    double rz_pose = 0;
+    if (pos) {
+      for (int t = tid; t < 6 * F; t += nthr) {
+        s_rp[t] = s_bp[t];
+        s_xp[t] = 0;
+        s_pp[t] = 0;
+        s_qp[t] = 0;
+      }
+      __syncthreads();
+      double v = 0;
+      for (int t = tid; t < 6 * F; t += nthr) {
+        const int k = t / 6, a = t % 6;
+        double s = 0;
+        for (int c = 0; c < 6; c++) s += s_M[36 * k + a * 6 + c] * s_rp[6 * k + c];
+        s_zp[t] = s;
+        v += s_rp[t] * s;
+      }
+      rz_pose = block_sum(v, 0);
+    }
+    // ---- initial residual, z = M^-1 r, row-local part of the first matvec (one thread per row)
+    double rz_part[1] = {0};
+    wide_segments(sg0, sg1, pos, 0, [&](int i, double (&red)[6]) {
+      if (P.pt_fixed && P.pt_fixed[i]) {  // no unknowns: z = 0 for this row
+        st4(minvA, i, 0, 0, 0, 0);
+        st4(minvB, i, 0, 0, 0, 0);
+        st4(P.rvec, i, 0, 0, 0);
+        st4(P.xcg, i, 0, 0, 0);
+        st4(P.zvec, i, 0, 0, 0);
+        st4(P.pvec, i, 0, 0, 0);
+        st4(P.qvec, i, 0, 0, 0);
+        wide_row_local(i, true, 0.0, V3{0, 0, 0}, pos, red);
+        return;
+      }
+      const D4 r = ld4(P.bvec, i);
+      st4(P.rvec, i, r.x, r.y, r.z);
+      st4(P.xcg, i, 0, 0, 0);
+      const D4 d0 = ld4(P.dg, 2 * (size_t)i), d1 = ld4(P.dg, 2 * (size_t)i + 1);  // 00 01 02 11 | 12 22 su -
+      const double a = d0.x + lambda, b = d0.y, c = d0.z, e = d0.w + lambda, f = d1.x, g = d1.y + lambda;
+      const double C00 = e * g - f * f, C01 = c * f - b * g, C02 = b * f - c * e;  // symmetric 3x3 inverse by cofactors
+      const double det = a * C00 + b * C01 + c * C02;
+      const double id = 1.0 / det;
+      const double m00 = C00 * id, m01 = C01 * id, m02 = C02 * id;
+      const double m11 = (a * g - c * c) * id, m12 = (b * c - a * f) * id, m22 = (a * e - b * b) * id;
+      st4(minvA, i, m00, m01, m02, m11);
+      st4(minvB, i, m12, m22, d1.z, 0.0);
+      const V3 z{m00 * r.x + m01 * r.y + m02 * r.z, m01 * r.x + m11 * r.y + m12 * r.z,
+                 m02 * r.x + m12 * r.y + m22 * r.z};
+      st4(P.zvec, i, z.x, z.y, z.z);
+      if (P.world > 1) xpush3(P.xz, i, z);
+      rz_part[0] += r.x * z.x + r.y * z.y + r.z * z.z;
+      wide_row_local(i, false, d1.z, z, pos, red);
+    });
+    grid_reduce<1>(rz_part, 0);
+    double rz = s_scal[0] + rz_pose;
+    const double rz0 = rz;
+    if (!(rz0 > 0)) return isfinite(rz0);  // b == 0: delta = 0 (xcg is zero already)
+    const double stop = P.pcg_tol * P.pcg_tol * rz0;
+    double beta = 0;
+    bool ok = true;
+    int it = 0;
+    const int qr = tid / kTPR, ql = tid % kTPR;
+    const int RPP = nthr / kTPR;  // row groups per pass
+    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+    for (; it < P.pcg_max_iter; it++) {
+      const bool first = (it == 0);
+      const int wbuf = it & 1;  // wseg_part buffer holding this iteration's pose partials
+      // ---- phase 1: w = (H + lambda I) z ; p = z + beta p ; q = w + beta q ; partial p.q
+      //      (regulariser gathers only: the row-local part came with z). No block syncs: warps run independently.
+      const long long tm0 = clock64();
+      double pq_part[1] = {0};
+      for (int base = r0; base < r1; base += RPP) {
+        const int i = base + qr;
+        const bool valid = i < r1 && !(P.pt_fixed && P.pt_fixed[i]);
+        double w0 = 0, w1 = 0, w2 = 0;
+        D4 zi{0, 0, 0, 0}, wl{0, 0, 0, 0}, po{0, 0, 0, 0}, qo{0, 0, 0, 0};
+        if (valid) {
+          const int a_beg = P.inc_ptr[i], a1 = P.inc_ptr[i + 1];
+          const int d_beg = P.D > 0 ? P.dinc_ptr[i] : 0, d1 = P.D > 0 ? P.dinc_ptr[i + 1] : 0;
+          zi = ld4(P.zvec, i);
+          if (ql == 0) {
+            wl = ld4(P.wvec, i);
+            if (!first) {
+              po = ld4(P.pvec, i);
+              qo = ld4(P.qvec, i);
+            }
+          }
+          // lane l takes incidences a_beg + l, + kTPR, ...: batches of 3 per lane, every load of a level first
+          for (int a0 = a_beg + ql; a0 < a1; a0 += 3 * kTPR) {
+            int oth[3];
+            D4 cf[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const int a = min(a0 + kTPR * k, a1 - 1);
+              oth[k] = P.inc_other[a];
+              cf[k] = ld4(P.wrec, a);
+            }
+            D4 zo[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) zo[k] = ld4(P.zvec, oth[k]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              if (a0 + kTPR * k < a1) {
+                const double dx = zi.x - zo[k].x, dy = zi.y - zo[k].y, dz = zi.z - zo[k].z;
+                const double ud = cf[k].y * dx + cf[k].z * dy + cf[k].w * dz;
+                w0 += cf[k].x * dx + cf[k].y * ud;
+                w1 += cf[k].x * dy + cf[k].z * ud;
+                w2 += cf[k].x * dz + cf[k].w * ud;
+              }
+            }
+          }
+          constexpr int kDB = 2;
+          for (int a0 = d_beg + ql; a0 < d1; a0 += kDB * kTPR) {
+            D4 rec[kDB];
+#pragma unroll
+            for (int k = 0; k < kDB; k++) rec[k] = ld4(P.wdrec, min(a0 + kTPR * k, d1 - 1));
+            D4 zp[kDB], zm[kDB], zn[kDB];
+#pragma unroll
+            for (int k = 0; k < kDB; k++) {
+              zp[k] = ld4(P.zvec, __double2loint(rec[k].x));
+              zm[k] = ld4(P.zvec, __double2hiint(rec[k].x));
+              zn[k] = ld4(P.zvec, __double2loint(rec[k].y));
+            }
+#pragma unroll
+            for (int k = 0; k < kDB; k++) {
+              if (a0 + kTPR * k < d1) {
+                w0 += rec[k].z * ((zi.x + zp[k].x) - (zm[k].x + zn[k].x));
+                w1 += rec[k].z * ((zi.y + zp[k].y) - (zm[k].y + zn[k].y));
+                w2 += rec[k].z * ((zi.z + zp[k].z) - (zm[k].z + zn[k].z));
+              }
+            }
+          }
+        }
+        // reduction over the lanes of the row (whole warp participates; lanes of invalid rows carry zeros)
+#pragma unroll
+        for (int o = 1; o < kTPR; o <<= 1) {
+          w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+          w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+          w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+        }
+        if (valid && ql == 0) {
+          const double p0 = zi.x + beta * po.x, p1 = zi.y + beta * po.y, p2 = zi.z + beta * po.z;
+          const double q0 = (w0 + wl.x) + beta * qo.x, q1 = (w1 + wl.y) + beta * qo.y, q2 = (w2 + wl.z) + beta * qo.z;
+          st4(P.pvec, i, p0, p1, p2);
+          st4(P.qvec, i, q0, q1, q2);
+          pq_part[0] += p0 * q0 + p1 * q1 + p2 * q2;
+        }
+      }
+      const long long tm1 = clock64();
+      double pq;
+      long long tp0;
+      if (pos && P.world == 1) {
+        // p.q over the grid and the pose rows of the matvec in ONE round trip: after the barrier warp 0 sums the
+        // CTAs' slots while the other warps sum the segment partials of the pose slots and run their recurrences
+        double v = pq_part[0];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        const int par = gen & 1;
+        if (tid == 0) {
+          double t = s_red[0];
+          for (int w = 1; w < nw; w++) t += s_red[w];
+          P.slots[((size_t)par * gridDim.x + blockIdx.x) * kSlotVals] = t;
+        }
+        barrier();
+        tp0 = clock64();
+        double pv = 0;
+        if (tid < 32) {
+          double t = 0;
+          for (int c0 = lane; c0 < (int)gridDim.x; c0 += 8 * 32) {
+            double o[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              o[u] = __ldcg(P.slots + ((size_t)par * gridDim.x + min(c0 + 32 * u, (int)gridDim.x - 1)) * kSlotVals);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              if (c0 + 32 * u < (int)gridDim.x) t += o[u];
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+          if (lane == 0) s_scal[0] = t;
+        } else {
+          for (int t = tid - 32; t < 6 * F; t += nthr - 32) {
+            const double w = lambda * s_zp[t] + sum_wseg_partials_of(P, t / 6, t % 6, wbuf);
+            const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+            const double qp = first ? w : w + beta * s_qp[t];
+            s_pp[t] = pp;
+            s_qp[t] = qp;
+            pv += pp * qp;
+          }
+        }
+        const double ps = block_sum(pv, 1);  // its block sync publishes s_scal[0]
+        pq = s_scal[0] + ps;
+      } else {
+        grid_reduce<1>(pq_part, 0, pos ? 1 : 0, wbuf);
+        pq = s_scal[0];
+        tp0 = clock64();
+        if (pos) {
+          // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (replicated per CTA)
+          double v = 0;
+          for (int t = tid; t < 6 * F; t += nthr) {
+            const double w = lambda * s_zp[t] + (P.world > 1 ? xextra(t) : sum_wseg_partials_of(P, t / 6, t % 6, wbuf));
+            const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+            const double qp = first ? w : w + beta * s_qp[t];
+            s_pp[t] = pp;
+            s_qp[t] = qp;
+            v += pp * qp;
+          }
+          pq += block_sum(v, 1);
+        }
+      }
+      prof[13] += clock64() - tp0;  // pose rows of the matvec
+      const long long tm2 = clock64();
+      if (!(pq > 0) || !isfinite(pq)) {
+        ok = false;
+        break;
+      }
+      const double alpha = rz / pq;
+      // ---- phase 2: x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z ; row-local part of the next matvec
+      double rzn_pose = 0;
+      if (pos) {
+        for (int t = tid; t < 6 * F; t += nthr) {
+          s_xp[t] += alpha * s_pp[t];
+          s_rp[t] -= alpha * s_qp[t];
+        }
+        __syncthreads();
+        double v = 0;
+        for (int t = tid; t < 6 * F; t += nthr) {
+          const int k = t / 6, a = t % 6;
+          double s = 0;
+          for (int c = 0; c < 6; c++) s += s_M[36 * k + a * 6 + c] * s_rp[6 * k + c];
+          s_zp[t] = s;
+          v += s_rp[t] * s;
+        }
+        rzn_pose = block_sum(v, 0);  // (its block sync also publishes z_p to the rows below)
+      }
+      double rzn_part[1] = {0};
+      wide_segments(sg0, sg1, pos, wbuf ^ 1, [&](int i, double (&red)[6]) {
+        if (P.pt_fixed && P.pt_fixed[i]) {
+          wide_row_local(i, true, 0.0, V3{0, 0, 0}, pos, red);
+          return;
+        }
+        const D4 xo = ld4(P.xcg, i), po = ld4(P.pvec, i), ro = ld4(P.rvec, i), qo = ld4(P.qvec, i);
+        const D4 mA = ld4(minvA, i), mB = ld4(minvB, i);
+        st4(P.xcg, i, xo.x + alpha * po.x, xo.y + alpha * po.y, xo.z + alpha * po.z);
+        const V3 ri{ro.x - alpha * qo.x, ro.y - alpha * qo.y, ro.z - alpha * qo.z};
+        st4(P.rvec, i, ri.x, ri.y, ri.z);
+        const V3 z{mA.x * ri.x + mA.y * ri.y + mA.z * ri.z, mA.y * ri.x + mA.w * ri.y + mB.x * ri.z,
+                   mA.z * ri.x + mB.x * ri.y + mB.y * ri.z};
+        st4(P.zvec, i, z.x, z.y, z.z);
+        if (P.world > 1) xpush3(P.xz, i, z);
+        rzn_part[0] += ri.x * z.x + ri.y * z.y + ri.z * z.z;
+        wide_row_local(i, false, mB.z, z, pos, red);
+      });
+      const long long tm3 = clock64();
+      grid_reduce<1>(rzn_part, 0);
+      const long long tm4 = clock64();
+      prof[1] += tm1 - tm0;  // matvec pass
+      prof[2] += tm2 - tm1;  // pq reduce (incl. barrier)
+      prof[3] += tm3 - tm2;  // update pass
+      prof[4] += tm4 - tm3;  // rz reduce (incl. barrier)
+      const double rzn = s_scal[0] + rzn_pose;
+      if (!isfinite(rzn)) {
+        ok = false;
+        it++;
+        break;
+      }
+      beta = rzn / rz;
+      rz = rzn;
+      if (rz <= stop) {
+        it++;
+        break;
+      }
+    }
+    pcg_iters += it;
+    return ok;
+  }
+
+  // ================================================================================================
   // Cluster-native CG loop for a tracking frame (cluster mode, resident, one chunk per CTA, one pose, no dampers).
   // Nothing in the loop touches global memory: z of the out-of-chunk neighbours and the reduction values are PUSHED
   // into the consumers' shared memory (remote stores before the cluster barrier, local loads after it).
@@ -2309,7 +2790,7 @@ struct Engine {
       const long long ts0 = clock64();
       bool solved;
       if constexpr (WIDE) {
-        solved = pcg();
+        solved = pcg_wide();
       } else {
         const bool native = P.cluster_mode && P.resident && P.F == 1 && P.D == 0 && !P.points_fixed &&
                             P.n_chunks == (int)gridDim.x && !P.no_dsmem && P.push_ptr != nullptr;
@@ -2496,8 +2977,14 @@ struct Engine {
         st->xfail = xdead ? 1 : 0;
         st->lambda_final = lambda;
         prof[15] = clock64() - trun0;
-        for (int i = 0; i < 16; i++) st->prof[i] = prof[i];
+        for (int i = 0; i < 16; i++)
+          if (!WIDE || i < 8 || i > 10) st->prof[i] = prof[i];
       }
+    }
+    if (WIDE && tid == 0) {  // slowest / fastest CTA in the matvec pass, slowest in the update pass (diagnostics)
+      atomicMax(reinterpret_cast<long long*>(&P.stats->prof[8]), prof[1]);
+      atomicMax(reinterpret_cast<long long*>(&P.stats->prof[9]), prof[3]);
+      atomicMax(reinterpret_cast<long long*>(&P.stats->prof[10]), -prof[1]);
     }
     // a cluster must not retire CTAs while others may still arrive at the hardware barrier
     if (P.cluster_mode) barrier();
@@ -2528,6 +3015,12 @@ size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec) {
     if (block_prec) bytes += (size_t)((res_rows + kPrecBlock - 1) / kPrecBlock) * kPN * kPS * sizeof(float);
     return bytes + 16;
   }
+  return d * sizeof(double) + 16;
+}
+
+size_t engine_smem_bytes_wide(int F) {
+  const size_t d = (size_t)F * (7 + 7 + 36 + 6 * 6) + 32 * kChunkVals + 32 + 2 + 6 +
+                   std::max((size_t)21 * F, (size_t)16 * kMaxRows);
   return d * sizeof(double) + 16;
 }
 

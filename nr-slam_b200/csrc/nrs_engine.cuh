@@ -146,6 +146,18 @@ struct Params {
   double* zvec;        // [4V] preconditioned residual — the one vector neighbours read during the CG loop
   double* chunk_part;  // [2][n_chunks * kChunkVals]
   double* slots;       // [2][G * kSlotVals]
+  // wide CG loop (Engine<true>::pcg_wide): every CTA owns ONE contiguous row range of equal length, cut into segments
+  // at the pose-slot boundaries; the pose partials of the matvec are reduced per segment, not per 128-row chunk
+  int n_wseg;
+  const int* wseg_ptr;     // [G + 1] segments of CTA b
+  const int* wseg_begin;   // [n_wseg] rows of the segment
+  const int* wseg_end;
+  const int* kf_wseg_ptr;  // [F + 1] the segments of a pose slot are contiguous (rows are slot-major)
+  double* wseg_part;       // [2][n_wseg * 8] pose partials of the CG matvec per segment
+  double* wvec;            // [4V] row-local part of the next matvec ((lambda + s) z + B^T t), written where z is
+  double* wrec;            // [2P * 4] s, u[3] of the pair edge in incidence order (expanded once per solve)
+  double* wdrec;           // [4D * 4] per damper incidence, one 32-byte record: the three other vertices ordered
+                           //          (+, -, -) as int32 and the coefficient
   unsigned long long* bar;
   EngineStats* stats;
 
@@ -171,6 +183,8 @@ struct Params {
 int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_t stream);
 // Shared memory needed for F poses (+ the resident chunk state when res_rows > 0).
 size_t engine_smem_bytes(int F, int res_rows, int res_inc, int block_prec);
+// Shared memory of the wide variant (no per-row CG records, H_pp aliases the linearisation's row records).
+size_t engine_smem_bytes_wide(int F);
 // Extra shared memory of the cluster-native loop: pushed halo rows and the coarse (aggregate) level.
 size_t engine_smem_extra(int res_inc, int halo_rows, int coarse);
 // Largest co-resident grid for a cooperative launch / largest cluster that can be scheduled (0 if none).
