@@ -76,11 +76,24 @@ class MaskFilter(C.Structure):
 FILTER_BRIGHT, FILTER_BORDER, FILTER_PREDEFINED = range(3)
 
 
+_PTR_TYPES = {}
+
+
+def _pointer_type(ctype):
+    t = _PTR_TYPES.get(ctype)
+    if t is None:
+        t = _PTR_TYPES[ctype] = C.POINTER(ctype)
+    return t
+
+
 def ptr(a, ctype):
     """numpy array -> typed ctypes pointer (None passes NULL)."""
     if a is None:
         return None
-    return a.ctypes.data_as(C.POINTER(ctype))
+    # (ndarray.ctypes builds a helper object per call: 5 us; a frame passes two dozen pointers)
+    p = C.cast(a.__array_interface__["data"][0], _pointer_type(ctype))
+    p._keep = a  # a temporary passed straight into a call stays alive as long as its pointer
+    return p
 
 
 class GraphArrays:

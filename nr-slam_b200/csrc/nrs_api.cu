@@ -68,8 +68,8 @@ int frame_threads(int items) {
   if (items < 512) return 1;
   static const int cap = [] {
     const char* e = getenv("NRSLAM_B200_HOST_THREADS");
-    const int v = e ? atoi(e) : 4;
-    return v < 1 ? 1 : (v > 4 ? 4 : v);
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
   }();
   const int hw = (int)std::thread::hardware_concurrency();
   return std::max(1, std::min(cap, hw > 1 ? hw - 1 : 1));
@@ -187,12 +187,45 @@ struct HostProblem {
   std::vector<int> ops, op_args;
 };
 
+// Copies into the pinned input arena can be deferred and run by the staging threads in one go (stage_problem): the
+// arena fill of a tracking frame is ~1 MB in two dozen pieces, 0.3 ms on one thread.
+struct CopyJob {
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+thread_local std::vector<CopyJob>* t_defer = nullptr;
+
 template <typename T>
 size_t put(Arena& a, const std::vector<T>& v, size_t min_elems = 1) {
   const size_t n = std::max(v.size(), min_elems);
   const size_t off = a.take<T>(n);
-  if (!v.empty()) memcpy(a.h<T>(off), v.data(), v.size() * sizeof(T));
+  if (!v.empty()) {
+    const size_t bytes = v.size() * sizeof(T);
+    if (t_defer && bytes >= 4096)
+      t_defer->push_back(CopyJob{a.h<T>(off), v.data(), bytes});  // the source outlives flush_copies()
+    else
+      memcpy(a.h<T>(off), v.data(), bytes);
+  }
   return off;
+}
+
+// Runs the deferred copies on the pool in 32 KB pieces (dynamic distribution).
+void flush_copies(HostPool& pool, std::vector<CopyJob>& jobs) {
+  t_defer = nullptr;
+  if (jobs.empty()) return;
+  constexpr size_t kPiece = 32 * 1024;
+  std::vector<CopyJob> pieces;
+  for (const CopyJob& j : jobs)
+    for (size_t o = 0; o < j.bytes; o += kPiece)
+      pieces.push_back(CopyJob{static_cast<char*>(j.dst) + o, static_cast<const char*>(j.src) + o, std::min(kPiece, j.bytes - o)});
+  std::atomic<size_t> next{0};
+  pool.run([&](int, int) {
+    for (size_t k = next.fetch_add(1, std::memory_order_relaxed); k < pieces.size();
+         k = next.fetch_add(1, std::memory_order_relaxed))
+      memcpy(pieces[k].dst, pieces[k].src, pieces[k].bytes);
+  });
+  jobs.clear();
 }
 
 int env_int(const char* name, int dflt) {
@@ -711,13 +744,18 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   }
   std::vector<int> inc_pos;
   if (direct) {
-    direct_inc_pos(dplan, inc_ptr, inc_other, inc_pos);
+    direct_inc_pos(dplan, inc_ptr, inc_other, inc_pos, &ctx->pool);
     const size_t T1 = (size_t)dplan.n_nodes + 2;
     sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 4); sz(T1 * 8); sz(T1 * 8);
     sz(dplan.bnd.size() * 4); sz(dplan.bpath.size() * 4); sz(dplan.inv.size() * 4); sz(inc_pos.size() * 4);
   }
   need += 8192;
   if (!st.in.reserve(need, true)) return fail(ctx, NRSLAM_B200_ERR_ALLOC, "input arena allocation failed");
+  std::vector<CopyJob> copy_jobs;
+  struct DeferGuard {  // every return path leaves put() in its immediate mode
+    ~DeferGuard() { t_defer = nullptr; }
+  } defer_guard;
+  if (ctx->pool.threads() > 1) t_defer = &copy_jobs;
   Arena& in = st.in;
   Params& p = st.p;
   memset(&p, 0, sizeof(p));
@@ -809,6 +847,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     dp.u_off = in.d<long long>(put(in, dplan.u_off));
     st.dq.inc_pos = in.d<int>(put(in, inc_pos));
   }
+  flush_copies(ctx->pool, copy_jobs);
   apply_plan(p, planA);
   st.h2d_bytes = in.used();
   st.block = planA.block;
@@ -944,9 +983,10 @@ void finish_async(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats) {
   stats->lambda_final = es->lambda_final;
 }
 
-// Launch the staged program, bring the results back, fill stats. Blocks until done.
-int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool copy_back = true,
-               const Params* override_params = nullptr, bool plan2 = false) {
+// run_staged in two halves: queue the launch and the copy back (between the events ev0 / ev1), then wait and collect.
+// The caller may do host work in between.
+int run_staged_begin(nrslam_b200_ctx* ctx, Staged& st, bool copy_back = true, const Params* override_params = nullptr,
+                     bool plan2 = false) {
   if (!st.valid) return fail(ctx, NRSLAM_B200_ERR_ARG, "no staged problem");
   NRS_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   const bool direct = st.use_direct && !override_params && !plan2;
@@ -961,6 +1001,12 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
   else
     NRS_CUDA(ctx, cudaMemcpyAsync(st.out.h<char>(st.o_stats), st.out.d<char>(st.o_stats), sizeof(EngineStats),
                                   cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+int run_staged_end(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool copy_back = true,
+                   const Params* override_params = nullptr, bool plan2 = false) {
+  const bool direct = st.use_direct && !override_params && !plan2;
   NRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (stats) {
     const EngineStats* es = st.out.h<EngineStats>(st.o_stats);
@@ -1013,6 +1059,14 @@ int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool 
     }
   }
   return 0;
+}
+
+// Launch the staged program, bring the results back, fill stats. Blocks until done.
+int run_staged(nrslam_b200_ctx* ctx, Staged& st, nrslam_b200_stats* stats, bool copy_back = true,
+               const Params* override_params = nullptr, bool plan2 = false) {
+  const int rc = run_staged_begin(ctx, st, copy_back, override_params, plan2);
+  if (rc) return rc;
+  return run_staged_end(ctx, st, stats, copy_back, override_params, plan2);
 }
 
 Cam to_cam(const nrslam_b200_camera* c) {
@@ -1341,8 +1395,8 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
 
   hprof.mark("fill_rows");
   // ---- regulariser selection (:251-336). A pair is owned by the first endpoint that reaches it.
-  std::vector<int> pair_stamp(g->n_edges, 0);  // spatial_connections_ids de-duplication, keyed by graph edge
-  std::set<int> lost_ordered;                  // absl::btree_set<ID> (:222)
+  std::vector<unsigned char> pair_stamp(g->n_edges, 0);  // spatial_connections_ids de-duplication, keyed by graph edge
+  std::vector<unsigned char> lost_flag(M, 0);            // absl::btree_set<ID> (:222): flags now, ascending ids below
   std::vector<int> ent;
   // GetEdges of every point (sort of its connections, regularization_graph.cc:71-87) is independent of the other
   // points: host threads fill the sorted lists, the order-dependent selection below walks them sequentially
@@ -1359,26 +1413,37 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
       std::copy(loc.begin(), loc.end(), ent_flat.begin() + ent_ptr[idx]);
     }
   });
-  ctx->pool.end();
-  for (int idx = 0; idx < n; idx++) {
-    int n_regularizers = 0;
-    for (int q = 0; q < ent_cnt[idx]; q++) {
-      const int pe = ent_flat[ent_ptr[idx] + q];
-      const int other = g->col[pe], ge = g->eid[pe];
-      if (n_regularizers > regularizers_per_point || g->status[ge] == NRSLAM_EDGE_BAD) break;  // :258-261
-      if (vfs[other] < 0 || vfs[other] != NRSLAM_TRACKED_WITH_3D) {                             // :264-273
-        if (vfs[other] >= 0 && vfs[other] != NRSLAM_JUST_TRIANGULATED) lost_ordered.insert(other);
-        continue;
+  {
+    const int32_t *gcol = g->col, *geid = g->eid;
+    const uint8_t* gstatus = g->status;
+    const float *gweight = g->weight, *gfirst = g->first_distance;
+    const size_t cap = (size_t)std::min<long long>(ent_ptr[n], (long long)n * (regularizers_per_point + 1));
+    hp.pair_i.reserve(cap);
+    hp.pair_j.reserve(cap);
+    hp.pair_w.reserve(cap);
+    hp.pair_d0.reserve(cap);
+    for (int idx = 0; idx < n; idx++) {
+      int n_regularizers = 0;
+      const int* el = ent_flat.data() + ent_ptr[idx];
+      for (int q = 0, nq = ent_cnt[idx]; q < nq; q++) {
+        const int pe = el[q];
+        const int other = gcol[pe], ge = geid[pe];
+        if (n_regularizers > regularizers_per_point || gstatus[ge] == NRSLAM_EDGE_BAD) break;  // :258-261
+        const int vs = vfs[other];
+        if (vs != NRSLAM_TRACKED_WITH_3D) {  // :264-273 (negative: not in the frame)
+          if (vs >= 0 && vs != NRSLAM_JUST_TRIANGULATED) lost_flag[other] = 1;
+          continue;
+        }
+        const int idx_other = opt_index[other];
+        if (idx_other < 0) continue;   // inconsistent input: TRACKED_WITH_3D in the frame but not optimised
+        if (pair_stamp[ge]) continue;  // :277-279
+        pair_stamp[ge] = 1;
+        hp.pair_i.push_back(idx);
+        hp.pair_j.push_back(idx_other);
+        hp.pair_w.push_back((double)gweight[ge]);
+        hp.pair_d0.push_back((double)gfirst[ge]);
+        n_regularizers++;
       }
-      const int idx_other = opt_index[other];
-      if (idx_other < 0) continue;   // inconsistent input: TRACKED_WITH_3D in the frame but not optimised
-      if (pair_stamp[ge]) continue;  // :277-279
-      pair_stamp[ge] = 1;
-      hp.pair_i.push_back(idx);
-      hp.pair_j.push_back(idx_other);
-      hp.pair_w.push_back((double)g->weight[ge]);
-      hp.pair_d0.push_back((double)g->first_distance[ge]);
-      n_regularizers++;
     }
   }
   // ---- lost neighbours (:476-537): one extra vertex each, unary SpatialRegularizerFixed edges to at most 11
@@ -1386,7 +1451,9 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
   // graph is only modified by UpdateVertex, whose weights / statuses the reference does see when it queries
   // GetEdges for the lost points — so the unary edge list is built after the refresh).
   hprof.mark("select_regularisers");
-  const std::vector<int> lost_list(lost_ordered.begin(), lost_ordered.end());
+  std::vector<int> lost_list;
+  for (int v = 0; v < M; v++)
+    if (lost_flag[v]) lost_list.push_back(v);
   const int n_lost = (int)lost_list.size();
   hp.n_sort = n;
   hp.direct = env_int("NRSLAM_B200_DIRECT", 1) != 0;
@@ -1402,8 +1469,10 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
   hprof.mark("stage");
   const double t1 = wall_ms();
   if (stats) stats->h2d_bytes += (int64_t)st.h2d_bytes;
+  ctx->pool.end();  // the staging threads sleep while the main rounds run on the device ...
   rc = run_staged(ctx, st, stats);
   if (rc) return rc;
+  if (frame_threads(n) > 1) ctx->pool.begin();  // ... and spin again for the graph refresh and the lost-point staging
   hprof.mark("run1");
 
   const double* pose = st.out.h<double>(st.o_pose);
@@ -1423,10 +1492,13 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
     if (deformation_out)
       for (int k = 0; k < 3; k++) deformation_out[3 * (size_t)idx + k] = d[k];
   }
+  // order statistics of the sorted magnitudes (:411-416 sorts a copy; the two elements are the same by selection)
   std::vector<float> sorted(mags);
-  std::sort(sorted.begin(), sorted.end());
-  const float q1 = sorted[(int)(sorted.size() * 0.25f)];
-  const float q3 = sorted[(int)(sorted.size() * 0.75f)];
+  const int iq1 = (int)(sorted.size() * 0.25f), iq3 = (int)(sorted.size() * 0.75f);
+  std::nth_element(sorted.begin(), sorted.begin() + iq3, sorted.end());
+  const float q3 = sorted[iq3];
+  std::nth_element(sorted.begin(), sorted.begin() + iq1, sorted.begin() + iq3 + 1);
+  const float q1 = sorted[iq1];
   const float th_ = 1.5f * (q3 - q1);
   std::vector<char> inliers(n, 1);
   std::vector<uint8_t> status(n, NRSLAM_TRACKED_WITH_3D);
@@ -1463,16 +1535,26 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
   // two endpoint positions only, regularization_graph.cc:89-128), so the loop is order independent: host threads take
   // ranges of points. An edge with two accepted endpoints is written twice with identical values — through relaxed
   // atomics-free stores of the same bits, which is benign on every platform this library targets.
-  ctx->pool.run([&](int t, int nt) {
-    const int b = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt);
-    for (int idx = b; idx < e; idx++) {
-      if (!inliers[idx]) continue;
-      const int good = graph_update_vertex(g, point_vertex[idx], last_pos);
-      if (good < regularizers_per_point * 0.5) status[idx] = NRSLAM_BAD;
-    }
-  });
+  // The lost-point stage below reads the refreshed weights / statuses of the edges at the LOST vertices only, so the
+  // points adjacent to a lost vertex are refreshed first and the rest of the loop runs while the lost-point kernel
+  // is on the device (same result: the loop is order independent).
+  std::vector<char> prio(n, n_lost > 0 ? 0 : 1);
+  for (int v = 0; v < n_lost; v++)
+    for (int pe = g->rowptr[lost_list[v]]; pe < g->rowptr[lost_list[v] + 1]; pe++)
+      if (opt_index[g->col[pe]] >= 0) prio[opt_index[g->col[pe]]] = 1;
+  auto refresh = [&](char which) {
+    ctx->pool.run([&](int t, int nt) {
+      const int b = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt);
+      for (int idx = b; idx < e; idx++) {
+        if (!inliers[idx] || prio[idx] != which) continue;
+        const int good = graph_update_vertex(g, point_vertex[idx], last_pos);
+        if (good < regularizers_per_point * 0.5) status[idx] = NRSLAM_BAD;
+      }
+    });
+  };
+  refresh(1);
+  bool rest_done = n_lost == 0;
   hprof.mark("update_vertex");
-  if (status_out) memcpy(status_out, status.data(), n);
   if (stats) {
     stats->n_reproj_edges = n;
     stats->n_pair_edges = (int)hp.pair_i.size();
@@ -1603,7 +1685,11 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
       if (rc) return rc;
       if (stats) stats->h2d_bytes += (int64_t)st2.h2d_bytes;
       hprof.mark("lost_setup");
-      rc = run_staged(ctx, st2, stats);
+      rc = run_staged_begin(ctx, st2);
+      if (rc) return rc;
+      refresh(0);  // the rest of the graph refresh, behind the lost-point kernel
+      rest_done = true;
+      rc = run_staged_end(ctx, st2, stats);
       if (rc) return rc;
       hprof.mark("run2");
       const double* xl = st2.out.h<double>(st2.o_x);
@@ -1617,6 +1703,8 @@ int pose_deform_impl(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, int32_
     if (n_lost_out) *n_lost_out = n_lost;
     if (stats) stats->n_fixed_edges = n_un;
   }
+  if (!rest_done) refresh(0);
+  if (status_out) memcpy(status_out, status.data(), n);
   hprof.print("pose_deform");
   if (stats) stats->host_ms = (float)(wall_ms() - t0);
   return 0;

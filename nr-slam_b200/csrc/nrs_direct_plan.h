@@ -21,6 +21,7 @@
 //
 // All index lists are in vertex (3x3 block) units.
 #pragma once
+#include <type_traits>
 #include <stdint.h>
 #include <string.h>
 
@@ -331,20 +332,32 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
 
 // Front position of the other endpoint of every pair incidence (rows already renumbered): inc_pos[a] >= 0 when the
 // block (other, row) belongs to the panel of owner(row), i.e. `other` is eliminated after `row`; -1 otherwise.
+template <typename Pool = void>
 inline void direct_inc_pos(const DirectPlanHost& pl, const std::vector<int>& inc_ptr, const std::vector<int>& inc_other,
-                           std::vector<int>& inc_pos) {
+                           std::vector<int>& inc_pos, Pool* pool = nullptr) {
   inc_pos.assign(inc_other.size(), -1);
-  for (int v = 0; v < pl.V; v++) {
-    const int t = pl.owner[v];
-    const int* bb = pl.bnd.data() + pl.bnd_ptr[t];
-    for (int a = inc_ptr[v]; a < inc_ptr[v + 1]; a++) {
-      const int o = inc_other[a];
-      if (o <= v || o >= pl.V) continue;  // earlier in the elimination order, or a fixed row (not an unknown)
-      if (o < pl.vb[t] + pl.nv[t] && o < pl.V)
-        inc_pos[a] = o - pl.vb[t];
-      else
-        inc_pos[a] = pl.nv[t] + (int)(std::lower_bound(bb, bb + pl.nbv[t], o) - bb);
+  auto rows = [&](int v0, int v1) {
+    for (int v = v0; v < v1; v++) {
+      const int t = pl.owner[v];
+      const int* bb = pl.bnd.data() + pl.bnd_ptr[t];
+      for (int a = inc_ptr[v]; a < inc_ptr[v + 1]; a++) {
+        const int o = inc_other[a];
+        if (o <= v || o >= pl.V) continue;  // earlier in the elimination order, or a fixed row (not an unknown)
+        if (o < pl.vb[t] + pl.nv[t] && o < pl.V)
+          inc_pos[a] = o - pl.vb[t];
+        else
+          inc_pos[a] = pl.nv[t] + (int)(std::lower_bound(bb, bb + pl.nbv[t], o) - bb);
+      }
     }
+  };
+  if constexpr (std::is_void<Pool>::value) {
+    rows(0, pl.V);
+  } else {
+    // rows are independent: the staging threads take ranges
+    if (pool && pl.V >= 512)
+      pool->run([&](int t, int nt) { rows((int)((long long)pl.V * t / nt), (int)((long long)pl.V * (t + 1) / nt)); });
+    else
+      rows(0, pl.V);
   }
 }
 
