@@ -62,6 +62,19 @@ int host_threads(int items, int problem_size) {
   return std::max(1, std::min(std::min(items, hw > 0 ? hw : 1), cap));
 }
 
+// fn(begin, end) over [0, N) on n_threads short-lived threads (BA-sized loops: a spawn costs ~30 us).
+template <typename Fn>
+void par_ranges(int n_threads, size_t N, Fn fn) {
+  if (n_threads <= 1 || N < 8192) {
+    fn((size_t)0, N);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; t++) th.emplace_back([=] { fn(N * t / n_threads, N * (t + 1) / n_threads); });
+  fn((size_t)0, N / n_threads);
+  for (auto& x : th) x.join();
+}
+
 // Host threads for the per-frame staging loops of the tracking path (a few thousand independent items of ~0.3 us):
 // at most 4, none below 512 items; NRSLAM_B200_HOST_THREADS caps it like the BA staging.
 int frame_threads(int items) {
@@ -211,9 +224,24 @@ size_t put(Arena& a, const std::vector<T>& v, size_t min_elems = 1) {
 }
 
 // Runs the deferred copies on the pool in 32 KB pieces (dynamic distribution).
-void flush_copies(HostPool& pool, std::vector<CopyJob>& jobs) {
+void flush_copies(HostPool& pool, std::vector<CopyJob>& jobs, int spawn_threads = 1) {
   t_defer = nullptr;
   if (jobs.empty()) return;
+  if (pool.threads() == 1 && spawn_threads > 1) {  // BA window: no persistent pool, megabytes to copy
+    size_t total = 0;
+    for (const CopyJob& j : jobs) total += j.bytes;
+    std::vector<size_t> acc(jobs.size() + 1, 0);
+    for (size_t k = 0; k < jobs.size(); k++) acc[k + 1] = acc[k] + jobs[k].bytes;
+    par_ranges(spawn_threads, total, [&](size_t b, size_t e) {
+      for (size_t k = 0; k < jobs.size(); k++) {
+        const size_t lo = std::max(b, acc[k]), hi = std::min(e, acc[k + 1]);
+        if (lo < hi)
+          memcpy(static_cast<char*>(jobs[k].dst) + (lo - acc[k]), static_cast<const char*>(jobs[k].src) + (lo - acc[k]), hi - lo);
+      }
+    });
+    jobs.clear();
+    return;
+  }
   constexpr size_t kPiece = 32 * 1024;
   std::vector<CopyJob> pieces;
   for (const CopyJob& j : jobs)
@@ -297,11 +325,16 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
     for (auto& th : pool) th.join();
   }
   }
-  for (int nw = 0; nw < V; nw++) row_of[old_of_new[nw]] = nw;
+  const int pt = host_threads(64, V);  // the gathers below are independent per row / per edge
+  par_ranges(pt, (size_t)V, [&](size_t b, size_t e) {
+    for (size_t nw = b; nw < e; nw++) row_of[old_of_new[nw]] = (int)nw;
+  });
   auto permute = [&](std::vector<double>& v, int stride) {
     std::vector<double> o(v.size());
-    for (int nw = 0; nw < V; nw++)
-      for (int a = 0; a < stride; a++) o[(size_t)stride * nw + a] = v[(size_t)stride * old_of_new[nw] + a];
+    par_ranges(pt, (size_t)V, [&](size_t b, size_t e) {
+      for (size_t nw = b; nw < e; nw++)
+        for (int a = 0; a < stride; a++) o[(size_t)stride * nw + a] = v[(size_t)stride * old_of_new[nw] + a];
+    });
     v.swap(o);
   };
   permute(hp.x_seed, 4);
@@ -312,9 +345,15 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
     for (int nw = 0; nw < V; nw++) o[nw] = hp.pt_kf[old_of_new[nw]];
     hp.pt_kf.swap(o);
   }
-  for (auto& v : hp.pair_i) v = row_of[v];
-  for (auto& v : hp.pair_j) v = row_of[v];
-  for (auto& v : hp.dmp_v) v = row_of[v];
+  par_ranges(pt, hp.pair_i.size(), [&](size_t b, size_t e) {
+    for (size_t t = b; t < e; t++) {
+      hp.pair_i[t] = row_of[hp.pair_i[t]];
+      hp.pair_j[t] = row_of[hp.pair_j[t]];
+    }
+  });
+  par_ranges(pt, hp.dmp_v.size(), [&](size_t b, size_t e) {
+    for (size_t t = b; t < e; t++) hp.dmp_v[t] = row_of[hp.dmp_v[t]];
+  });
   if (forced_old_of_new) {  // per-row extras of the lost-point problem
     auto permute_u8 = [&](std::vector<unsigned char>& v) {
       if (v.empty()) return;
@@ -755,7 +794,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   struct DeferGuard {  // every return path leaves put() in its immediate mode
     ~DeferGuard() { t_defer = nullptr; }
   } defer_guard;
-  if (ctx->pool.threads() > 1) t_defer = &copy_jobs;
+  if (ctx->pool.threads() > 1 || V >= 4096) t_defer = &copy_jobs;
   Arena& in = st.in;
   Params& p = st.p;
   memset(&p, 0, sizeof(p));
@@ -847,7 +886,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     dp.u_off = in.d<long long>(put(in, dplan.u_off));
     st.dq.inc_pos = in.d<int>(put(in, inc_pos));
   }
-  flush_copies(ctx->pool, copy_jobs);
+  flush_copies(ctx->pool, copy_jobs, host_threads(64, V));
   apply_plan(p, planA);
   st.h2d_bytes = in.used();
   st.block = planA.block;
@@ -2202,6 +2241,7 @@ int nrslam_b200_local_ba_sharded(nrslam_b200_ctx* ctx, const nrslam_b200_camera*
   p.pair_cnt = xin.d<unsigned char>(put(xin, sp.pair_cnt));
   p.dmp_cnt = xin.d<unsigned char>(put(xin, sp.dmp_cnt));
   p.world = sh.world;
+  p.xfused = env_int("NRSLAM_B200_XFUSED", 1);
   p.rank = sh.rank;
   p.xstride = sh.xstride;
   p.xepoch0 = sh.epoch;

@@ -44,6 +44,11 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsig
 }
 
 // system scope: flags of the multi-GPU exchange live in peer-mapped memory
+__device__ __forceinline__ unsigned long long atom_acqrel_add_u64(unsigned long long* p, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -271,10 +276,96 @@ __device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int
   if (tid < n) {
     const bool mx = (maxmask >> tid) & 1;
     double s = mx ? -DBL_MAX : 0.0;
-    for (int r = 0; r < W; r++) {
-      const double o = __ldcg(P.xred[P.rank] + half + (size_t)r * P.xstride + tid);
-      s = mx ? fmax(s, o) : s + o;
+    double o[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(P.xred[P.rank] + half + (size_t)min(r, W - 1) * P.xstride + tid);
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++)
+      if (r < W) s = mx ? fmax(s, o[r]) : s + o[r];
+    s_scal[tid] = s;
+  }
+  __syncthreads();
+  return XRet{xe, half, gen, dead};
+}
+
+// ---- fused grid reduction + multi-GPU exchange (landmark-sharded BA, cooperative-grid mode): ONE synchronisation
+// instead of grid barrier -> exchange by CTA 0 -> grid barrier. Every CTA has written its partials to its slot and
+// arrives on the grid counter; the LAST CTA to arrive sums the slots (fixed order), adds this rank's pose partials
+// (kind 1: 6 F CG values from the segment / chunk partials, kind 2: 27 F linearisation blocks), pushes the record into
+// every rank's buffer and releases this rank's flag on every rank at system scope. ALL CTAs then acquire-poll the
+// flags of all ranks in their own buffer — their own rank's flag doubles as the local grid barrier — and combine the
+// records in rank order: every CTA of every GPU derives bit-identical values. Halo rows pushed before the call are
+// covered: CTA stores -> acq_rel arrive -> last CTA's system fence + flag -> acquire at the readers.
+__device__ __noinline__ XRet xreduce_impl(const Params& P, double* s_scal, int* s_flag, int n, unsigned maxmask, int kind,
+                                          int par, int xpar, unsigned long long xe, unsigned gen, int dead) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  xe++;
+  gen++;
+  const unsigned long long epoch = P.xepoch0 + xe;
+  const int W = P.world;
+  const size_t half = (size_t)(epoch & 1) * W * P.xstride;
+  const size_t rec = half + (size_t)P.rank * P.xstride;
+  __syncthreads();  // the slot of this CTA (and everything else it wrote) precedes the arrive
+  if (tid == 0) s_flag[1] = (atom_acqrel_add_u64(P.bar, 1ULL) + 1 == (unsigned long long)gen * gridDim.x) ? 1 : 0;
+  __syncthreads();
+  if (s_flag[1]) {
+    const int G = (int)gridDim.x;
+    if (tid < 32 * n) {
+      const int k = tid >> 5, lane = tid & 31;
+      const bool mx = (maxmask >> k) & 1;
+      double s = mx ? -DBL_MAX : 0.0;
+      for (int c0 = lane; c0 < G; c0 += 8 * 32) {
+        double o[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) o[u] = __ldcg(P.slots + ((size_t)par * G + min(c0 + 32 * u, G - 1)) * kSlotVals + k);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (c0 + 32 * u < G) s = mx ? fmax(s, o[u]) : s + o[u];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, s, off);
+        s = mx ? fmax(s, o) : s + o;
+      }
+      if (lane == 0)
+        for (int r = 0; r < W; r++) P.xred[r][rec + k] = s;
     }
+    const int per = (kind == 1) ? 6 : 27;
+    const int nx = (kind == 0) ? 0 : per * P.F;
+    for (int t = tid; t < nx; t += nthr) {
+      const double s = (kind == 1 && P.wide) ? sum_wseg_partials_of(P, t / per, t % per, xpar)
+                                             : sum_chunk_partials_of(P, t / per, t % per, xpar);
+      for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
+    }
+    __syncthreads();
+    if (tid < W) {
+      __threadfence_system();
+      st_release_sys_u64(P.xflag[tid] + P.rank, epoch);
+    }
+  }
+  if (tid < W && (!dead || tid == P.rank)) {  // after a time-out only the local barrier is kept
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys_u64(P.xflag[P.rank] + tid) < epoch) {
+      if ((++spins & 63u) == 0 && tid != P.rank) {
+        if (__ldcg(P.xabort) || global_timer_ns() - t0 > P.xtimeout_ns) {
+          *P.xabort = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (__ldcg(P.xabort)) dead = 1;
+  if (tid < n) {
+    const bool mx = (maxmask >> tid) & 1;
+    double s = mx ? -DBL_MAX : 0.0;
+    double o[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(P.xred[P.rank] + half + (size_t)min(r, W - 1) * P.xstride + tid);
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++)
+      if (r < W) s = mx ? fmax(s, o[r]) : s + o[r];
     s_scal[tid] = s;
   }
   __syncthreads();
@@ -481,6 +572,14 @@ struct Engine {
       for (int w = 1; w < nw; w++) s = ((maxmask >> tid) & 1) ? fmax(s, s_red[w * N + tid]) : s + s_red[w * N + tid];
       P.slots[((size_t)par * gridDim.x + blockIdx.x) * kSlotVals + tid] = s;
     }
+    if (P.world > 1 && P.xfused) {  // one synchronisation for the grid and the ranks (xreduce_impl)
+      const XRet r = xreduce_impl(P, s_scal, s_flag, N, maxmask, xkind, par, xpar >= 0 ? xpar : par, xe, gen, xdead ? 1 : 0);
+      xe = r.xe;
+      xcur = r.xcur;
+      gen = r.gen;
+      xdead = r.dead != 0;
+      return;
+    }
     barrier();
     if (tid < 32 * N) {
       const int k = tid >> 5;
@@ -522,8 +621,15 @@ struct Engine {
   }
   // Value t of the pose records of the last exchange, summed over the ranks in rank order.
   __device__ __forceinline__ double xextra(int t) {
+    // every rank's load is issued before the first add (a plain accumulate loop pays one L2 round trip per rank)
+    const double* base = P.xred[P.rank] + xcur + 8 + t;
+    double o[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(base + (size_t)min(r, P.world - 1) * P.xstride);
     double s = 0;
-    for (int r = 0; r < P.world; r++) s += __ldcg(P.xred[P.rank] + xcur + (size_t)r * P.xstride + 8 + t);
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++)
+      if (r < P.world) s += o[r];
     return s;
   }
   // Refresh the halo copies of owned row i on the ranks that read it.

@@ -165,6 +165,7 @@ struct Params {
   // and keeps read-only halo copies of the rows its regulariser edges reach on other ranks. The exchange buffers of
   // all ranks are peer-mapped (CUDA IPC): owners PUSH the halo values and their partial sums over NVLink, then signal.
   int world, rank;
+  int xfused;                      // 1: grid reduction and exchange in one synchronisation (xreduce_impl)
   int xstride;                     // doubles per (parity, source rank) record of the reduction buffer: 8 + 27 F
   unsigned long long xepoch0;      // exchanges completed by earlier launches (the flags count up monotonically)
   unsigned long long xtimeout_ns;  // a peer that does not arrive within this time aborts the exchange (no hang)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nrslam_b200  # noqa
 from nrslam_b200 import api, synth
 core = api.Core()
-q = synth.ba_problem("c3")
+q = synth.ba_problem(sys.argv[1] if len(sys.argv) > 1 else "c3")
 for rep in range(3):
     t0 = time.perf_counter()
     r = core.local_ba(q["cam"], q["kf_pose"], q["obs_kf"], q["obs_vertex"], q["uv"], q["X"], q["graph"], q["scale"])
