@@ -391,8 +391,9 @@ struct Plan {
   std::vector<int> chunk_kf, chunk_begin, chunk_end, kf_chunk_ptr;
   const int *d_chunk_kf = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_kf_chunk_ptr = nullptr;
   // wide CG loop: one contiguous row range per CTA, cut into segments at the pose-slot boundaries
-  std::vector<int> wseg_ptr, wseg_begin, wseg_end, kf_wseg_ptr;
-  const int *d_wseg_ptr = nullptr, *d_wseg_begin = nullptr, *d_wseg_end = nullptr, *d_kf_wseg_ptr = nullptr;
+  std::vector<int> wseg_ptr, wseg_begin, wseg_end, wseg_kf, kf_wseg_ptr;
+  const int *d_wseg_ptr = nullptr, *d_wseg_begin = nullptr, *d_wseg_end = nullptr, *d_wseg_kf = nullptr,
+            *d_kf_wseg_ptr = nullptr;
   // halo push lists of the cluster-native CG loop (built when the plan qualifies for it)
   int halo_rows = 0, coarse = 0;
   std::vector<int> inc_halo, push_ptr, push_row, push_dst, xinc_ptr, xinc_idx;
@@ -588,6 +589,7 @@ int make_plan(nrslam_b200_ctx* ctx, const HostProblem& hp, const std::vector<int
         const int e = std::min(r1, kf_begin[std::min(k, F - 1) + 1]);
         pl.wseg_begin.push_back(r);
         pl.wseg_end.push_back(e);
+        pl.wseg_kf.push_back(std::min(k, F - 1));
         pl.kf_wseg_ptr[std::min(k, F - 1) + 1]++;
         r = e;
       }
@@ -605,7 +607,8 @@ void apply_plan(Params& p, const Plan& pl) {
   p.chunk_kf = pl.d_chunk_kf; p.chunk_begin = pl.d_chunk_begin; p.chunk_end = pl.d_chunk_end;
   p.kf_chunk_ptr = pl.d_kf_chunk_ptr;
   p.n_wseg = (int)pl.wseg_begin.size();
-  p.wseg_ptr = pl.d_wseg_ptr; p.wseg_begin = pl.d_wseg_begin; p.wseg_end = pl.d_wseg_end; p.kf_wseg_ptr = pl.d_kf_wseg_ptr;
+  p.wseg_ptr = pl.d_wseg_ptr; p.wseg_begin = pl.d_wseg_begin; p.wseg_end = pl.d_wseg_end; p.wseg_kf = pl.d_wseg_kf;
+  p.kf_wseg_ptr = pl.d_kf_wseg_ptr;
   p.coarse = pl.coarse;
   p.halo_rows = pl.halo_rows; p.inc_halo = pl.d_inc_halo; p.push_ptr = pl.d_push_ptr; p.push_row = pl.d_push_row;
   p.push_dst = pl.d_push_dst;
@@ -778,7 +781,8 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   sz((size_t)V); sz((size_t)V); sz((size_t)P);
   sz((size_t)max_chunks * 4 * 3 * 2); sz(((size_t)F + 1) * 4 * 2);
   for (Plan* pl : {&planA, &planB}) {
-    sz(pl->wseg_ptr.size() * 4); sz(pl->wseg_begin.size() * 4); sz(pl->wseg_end.size() * 4); sz(pl->kf_wseg_ptr.size() * 4);
+    sz(pl->wseg_ptr.size() * 4); sz(pl->wseg_begin.size() * 4); sz(pl->wseg_end.size() * 4); sz(pl->wseg_kf.size() * 4);
+    sz(pl->kf_wseg_ptr.size() * 4);
     sz(pl->inc_halo.size() * 4); sz(pl->push_ptr.size() * 4); sz(pl->push_row.size() * 4); sz(pl->push_dst.size() * 4); sz(pl->xinc_ptr.size() * 4); sz(pl->xinc_idx.size() * 4);
   }
   std::vector<int> inc_pos;
@@ -859,6 +863,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
       pl->d_wseg_ptr = in.d<int>(put(in, pl->wseg_ptr));
       pl->d_wseg_begin = in.d<int>(put(in, pl->wseg_begin));
       pl->d_wseg_end = in.d<int>(put(in, pl->wseg_end));
+      pl->d_wseg_kf = in.d<int>(put(in, pl->wseg_kf));
       pl->d_kf_wseg_ptr = in.d<int>(put(in, pl->kf_wseg_ptr));
     }
     if (!pl->push_ptr.empty()) {

@@ -200,10 +200,9 @@ __device__ __forceinline__ double sum_chunk_partials_of(const Params& P, int k, 
 }
 
 // The same over the segment partials of the wide CG loop (Engine<true>::pcg_wide).
-__device__ __forceinline__ double sum_wseg_partials_of(const Params& P, int k, int v, int par) {
-  const int c1 = P.kf_wseg_ptr[k + 1];
+__device__ __forceinline__ double sum_wseg_range(const Params& P, int cb, int c1, int v, int par) {
   double s = 0;
-  for (int c0 = P.kf_wseg_ptr[k]; c0 < c1; c0 += 8) {
+  for (int c0 = cb; c0 < c1; c0 += 8) {
     double t[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
@@ -216,78 +215,16 @@ __device__ __forceinline__ double sum_wseg_partials_of(const Params& P, int k, i
   }
   return s;
 }
+__device__ __forceinline__ double sum_wseg_partials_of(const Params& P, int k, int v, int par) {
+  return sum_wseg_range(P, P.kf_wseg_ptr[k], P.kf_wseg_ptr[k + 1], v, par);
+}
 
-// ---- multi-GPU exchange of the landmark-sharded BA (cooperative-grid mode only). Called by every CTA with this
-// GPU's totals in s_scal[0..n): CTA 0 pushes them (and, kind 1 / 2, this rank's 6 F CG pose partials / 27 F
-// linearisation pose blocks summed over its chunks) into the record [parity][rank] of EVERY rank's reduction buffer,
-// signals every rank and waits for every rank's signal; a second grid barrier releases the other CTAs. All ranks
-// then combine the records in rank order, so every CTA of every GPU derives bit-identical values and takes the same
-// branches. Halo rows pushed before the call are covered by the same signal (CTA stores -> grid barrier ->
-// system fence -> flag).
 struct XRet {
   unsigned long long xe;
   size_t xcur;
   unsigned gen;
   int dead;
 };
-__device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int n, unsigned maxmask, int kind,
-                                            int par, unsigned long long xe, unsigned gen, int dead) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  xe++;
-  const unsigned long long epoch = P.xepoch0 + xe;
-  const int W = P.world;
-  const size_t half = (size_t)(epoch & 1) * W * P.xstride;
-  const size_t rec = half + (size_t)P.rank * P.xstride;
-  if (blockIdx.x == 0) {
-    for (int t = tid; t < n * W; t += nthr) P.xred[t / n][rec + t % n] = s_scal[t % n];
-    const int per = (kind == 1) ? 6 : 27;
-    const int nx = (kind == 0) ? 0 : per * P.F;
-    for (int t = tid; t < nx; t += nthr) {
-      const double s = (kind == 1 && P.wide) ? sum_wseg_partials_of(P, t / per, t % per, par)
-                                             : sum_chunk_partials_of(P, t / per, t % per, par);
-      for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
-    }
-    __syncthreads();
-    if (tid < W) {
-      __threadfence_system();
-      st_release_sys_u64(P.xflag[tid] + P.rank, epoch);
-      if (!dead) {
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys_u64(P.xflag[P.rank] + tid) < epoch) {
-          if (global_timer_ns() - t0 > P.xtimeout_ns) {
-            *P.xabort = 1;
-            break;
-          }
-        }
-      }
-    }
-  }
-  // grid barrier (release-add / acquire-poll, as Engine::barrier in grid mode)
-  gen++;
-  __syncthreads();
-  if (tid == 0) {
-    red_release_add_u64(P.bar, 1ULL);
-    const unsigned long long target = (unsigned long long)gen * gridDim.x;
-    while (ld_acquire_u64(P.bar) < target) {
-    }
-  }
-  __syncthreads();
-  if (__ldcg(P.xabort)) dead = 1;  // uniform over the grid: written before the barrier
-  if (tid < n) {
-    const bool mx = (maxmask >> tid) & 1;
-    double s = mx ? -DBL_MAX : 0.0;
-    double o[kMaxWorld];
-#pragma unroll
-    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(P.xred[P.rank] + half + (size_t)min(r, W - 1) * P.xstride + tid);
-#pragma unroll
-    for (int r = 0; r < kMaxWorld; r++)
-      if (r < W) s = mx ? fmax(s, o[r]) : s + o[r];
-    s_scal[tid] = s;
-  }
-  __syncthreads();
-  return XRet{xe, half, gen, dead};
-}
-
 // ---- fused grid reduction + multi-GPU exchange (landmark-sharded BA, cooperative-grid mode): ONE synchronisation
 // instead of grid barrier -> exchange by CTA 0 -> grid barrier. Every CTA has written its partials to its slot and
 // arrives on the grid counter; the LAST CTA to arrive sums the slots (fixed order), adds this rank's pose partials
@@ -296,8 +233,8 @@ __device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int
 // flags of all ranks in their own buffer — their own rank's flag doubles as the local grid barrier — and combine the
 // records in rank order: every CTA of every GPU derives bit-identical values. Halo rows pushed before the call are
 // covered: CTA stores -> acq_rel arrive -> last CTA's system fence + flag -> acquire at the readers.
-__device__ __noinline__ XRet xreduce_impl(const Params& P, double* s_scal, int* s_flag, int n, unsigned maxmask, int kind,
-                                          int par, int xpar, unsigned long long xe, unsigned gen, int dead) {
+__device__ __forceinline__ XRet xreduce_impl(const Params& P, double* s_scal, int* s_flag, int n, unsigned maxmask,
+                                             int kind, int par, int xpar, unsigned long long xe, unsigned gen, int dead) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   xe++;
   gen++;
@@ -372,12 +309,99 @@ __device__ __noinline__ XRet xreduce_impl(const Params& P, double* s_scal, int* 
   return XRet{xe, half, gen, dead};
 }
 
+// ---- multi-GPU exchange of the landmark-sharded BA (cooperative-grid mode only). Called by every CTA with this
+// GPU's totals in s_scal[0..n): CTA 0 pushes them (and, kind 1 / 2, this rank's 6 F CG pose partials / 27 F
+// linearisation pose blocks summed over its chunks) into the record [parity][rank] of EVERY rank's reduction buffer,
+// signals every rank and waits for every rank's signal; a second grid barrier releases the other CTAs. All ranks
+// then combine the records in rank order, so every CTA of every GPU derives bit-identical values and takes the same
+// branches. Halo rows pushed before the call are covered by the same signal (CTA stores -> grid barrier ->
+// system fence -> flag).
+__device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int n, unsigned maxmask, int kind,
+                                            int par, unsigned long long xe, unsigned gen, int dead) {
+  // par: bit 0 = parity of the grid-reduction slots, bit 1 = buffer of the pose partials (CG loops)
+  if (P.xfused)
+    return xreduce_impl(P, s_scal, reinterpret_cast<int*>(s_scal + 28), n, maxmask, kind, par & 1, par >> 1, xe, gen, dead);
+  par >>= 1;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  xe++;
+  const unsigned long long epoch = P.xepoch0 + xe;
+  const int W = P.world;
+  const size_t half = (size_t)(epoch & 1) * W * P.xstride;
+  const size_t rec = half + (size_t)P.rank * P.xstride;
+  if (blockIdx.x == 0) {
+    for (int t = tid; t < n * W; t += nthr) P.xred[t / n][rec + t % n] = s_scal[t % n];
+    const int per = (kind == 1) ? 6 : 27;
+    const int nx = (kind == 0) ? 0 : per * P.F;
+    for (int t = tid; t < nx; t += nthr) {
+      const double s = (kind == 1 && P.wide) ? sum_wseg_partials_of(P, t / per, t % per, par)
+                                             : sum_chunk_partials_of(P, t / per, t % per, par);
+      for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
+    }
+    __syncthreads();
+    if (tid < W) {
+      __threadfence_system();
+      st_release_sys_u64(P.xflag[tid] + P.rank, epoch);
+      if (!dead) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys_u64(P.xflag[P.rank] + tid) < epoch) {
+          if (global_timer_ns() - t0 > P.xtimeout_ns) {
+            *P.xabort = 1;
+            break;
+          }
+        }
+      }
+    }
+  }
+  // grid barrier (release-add / acquire-poll, as Engine::barrier in grid mode)
+  gen++;
+  __syncthreads();
+  if (tid == 0) {
+    red_release_add_u64(P.bar, 1ULL);
+    const unsigned long long target = (unsigned long long)gen * gridDim.x;
+    while (ld_acquire_u64(P.bar) < target) {
+    }
+  }
+  __syncthreads();
+  if (__ldcg(P.xabort)) dead = 1;  // uniform over the grid: written before the barrier
+  if (tid < n) {
+    const bool mx = (maxmask >> tid) & 1;
+    double s = mx ? -DBL_MAX : 0.0;
+    double o[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(P.xred[P.rank] + half + (size_t)min(r, W - 1) * P.xstride + tid);
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; r++)
+      if (r < W) s = mx ? fmax(s, o[r]) : s + o[r];
+    s_scal[tid] = s;
+  }
+  __syncthreads();
+  return XRet{xe, half, gen, dead};
+}
+
+// Value t of the pose records of the last exchange, summed over the ranks in rank order. Every rank's load is issued
+// before the first add (a plain accumulate loop pays one L2 round trip per rank); a real call keeps its eight values
+// in flight out of the single-GPU loops' register budget.
+__device__ __noinline__ double xextra_of(const Params& P, size_t xcur, int t) {
+  const double* base = P.xred[P.rank] + xcur + 8 + t;
+  double o[kMaxWorld];
+#pragma unroll
+  for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(base + (size_t)min(r, P.world - 1) * P.xstride);
+  double s = 0;
+#pragma unroll
+  for (int r = 0; r < kMaxWorld; r++)
+    if (r < P.world) s += o[r];
+  return s;
+}
+
 static_assert((kPN / 4) % kTPR == 0, "the lanes of a row split the float4 columns of the block preconditioner evenly");
 
 // WIDE: the variant for large windows (cooperative grid, vectors in global memory): compiled without the
 // shared-memory-resident and cluster-native paths so that it fits 128 registers and TWO CTAs share an SM — the big
 // BA matvec is a chain of dependent L2 gathers per row, and twice the warps hide twice the latency.
-template <bool WIDE>
+// SHARD: the variant a landmark-sharded rank launches (world > 1). The single-GPU kernels are compiled without any
+// of the exchange paths: their mere presence (call sites of the exchange functions inside the CG loops) cost the
+// single-GPU BA 8 % through register allocation.
+template <bool WIDE, bool SHARD>
 struct Engine {
   const Params& P;
   // shared memory
@@ -572,16 +596,10 @@ struct Engine {
       for (int w = 1; w < nw; w++) s = ((maxmask >> tid) & 1) ? fmax(s, s_red[w * N + tid]) : s + s_red[w * N + tid];
       P.slots[((size_t)par * gridDim.x + blockIdx.x) * kSlotVals + tid] = s;
     }
-    if (P.world > 1 && P.xfused) {  // one synchronisation for the grid and the ranks (xreduce_impl)
-      const XRet r = xreduce_impl(P, s_scal, s_flag, N, maxmask, xkind, par, xpar >= 0 ? xpar : par, xe, gen, xdead ? 1 : 0);
-      xe = r.xe;
-      xcur = r.xcur;
-      gen = r.gen;
-      xdead = r.dead != 0;
-      return;
-    }
-    barrier();
-    if (tid < 32 * N) {
+    // sharded runs with the fused exchange synchronise the grid and the ranks in ONE step inside xexchange()
+    const bool fused = (SHARD && P.world > 1) && P.xfused;
+    if (!fused) barrier();
+    if (!fused && tid < 32 * N) {
       const int k = tid >> 5;
       const bool mx = (maxmask >> k) & 1;
       double s = mx ? -DBL_MAX : 0.0;
@@ -606,7 +624,7 @@ struct Engine {
       if (lane == 0) s_scal[k] = s;
     }
     __syncthreads();
-    if (P.world > 1) xexchange(N, maxmask, xkind, xpar >= 0 ? xpar : par);
+    if ((SHARD && P.world > 1)) xexchange(N, maxmask, xkind, par + 2 * (xpar >= 0 ? xpar : par));
   }
 
   // ---- multi-GPU (landmark-sharded BA): see xexchange_impl. The exchange is a free function that gets the engine
@@ -620,18 +638,7 @@ struct Engine {
     xdead = r.dead != 0;
   }
   // Value t of the pose records of the last exchange, summed over the ranks in rank order.
-  __device__ __forceinline__ double xextra(int t) {
-    // every rank's load is issued before the first add (a plain accumulate loop pays one L2 round trip per rank)
-    const double* base = P.xred[P.rank] + xcur + 8 + t;
-    double o[kMaxWorld];
-#pragma unroll
-    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(base + (size_t)min(r, P.world - 1) * P.xstride);
-    double s = 0;
-#pragma unroll
-    for (int r = 0; r < kMaxWorld; r++)
-      if (r < P.world) s += o[r];
-    return s;
-  }
+  __device__ __forceinline__ double xextra(int t) { return xextra_of(P, xcur, t); }
   // Refresh the halo copies of owned row i on the ranks that read it.
   __device__ __forceinline__ void xpush3(double* const* base, int i, const V3& v) {
     for (int a = P.xp_ptr[i]; a < P.xp_ptr[i + 1]; a++) {
@@ -1304,7 +1311,7 @@ struct Engine {
                  m02 * r.x + m12 * r.y + m22 * r.z};
       st3(P.zvec, i, z);
       if (res) st3s(s_z, li, z);
-      if (P.world > 1) xpush3(P.xz, i, z);
+      if ((SHARD && P.world > 1)) xpush3(P.xz, i, z);
       rz_part[0] += r.x * z.x + r.y * z.y + r.z * z.z;
     });
     if (bprec) {
@@ -1342,7 +1349,7 @@ struct Engine {
     int it = 0;
     // quad mapping of the loop and the per-row constants, kept in registers when this CTA owns at most one chunk
     const int qr = tid / kTPR, ql = tid % kTPR;
-    const bool single = !WIDE && P.n_chunks <= (int)gridDim.x && P.world == 1;
+    const bool single = !WIDE && P.n_chunks <= (int)gridDim.x && (!SHARD || P.world == 1);
     bool my_fixed = false;
     int my_kf = -1, my_a0 = 0, my_a1 = 0, my_cb = 0, my_ce = 0, my_kc0 = 0, my_kc1 = 0;
     double my_su = 0;
@@ -1593,7 +1600,7 @@ struct Engine {
           // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (replicated per CTA)
           for (int t = tid; t < 6 * F; t += nthr) {
             const int k = t / 6, a = t % 6;
-            const double w = lambda * s_zp[t] + (P.world > 1 ? xextra(t) : sum_chunk_partials(k, a, par));
+            const double w = lambda * s_zp[t] + ((SHARD && P.world > 1) ? xextra(t) : sum_chunk_partials(k, a, par));
             s_pp[t] = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
             s_qp[t] = first ? w : w + beta * s_qp[t];
           }
@@ -1634,7 +1641,7 @@ struct Engine {
                        m1.x * ri.x + m2.x * ri.y + m2.y * ri.z};
             st3(P.zvec, i, z);
             if (res) st3s(s_z, li, z);
-            if (P.world > 1) xpush3(P.xz, i, z);
+            if ((SHARD && P.world > 1)) xpush3(P.xz, i, z);
             rzn_part[0] += ri.x * z.x + ri.y * z.y + ri.z * z.z;
           }
         }
@@ -1712,62 +1719,52 @@ struct Engine {
 
   // Row-local part of the NEXT matvec, evaluated where z_i is produced (initial residual, update pass):
   // wl_i = (lambda + s_unary) z_i + B_i^T t_i with t_i = omega_i (A_i z_p + B_i z_i), and the row's pose partial
-  // A_i^T t_i added to red. A fixed row (z_i = 0) still feeds the pose rows. The Jacobian is component-major here.
-  __device__ __forceinline__ void wide_row_local(int i, bool fixed, double su, const V3& z, bool pos, double (&red)[6]) {
-    const int kf = P.pt_kf[i];
+  // A_i^T t_i added to red. A fixed row (z_i = 0) still feeds the pose rows. The Jacobian is component-major; a row
+  // without a reprojection edge stores omega = 0 and zero blocks, so nothing is branched on and the ten loads can be
+  // issued together with the caller's (j: loaded by the caller before it needs z).
+  __device__ __forceinline__ void wide_load_jac(int i, double2 (&j)[10]) {
     const double2* jt = reinterpret_cast<const double2*>(P.jac) + i;
     const size_t V = (size_t)P.V;
+#pragma unroll
+    for (int k = 0; k < 10; k++) j[k] = jt[k * V];
+  }
+  __device__ __forceinline__ void wide_row_local(int i, int kf, bool fixed, double su, const V3& z, bool pos,
+                                                 const double2 (&j)[10], double (&red)[6]) {
     V3 wl{(lambda + su) * z.x, (lambda + su) * z.y, (lambda + su) * z.z};
-    if (kf >= 0) {
-      double2 j[10];
-#pragma unroll
-      for (int k = 0; k < 10; k++) j[k] = jt[k * V];
-      const double omega = j[9].x;
-      if (omega != 0) {
-        double A[12], B[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-          A[2 * k] = j[k].x;
-          A[2 * k + 1] = j[k].y;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          B[2 * k] = j[6 + k].x;
-          B[2 * k + 1] = j[6 + k].y;
-        }
-        double jp0 = 0, jp1 = 0;
-        if (pos) {
-          const double* pk = s_zp + 6 * kf;
-#pragma unroll
-          for (int a = 0; a < 6; a++) {
-            jp0 += A[a] * pk[a];
-            jp1 += A[6 + a] * pk[a];
-          }
-        }
-        const double t0 = omega * (jp0 + B[0] * z.x + B[1] * z.y + B[2] * z.z);
-        const double t1 = omega * (jp1 + B[3] * z.x + B[4] * z.y + B[5] * z.z);
-        wl.x += B[0] * t0 + B[3] * t1;
-        wl.y += B[1] * t0 + B[4] * t1;
-        wl.z += B[2] * t0 + B[5] * t1;
-        if (pos) {
-#pragma unroll
-          for (int a = 0; a < 6; a++) red[a] += A[a] * t0 + A[6 + a] * t1;
-        }
-      }
+    const double omega = j[9].x;
+    double jp0 = 0, jp1 = 0;
+    if (pos) {
+      const double* pk = s_zp + 6 * kf;
+      jp0 = j[0].x * pk[0] + j[0].y * pk[1] + j[1].x * pk[2] + j[1].y * pk[3] + j[2].x * pk[4] + j[2].y * pk[5];
+      jp1 = j[3].x * pk[0] + j[3].y * pk[1] + j[4].x * pk[2] + j[4].y * pk[3] + j[5].x * pk[4] + j[5].y * pk[5];
+    }
+    // B = [j6.x j6.y j7.x ; j7.y j8.x j8.y]
+    const double t0 = omega * (jp0 + j[6].x * z.x + j[6].y * z.y + j[7].x * z.z);
+    const double t1 = omega * (jp1 + j[7].y * z.x + j[8].x * z.y + j[8].y * z.z);
+    wl.x += j[6].x * t0 + j[7].y * t1;
+    wl.y += j[6].y * t0 + j[8].x * t1;
+    wl.z += j[7].x * t0 + j[8].y * t1;
+    if (pos) {
+      red[0] += j[0].x * t0 + j[3].x * t1;
+      red[1] += j[0].y * t0 + j[3].y * t1;
+      red[2] += j[1].x * t0 + j[4].x * t1;
+      red[3] += j[1].y * t0 + j[4].y * t1;
+      red[4] += j[2].x * t0 + j[5].x * t1;
+      red[5] += j[2].y * t0 + j[5].y * t1;
     }
     if (!fixed) st4(P.wvec, i, wl.x, wl.y, wl.z);
   }
 
-  // One thread per row over this CTA's segments; fn(i, red) adds the row's pose partial to red. The partials of a
+  // One thread per row over this CTA's segments; fn(i, slot, red) adds the row's pose partial to red. The partials of a
   // segment are summed in a fixed order (lanes, warps) and stored to wseg_part[buf][segment].
   template <typename Fn>
   __device__ __forceinline__ void wide_segments(int sg0, int sg1, bool pos, int buf, Fn fn) {
     const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
     int slot = 0;
     for (int sg = sg0; sg < sg1; sg++) {
-      const int se = P.wseg_end[sg];
+      const int se = P.wseg_end[sg], kf = P.wseg_kf[sg];
       double red[6] = {0, 0, 0, 0, 0, 0};
-      for (int i = P.wseg_begin[sg] + tid; i < se; i += nthr) fn(i, red);
+      for (int i = P.wseg_begin[sg] + tid; i < se; i += nthr) fn(i, kf, red);
       if (pos) {
 #pragma unroll
         for (int a = 0; a < 6; a++) {
@@ -1855,7 +1852,9 @@ struct Engine {
     }
     // ---- initial residual, z = M^-1 r, row-local part of the first matvec (one thread per row)
     double rz_part[1] = {0};
-    wide_segments(sg0, sg1, pos, 0, [&](int i, double (&red)[6]) {
+    wide_segments(sg0, sg1, pos, 0, [&](int i, int kf, double (&red)[6]) {
+      double2 j[10];
+      wide_load_jac(i, j);
       if (P.pt_fixed && P.pt_fixed[i]) {  // no unknowns: z = 0 for this row
         st4(minvA, i, 0, 0, 0, 0);
         st4(minvB, i, 0, 0, 0, 0);
@@ -1864,7 +1863,7 @@ struct Engine {
         st4(P.zvec, i, 0, 0, 0);
         st4(P.pvec, i, 0, 0, 0);
         st4(P.qvec, i, 0, 0, 0);
-        wide_row_local(i, true, 0.0, V3{0, 0, 0}, pos, red);
+        wide_row_local(i, kf, true, 0.0, V3{0, 0, 0}, pos, j, red);
         return;
       }
       const D4 r = ld4(P.bvec, i);
@@ -1882,9 +1881,9 @@ struct Engine {
       const V3 z{m00 * r.x + m01 * r.y + m02 * r.z, m01 * r.x + m11 * r.y + m12 * r.z,
                  m02 * r.x + m12 * r.y + m22 * r.z};
       st4(P.zvec, i, z.x, z.y, z.z);
-      if (P.world > 1) xpush3(P.xz, i, z);
+      if ((SHARD && P.world > 1)) xpush3(P.xz, i, z);
       rz_part[0] += r.x * z.x + r.y * z.y + r.z * z.z;
-      wide_row_local(i, false, d1.z, z, pos, red);
+      wide_row_local(i, kf, false, d1.z, z, pos, j, red);
     });
     grid_reduce<1>(rz_part, 0);
     double rz = s_scal[0] + rz_pose;
@@ -1897,6 +1896,12 @@ struct Engine {
     const int qr = tid / kTPR, ql = tid % kTPR;
     const int RPP = nthr / kTPR;  // row groups per pass
     const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+    // segment range of the first pose value this thread sums after the p.q barrier (fixed over the loop)
+    int my_c0 = 0, my_c1 = 0;
+    if (tid >= 32 && tid - 32 < 6 * F) {
+      my_c0 = P.kf_wseg_ptr[(tid - 32) / 6];
+      my_c1 = P.kf_wseg_ptr[(tid - 32) / 6 + 1];
+    }
     for (; it < P.pcg_max_iter; it++) {
       const bool first = (it == 0);
       const int wbuf = it & 1;  // wseg_part buffer holding this iteration's pose partials
@@ -1984,7 +1989,7 @@ struct Engine {
       const long long tm1 = clock64();
       double pq;
       long long tp0;
-      if (pos && P.world == 1) {
+      if (pos && (!SHARD || P.world == 1)) {
         // p.q over the grid and the pose rows of the matvec in ONE round trip: after the barrier warp 0 sums the
         // CTAs' slots while the other warps sum the segment partials of the pose slots and run their recurrences
         double v = pq_part[0];
@@ -2017,7 +2022,8 @@ struct Engine {
           if (lane == 0) s_scal[0] = t;
         } else {
           for (int t = tid - 32; t < 6 * F; t += nthr - 32) {
-            const double w = lambda * s_zp[t] + sum_wseg_partials_of(P, t / 6, t % 6, wbuf);
+            const double w = lambda * s_zp[t] + (t == tid - 32 ? sum_wseg_range(P, my_c0, my_c1, t % 6, wbuf)
+                                                               : sum_wseg_partials_of(P, t / 6, t % 6, wbuf));
             const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
             const double qp = first ? w : w + beta * s_qp[t];
             s_pp[t] = pp;
@@ -2035,7 +2041,7 @@ struct Engine {
           // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (replicated per CTA)
           double v = 0;
           for (int t = tid; t < 6 * F; t += nthr) {
-            const double w = lambda * s_zp[t] + (P.world > 1 ? xextra(t) : sum_wseg_partials_of(P, t / 6, t % 6, wbuf));
+            const double w = lambda * s_zp[t] + ((SHARD && P.world > 1) ? xextra(t) : sum_wseg_partials_of(P, t / 6, t % 6, wbuf));
             const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
             const double qp = first ? w : w + beta * s_qp[t];
             s_pp[t] = pp;
@@ -2071,22 +2077,25 @@ struct Engine {
         rzn_pose = block_sum(v, 0);  // (its block sync also publishes z_p to the rows below)
       }
       double rzn_part[1] = {0};
-      wide_segments(sg0, sg1, pos, wbuf ^ 1, [&](int i, double (&red)[6]) {
+      wide_segments(sg0, sg1, pos, wbuf ^ 1, [&](int i, int kf, double (&red)[6]) {
+        // one level of loads: the vectors, the preconditioner block and the Jacobian of the row
+        const D4 ro = ld4(P.rvec, i), qo = ld4(P.qvec, i), mA = ld4(minvA, i), mB = ld4(minvB, i);
+        double2 j[10];
+        wide_load_jac(i, j);
         if (P.pt_fixed && P.pt_fixed[i]) {
-          wide_row_local(i, true, 0.0, V3{0, 0, 0}, pos, red);
+          wide_row_local(i, kf, true, 0.0, V3{0, 0, 0}, pos, j, red);
           return;
         }
-        const D4 xo = ld4(P.xcg, i), po = ld4(P.pvec, i), ro = ld4(P.rvec, i), qo = ld4(P.qvec, i);
-        const D4 mA = ld4(minvA, i), mB = ld4(minvB, i);
-        st4(P.xcg, i, xo.x + alpha * po.x, xo.y + alpha * po.y, xo.z + alpha * po.z);
+        const D4 xo = ld4(P.xcg, i), po = ld4(P.pvec, i);
         const V3 ri{ro.x - alpha * qo.x, ro.y - alpha * qo.y, ro.z - alpha * qo.z};
-        st4(P.rvec, i, ri.x, ri.y, ri.z);
         const V3 z{mA.x * ri.x + mA.y * ri.y + mA.z * ri.z, mA.y * ri.x + mA.w * ri.y + mB.x * ri.z,
                    mA.z * ri.x + mB.x * ri.y + mB.y * ri.z};
+        st4(P.rvec, i, ri.x, ri.y, ri.z);
         st4(P.zvec, i, z.x, z.y, z.z);
-        if (P.world > 1) xpush3(P.xz, i, z);
+        if ((SHARD && P.world > 1)) xpush3(P.xz, i, z);
         rzn_part[0] += ri.x * z.x + ri.y * z.y + ri.z * z.z;
-        wide_row_local(i, false, mB.z, z, pos, red);
+        wide_row_local(i, kf, false, mB.z, z, pos, j, red);
+        st4(P.xcg, i, xo.x + alpha * po.x, xo.y + alpha * po.y, xo.z + alpha * po.z);
       });
       const long long tm3 = clock64();
       grid_reduce<1>(rzn_part, 0);
@@ -2858,7 +2867,7 @@ struct Engine {
     const bool pts = !P.points_fixed, pos = !P.poses_fixed;
     const long long tl0 = clock64();
     if (pts) {  // estimates written by other CTAs / ranks (restore, reset) are visible
-      if (P.world > 1) xsync(); else barrier();
+      if ((SHARD && P.world > 1)) xsync(); else barrier();
     }
     double acc[2] = {0, 0};  // chi2, max diagonal
     if (P.P > 0 || P.D > 0) {
@@ -2874,7 +2883,7 @@ struct Engine {
     if (pos) {
       for (int t = tid; t < 27 * F; t += nthr) {
         const int k = t / 27, v = t % 27;
-        const double s = (P.world > 1) ? xextra(t) : sum_chunk_partials(k, v, par);
+        const double s = ((SHARD && P.world > 1)) ? xextra(t) : sum_chunk_partials(k, v, par);
         if (v < 21)
           s_H[21 * k + v] = s;
         else
@@ -2916,7 +2925,7 @@ struct Engine {
             st3(P.x_bak, i, x);
             x.x += d.x; x.y += d.y; x.z += d.z;
             st3(P.x, i, x);
-            if (P.world > 1) xpush3(P.xx, i, x);
+            if ((SHARD && P.world > 1)) xpush3(P.xx, i, x);
             acc2[1] += d.x * (lambda * d.x + bb.x) + d.y * (lambda * d.y + bb.y) + d.z * (lambda * d.z + bb.z);
           });
         }
@@ -2927,7 +2936,7 @@ struct Engine {
           __syncthreads();
         }
         if (pts) {  // updated point estimates are read across CTAs (and ranks) by the regulariser edges
-          if (P.world > 1) xsync(); else barrier();
+          if ((SHARD && P.world > 1)) xsync(); else barrier();
         }
         if (P.P > 0 || P.D > 0) edges_pass<false>(acc2[0]);
         double dummy = 0;
@@ -2957,7 +2966,7 @@ struct Engine {
             for_rows([&](int i) {
               const V3 xb = ld3p(P.x_bak, i);
               st3(P.x, i, xb);
-              if (P.world > 1) xpush3(P.xx, i, xb);
+              if ((SHARD && P.world > 1)) xpush3(P.xx, i, xb);
             });
           if (pos) {
             __syncthreads();
@@ -3066,7 +3075,7 @@ struct Engine {
       }
     }
     __syncthreads();
-    if (P.world > 1) xsync();  // no push of this launch is in flight when any rank's kernel ends
+    if ((SHARD && P.world > 1)) xsync();  // no push of this launch is in flight when any rank's kernel ends
     if (blockIdx.x == 0) {
       for (int t = tid; t < 7 * F; t += nthr) P.pose[t] = s_pose[t];
       if (tid == 0) {
@@ -3099,13 +3108,26 @@ struct Engine {
 
 __global__ void __launch_bounds__(kMaxBlock, 1) nrs_lm_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) double nrs_smem[];
-  Engine<false> eng(p, nrs_smem);
+  Engine<false, false> eng(p, nrs_smem);
   eng.run();
 }
 
 __global__ void __launch_bounds__(kMaxBlock, 2) nrs_lm_kernel_wide(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) double nrs_smem[];
-  Engine<true> eng(p, nrs_smem);
+  Engine<true, false> eng(p, nrs_smem);
+  eng.run();
+}
+
+// the same two for a rank of a landmark-sharded BA
+__global__ void __launch_bounds__(kMaxBlock, 1) nrs_lm_kernel_shard(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) double nrs_smem[];
+  Engine<false, true> eng(p, nrs_smem);
+  eng.run();
+}
+
+__global__ void __launch_bounds__(kMaxBlock, 2) nrs_lm_kernel_wide_shard(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) double nrs_smem[];
+  Engine<true, true> eng(p, nrs_smem);
   eng.run();
 }
 
@@ -3138,16 +3160,17 @@ size_t engine_smem_extra(int res_inc, int halo_rows, int coarse) {
   return b;
 }
 
-static const void* kernel_of(int wide) {
+static const void* kernel_of(int wide, int shard = 0) {
+  if (shard) return wide ? (const void*)nrs_lm_kernel_wide_shard : (const void*)nrs_lm_kernel_shard;
   return wide ? (const void*)nrs_lm_kernel_wide : (const void*)nrs_lm_kernel;
 }
 
 // The attribute belongs to the function in the CURRENT device's context, and several contexts on different devices
 // may live in one process (opt.device): it is set on every call instead of being cached process-wide (a cache made a
 // second device miss it; the call costs microseconds and is thread safe).
-static bool set_smem(size_t smem, int wide = 0) {
+static bool set_smem(size_t smem, int wide = 0, int shard = 0) {
   if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(kernel_of(wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kernel_of(wide, shard), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
@@ -3194,7 +3217,8 @@ int engine_max_cluster(int block, size_t smem) {
 
 int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_t stream) {
   const int wide = (p.wide && !p.cluster_mode) ? 1 : 0;
-  if (!set_smem(smem, wide)) return (int)cudaErrorInvalidValue;
+  const int shard = (p.world > 1 && !p.cluster_mode) ? 1 : 0;  // a sharded rank never runs in cluster mode
+  if (!set_smem(smem, wide, shard)) return (int)cudaErrorInvalidValue;
   void* args[] = {const_cast<Params*>(&p)};
   if (p.cluster_mode) {
     cudaLaunchConfig_t cfg = {};
@@ -3213,7 +3237,7 @@ int launch_engine(const Params& p, int grid, int block, size_t smem, cudaStream_
   }
   cudaError_t e = cudaMemsetAsync(p.bar, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return (int)e;
-  e = cudaLaunchCooperativeKernel(kernel_of(wide), dim3(grid), dim3(block), args, smem, stream);
+  e = cudaLaunchCooperativeKernel(kernel_of(wide, shard), dim3(grid), dim3(block), args, smem, stream);
   return (int)e;
 }
 

@@ -152,6 +152,7 @@ struct Params {
   const int* wseg_ptr;     // [G + 1] segments of CTA b
   const int* wseg_begin;   // [n_wseg] rows of the segment
   const int* wseg_end;
+  const int* wseg_kf;      // [n_wseg] pose slot of the segment
   const int* kf_wseg_ptr;  // [F + 1] the segments of a pose slot are contiguous (rows are slot-major)
   double* wseg_part;       // [2][n_wseg * 8] pose partials of the CG matvec per segment
   double* wvec;            // [4V] row-local part of the next matvec ((lambda + s) z + B^T t), written where z is
