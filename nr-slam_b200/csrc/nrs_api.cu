@@ -607,6 +607,7 @@ void apply_plan(Params& p, const Plan& pl) {
   p.chunk_kf = pl.d_chunk_kf; p.chunk_begin = pl.d_chunk_begin; p.chunk_end = pl.d_chunk_end;
   p.kf_chunk_ptr = pl.d_kf_chunk_ptr;
   p.n_wseg = (int)pl.wseg_begin.size();
+  p.wide_prefetch = env_int("NRSLAM_B200_WIDE_PREFETCH", 0);  // measured: configs[3] -1.8 %, configs[2] +2 %
   p.wseg_ptr = pl.d_wseg_ptr; p.wseg_begin = pl.d_wseg_begin; p.wseg_end = pl.d_wseg_end; p.wseg_kf = pl.d_wseg_kf;
   p.kf_wseg_ptr = pl.d_kf_wseg_ptr;
   p.coarse = pl.coarse;

@@ -102,6 +102,7 @@ __device__ __forceinline__ D4 ld4(const double* base, size_t i) {
                : "memory");
   return r;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st4(double* base, size_t i, double x, double y, double z, double w = 0.0) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(base + 4 * i), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
 }
@@ -1924,6 +1925,13 @@ struct Engine {
               po = ld4(P.pvec, i);
               qo = ld4(P.qvec, i);
             }
+          }
+          // the damper records of this lane are fetched into L1 while the spring batch walks its two dependent
+          // levels (record -> z): their loads below are L1 hits instead of one more L2 round trip per batch
+          if (P.wide_prefetch) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (d_beg + ql + kTPR * k < d1) prefetch_l1(P.wdrec + 4 * (size_t)(d_beg + ql + kTPR * k));
           }
           // lane l takes incidences a_beg + l, + kTPR, ...: batches of 3 per lane, every load of a level first
           for (int a0 = a_beg + ql; a0 < a1; a0 += 3 * kTPR) {

@@ -148,6 +148,7 @@ struct Params {
   double* slots;       // [2][G * kSlotVals]
   // wide CG loop (Engine<true>::pcg_wide): every CTA owns ONE contiguous row range of equal length, cut into segments
   // at the pose-slot boundaries; the pose partials of the matvec are reduced per segment, not per 128-row chunk
+  int wide_prefetch;       // 1: L1 prefetch of the damper records in the matvec pass
   int n_wseg;
   const int* wseg_ptr;     // [G + 1] segments of CTA b
   const int* wseg_begin;   // [n_wseg] rows of the segment
