@@ -691,6 +691,15 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
     if (dsmem > 226 * 1024 || direct_max_grid(dsmem) < dplan.G ||
         (Vu + dplan.G - 1) / dplan.G > direct_block_threads())
       direct = false;
+    if (getenv("NRSLAM_B200_DIRECT_DEBUG")) {
+      fprintf(stderr, "[nrs direct] V %d depth %d G %d fits %d: smem %zu B (panel %zu doubles, scratch %d, max_nv %d, "
+              "max_rows %d, max_path %d) separators:", Vu, depth, dplan.G, direct ? 1 : 0, dsmem, (size_t)dplan.smem_doubles,
+              dscratch, dmaxnv, dplan.max_rows, dplan.max_path);
+      for (int t = 1; t <= dplan.n_nodes && t < 16; t++) fprintf(stderr, " %d", dplan.nv[t]);
+      fprintf(stderr, " | boundaries:");
+      for (int t = 1; t <= dplan.n_nodes && t < 16; t++) fprintf(stderr, " %d", dplan.nbv[t]);
+      fprintf(stderr, "\n");
+    }
   }
   hprof.mark("direct_plan");
   sort_rows(hp, st.row_of, direct ? &dplan.old_of_new : nullptr);
@@ -1813,41 +1822,45 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
   // sorted neighbour lists are cached per map point; (pair, keyframe) de-duplication is keyed by graph edge
   // The sorted list of a map point is stored as (neighbour, edge) pairs, already cut at the first weight < min_weight
   // (GetEdges) and at the first BAD edge (the loops' break; BAD sorts last), so the scans below read sequential memory.
-  std::vector<int> nb_ptr(M + 1, -1), nb_cnt(M, 0);
-  std::vector<int> nb_pair;  // 2 ints per entry: neighbour vertex, undirected edge id
+  // Entries of map point mp live at [rowptr[mp], rowptr[mp] + nb_cnt[mp]) of nb_pair (capacity = its degree), so the
+  // observed map points are sorted independently of each other: host threads take ranges of them.
+  std::vector<int> nb_cnt(M, 0);
+  std::vector<int> nb_pair(2 * (size_t)g->rowptr[M]);  // 2 ints per entry: neighbour vertex, undirected edge id
+  const int* nb_ptr = g->rowptr;
   {
-    std::vector<std::pair<unsigned long long, int>> keyed;
-    nb_pair.reserve(2 * (size_t)g->rowptr[M]);
     std::vector<char> seen(M, 0);
-    for (int o = 0; o < O; o++) {
-      const int mp = obs_vertex[o];
-      if (seen[mp]) continue;
-      seen[mp] = 1;
-      // GetEdges order (regularization_graph.cc:61-87): status asc, weight desc, neighbour asc — one 64-bit key
-      // (weights are non-negative floats: their bit patterns order like their values)
-      keyed.clear();
-      for (int p = g->rowptr[mp]; p < g->rowptr[mp + 1]; p++) {
-        const int ge = g->eid[p];
-        unsigned wb;
-        const float wgt = g->weight[ge];
-        memcpy(&wb, &wgt, 4);
-        const unsigned long long key = ((unsigned long long)(g->status[ge] & 3u) << 62) |
-                                       ((unsigned long long)(0xFFFFFFFFu - wb) << 30) |
-                                       (unsigned long long)(g->col[p] & 0x3FFFFFFF);
-        keyed.emplace_back(key, p);
+    for (int o = 0; o < O; o++) seen[obs_vertex[o]] = 1;
+    par_ranges(host_threads(64, O), (size_t)M, [&](size_t mb, size_t me) {
+      std::vector<std::pair<unsigned long long, int>> keyed;
+      for (size_t mq = mb; mq < me; mq++) {
+        const int mp = (int)mq;
+        if (!seen[mp]) continue;
+        // GetEdges order (regularization_graph.cc:61-87): status asc, weight desc, neighbour asc — one 64-bit key
+        // (weights are non-negative floats: their bit patterns order like their values)
+        keyed.clear();
+        for (int p = g->rowptr[mp]; p < g->rowptr[mp + 1]; p++) {
+          const int ge = g->eid[p];
+          unsigned wb;
+          const float wgt = g->weight[ge];
+          memcpy(&wb, &wgt, 4);
+          const unsigned long long key = ((unsigned long long)(g->status[ge] & 3u) << 62) |
+                                         ((unsigned long long)(0xFFFFFFFFu - wb) << 30) |
+                                         (unsigned long long)(g->col[p] & 0x3FFFFFFF);
+          keyed.emplace_back(key, p);
+        }
+        std::sort(keyed.begin(), keyed.end());
+        int* dst = nb_pair.data() + 2 * (size_t)g->rowptr[mp];
+        int cnt = 0;
+        for (const auto& kp : keyed) {
+          const int ge = g->eid[kp.second];
+          if (g->weight[ge] < min_w || g->status[ge] == NRSLAM_EDGE_BAD) break;  // GetEdges cut ; :1035-1037 break
+          dst[2 * cnt] = g->col[kp.second];
+          dst[2 * cnt + 1] = ge;
+          cnt++;
+        }
+        nb_cnt[mp] = cnt;
       }
-      std::sort(keyed.begin(), keyed.end());
-      nb_ptr[mp] = (int)nb_pair.size() / 2;
-      int cnt = 0;
-      for (const auto& kp : keyed) {
-        const int ge = g->eid[kp.second];
-        if (g->weight[ge] < min_w || g->status[ge] == NRSLAM_EDGE_BAD) break;  // GetEdges cut ; :1035-1037 break
-        nb_pair.push_back(g->col[kp.second]);
-        nb_pair.push_back(ge);
-        cnt++;
-      }
-      nb_cnt[mp] = cnt;
-    }
+    });
   }
   // Keyframes are independent here (a spring joins two points of ONE keyframe, a damper reads keyframes k and k + 1,
   // the reference's de-duplication maps are per keyframe): host threads take keyframes round robin, every keyframe

@@ -21,6 +21,7 @@
 //
 // All index lists are in vertex (3x3 block) units.
 #pragma once
+#include <functional>
 #include <type_traits>
 #include <stdint.h>
 #include <string.h>
@@ -118,7 +119,66 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
         }
       const int ax = (mx[0] - mn[0] >= mx[1] - mn[1]) ? 0 : 1;
       for (int k = lo; k < hi; k++) key[k] = ((uint64_t)fkey(uv[2 * (size_t)ord[k] + ax]) << 32) | (uint32_t)ord[k];
-      std::nth_element(key.begin() + lo, key.begin() + mid, key.begin() + hi);
+      if (t <= 3 && hi - lo >= 256) {
+        // The separators of the top two levels are the largest fronts (the root's must fit the shared memory of one
+        // SM, and they sit on every CTA's critical path): instead of the exact median, take the cut position within
+        // +-8 % of it whose cut edges have the smallest vertex cover (= the largest matching of the bipartite cut
+        // graph). Ties go to the position closest to the median.
+        std::sort(key.begin() + lo, key.begin() + hi);
+        std::vector<int> rank(V, -1);
+        for (int k = lo; k < hi; k++) rank[(int)(uint32_t)key[k]] = k;
+        const int step = std::max(1, (hi - lo) / 50);
+        int best_mid = mid, best_cover = -1;
+        std::vector<int> lidx(V, -1), l_ptr, l_adj, mt, stamp;
+        for (int c = 0; c < 9; c++) {
+          const int off = (c == 0) ? 0 : ((c + 1) / 2) * ((c & 1) ? 1 : -1);  // 0, +1, -1, +2, -2, ...
+          const int m = mid + off * step;
+          std::vector<std::pair<int, int>> ed;
+          int nl = 0, nr = 0;
+          std::vector<int> touched;
+          for (size_t e = 0; e < pair_i.size(); e++) {
+            int a = pair_i[e], b2 = pair_j[e];
+            if (rank[a] < 0 || rank[b2] < 0 || (rank[a] < m) == (rank[b2] < m)) continue;
+            if (rank[a] >= m) std::swap(a, b2);
+            if (lidx[a] < 0) { lidx[a] = nl++; touched.push_back(a); }
+            if (lidx[b2] < 0) { lidx[b2] = nr++; touched.push_back(b2); }
+            ed.emplace_back(lidx[a], lidx[b2]);
+          }
+          for (int v : touched) lidx[v] = -1;
+          l_ptr.assign(nl + 1, 0);
+          for (auto& x : ed) l_ptr[x.first + 1]++;
+          for (int k = 0; k < nl; k++) l_ptr[k + 1] += l_ptr[k];
+          l_adj.resize(ed.size());
+          {
+            std::vector<int> w(l_ptr.begin(), l_ptr.end() - 1);
+            for (auto& x : ed) l_adj[w[x.first]++] = x.second;
+          }
+          mt.assign(nr, -1);
+          stamp.assign(nr, -1);
+          std::function<bool(int, int)> aug = [&](int u, int st) -> bool {
+            for (int a = l_ptr[u]; a < l_ptr[u + 1]; a++) {
+              const int r = l_adj[a];
+              if (stamp[r] == st) continue;
+              stamp[r] = st;
+              if (mt[r] < 0 || aug(mt[r], st)) {
+                mt[r] = u;
+                return true;
+              }
+            }
+            return false;
+          };
+          int cover = 0;
+          for (int u = 0; u < nl; u++) cover += aug(u, u) ? 1 : 0;
+          if (best_cover < 0 || cover < best_cover) {
+            best_cover = cover;
+            best_mid = m;
+          }
+        }
+        hi_of[2 * t] = best_mid;
+        lo_of[2 * t + 1] = best_mid;
+      } else {
+        std::nth_element(key.begin() + lo, key.begin() + mid, key.begin() + hi);
+      }
       for (int k = lo; k < hi; k++) ord[k] = (int)(uint32_t)key[k];
     }
     for (int l = 0; l < n_leaf; l++)
@@ -143,35 +203,97 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
     std::vector<int> w(cut_ptr.begin(), cut_ptr.end() - 1);
     for (size_t e = 0; e < pair_i.size(); e++) cut_e[w[node_of[e]]++] = (int)e;
   }
-  // (3) separators, top down: greedy vertex cover (highest remaining cut degree first, ties: first touched) of the
-  // node's cut edges whose endpoints are not already in an ancestor's separator
+  // (3) separators, top down: a MINIMUM vertex cover of the node's cut edges whose endpoints are not already in an
+  // ancestor's separator. The cut edges of a node join its left and its right subtree — a bipartite graph — so the
+  // minimum cover follows from a maximum matching (Koenig): with Z = the vertices reachable from the unmatched left
+  // vertices along alternating paths, cover = (left \ Z) + (right & Z). Augmenting paths in a fixed vertex order keep
+  // the plan deterministic. (The first version took vertices greedily by remaining cut degree: covers 10-20 % larger,
+  // and the root front of 2 frames in 8 no longer fitted the shared memory of one SM.)
   std::vector<std::vector<int>> own(T + 1);
   std::vector<char> insep(V, 0);
   {
-    std::vector<int> deg(V, 0), touched;
+    std::vector<int> lid(V, -1), verts, side, match, eptr, eadj, seen_stamp;
+    std::vector<char> inz;
     for (int t = 1; t < n_leaf; t++) {
-      touched.clear();
+      int level = 0;
+      while ((1 << (level + 1)) <= t) level++;
+      const int sbit = depth - 1 - level;  // leaf-index bit that tells the node's left subtree from its right one
+      verts.clear();
+      std::vector<std::pair<int, int>> edges;  // (left local id, right local id)
+      auto local = [&](int v) {
+        if (lid[v] < 0) {
+          lid[v] = (int)verts.size();
+          verts.push_back(v);
+        }
+        return lid[v];
+      };
       for (int c = cut_ptr[t]; c < cut_ptr[t + 1]; c++) {
-        const int a = pair_i[cut_e[c]], b2 = pair_j[cut_e[c]];
+        int a = pair_i[cut_e[c]], b2 = pair_j[cut_e[c]];
         if (insep[a] || insep[b2]) continue;
-        if (!deg[a]++) touched.push_back(a);
-        if (!deg[b2]++) touched.push_back(b2);
+        if ((leaf[a] >> sbit) & 1) std::swap(a, b2);  // a: left subtree, b2: right subtree
+        const int la = local(a), lb = local(b2);
+        edges.emplace_back(la, lb);
       }
-      std::vector<int>& sep = own[t];
-      for (;;) {
-        int best = -1;
-        for (int v : touched)
-          if (deg[v] > 0 && (best < 0 || deg[v] > deg[best])) best = v;
-        if (best < 0) break;
-        sep.push_back(best);
-        insep[best] = 1;
-        deg[best] = 0;
-        for (int a = adj_ptr[best]; a < adj_ptr[best + 1]; a++) {
-          const int o = adj[a];
-          if (!insep[o] && deg[o] > 0 && lca(best, o) == t) deg[o]--;  // edge (best, o) is covered
+      const int nl = (int)verts.size();
+      side.assign(nl, 0);
+      for (int k = 0; k < nl; k++) side[k] = (leaf[verts[k]] >> sbit) & 1;
+      eptr.assign(nl + 1, 0);
+      for (auto& ed : edges) eptr[ed.first + 1]++;
+      for (int k = 0; k < nl; k++) eptr[k + 1] += eptr[k];
+      eadj.resize(edges.size());
+      {
+        std::vector<int> w(eptr.begin(), eptr.end() - 1);
+        for (auto& ed : edges) eadj[w[ed.first]++] = ed.second;
+      }
+      match.assign(nl, -1);
+      seen_stamp.assign(nl, -1);
+      // Kuhn's augmenting paths from every left vertex, in local-id (first touched) order
+      std::function<bool(int, int)> augment = [&](int u, int stamp) -> bool {
+        for (int a = eptr[u]; a < eptr[u + 1]; a++) {
+          const int r = eadj[a];
+          if (seen_stamp[r] == stamp) continue;
+          seen_stamp[r] = stamp;
+          if (match[r] < 0 || augment(match[r], stamp)) {
+            match[r] = u;
+            match[u] = r;
+            return true;
+          }
+        }
+        return false;
+      };
+      for (int u = 0; u < nl; u++)
+        if (!side[u] && eptr[u + 1] > eptr[u]) augment(u, u);
+      // alternating reachability from the unmatched left vertices
+      inz.assign(nl, 0);
+      std::vector<int> stack;
+      for (int u = 0; u < nl; u++)
+        if (!side[u] && match[u] < 0) {
+          inz[u] = 1;
+          stack.push_back(u);
+        }
+      while (!stack.empty()) {
+        const int u = stack.back();
+        stack.pop_back();
+        for (int a = eptr[u]; a < eptr[u + 1]; a++) {
+          const int r = eadj[a];
+          if (match[u] == r || inz[r]) continue;  // unmatched edges left -> right
+          inz[r] = 1;
+          const int u2 = match[r];                // matched edge right -> left
+          if (u2 >= 0 && !inz[u2]) {
+            inz[u2] = 1;
+            stack.push_back(u2);
+          }
         }
       }
-      for (int v : touched) deg[v] = 0;
+      std::vector<int>& sep = own[t];
+      for (int k = 0; k < nl; k++) {
+        const bool in_cover = side[k] ? (inz[k] != 0) : (inz[k] == 0 && eptr[k + 1] > eptr[k]);
+        if (in_cover) {
+          sep.push_back(verts[k]);
+          insep[verts[k]] = 1;
+        }
+      }
+      for (int v : verts) lid[v] = -1;
       std::sort(sep.begin(), sep.end());
     }
     for (int l = 0; l < n_leaf; l++) {
