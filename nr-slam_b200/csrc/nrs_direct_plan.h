@@ -62,6 +62,11 @@ inline int direct_depth(int V, int max_ctas, int min_leaf = 8) {
 
 // Builds the plan. uv: [2V] pixel coordinates (caller rows); pair_i / pair_j: regulariser pairs (caller rows).
 // After the call the caller permutes its rows with plan.old_of_new and then calls direct_inc_pos with the new ids.
+#ifndef NRS_DIRECT_SCAN_NODES
+#define NRS_DIRECT_SCAN_NODES 3
+#endif
+constexpr int kScanNodes = NRS_DIRECT_SCAN_NODES;  // heap indices 1..kScanNodes get the cut-position scan (3 = two levels)
+
 inline void build_direct_plan(int V, const double* uv, const std::vector<int>& pair_i, const std::vector<int>& pair_j,
                               int depth, DirectPlanHost& pl, bool with_pose = true) {
   pl.V = V;
@@ -119,7 +124,7 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
         }
       const int ax = (mx[0] - mn[0] >= mx[1] - mn[1]) ? 0 : 1;
       for (int k = lo; k < hi; k++) key[k] = ((uint64_t)fkey(uv[2 * (size_t)ord[k] + ax]) << 32) | (uint32_t)ord[k];
-      if (t <= 3 && hi - lo >= 256) {
+      if (t <= kScanNodes && hi - lo >= 128) {
         // The separators of the top two levels are the largest fronts (the root's must fit the shared memory of one
         // SM, and they sit on every CTA's critical path): instead of the exact median, take the cut position within
         // +-8 % of it whose cut edges have the smallest vertex cover (= the largest matching of the bipartite cut
@@ -127,6 +132,9 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
         std::sort(key.begin() + lo, key.begin() + hi);
         std::vector<int> rank(V, -1);
         for (int k = lo; k < hi; k++) rank[(int)(uint32_t)key[k]] = k;
+        std::vector<int> node_edges;
+        for (size_t e = 0; e < pair_i.size(); e++)
+          if (rank[pair_i[e]] >= 0 && rank[pair_j[e]] >= 0) node_edges.push_back((int)e);
         const int step = std::max(1, (hi - lo) / 50);
         int best_mid = mid, best_cover = -1;
         std::vector<int> lidx(V, -1), l_ptr, l_adj, mt, stamp;
@@ -136,9 +144,9 @@ inline void build_direct_plan(int V, const double* uv, const std::vector<int>& p
           std::vector<std::pair<int, int>> ed;
           int nl = 0, nr = 0;
           std::vector<int> touched;
-          for (size_t e = 0; e < pair_i.size(); e++) {
+          for (int e : node_edges) {
             int a = pair_i[e], b2 = pair_j[e];
-            if (rank[a] < 0 || rank[b2] < 0 || (rank[a] < m) == (rank[b2] < m)) continue;
+            if ((rank[a] < m) == (rank[b2] < m)) continue;
             if (rank[a] >= m) std::swap(a, b2);
             if (lidx[a] < 0) { lidx[a] = nl++; touched.push_back(a); }
             if (lidx[b2] < 0) { lidx[b2] = nr++; touched.push_back(b2); }
