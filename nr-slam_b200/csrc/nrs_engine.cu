@@ -244,9 +244,11 @@ __device__ __forceinline__ XRet xreduce_impl(const Params& P, double* s_scal, in
   const size_t half = (size_t)(epoch & 1) * W * P.xstride;
   const size_t rec = half + (size_t)P.rank * P.xstride;
   __syncthreads();  // the slot of this CTA (and everything else it wrote) precedes the arrive
+  const unsigned long long ta = global_timer_ns();
   if (tid == 0) s_flag[1] = (atom_acqrel_add_u64(P.bar, 1ULL) + 1 == (unsigned long long)gen * gridDim.x) ? 1 : 0;
   __syncthreads();
   if (s_flag[1]) {
+    const unsigned long long tl0 = global_timer_ns();
     const int G = (int)gridDim.x;
     if (tid < 32 * n) {
       const int k = tid >> 5, lane = tid & 31;
@@ -270,15 +272,47 @@ __device__ __forceinline__ XRet xreduce_impl(const Params& P, double* s_scal, in
     }
     const int per = (kind == 1) ? 6 : 27;
     const int nx = (kind == 0) ? 0 : per * P.F;
-    for (int t = tid; t < nx; t += nthr) {
-      const double s = (kind == 1 && P.wide) ? sum_wseg_partials_of(P, t / per, t % per, xpar)
-                                             : sum_chunk_partials_of(P, t / per, t % per, xpar);
-      for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = s;
+    const bool segs = kind == 1 && P.wide;
+    const int* rptr = segs ? P.kf_wseg_ptr : P.kf_chunk_ptr;
+    const double* part = segs ? P.wseg_part + (size_t)xpar * P.n_wseg * 8 : P.chunk_part + (size_t)xpar * P.n_chunks * kChunkVals;
+    const int pstride = segs ? 8 : kChunkVals;
+    const int npart = segs ? P.n_wseg : P.n_chunks;  // (an empty pose slot at the end of the list must not read past it)
+    // up to four values per thread and round: first the ranges, then the first eight partials of each value (all in
+    // flight together: this CTA is the critical path of every GPU), then the rare longer tails
+    for (int t0 = tid; t0 < nx; t0 += 4 * nthr) {
+      int cb[4], ce[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = min(t0 + u * nthr, nx - 1);
+        cb[u] = rptr[t / per];
+        ce[u] = rptr[t / per + 1];
+      }
+      double o[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v = min(t0 + u * nthr, nx - 1) % per;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          o[u][q] = __ldcg(part + (size_t)min(min(cb[u] + q, max(ce[u] - 1, cb[u])), npart - 1) * pstride + v);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = t0 + u * nthr;
+        if (t >= nx) continue;
+        double sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (cb[u] + q < ce[u]) sum += o[u][q];
+        for (int c = cb[u] + 8; c < ce[u]; c++) sum += __ldcg(part + (size_t)c * pstride + t % per);
+        for (int r = 0; r < W; r++) P.xred[r][rec + 8 + t] = sum;
+      }
     }
     __syncthreads();
-    if (tid < W) {
-      __threadfence_system();
-      st_release_sys_u64(P.xflag[tid] + P.rank, epoch);
+    const unsigned long long tl1 = global_timer_ns();
+    if (tid < W) st_release_sys_u64(P.xflag[tid] + P.rank, epoch);  // release: cumulative over the CTA's stores above
+    if (tid == 0) {  // diagnostics (ns): the last CTA's sums + record stores, its fence + flag stores
+      atomicAdd(reinterpret_cast<unsigned long long*>(&P.stats->prof[8]), tl1 - tl0);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&P.stats->prof[9]), global_timer_ns() - tl1);
     }
   }
   if (tid < W && (!dead || tid == P.rank)) {  // after a time-out only the local barrier is kept
@@ -292,8 +326,12 @@ __device__ __forceinline__ XRet xreduce_impl(const Params& P, double* s_scal, in
         }
       }
     }
+    if (blockIdx.x == 0 && tid == P.rank)  // diagnostics (ns): CTA 0 from its arrival to its own rank's flag ...
+      atomicAdd(reinterpret_cast<unsigned long long*>(&P.stats->prof[10]), global_timer_ns() - ta);
   }
   __syncthreads();
+  if (blockIdx.x == 0 && tid == 0)  // ... and to the flags of all ranks
+    atomicAdd(reinterpret_cast<unsigned long long*>(&P.stats->prof[11]), global_timer_ns() - ta);
   if (__ldcg(P.xabort)) dead = 1;
   if (tid < n) {
     const bool mx = (maxmask >> tid) & 1;
@@ -2048,13 +2086,42 @@ struct Engine {
         if (pos) {
           // pose rows: w_p = lambda z_p + sum_i A_i^T t_i ; p_p, q_p by the same recurrences (replicated per CTA)
           double v = 0;
-          for (int t = tid; t < 6 * F; t += nthr) {
-            const double w = lambda * s_zp[t] + ((SHARD && P.world > 1) ? xextra(t) : sum_wseg_partials_of(P, t / 6, t % 6, wbuf));
-            const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
-            const double qp = first ? w : w + beta * s_qp[t];
-            s_pp[t] = pp;
-            s_qp[t] = qp;
-            v += pp * qp;
+          if (SHARD && P.world > 1) {
+            // three values per thread and round, the records of every rank in flight together (one L2 round trip)
+            const double* base = P.xred[P.rank] + xcur + 8;
+            for (int t0 = tid; t0 < 6 * F; t0 += 3 * nthr) {
+              double o[3][kMaxWorld];
+#pragma unroll
+              for (int u = 0; u < 3; u++) {
+                const int t = min(t0 + u * nthr, 6 * F - 1);
+#pragma unroll
+                for (int r = 0; r < kMaxWorld; r++) o[u][r] = __ldcg(base + t + (size_t)min(r, P.world - 1) * P.xstride);
+              }
+#pragma unroll
+              for (int u = 0; u < 3; u++) {
+                const int t = t0 + u * nthr;
+                if (t >= 6 * F) continue;
+                double xs = 0;
+#pragma unroll
+                for (int r = 0; r < kMaxWorld; r++)
+                  if (r < P.world) xs += o[u][r];
+                const double w = lambda * s_zp[t] + xs;
+                const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+                const double qp = first ? w : w + beta * s_qp[t];
+                s_pp[t] = pp;
+                s_qp[t] = qp;
+                v += pp * qp;
+              }
+            }
+          } else {
+            for (int t = tid; t < 6 * F; t += nthr) {
+              const double w = lambda * s_zp[t] + sum_wseg_partials_of(P, t / 6, t % 6, wbuf);
+              const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+              const double qp = first ? w : w + beta * s_qp[t];
+              s_pp[t] = pp;
+              s_qp[t] = qp;
+              v += pp * qp;
+            }
           }
           pq += block_sum(v, 1);
         }
@@ -3101,10 +3168,10 @@ struct Engine {
         st->lambda_final = lambda;
         prof[15] = clock64() - trun0;
         for (int i = 0; i < 16; i++)
-          if (!WIDE || i < 8 || i > 10) st->prof[i] = prof[i];
+          if (!(WIDE || SHARD) || i < 8 || i > 11) st->prof[i] = prof[i];
       }
     }
-    if (WIDE && tid == 0) {  // slowest / fastest CTA in the matvec pass, slowest in the update pass (diagnostics)
+    if (WIDE && !SHARD && tid == 0) {  // slowest / fastest CTA in the matvec pass, slowest in the update pass (diagnostics)
       atomicMax(reinterpret_cast<long long*>(&P.stats->prof[8]), prof[1]);
       atomicMax(reinterpret_cast<long long*>(&P.stats->prof[9]), prof[3]);
       atomicMax(reinterpret_cast<long long*>(&P.stats->prof[10]), -prof[1]);

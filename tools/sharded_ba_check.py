@@ -28,6 +28,8 @@ def main():
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    if rank != 0:  # phase counters (NRSLAM_B200_PROF) from one rank only: the ranks' stderr lines interleave
+        os.environ.pop("NRSLAM_B200_PROF", None)
     kw = {k: v for k, v in dict(n=a.landmarks, n_kf=a.keyframes, run=a.visible).items() if v is not None}
     p = synth.ba_problem(a.config, **kw)
     args = (p["cam"], p["kf_pose"], p["obs_kf"], p["obs_vertex"], p["uv"], p["X"], p["graph"], p["scale"])
