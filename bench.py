@@ -481,6 +481,13 @@ def main():
         stb.update({k: b["stats"][k] for k in ("n_reproj_edges", "n_points", "n_poses", "n_pair_edges",
                                                 "n_spring_edges", "n_damper_edges")})
         alg_b, bsw, bmv = algorithmic_bytes(stb)
+        traffic_b = None
+        if tag == "c3":  # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
+            try:
+                traffic_b = json.load(open(os.path.join(ROOT, "profiles", "r02_lm_ba_wide_ncu_summary.json")))[
+                    "dram_bytes_per_launch"]
+            except Exception:
+                pass
         return {"metric": "deformable_ba_lm_iterations_per_sec", "unit": "iters/s",
                 "value": world * ks * sb["lm_iterations"] / (ms * 1e-3),
                 "e2e_value": world * b["stats"]["lm_iterations"] / (e2e_ms * 1e-3),
@@ -490,6 +497,7 @@ def main():
                 "pcg_iterations": sb["pcg_iterations"], "grid_ctas": sb["grid_ctas"],
                 "roofline": {"bound": "hbm", "achieved": alg_b / (ms / ks * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": alg_b / (ms / ks * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             "traffic": traffic_b, "algorithmic_bytes_per_launch": alg_b,
                              "bytes_per_sweep": bsw, "bytes_per_matvec": bmv}}
 
     if not args.no_ba:

@@ -276,16 +276,15 @@ __device__ __forceinline__ XRet xreduce_impl(const Params& P, double* s_scal, in
     const int* rptr = segs ? P.kf_wseg_ptr : P.kf_chunk_ptr;
     const double* part = segs ? P.wseg_part + (size_t)xpar * P.n_wseg * 8 : P.chunk_part + (size_t)xpar * P.n_chunks * kChunkVals;
     const int pstride = segs ? 8 : kChunkVals;
-    const int npart = segs ? P.n_wseg : P.n_chunks;  // (an empty pose slot at the end of the list must not read past it)
     // up to four values per thread and round: first the ranges, then the first eight partials of each value (all in
     // flight together: this CTA is the critical path of every GPU), then the rare longer tails
     for (int t0 = tid; t0 < nx; t0 += 4 * nthr) {
       int cb[4], ce[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int t = min(t0 + u * nthr, nx - 1);
-        cb[u] = rptr[t / per];
-        ce[u] = rptr[t / per + 1];
+        const int t = t0 + u * nthr;
+        cb[u] = t < nx ? rptr[t / per] : 0;
+        ce[u] = t < nx ? rptr[t / per + 1] : 0;
       }
       double o[4][8];
 #pragma unroll
@@ -293,7 +292,7 @@ __device__ __forceinline__ XRet xreduce_impl(const Params& P, double* s_scal, in
         const int v = min(t0 + u * nthr, nx - 1) % per;
 #pragma unroll
         for (int q = 0; q < 8; q++)
-          o[u][q] = __ldcg(part + (size_t)min(min(cb[u] + q, max(ce[u] - 1, cb[u])), npart - 1) * pstride + v);
+          o[u][q] = (cb[u] + q < ce[u]) ? __ldcg(part + (size_t)(cb[u] + q) * pstride + v) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -338,7 +337,7 @@ __device__ __forceinline__ XRet xreduce_impl(const Params& P, double* s_scal, in
     double s = mx ? -DBL_MAX : 0.0;
     double o[kMaxWorld];
 #pragma unroll
-    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(P.xred[P.rank] + half + (size_t)min(r, W - 1) * P.xstride + tid);
+    for (int r = 0; r < kMaxWorld; r++) o[r] = r < W ? __ldcg(P.xred[P.rank] + half + (size_t)r * P.xstride + tid) : 0.0;
 #pragma unroll
     for (int r = 0; r < kMaxWorld; r++)
       if (r < W) s = mx ? fmax(s, o[r]) : s + o[r];
@@ -407,7 +406,7 @@ __device__ __noinline__ XRet xexchange_impl(const Params& P, double* s_scal, int
     double s = mx ? -DBL_MAX : 0.0;
     double o[kMaxWorld];
 #pragma unroll
-    for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(P.xred[P.rank] + half + (size_t)min(r, W - 1) * P.xstride + tid);
+    for (int r = 0; r < kMaxWorld; r++) o[r] = r < W ? __ldcg(P.xred[P.rank] + half + (size_t)r * P.xstride + tid) : 0.0;
 #pragma unroll
     for (int r = 0; r < kMaxWorld; r++)
       if (r < W) s = mx ? fmax(s, o[r]) : s + o[r];
@@ -424,7 +423,7 @@ __device__ __noinline__ double xextra_of(const Params& P, size_t xcur, int t) {
   const double* base = P.xred[P.rank] + xcur + 8 + t;
   double o[kMaxWorld];
 #pragma unroll
-  for (int r = 0; r < kMaxWorld; r++) o[r] = __ldcg(base + (size_t)min(r, P.world - 1) * P.xstride);
+  for (int r = 0; r < kMaxWorld; r++) o[r] = r < P.world ? __ldcg(base + (size_t)r * P.xstride) : 0.0;
   double s = 0;
 #pragma unroll
   for (int r = 0; r < kMaxWorld; r++)
@@ -2067,14 +2066,55 @@ struct Engine {
           for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
           if (lane == 0) s_scal[0] = t;
         } else {
-          for (int t = tid - 32; t < 6 * F; t += nthr - 32) {
-            const double w = lambda * s_zp[t] + (t == tid - 32 ? sum_wseg_range(P, my_c0, my_c1, t % 6, wbuf)
-                                                               : sum_wseg_partials_of(P, t / 6, t % 6, wbuf));
-            const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
-            const double qp = first ? w : w + beta * s_qp[t];
-            s_pp[t] = pp;
-            s_qp[t] = qp;
-            pv += pp * qp;
+          // three pose values per thread and round: the segment ranges first, then the first twelve partials of each
+          // value (all in flight together), then the rare longer tails — one L2 round trip instead of two per value
+          const int pstep = nthr - 32;
+          const double* part = P.wseg_part + (size_t)wbuf * P.n_wseg * 8;
+          if (6 * F <= pstep) {  // one value per thread (<= 37 poses): nothing to batch
+            const int t = tid - 32;
+            if (t < 6 * F) {
+              const double w = lambda * s_zp[t] + sum_wseg_range(P, my_c0, my_c1, t % 6, wbuf);
+              const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+              const double qp = first ? w : w + beta * s_qp[t];
+              s_pp[t] = pp;
+              s_qp[t] = qp;
+              pv += pp * qp;
+            }
+          } else
+          for (int t0 = tid - 32; t0 < 6 * F; t0 += 3 * pstep) {
+            int cb[3], ce[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int t = t0 + u * pstep, k = min(t, 6 * F - 1) / 6;
+              const bool mine = (u == 0 && t0 == tid - 32);
+              cb[u] = mine ? my_c0 : (t < 6 * F ? P.kf_wseg_ptr[k] : 0);
+              ce[u] = mine ? my_c1 : (t < 6 * F ? P.kf_wseg_ptr[k + 1] : 0);
+            }
+            double o[3][12];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int t = t0 + u * pstep, a = min(t, 6 * F - 1) % 6;
+              // predicated, not clamped: clamped duplicates of every thread of every CTA hammer ONE L2 line
+#pragma unroll
+              for (int q = 0; q < 12; q++)
+                o[u][q] = (t < 6 * F && cb[u] + q < ce[u]) ? __ldcg(part + (size_t)(cb[u] + q) * 8 + a) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int t = t0 + u * pstep;
+              if (t >= 6 * F) continue;
+              double sum = 0;
+#pragma unroll
+              for (int q = 0; q < 12; q++)
+                if (cb[u] + q < ce[u]) sum += o[u][q];
+              for (int c = cb[u] + 12; c < ce[u]; c++) sum += __ldcg(part + (size_t)c * 8 + t % 6);
+              const double w = lambda * s_zp[t] + sum;
+              const double pp = first ? s_zp[t] : s_zp[t] + beta * s_pp[t];
+              const double qp = first ? w : w + beta * s_qp[t];
+              s_pp[t] = pp;
+              s_qp[t] = qp;
+              pv += pp * qp;
+            }
           }
         }
         const double ps = block_sum(pv, 1);  // its block sync publishes s_scal[0]
@@ -2093,9 +2133,10 @@ struct Engine {
               double o[3][kMaxWorld];
 #pragma unroll
               for (int u = 0; u < 3; u++) {
-                const int t = min(t0 + u * nthr, 6 * F - 1);
+                const int t = t0 + u * nthr;
 #pragma unroll
-                for (int r = 0; r < kMaxWorld; r++) o[u][r] = __ldcg(base + t + (size_t)min(r, P.world - 1) * P.xstride);
+                for (int r = 0; r < kMaxWorld; r++)
+                  o[u][r] = (t < 6 * F && r < P.world) ? __ldcg(base + t + (size_t)r * P.xstride) : 0.0;
               }
 #pragma unroll
               for (int u = 0; u < 3; u++) {

@@ -147,3 +147,17 @@ def test_symbolic_plan_is_reused_across_frames(core):
     r5 = core.pose_deform(q["cam"], q["uv"], q["X_rest"], q["point_vertex"], q["vertex_frame_status"], q["graph"].copy(),
                           q["scale"], q["seed_pose"], q["last_world_position"])
     assert r5["stats"]["plan_reused"] == 0 and r5["stats"]["direct_solves"] > 0
+
+
+@pytest.mark.parametrize("seed", list(range(1235, 1243)))
+def test_every_bench_rank_frame_runs_on_the_exact_solve_engine(core, seed):
+    """bench.py --gpus N tracks the configs[1] frame of seed 1235 + rank on rank `rank`. The root front of the
+    factorisation must fit the shared memory of one SM on every one of them (with median cuts and a greedy separator 2 of
+    the 8 did not, fell back to the CG engine and tripled the max-over-ranks step): every LM trial of the main rounds
+    and of the lost-point stage is an exact solve, none a CG iteration."""
+    p = synth.tracking_problem("c2", seed=seed)
+    r0, r1 = core.track_pose_and_deform(p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"],
+                                        p["graph"].copy(), p["scale"], p["seed_pose"], p["last_world_position"])
+    s = r1["stats"]
+    assert r1["rc"] == 0 and s["pcg_iterations"] == 0 and s["solve_failures"] == 0
+    assert s["direct_solves"] == s["lm_trials"] > 0
