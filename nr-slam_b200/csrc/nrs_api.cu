@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <malloc.h>
 #include <cstring>
 #include <cstdio>
 #include <numeric>
@@ -284,6 +285,7 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
   if (!forced_old_of_new && (hp.n_sort <= 1 || hp.points_fixed)) return;
   std::vector<int> old_of_new(V);
   std::iota(old_of_new.begin(), old_of_new.end(), 0);
+  bool rows_done = false;  // the per-keyframe sort below permutes the row arrays itself
   if (forced_old_of_new) {
     // elimination order of the exact solve (nrs_direct_plan.h); it may cover a prefix (the unknown rows) only
     std::copy(forced_old_of_new->begin(), forced_old_of_new->end(), old_of_new.begin());
@@ -292,6 +294,8 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
   const int n_threads = host_threads(hp.F, V);
   auto work = [&](int tix) {
   std::vector<std::pair<uint32_t, int>> keyed;
+  std::vector<double> tmp;
+  std::vector<int> tmpi;
   for (int k = tix; k < hp.F; k += n_threads) {
     const int b = hp.kf_begin[k], e = std::min(hp.kf_begin[k + 1], hp.n_sort);
     if (e - b < 2) continue;
@@ -314,6 +318,22 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
     }
     std::sort(keyed.begin(), keyed.end());
     for (int t = 0; t < e - b; t++) old_of_new[b + t] = keyed[t].second;
+    // rows only move inside their keyframe: permute them here, through a temporary that stays in cache (the
+    // whole-array gathers cost three extra passes over 16 MB and six thread spawns on a 200k-row window)
+    const int nk = e - b;
+    tmp.resize(4 * (size_t)nk);
+    auto gather = [&](std::vector<double>& v, int stride) {
+      for (int t = 0; t < nk; t++)
+        for (int a = 0; a < stride; a++) tmp[(size_t)stride * t + a] = v[(size_t)stride * keyed[t].second + a];
+      std::copy(tmp.begin(), tmp.begin() + (size_t)stride * nk, v.begin() + (size_t)stride * b);
+    };
+    gather(hp.x_seed, 4);
+    gather(hp.rest, 4);
+    gather(hp.uv, 2);
+    tmpi.resize(nk);
+    for (int t = 0; t < nk; t++) tmpi[t] = hp.pt_kf[keyed[t].second];
+    std::copy(tmpi.begin(), tmpi.end(), hp.pt_kf.begin() + b);
+    for (int t = 0; t < nk; t++) row_of[keyed[t].second] = b + t;
   }
   };
   if (n_threads == 1) {
@@ -324,8 +344,10 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
     work(0);
     for (auto& th : pool) th.join();
   }
+  rows_done = true;
   }
   const int pt = host_threads(64, V);  // the gathers below are independent per row / per edge
+  if (!rows_done) {
   par_ranges(pt, (size_t)V, [&](size_t b, size_t e) {
     for (size_t nw = b; nw < e; nw++) row_of[old_of_new[nw]] = (int)nw;
   });
@@ -344,6 +366,7 @@ void sort_rows(HostProblem& hp, std::vector<int>& row_of, const std::vector<int>
     std::vector<int> o(V);
     for (int nw = 0; nw < V; nw++) o[nw] = hp.pt_kf[old_of_new[nw]];
     hp.pt_kf.swap(o);
+  }
   }
   par_ranges(pt, hp.pair_i.size(), [&](size_t b, size_t e) {
     for (size_t t = b; t < e; t++) {
@@ -705,6 +728,15 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
   sort_rows(hp, st.row_of, direct ? &dplan.old_of_new : nullptr);
   hprof.mark("sort_rows");
 
+  std::vector<int> dinc_ptr(V + 1, 0), dinc_ent(4 * (size_t)D);
+  auto damper_csr = [&] {
+    for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ptr[hp.dmp_v[t] + 1]++;
+    for (int i = 0; i < V; i++) dinc_ptr[i + 1] += dinc_ptr[i];
+    std::vector<int> w(dinc_ptr.begin(), dinc_ptr.end() - 1);
+    for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ent[w[hp.dmp_v[t]]++] = (int)t;  // id*4 + role
+  };
+  std::thread damper_thread;  // the damper lists do not depend on the pair lists: second host thread on BA windows
+  if (D >= 4096 && host_threads(2, V) > 1) damper_thread = std::thread(damper_csr);
   // incidence lists
   std::vector<int> inc_ptr(V + 1, 0), inc_other(2 * (size_t)P), inc_ent(2 * (size_t)P), inc_row(2 * (size_t)P);
   for (int e = 0; e < P; e++) {
@@ -725,13 +757,7 @@ int stage_problem(nrslam_b200_ctx* ctx, Staged& st, HostProblem& hp) {
       inc_row[a] = hp.pair_j[e];
     }
   }
-  std::vector<int> dinc_ptr(V + 1, 0), dinc_ent(4 * (size_t)D);
-  for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ptr[hp.dmp_v[t] + 1]++;
-  for (int i = 0; i < V; i++) dinc_ptr[i + 1] += dinc_ptr[i];
-  {
-    std::vector<int> w(dinc_ptr.begin(), dinc_ptr.end() - 1);
-    for (size_t t = 0; t < 4 * (size_t)D; t++) dinc_ent[w[hp.dmp_v[t]]++] = (int)t;  // id*4 + role
-  }
+  if (damper_thread.joinable()) damper_thread.join(); else damper_csr();
 
   hprof.mark("incidences");
   // ---- launch plans. Tracking stages its lost-point rows behind the optimised ones: the main rounds run on the
@@ -1174,6 +1200,15 @@ int nrslam_b200_create(const nrslam_b200_options* opt, nrslam_b200_ctx** out) {
   if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess) return NRSLAM_B200_ERR_CUDA;
   if (prop.major != 10) return NRSLAM_B200_ERR_NO_DEVICE;  // sm_100a cubin only
   if (cudaSetDevice(o.device) != cudaSuccess) return NRSLAM_B200_ERR_CUDA;
+  // The staging of a BA window allocates ~60 MB of host vectors per call. Above glibc's mmap threshold every one of
+  // them is a fresh mapping whose pages fault in on first touch and are unmapped again on free: 10 of the 19 ms of
+  // host staging on configs[3]. Serving them from the heap and not trimming it keeps the pages across calls.
+  // (Process-wide allocator knobs: NRSLAM_B200_MALLOC_TUNE=0 leaves them alone.)
+  if (env_int("NRSLAM_B200_MALLOC_TUNE", 1)) {
+    mallopt(M_MMAP_THRESHOLD, 512 << 20);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 64 << 20);
+  }
   nrslam_b200_ctx* ctx = new nrslam_b200_ctx();
   ctx->opt = o;
   ctx->device = o.device;
@@ -1817,6 +1852,8 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
     hp.pt_kf[o] = obs_kf[o];
   }
   for (int k = 0; k < F; k++) hp.kf_begin[k + 1] += hp.kf_begin[k];
+  HostProf hprof;
+  hprof.mark("rows");
 
   // ---- springs inside a keyframe, dampers to the next newer keyframe (:982-1136)
   // sorted neighbour lists are cached per map point; (pair, keyframe) de-duplication is keyed by graph edge
@@ -1862,6 +1899,7 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
       }
     });
   }
+  hprof.mark("nb_lists");
   // Keyframes are independent here (a spring joins two points of ONE keyframe, a damper reads keyframes k and k + 1,
   // the reference's de-duplication maps are per keyframe): host threads take keyframes round robin, every keyframe
   // fills its own edge lists in the reference's order, and the lists are concatenated in keyframe order afterwards, so
@@ -1875,12 +1913,11 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
   auto work = [&](int tix) {
     std::vector<int> cur(M, -1), nxt(M, -1);  // inserted_landmarks[k][mappoint] -> row
     std::vector<int> spring_stamp(g->n_edges, -1), damper_stamp(g->n_edges, -1);
+    KfEdges out;  // per-thread scratch that keeps its capacity: the keyframe's lists are stored at their exact size
+                  // (worst-case reserves per keyframe were 8x oversized and paid for in page faults)
     for (int k = tix; k < F; k += n_threads) {
-      KfEdges& out = per_kf[k];
       const bool has_next = k + 1 < F;
-      const int nk = hp.kf_begin[k + 1] - hp.kf_begin[k];
-      out.pair_i.reserve(6 * (size_t)nk); out.pair_j.reserve(6 * (size_t)nk); out.pair_d0.reserve(6 * (size_t)nk);
-      out.dmp_v.reserve(20 * (size_t)nk); out.dmp_w.reserve(5 * (size_t)nk);
+      out.pair_i.clear(); out.pair_j.clear(); out.pair_d0.clear(); out.dmp_v.clear(); out.dmp_w.clear();
       for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) cur[obs_vertex[o]] = o;
       if (has_next)
         for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) nxt[obs_vertex[o]] = o;
@@ -1930,6 +1967,7 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
       for (int o = hp.kf_begin[k]; o < hp.kf_begin[k + 1]; o++) cur[obs_vertex[o]] = -1;
       if (has_next)
         for (int o = hp.kf_begin[k + 1]; o < hp.kf_begin[k + 2]; o++) nxt[obs_vertex[o]] = -1;
+      per_kf[k] = out;
     }
   };
   if (n_threads == 1) {
@@ -1940,21 +1978,37 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
     work(0);
     for (auto& th : pool) th.join();
   }
-  size_t np = 0, nd = 0;
-  for (const auto& e : per_kf) {
-    np += e.pair_i.size();
-    nd += e.dmp_w.size();
+  hprof.mark("kf_edges");
+  // concatenation in keyframe order: offsets by prefix sums, the copies on the same threads
+  std::vector<size_t> poff(F + 1, 0), doff(F + 1, 0);
+  for (int k = 0; k < F; k++) {
+    poff[k + 1] = poff[k] + per_kf[k].pair_i.size();
+    doff[k + 1] = doff[k] + per_kf[k].dmp_w.size();
   }
-  hp.pair_i.reserve(np); hp.pair_j.reserve(np); hp.pair_d0.reserve(np);
-  hp.dmp_v.reserve(4 * nd); hp.dmp_w.reserve(nd);
-  for (const auto& e : per_kf) {
-    hp.pair_i.insert(hp.pair_i.end(), e.pair_i.begin(), e.pair_i.end());
-    hp.pair_j.insert(hp.pair_j.end(), e.pair_j.begin(), e.pair_j.end());
-    hp.pair_d0.insert(hp.pair_d0.end(), e.pair_d0.begin(), e.pair_d0.end());
-    hp.dmp_v.insert(hp.dmp_v.end(), e.dmp_v.begin(), e.dmp_v.end());
-    hp.dmp_w.insert(hp.dmp_w.end(), e.dmp_w.begin(), e.dmp_w.end());
+  const size_t np = poff[F], nd = doff[F];
+  hp.pair_i.resize(np); hp.pair_j.resize(np); hp.pair_d0.resize(np);
+  hp.dmp_v.resize(4 * nd); hp.dmp_w.resize(nd);
+  auto concat = [&](int tix) {
+    for (int k = tix; k < F; k += n_threads) {
+      const KfEdges& e = per_kf[k];
+      std::copy(e.pair_i.begin(), e.pair_i.end(), hp.pair_i.begin() + poff[k]);
+      std::copy(e.pair_j.begin(), e.pair_j.end(), hp.pair_j.begin() + poff[k]);
+      std::copy(e.pair_d0.begin(), e.pair_d0.end(), hp.pair_d0.begin() + poff[k]);
+      std::copy(e.dmp_v.begin(), e.dmp_v.end(), hp.dmp_v.begin() + 4 * doff[k]);
+      std::copy(e.dmp_w.begin(), e.dmp_w.end(), hp.dmp_w.begin() + doff[k]);
+    }
+  };
+  if (n_threads == 1) {
+    concat(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(concat, t);
+    concat(0);
+    for (auto& th : pool) th.join();
   }
   hp.pair_w.assign(np, -1.0);
+  hprof.mark("concat");
+  hprof.print("build_ba_problem");
   hp.ops = {OP_CLEAR_LEVELS, OP_RESET, OP_OPTIMIZE};
   hp.op_args = {0, 0, iterations};
   hp.n_sort = O;

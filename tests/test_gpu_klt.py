@@ -135,6 +135,20 @@ def test_full_size_properties(core):
     b.close()
 
 
+def test_full_size_matches_the_oracle(core):
+    """The image pair and the 2000 points bench.py tracks on rank 0 (configs[1]): statuses and positions against the
+    oracle at full size (the oracle takes ~0.2 s here), same bars as the 600-point cases."""
+    p = synth.klt_pair(seed=77, n_points=2000)
+    a = oracle_lib.OracleKLT()
+    a.set_reference(p["ref"], p["pts"])
+    b = api.KLT(core)
+    b.set_reference(p["ref"], p["pts"])
+    ra = a.track(p["cur"], p["pts"], p["status"])
+    rb = b.track(p["cur"], p["pts"], p["status"])
+    compare_track(ra, rb, p["status"])
+    b.close()
+
+
 def test_rejects_unsupported_window(core):
     with pytest.raises(api.NrslamError):
         api.KLT(core, win=15)
