@@ -1840,16 +1840,24 @@ int build_ba_problem(nrslam_b200_ctx* ctx, const nrslam_b200_options& opt, const
   hp.uv.resize(2 * (size_t)O);
   hp.pt_kf.resize(O);
   hp.kf_begin.assign(F + 1, 0);
-  for (int o = 0; o < O; o++) {
-    if (obs_kf[o] < 0 || obs_kf[o] >= F || (o > 0 && obs_kf[o] < obs_kf[o - 1]) || obs_vertex[o] < 0 ||
-        obs_vertex[o] >= M)
-      return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba: observations must be grouped by keyframe slot");
-    hp.kf_begin[obs_kf[o] + 1]++;
-    for (int k = 0; k < 3; k++) hp.x_seed[4 * (size_t)o + k] = X_io[3 * (size_t)o + k];
-    hp.x_seed[4 * (size_t)o + 3] = 0;
-    hp.uv[2 * (size_t)o] = uv[2 * (size_t)o];
-    hp.uv[2 * (size_t)o + 1] = uv[2 * (size_t)o + 1];
-    hp.pt_kf[o] = obs_kf[o];
+  {
+    std::atomic<int> bad{0};
+    par_ranges(host_threads(64, O), (size_t)O, [&](size_t ob, size_t oe) {  // rows are independent: threads take ranges
+      for (size_t o = ob; o < oe; o++) {
+        if (obs_kf[o] < 0 || obs_kf[o] >= F || (o > 0 && obs_kf[o] < obs_kf[o - 1]) || obs_vertex[o] < 0 ||
+            obs_vertex[o] >= M) {
+          bad.store(1, std::memory_order_relaxed);
+          return;
+        }
+        for (int k = 0; k < 3; k++) hp.x_seed[4 * o + k] = X_io[3 * o + k];
+        hp.x_seed[4 * o + 3] = 0;
+        hp.uv[2 * o] = uv[2 * o];
+        hp.uv[2 * o + 1] = uv[2 * o + 1];
+        hp.pt_kf[o] = obs_kf[o];
+      }
+    });
+    if (bad.load()) return fail(ctx, NRSLAM_B200_ERR_ARG, "local_ba: observations must be grouped by keyframe slot");
+    for (int o = 0; o < O; o++) hp.kf_begin[obs_kf[o] + 1]++;
   }
   for (int k = 0; k < F; k++) hp.kf_begin[k + 1] += hp.kf_begin[k];
   HostProf hprof;
@@ -2409,8 +2417,10 @@ int nrslam_b200_local_ba(nrslam_b200_ctx* ctx, const nrslam_b200_camera* cam, in
   for (int i = 0; i < 7 * F; i++)
     if (!std::isfinite(pose[i])) return fail(ctx, NRSLAM_B200_NUM_NONFINITE, "local_ba: non-finite pose");
   for (int k = 0; k < F; k++) pose_to_f7(pose + 7 * k, kf_pose_io + 7 * k);  // :1146-1151
-  for (int o = 0; o < O; o++)
-    for (int k = 0; k < 3; k++) X_io[3 * (size_t)o + k] = (float)xd[4 * (size_t)st.row_of[o] + k];  // :1153-1160
+  par_ranges(host_threads(64, O), (size_t)O, [&](size_t ob, size_t oe) {
+    for (size_t o = ob; o < oe; o++)
+      for (int k = 0; k < 3; k++) X_io[3 * o + k] = (float)xd[4 * (size_t)st.row_of[o] + k];  // :1153-1160
+  });
   if (stats) {
     stats->n_reproj_edges = O;
     stats->n_spring_edges = (int)hp.pair_i.size();
