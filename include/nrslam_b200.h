@@ -23,6 +23,10 @@
  *     (1 = fewer points than the reference needs, nothing done). Never throws, never aborts.
  *     nrslam_b200_last_error(ctx) returns a description of the last non-zero return.
  *   - a ctx is single-caller (not re-entrant); calls block until results are in the host buffers.
+ *   - host side effects: nrslam_b200_create() raises glibc's mmap / trim thresholds (mallopt) so that the ~60 MB of
+ *     staging vectors of a BA call are served from the heap instead of fresh mappings (process-wide; set
+ *     NRSLAM_B200_MALLOC_TUNE=0 to leave the allocator alone), and the tracking calls keep up to 8 staging threads
+ *     (NRSLAM_B200_HOST_THREADS caps them) that spin only while a call is staging.
  *   - there is NO CPU fallback: every entry point that computes fails with NRSLAM_B200_ERR_NO_DEVICE
  *     when no sm_100 device is present.
  */
