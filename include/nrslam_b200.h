@@ -256,6 +256,26 @@ int32_t nrslam_b200_graph_get_edges(const nrslam_b200_graph* g, int32_t vertex, 
                                     int32_t capacity);
 int32_t nrslam_b200_graph_update_vertex(nrslam_b200_graph* g, int32_t vertex, const float* positions);
 
+/* ---- RegularizationGraph construction: AddEdge / SetSigma (map/regularization_graph.cc:33-55) ---------------
+ * A graph STORE owns the edge records and their adjacency across frames, so a host keeps ONE resident graph instead of
+ * rebuilding a CSR per call: Map::InitializeRegularizationGraph (map.cc:139-167) and Mapping's insertion of newly
+ * triangulated landmarks (mapping.cc:238-256) become add_edges batches; the optimisation entry points take the store's
+ * CSR view and refresh its attribute arrays in place (pose_deform's UpdateVertex loop writes straight into the store).
+ *   add_edges: for k < n: AddEdge(v1[k], v2[k], relative_position[3k..]): distance = |relative_position|,
+ *     first / min / max distance = distance, weight = exp(-d^2 / (2 sigma^2)), status NEUTRAL. Vertices are dense
+ *     indices >= 0 in ascending MapPoint id; the store grows to the largest index seen. An EXISTING pair is replaced
+ *     (attributes reset), exactly like graph_[a][b] = edge does; v1 == v2 or a negative index is an argument error.
+ *   set_sigma: SetSigma (:33-36): later edges and min_weight use the new sigma, existing weights stay.
+ *   view: fills *out with pointers into the store (rows and row entries ascending); valid until the next add_edges /
+ *     destroy. Returns 0, < 0 on an argument error. */
+typedef struct nrslam_b200_graph_store nrslam_b200_graph_store;
+int nrslam_b200_graph_store_create(float weight_sigma, float stretching_th, nrslam_b200_graph_store** out);
+void nrslam_b200_graph_store_destroy(nrslam_b200_graph_store* store);
+int nrslam_b200_graph_store_add_edges(nrslam_b200_graph_store* store, int32_t n, const int32_t* v1, const int32_t* v2,
+                                      const float* relative_position);
+int nrslam_b200_graph_store_set_sigma(nrslam_b200_graph_store* store, float weight_sigma);
+int nrslam_b200_graph_store_view(nrslam_b200_graph_store* store, nrslam_b200_graph* out);
+
 /* ---- LucasKanadeTracker (matching/lucas_kanade_tracker.h:55-92) -------------------------------
  * One tracker object per reference image. Images are 8-bit single channel, `pitch` bytes per row.
  * win_size must be 21 (the only window the reference uses, modules/SLAM/system.cc:78-83).

@@ -14,7 +14,7 @@ import weakref
 
 import numpy as np
 
-from .abi import (Camera, FILTER_BORDER, FILTER_BRIGHT, FILTER_PREDEFINED, Graph, MaskFilter, Options, Stats,  # noqa: F401
+from .abi import (Camera, FILTER_BORDER, FILTER_BRIGHT, FILTER_PREDEFINED, Graph, GraphArrays, MaskFilter, Options, Stats,  # noqa: F401
                   ptr)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -44,12 +44,81 @@ def load():
         lib.nrslam_b200_last_error.restype = C.c_char_p
         lib.nrslam_b200_graph_get_edges.restype = C.c_int32
         lib.nrslam_b200_graph_update_vertex.restype = C.c_int32
+        lib.nrslam_b200_graph_store_destroy.restype = None
+        lib.nrslam_b200_graph_store_destroy.argtypes = [C.c_void_p]
+        lib.nrslam_b200_graph_store_add_edges.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
+                                                          C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        lib.nrslam_b200_graph_store_set_sigma.argtypes = [C.c_void_p, C.c_float]
+        lib.nrslam_b200_graph_store_view.argtypes = [C.c_void_p, C.POINTER(Graph)]
         lib.nrslam_b200_klt_num_points.restype = C.c_int32
         lib.nrslam_b200_pre_last_ms.restype = C.c_float
         lib.nrslam_b200_pre_last_launches.restype = C.c_int32
         lib.nrslam_b200_tri_last_ms.restype = C.c_float
         _LIB = lib
     return _LIB
+
+
+class GraphStore:
+    """RegularizationGraph as the library's owning store (include/nrslam_b200.h: nrslam_b200_graph_store_*): AddEdge /
+    SetSigma (map/regularization_graph.cc:33-55) and a CSR view whose attribute arrays the optimisation entry points
+    refresh in place. Pure host code: works without a GPU."""
+
+    def __init__(self, weight_sigma, stretching_th=1.1):
+        self.L = load()
+        self._h = C.c_void_p()
+        rc = self.L.nrslam_b200_graph_store_create(C.c_float(weight_sigma), C.c_float(stretching_th), C.byref(self._h))
+        if rc:
+            raise ValueError("graph_store_create: %d" % rc)
+
+    def add_edges(self, v1, v2, relative_position):
+        v1 = np.ascontiguousarray(v1, np.int32)
+        v2 = np.ascontiguousarray(v2, np.int32)
+        rel = np.ascontiguousarray(relative_position, np.float32).reshape(-1, 3)
+        assert len(v1) == len(v2) == len(rel)
+        return self.L.nrslam_b200_graph_store_add_edges(self._h, len(v1), ptr(v1, C.c_int32), ptr(v2, C.c_int32),
+                                                        ptr(rel, C.c_float))
+
+    def set_sigma(self, sigma):
+        return self.L.nrslam_b200_graph_store_set_sigma(self._h, C.c_float(sigma))
+
+    @property
+    def n_vertices(self):
+        return self.struct().n_vertices
+
+    @property
+    def n_edges(self):
+        return self.struct().n_edges
+
+    def struct(self):
+        """The store's CSR view as an abi.Graph (valid until the next add_edges / close)."""
+        g = Graph()
+        rc = self.L.nrslam_b200_graph_store_view(self._h, C.byref(g))
+        if rc:
+            raise ValueError("graph_store_view: %d" % rc)
+        return g
+
+    def arrays(self):
+        """Copies of the view as an abi.GraphArrays (for comparisons)."""
+        g = self.struct()
+        M, E = g.n_vertices, g.n_edges
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(p, shape=(n,)).astype(dt).copy() if n else np.zeros(0, dt)
+        return GraphArrays(arr(g.rowptr, M + 1, np.int32) if M or E else np.zeros(1, np.int32), arr(g.col, 2 * E, np.int32),
+                           arr(g.eid, 2 * E, np.int32), arr(g.weight, E, np.float32), arr(g.first_distance, E, np.float32),
+                           arr(g.min_distance, E, np.float32), arr(g.max_distance, E, np.float32),
+                           arr(g.status, E, np.uint8), g.weight_sigma, g.stretching_th)
+
+    def close(self):
+        if self._h:
+            self.L.nrslam_b200_graph_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def default_options():

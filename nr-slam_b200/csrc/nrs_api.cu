@@ -20,6 +20,7 @@
 #include <numeric>
 #include <set>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "nrs_host.h"
@@ -1262,6 +1263,113 @@ int32_t nrslam_b200_graph_get_edges(const nrslam_b200_graph* g, int32_t vertex, 
   const int n = graph_sorted_entries(g, vertex, graph_min_weight(g), ent);
   for (int i = 0; i < n && i < capacity; i++) out_entries[i] = ent[i];
   return n;
+}
+
+// ---- RegularizationGraph::AddEdge / SetSigma as an owning store (regularization_graph.cc:33-55) --------------------
+}  // extern "C"
+struct nrslam_b200_graph_store {
+  float sigma = 0, stretching = 0;
+  int n_vertices = 0;
+  std::vector<int32_t> ev1, ev2;  // undirected edge -> endpoints (v1 < v2)
+  std::vector<float> weight, first_distance, min_distance, max_distance;
+  std::vector<uint8_t> status;
+  std::unordered_map<uint64_t, int32_t> index;  // (v1 << 32 | v2) -> edge id
+  bool dirty = true;
+  std::vector<int32_t> rowptr, col, eid;
+};
+extern "C" {
+int nrslam_b200_graph_store_create(float weight_sigma, float stretching_th, nrslam_b200_graph_store** out) {
+  if (!out || !(weight_sigma > 0)) return NRSLAM_B200_ERR_ARG;
+  *out = new nrslam_b200_graph_store();
+  (*out)->sigma = weight_sigma;
+  (*out)->stretching = stretching_th;
+  return 0;
+}
+
+void nrslam_b200_graph_store_destroy(nrslam_b200_graph_store* store) { delete store; }
+
+int nrslam_b200_graph_store_set_sigma(nrslam_b200_graph_store* store, float weight_sigma) {
+  if (!store || !(weight_sigma > 0)) return NRSLAM_B200_ERR_ARG;
+  store->sigma = weight_sigma;  // min_weight follows from sigma (graph_min_weight)
+  return 0;
+}
+
+int nrslam_b200_graph_store_add_edges(nrslam_b200_graph_store* st, int32_t n, const int32_t* v1, const int32_t* v2,
+                                      const float* rel) {
+  if (!st || n < 0 || (n > 0 && (!v1 || !v2 || !rel))) return NRSLAM_B200_ERR_ARG;
+  for (int k = 0; k < n; k++)
+    if (v1[k] < 0 || v2[k] < 0 || v1[k] == v2[k]) return NRSLAM_B200_ERR_ARG;  // nothing is modified on an error
+  for (int k = 0; k < n; k++) {
+    const int32_t a = std::min(v1[k], v2[k]), b = std::max(v1[k], v2[k]);
+    const float* r = rel + 3 * (size_t)k;
+    const float distance = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);  // Eigen::Vector3f::norm()
+    const uint64_t key = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
+    auto it = st->index.find(key);
+    int32_t e;
+    if (it == st->index.end()) {
+      e = (int32_t)st->ev1.size();
+      st->index.emplace(key, e);
+      st->ev1.push_back(a);
+      st->ev2.push_back(b);
+      st->weight.push_back(0);
+      st->first_distance.push_back(0);
+      st->min_distance.push_back(0);
+      st->max_distance.push_back(0);
+      st->status.push_back(0);
+      st->dirty = true;
+      st->n_vertices = std::max(st->n_vertices, b + 1);
+    } else {
+      e = it->second;  // graph_[a][b] = edge: the pair's record is replaced
+    }
+    st->weight[e] = interpolation_weight(distance, st->sigma);
+    st->first_distance[e] = st->min_distance[e] = st->max_distance[e] = distance;
+    st->status[e] = NRSLAM_EDGE_NEUTRAL;
+  }
+  return 0;
+}
+
+int nrslam_b200_graph_store_view(nrslam_b200_graph_store* st, nrslam_b200_graph* out) {
+  if (!st || !out) return NRSLAM_B200_ERR_ARG;
+  if (st->dirty) {
+    const int M = st->n_vertices, E = (int)st->ev1.size();
+    st->rowptr.assign(M + 1, 0);
+    for (int e = 0; e < E; e++) {
+      st->rowptr[st->ev1[e] + 1]++;
+      st->rowptr[st->ev2[e] + 1]++;
+    }
+    for (int v = 0; v < M; v++) st->rowptr[v + 1] += st->rowptr[v];
+    std::vector<std::pair<int32_t, int32_t>> ent(2 * (size_t)E);  // (neighbour, edge) per CSR slot
+    {
+      std::vector<int32_t> w(st->rowptr.begin(), st->rowptr.end() - 1);
+      for (int e = 0; e < E; e++) {
+        ent[w[st->ev1[e]]++] = {st->ev2[e], e};
+        ent[w[st->ev2[e]]++] = {st->ev1[e], e};
+      }
+    }
+    st->col.resize(2 * (size_t)E);
+    st->eid.resize(2 * (size_t)E);
+    for (int v = 0; v < M; v++) {  // row entries ascending by neighbour (the btree_map order)
+      std::sort(ent.begin() + st->rowptr[v], ent.begin() + st->rowptr[v + 1]);
+      for (int p = st->rowptr[v]; p < st->rowptr[v + 1]; p++) {
+        st->col[p] = ent[p].first;
+        st->eid[p] = ent[p].second;
+      }
+    }
+    st->dirty = false;
+  }
+  out->n_vertices = st->n_vertices;
+  out->n_edges = (int32_t)st->ev1.size();
+  out->rowptr = st->rowptr.data();
+  out->col = st->col.data();
+  out->eid = st->eid.data();
+  out->weight = st->weight.data();
+  out->first_distance = st->first_distance.data();
+  out->min_distance = st->min_distance.data();
+  out->max_distance = st->max_distance.data();
+  out->status = st->status.data();
+  out->weight_sigma = st->sigma;
+  out->stretching_th = st->stretching;
+  return 0;
 }
 
 int32_t nrslam_b200_graph_update_vertex(nrslam_b200_graph* g, int32_t vertex, const float* positions) {

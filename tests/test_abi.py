@@ -83,3 +83,77 @@ def test_graph_entry_points_match_oracle(lib, oracle):
         assert a == b
     for name in ("weight", "min_distance", "max_distance", "status"):
         assert np.array_equal(getattr(g1, name), getattr(g2, name)), name
+
+
+def test_graph_store_add_edges_matches_the_reference_semantics(lib, oracle):
+    """RegularizationGraph::AddEdge / SetSigma (map/regularization_graph.cc:33-55) through the owning store, against a
+    dictionary restatement: distance = |relative position| in fp32, weight = exp(-d^2 / (2 sigma^2)), status NEUTRAL,
+    min = max = first distance; inserting an existing pair again REPLACES its record; rows and row entries of the CSR
+    view ascend. Then the view drives the host UpdateVertex / GetEdges entry points like any caller-built CSR."""
+    rng = np.random.default_rng(5)
+    M = 60
+    pos = rng.normal(size=(M, 3)).astype(np.float32)
+    sigma = np.float32(0.8)
+    st = api.GraphStore(float(sigma), 1.1)
+    ref = {}
+
+    def weight(d, s):
+        return np.float32(np.exp(-(d * d) / (np.float32(2) * s * s)))
+
+    def add(pairs, s):
+        v1 = np.array([p[0] for p in pairs], np.int32)
+        v2 = np.array([p[1] for p in pairs], np.int32)
+        rel = pos[v2] - pos[v1]
+        assert st.add_edges(v1, v2, rel) == 0
+        for a, b, r in zip(v1, v2, rel):
+            d = np.float32(np.sqrt(np.float32(r[0] * r[0] + r[1] * r[1]) + np.float32(r[2] * r[2])))
+            ref[(min(a, b), max(a, b))] = d
+
+    # Map::InitializeRegularizationGraph: every pair of the first 25 landmarks (map.cc:139-167)
+    add([(i, j) for i in range(25) for j in range(i + 1, 25)], sigma)
+    g = st.arrays()
+    assert g.n_vertices == 25 and g.n_edges == 300
+    # Mapping: newly triangulated landmarks 25..59 connect to everything before them, in either argument order
+    add([(j, i) if (i + j) % 2 else (i, j) for i in range(25, M) for j in range(0, i, 3)], sigma)
+    g = st.arrays()
+    assert g.n_vertices == M and g.n_edges == len(ref)
+    # CSR view: rows ascending, entries ascending, both directions share one record
+    for v in range(M):
+        row = g.col[g.rowptr[v]:g.rowptr[v + 1]]
+        assert np.all(np.diff(row) > 0)
+        for p_ in range(g.rowptr[v], g.rowptr[v + 1]):
+            e = g.eid[p_]
+            d = ref[(min(v, g.col[p_]), max(v, g.col[p_]))]
+            assert abs(g.first_distance[e] - d) <= 2e-7 * max(d, 1) and g.min_distance[e] == g.max_distance[e] == g.first_distance[e]
+            assert abs(g.weight[e] - weight(g.first_distance[e], sigma)) <= 1e-6
+            assert g.status[e] == abi.EDGE_NEUTRAL
+    # the view behaves like a caller-built CSR: UpdateVertex writes straight into the store
+    moved = pos + rng.normal(scale=0.3, size=pos.shape).astype(np.float32)
+    g_ref = st.arrays()
+    s1 = st.struct()
+    for v in range(0, M, 7):
+        a = lib.nrslam_b200_graph_update_vertex(C.byref(s1), v, abi.ptr(moved, C.c_float))
+        assert a == oracle.graph_update_vertex(g_ref, v, moved)
+    after = st.arrays()
+    for name in ("weight", "min_distance", "max_distance", "status"):
+        assert np.array_equal(getattr(after, name), getattr(g_ref, name)), name
+    assert (after.max_distance > after.first_distance).any()
+    # AddEdge on an existing pair replaces the record; SetSigma changes later weights only
+    st.set_sigma(1.6)
+    e_before = after.n_edges
+    add([(3, 40)], np.float32(1.6))
+    again = st.arrays()
+    assert again.n_edges == e_before and again.weight_sigma == np.float32(1.6)
+    row = list(again.col[again.rowptr[3]:again.rowptr[4]])
+    e = again.eid[again.rowptr[3] + row.index(40)]
+    assert again.min_distance[e] == again.max_distance[e] == again.first_distance[e]
+    assert abs(again.weight[e] - weight(again.first_distance[e], np.float32(1.6))) <= 1e-6
+    assert again.status[e] == abi.EDGE_NEUTRAL
+    untouched = np.ones(again.n_edges, bool)
+    untouched[e] = False
+    assert np.array_equal(again.weight[untouched], after.weight[untouched])
+    # argument errors modify nothing
+    assert st.add_edges([1, 2], [1, 5], np.zeros((2, 3), np.float32)) < 0
+    assert st.add_edges([-1], [5], np.zeros((1, 3), np.float32)) < 0
+    assert st.arrays().n_edges == e_before
+    st.close()

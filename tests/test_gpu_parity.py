@@ -204,3 +204,27 @@ def test_full_size_c3_matches_the_oracle(core):
     """BASELINE configs[2] at FULL size (5k landmarks / 30 KFs / 50k observations) against the oracle: LM iteration and
     trial counts exact, chi2 trace 1e-5, poses 5e-6, points 5e-5."""
     _compare_with_full_size_fixture(core, "c3", 5e-6, 5e-5)
+
+
+def test_pose_deform_on_a_graph_store_view(core):
+    """The owning graph store (nrslam_b200_graph_store_*: AddEdge batches, one resident graph across frames) drives
+    CameraPoseAndDeformationOptimization like a caller-built CSR: same results bit for bit, and the call's graph refresh
+    (UpdateVertex loop) lands in the store's own attribute arrays."""
+    p = synth.tracking_problem("c1", n=400)
+    g0 = p["graph"]
+    v1 = np.repeat(np.arange(g0.n_vertices, dtype=np.int32), np.diff(g0.rowptr))
+    keep = v1 < g0.col
+    v1, v2 = v1[keep], g0.col[keep]
+    store = api.GraphStore(g0.weight_sigma, g0.stretching_th)
+    assert store.add_edges(v1, v2, p["last_world_position"][v2] - p["last_world_position"][v1]) == 0
+    arrays = store.arrays()
+    args = (p["cam"], p["uv"], p["X_rest"], p["point_vertex"], p["vertex_frame_status"])
+    a = core.pose_deform(*args, arrays, p["scale"], p["seed_pose"], p["last_world_position"])
+    b = core.pose_deform(*args, store, p["scale"], p["seed_pose"], p["last_world_position"])
+    for k in ("pose", "deformation", "X", "chi2", "status", "lost", "last_pos"):
+        assert np.array_equal(a[k], b[k]), k
+    after = store.arrays()
+    for name in ("weight", "min_distance", "max_distance", "status"):
+        assert np.array_equal(getattr(after, name), getattr(arrays, name)), name
+    assert (after.max_distance > after.first_distance).any()   # the refresh really wrote into the store
+    store.close()
