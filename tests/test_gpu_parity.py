@@ -10,7 +10,7 @@ Index bookkeeping (statuses, inlier flags, lost-id set, edge counts, graph statu
 import numpy as np
 import pytest
 
-from nrslam_b200 import abi, synth
+from nrslam_b200 import abi, api, synth
 
 pytestmark = pytest.mark.gpu
 
