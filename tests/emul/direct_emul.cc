@@ -96,3 +96,19 @@ extern "C" int direct_emul_solve(int32_t V, const double* uv, int32_t P, const i
   }
   return fail ? 1 : 0;
 }
+
+// Symbolic analysis only: stats[0..7] = depth, G, p_total, u_total, smem_doubles, max_path, root separator vertices
+// (pose pseudo-vertices included), largest separator below the root.
+extern "C" int direct_emul_plan(int32_t V, const double* uv, int32_t P, const int32_t* pair_i, const int32_t* pair_j,
+                                int32_t depth, int64_t* stats) {
+  using namespace nrs;
+  std::vector<int> pi(pair_i, pair_i + P), pj(pair_j, pair_j + P);
+  DirectPlanHost pl;
+  if (depth < 0) depth = direct_depth(V, 128);
+  build_direct_plan(V, uv, pi, pj, depth, pl);
+  int below = 0;
+  for (int t = 2; t <= pl.n_nodes; t++) below = std::max(below, pl.nv[t]);
+  stats[0] = pl.depth; stats[1] = pl.G; stats[2] = pl.p_total; stats[3] = pl.u_total;
+  stats[4] = (int64_t)pl.smem_doubles; stats[5] = pl.max_path; stats[6] = pl.nv[1]; stats[7] = below;
+  return 0;
+}

@@ -121,3 +121,29 @@ def test_not_positive_definite_is_reported():
     sy["dg"][:, [0, 3, 5]] -= 1e4
     rc, _, _, stats = solve_emulated(sy)
     assert rc == 1 and stats[7] != 0
+
+
+def kNN_pairs(n, k, seed):
+    rng = np.random.default_rng(seed)
+    uv = np.stack([rng.uniform(0, 640, n), rng.uniform(0, 480, n)], 1)
+    _, nb = cKDTree(uv).query(uv, k=k + 1)
+    a = np.repeat(np.arange(n), k)
+    b = nb[:, 1:].reshape(-1)
+    key = np.unique(np.minimum(a, b).astype(np.int64) * n + np.maximum(a, b))
+    return np.ascontiguousarray(uv), (key // n).astype(np.int32), (key % n).astype(np.int32)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_root_front_of_a_tracking_frame_fits_one_sm(seed):
+    """The root front is factorised redundantly by every CTA, so it must fit the shared memory of ONE SM or the frame
+    falls back to the CG engine (3x slower; 2 of the 8 frames bench.py tracks at N = 8 did with median cuts and a greedy
+    separator). 2000 uniformly scattered points with their full symmetric 10-NN graph (denser than the regulariser
+    selection of a frame, 11.4k pairs against 10.6k): the plan's busiest panel stays below 190 KB (127-172 KB measured;
+    the kernel's other buffers need ~25 KB of the 227 KB) and the root separator at or below 50 vertices (42-49)."""
+    uv, pi, pj = kNN_pairs(2000, 10, 100 + seed)
+    stats = np.zeros(8, np.int64)
+    rc = _lib().direct_emul_plan(C.c_int32(2000), _ptr(uv, C.c_double), C.c_int32(len(pi)), _ptr(pi, C.c_int32),
+                                 _ptr(pj, C.c_int32), C.c_int32(-1), _ptr(stats, C.c_int64))
+    assert rc == 0 and stats[0] == 7 and stats[1] == 128
+    assert stats[4] * 8 < 190 * 1024, "busiest panel %d KB" % (stats[4] * 8 // 1024)
+    assert stats[6] <= 50, "root separator of %d vertices" % stats[6]
